@@ -1,0 +1,225 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of oracle/libcaretta_oracle.so (the CPU restatement of the
+reference's pair path, see caretta_oracle.c for the reference file:line map).
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs.
+The product package (caretta_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcaretta_oracle.so")
+_lib = None
+
+_D = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_I64 = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_I32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_P = C.c_void_p
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "caretta_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.crt_o_rbf_matrix.argtypes = [_D, _D, C.c_int, C.c_int, C.c_int, C.c_double, _D]
+        L.crt_o_rbf_matrix.restype = None
+        L.crt_o_smith_waterman_score.argtypes = [_D, C.c_int, C.c_int, C.c_double]
+        L.crt_o_smith_waterman_score.restype = C.c_double
+        L.crt_o_smith_waterman.argtypes = [_D, C.c_int, C.c_int, C.c_double, _I64, _I64,
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.crt_o_smith_waterman.restype = C.c_int
+        L.crt_o_dtw_align.argtypes = [_D, C.c_int, C.c_int, C.c_double, C.c_double, _I64, _I64,
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_double), _P, _P]
+        L.crt_o_dtw_align.restype = None
+        L.crt_o_common_positions.argtypes = [_I64, _I64, C.c_int64, _I64, _I64]
+        L.crt_o_common_positions.restype = C.c_int64
+        L.crt_o_kabsch.argtypes = [_D, _D, C.c_int64, _D, _D]
+        L.crt_o_kabsch.restype = None
+        L.crt_o_apply_rotran.argtypes = [_D, C.c_int64, _D, _D, _D]
+        L.crt_o_apply_rotran.restype = None
+        L.crt_o_superpose_with_subset.argtypes = [_D, C.c_int64, _D, C.c_int64, _D, _D, C.c_int64, _D, _D, _P]
+        L.crt_o_superpose_with_subset.restype = None
+        L.crt_o_rmsd.argtypes = [_D, _D, C.c_int64]
+        L.crt_o_rmsd.restype = C.c_double
+        L.crt_o_tm_score.argtypes = [_D, _D, C.c_int64, C.c_int64, C.c_int64]
+        L.crt_o_tm_score.restype = C.c_double
+        L.crt_o_pair.argtypes = [_D, _D, C.c_int, _D, _D, C.c_int, C.c_int, C.c_double, C.c_double,
+                                 C.POINTER(C.c_double), _P, _P, _P, _P, _P, _P, _P, _P]
+        L.crt_o_pair.restype = C.c_int
+        L.crt_o_pair_f32model.argtypes = [_D, _D, C.c_int, _D, _D, C.c_int, C.c_int, C.c_double, C.c_double,
+                                          C.POINTER(C.c_double), _I64, _I64, C.POINTER(C.c_int64)]
+        L.crt_o_pair_f32model.restype = C.c_int
+        L.crt_o_pairwise_list.argtypes = [_D, _D, _I64, C.c_int, _I32, _I32, C.c_int64, C.c_double, C.c_double,
+                                          C.c_int, _D, _P, _P, _P, _P]
+        L.crt_o_pairwise_list.restype = None
+        L.crt_o_pairwise_all.argtypes = [_D, _D, _I64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _D]
+        L.crt_o_pairwise_all.restype = None
+        L.crt_o_rmsd_cov_tm.argtypes = [_I64, C.c_int, C.c_int64, _D, _I64, _D, _D, _D]
+        L.crt_o_rmsd_cov_tm.restype = C.c_int
+        L.crt_o_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _c(a, dt=np.float64):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def rbf_matrix(x, y, gamma: float) -> np.ndarray:
+    x, y = _c(x), _c(y)
+    S = np.empty((x.shape[0], y.shape[0]))
+    lib().crt_o_rbf_matrix(x, y, x.shape[0], y.shape[0], x.shape[1], gamma, S)
+    return S
+
+
+def smith_waterman_score(S, gap: float = 0.0) -> float:
+    S = _c(S)
+    return float(lib().crt_o_smith_waterman_score(S, S.shape[0], S.shape[1], gap))
+
+
+def smith_waterman(S, gap: float = 0.0):
+    """Returns (aln1, aln2, score); raises ValueError where the reference raises (no cell > 0)."""
+    S = _c(S)
+    n, m = S.shape
+    a1 = np.empty(n + m + 1, np.int64)
+    a2 = np.empty(n + m + 1, np.int64)
+    ln, sc = C.c_int64(0), C.c_double(0)
+    rc = lib().crt_o_smith_waterman(S, n, m, gap, a1, a2, C.byref(ln), C.byref(sc))
+    if rc != 0:
+        raise ValueError("smith_waterman: no positive cell (reference raises here)")
+    return a1[:ln.value].copy(), a2[:ln.value].copy(), sc.value
+
+
+def dtw_align(S, gap_open: float, gap_extend: float, want_matrices: bool = False):
+    S = _c(S)
+    n, m = S.shape
+    a1 = np.empty(n + m + 1, np.int64)
+    a2 = np.empty(n + m + 1, np.int64)
+    ln, sc = C.c_int64(0), C.c_double(0)
+    M = np.empty((n + 1, m + 1, 3)) if want_matrices else None
+    B = np.empty((n + 1, m + 1, 3), np.int64) if want_matrices else None
+    lib().crt_o_dtw_align(S, n, m, gap_open, gap_extend, a1, a2, C.byref(ln), C.byref(sc), _ptr(M), _ptr(B))
+    if want_matrices:
+        return a1[:ln.value].copy(), a2[:ln.value].copy(), sc.value, M, B
+    return a1[:ln.value].copy(), a2[:ln.value].copy(), sc.value
+
+
+def common_positions(a1, a2):
+    a1, a2 = _c(a1, np.int64), _c(a2, np.int64)
+    p1 = np.empty(max(len(a1), 1), np.int64)
+    p2 = np.empty(max(len(a1), 1), np.int64)
+    c = lib().crt_o_common_positions(a1, a2, len(a1), p1, p2)
+    return p1[:c].copy(), p2[:c].copy()
+
+
+def kabsch(x1, x2) -> Tuple[np.ndarray, np.ndarray]:
+    x1, x2 = _c(x1), _c(x2)
+    R, t = np.empty((3, 3)), np.empty(3)
+    lib().crt_o_kabsch(x1, x2, x1.shape[0], R, t)
+    return R, t
+
+
+def apply_rotran(x, R, t):
+    x = _c(x)
+    out = np.empty_like(x)
+    lib().crt_o_apply_rotran(x, x.shape[0], _c(R), _c(t), out)
+    return out
+
+
+def superpose_with_subset(c1, c2, k1, k2):
+    c1, c2, k1, k2 = _c(c1), _c(c2), _c(k1), _c(k2)
+    o1, o2, R = np.empty_like(c1), np.empty_like(c2), np.empty((3, 3))
+    lib().crt_o_superpose_with_subset(c1, c1.shape[0], c2, c2.shape[0], k1, k2, k1.shape[0], o1, o2, _ptr(R))
+    return o1, o2, R
+
+
+def rmsd(x, y) -> float:
+    x, y = _c(x), _c(y)
+    return float(lib().crt_o_rmsd(x, y, x.shape[0]))
+
+
+def tm_score(x, y, l1: int, l2: int) -> float:
+    x, y = _c(x), _c(y)
+    return float(lib().crt_o_tm_score(x, y, x.shape[0], l1, l2))
+
+
+def pair(t1, c1, t2, c2, gamma_t: float = 7.0, gamma_c: float = 0.03) -> dict:
+    """Full pair recipe; returns a dict with score, aln1, aln2, ncommon, R, rmsd, tm, score1, status."""
+    t1, c1, t2, c2 = _c(t1), _c(c1), _c(t2), _c(c2)
+    n, m, d = t1.shape[0], t2.shape[0], t1.shape[1]
+    a1 = np.empty(n + m + 1, np.int64)
+    a2 = np.empty(n + m + 1, np.int64)
+    ln, nc = np.zeros(1, np.int64), np.zeros(1, np.int64)
+    R = np.empty((3, 3))
+    sc = C.c_double(0)
+    rr, tt, s1 = np.zeros(1), np.zeros(1), np.zeros(1)
+    st = lib().crt_o_pair(t1, c1, n, t2, c2, m, d, gamma_t, gamma_c, C.byref(sc), _ptr(a1), _ptr(a2), _ptr(ln),
+                          _ptr(nc), _ptr(R), _ptr(rr), _ptr(tt), _ptr(s1))
+    return dict(score=sc.value, aln1=a1[:ln[0]].copy(), aln2=a2[:ln[0]].copy(), ncommon=int(nc[0]), R=R,
+                rmsd=float(rr[0]), tm=float(tt[0]), score1=float(s1[0]), status=int(st))
+
+
+def pair_f32model(t1, c1, t2, c2, gamma_t: float = 7.0, gamma_c: float = 0.03):
+    t1, c1, t2, c2 = _c(t1), _c(c1), _c(t2), _c(c2)
+    n, m, d = t1.shape[0], t2.shape[0], t1.shape[1]
+    a1 = np.empty(n + m + 1, np.int64)
+    a2 = np.empty(n + m + 1, np.int64)
+    ln, sc = C.c_int64(0), C.c_double(0)
+    lib().crt_o_pair_f32model(t1, c1, n, t2, c2, m, d, gamma_t, gamma_c, C.byref(sc), a1, a2, C.byref(ln))
+    return a1[:ln.value].copy(), a2[:ln.value].copy(), sc.value
+
+
+def pairwise_list(coords, tensors, offsets, pi, pj, gamma_t=7.0, gamma_c=0.03, nthreads=0, extras=True):
+    coords, tensors = _c(coords), _c(tensors)
+    offsets = _c(offsets, np.int64)
+    pi, pj = _c(pi, np.int32), _c(pj, np.int32)
+    n = len(pi)
+    score = np.empty(n)
+    rm = np.empty(n) if extras else None
+    tm = np.empty(n) if extras else None
+    nc = np.empty(n, np.int32) if extras else None
+    st = np.empty(n, np.int32) if extras else None
+    lib().crt_o_pairwise_list(coords, tensors, offsets, tensors.shape[1], pi, pj, n, gamma_t, gamma_c, nthreads,
+                              score, _ptr(rm), _ptr(tm), _ptr(nc), _ptr(st))
+    return dict(score=score, rmsd=rm, tm=tm, ncommon=nc, status=st)
+
+
+def pairwise_all(coords, tensors, offsets, gamma_t=7.0, gamma_c=0.03, nthreads=0) -> np.ndarray:
+    coords, tensors = _c(coords), _c(tensors)
+    offsets = _c(offsets, np.int64)
+    N = len(offsets) - 1
+    out = np.empty((N, N))
+    lib().crt_o_pairwise_all(coords, tensors, offsets, N, tensors.shape[1], gamma_t, gamma_c, nthreads, out)
+    return out
+
+
+def rmsd_cov_tm(aln, coords, offsets):
+    aln = _c(aln, np.int64)
+    coords = _c(coords)
+    offsets = _c(offsets, np.int64)
+    N, A = aln.shape
+    r, c, t = np.empty((N, N)), np.empty((N, N)), np.empty((N, N))
+    bad = lib().crt_o_rmsd_cov_tm(aln, N, A, coords, offsets, r, c, t)
+    return r, c, t, bad
+
+
+def num_threads() -> int:
+    return int(lib().crt_o_num_threads())
