@@ -1,0 +1,805 @@
+// crt_api.cu -- host side of the C ABI declared in include/caretta_b200.h.
+// Plain CUDA runtime; no torch types.  See crt_kernels.cuh for the kernels and DESIGN.md for the data layout.
+#include "../../include/caretta_b200.h"
+#include "crt_kernels.cuh"
+#include "crt_fill_f32.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace crt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(e_ == cudaErrorMemoryAllocation ? CRT_E_NOMEM : CRT_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;     // elements
+    int ensure(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return fail(CRT_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostUnit {
+    Unit u;
+    int C;          // columns per lane
+    int multi;      // n_strips > 1
+    double cost;    // G * m
+};
+
+}  // namespace
+
+struct crt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0, clock_khz = 0;
+    size_t mem_total = 0;
+
+    // chains
+    int N = 0, d = 0, D = 0;
+    long long total = 0;
+    std::vector<long long> offsets;      // host copy
+    int max_len = 0;
+    double mean[32];
+    DevBuf<double> coords, tensors, centroid, rec64;
+    DevBuf<long long> d_offsets;
+    DevBuf<int> chain_of, meta;
+    DevBuf<float> rec32;
+    DevBuf<float4> cols2;
+    double prep_gamma_t = -1, prep_gamma_c = -1;   // parameters the fp32 records were built with
+
+    // run workspaces
+    DevBuf<Unit> d_units;
+    DevBuf<uint4> tb;
+    DevBuf<unsigned char> rows2, bnd;
+    DevBuf<short2> path;
+    DevBuf<int> path_len, pair_istar, pair_zflag, ncommon, status;
+    DevBuf<double> score, score1, rmsd, tm;
+    DevBuf<float> f32tmp;
+
+    // last run
+    long long run_pairs = 0;
+    double elapsed_ms = 0, cell_updates = 0;
+    long long launches = 0;
+    std::vector<int> run_pi, run_pj;     // pair ids in result order
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- kernel dispatch
+struct Choice { int C; int n_strips; };
+
+// columns per lane: bounded by the registers the stage-1 column vectors need (C * D values per lane)
+int cmax_for(int precision, int D)
+{
+    if (precision == CRT_FP32) return D <= 10 ? 10 : 6;
+    return D <= 10 ? 4 : 3;
+}
+
+Choice choose_cols(int m, int precision, int D)
+{
+    static const int allowed64[] = {2, 3, 4, 5, 6, 8, 10};
+    static const int allowed32[] = {2, 4, 6, 8, 10, 10, 10};      // the fp32 fills pair columns: even C only
+    const int *allowed = precision == CRT_FP32 ? allowed32 : allowed64;
+    const int cmax = cmax_for(precision, D);
+    int ns = (m + 32 * cmax - 1) / (32 * cmax);
+    if (ns < 1) ns = 1;
+    int need = (m + 32 * ns - 1) / (32 * ns);
+    int C = cmax;
+    for (int q = 0; q < 7; ++q)
+        if (allowed[q] >= need) { C = allowed[q]; break; }
+    if (C > cmax) C = cmax;
+    return Choice{C, ns};
+}
+
+template <typename P, bool DIFF, bool CODES, int CMAX>
+int launch_fill_c(int C, bool multi, const Unit *units, int n, typename P::Args args, FillOut out, cudaStream_t st)
+{
+    const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int block = WARPS_PER_CTA * 32;
+#define CRT_CASE(CC)                                                                                         \
+    case CC:                                                                                                 \
+        if constexpr (CC <= CMAX) {                                                                          \
+            if (multi) k_fill<P, CC, DIFF, CODES, true><<<grid, block, 0, st>>>(units, n, args, out);         \
+            else k_fill<P, CC, DIFF, CODES, false><<<grid, block, 0, st>>>(units, n, args, out);             \
+            break;                                                                                           \
+        } else return fail(CRT_E_ARG, "no kernel for C=%d (max %d)", C, CMAX);
+    switch (C) {
+        CRT_CASE(2) CRT_CASE(3) CRT_CASE(4) CRT_CASE(5) CRT_CASE(6) CRT_CASE(8) CRT_CASE(10)
+    default: return fail(CRT_E_ARG, "no kernel for C=%d", C);
+    }
+#undef CRT_CASE
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int D>
+int launch_fill1_f32(int C, bool multi, const Unit *units, int n, Fill1Args args, FillOut out, cudaStream_t st)
+{
+#define CRT_CASE(CC)                                                                         \
+    case CC:                                                                                 \
+        if constexpr (CC * D <= 100) {                                                       \
+            if (multi) k_fill1_f32<D, CC, true><<<n, 32, 0, st>>>(units, n, args, out);       \
+            else k_fill1_f32<D, CC, false><<<n, 32, 0, st>>>(units, n, args, out);           \
+            break;                                                                           \
+        } else return fail(CRT_E_ARG, "no fp32 stage-1 kernel for C=%d D=%d", C, D);
+    switch (C) {
+        CRT_CASE(2) CRT_CASE(4) CRT_CASE(6) CRT_CASE(8) CRT_CASE(10)
+    default: return fail(CRT_E_ARG, "no fp32 stage-1 kernel for C=%d", C);
+    }
+#undef CRT_CASE
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_fill2_f32(int C, bool multi, const Unit *units, int n, Fill2Args args, FillOut out, cudaStream_t st)
+{
+#define CRT_CASE(CC)                                                                     \
+    case CC:                                                                             \
+        if (multi) k_fill2_f32<CC, true><<<n, 32, 0, st>>>(units, n, args, out);          \
+        else k_fill2_f32<CC, false><<<n, 32, 0, st>>>(units, n, args, out);              \
+        break;
+    switch (C) {
+        CRT_CASE(2) CRT_CASE(4) CRT_CASE(6) CRT_CASE(8) CRT_CASE(10)
+    default: return fail(CRT_E_ARG, "no fp32 stage-2 kernel for C=%d", C);
+    }
+#undef CRT_CASE
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pad_dim(int d)
+{
+    if (d <= 10) return 10;
+    if (d <= 16) return 16;
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------- unit building
+constexpr int MAX_PAIRS_PER_UNIT = 32;
+constexpr int TARGET_ROWS_PER_UNIT = 6144;
+
+void finish_unit(const crt_ctx *c, HostUnit &h, int precision)
+{
+    Choice ch = choose_cols(h.u.m, precision, c->D);
+    h.C = ch.C;
+    h.u.n_strips = ch.n_strips;
+    h.multi = ch.n_strips > 1;
+    h.u.tchunks = (h.u.G + 31 + 3) / 4;
+    h.cost = (double)h.u.G * (double)h.u.m;
+    (void)c;
+}
+
+// all-vs-all units in a deterministic order: column chain j ascending, runs of row chains ascending
+void build_all_units(const crt_ctx *c, int precision, std::vector<HostUnit> &out)
+{
+    out.clear();
+    for (int j = 1; j < c->N; ++j) {
+        int i = 0;
+        while (i < j) {
+            HostUnit h{};
+            h.u.row_chain0 = i;
+            h.u.row_base = c->offsets[i];
+            h.u.col_chain = j;
+            h.u.col_base = (int)c->offsets[j];
+            h.u.m = (int)(c->offsets[j + 1] - c->offsets[j]);
+            int cnt = 0, maxn = 0;
+            long long G = 0;
+            while (i < j && cnt < MAX_PAIRS_PER_UNIT) {
+                int n = (int)(c->offsets[i + 1] - c->offsets[i]);
+                if (cnt > 0 && G + n > TARGET_ROWS_PER_UNIT) break;
+                G += n; maxn = std::max(maxn, n); ++cnt; ++i;
+            }
+            h.u.G = (int)G;
+            h.u.n_pairs = cnt;
+            h.u.path_stride = maxn + h.u.m;
+            finish_unit(c, h, precision);
+            out.push_back(h);
+        }
+    }
+}
+
+// deal units to ranks: sort by cost (stable, descending), snake order
+void shard_units(std::vector<HostUnit> &units, int rank, int world)
+{
+    if (world <= 1) return;
+    std::vector<int> idx(units.size());
+    for (size_t q = 0; q < idx.size(); ++q) idx[q] = (int)q;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return units[a].cost > units[b].cost; });
+    std::vector<HostUnit> mine;
+    for (size_t q = 0; q < idx.size(); ++q) {
+        int round = (int)(q / world), pos = (int)(q % world);
+        int owner = (round & 1) ? world - 1 - pos : pos;
+        if (owner == rank) mine.push_back(units[idx[q]]);
+    }
+    // keep the deterministic (j, i0) order inside the shard
+    std::stable_sort(mine.begin(), mine.end(), [](const HostUnit &a, const HostUnit &b) {
+        if (a.u.col_chain != b.u.col_chain) return a.u.col_chain < b.u.col_chain;
+        return a.u.row_chain0 < b.u.row_chain0;
+    });
+    units.swap(mine);
+}
+
+void assign_pairs(std::vector<HostUnit> &units, std::vector<int> *pi, std::vector<int> *pj, long long *n_pairs, double *cells,
+                  const crt_ctx *c)
+{
+    long long p = 0;
+    double cu = 0;
+    if (pi) pi->clear();
+    if (pj) pj->clear();
+    for (auto &h : units) {
+        h.u.pair_base = (int)p;
+        for (int q = 0; q < h.u.n_pairs; ++q) {
+            if (pi) pi->push_back(h.u.row_chain0 + q);
+            if (pj) pj->push_back(h.u.col_chain);
+        }
+        p += h.u.n_pairs;
+        cu += 2.0 * (double)h.u.G * (double)h.u.m;
+    }
+    (void)c;
+    if (n_pairs) *n_pairs = p;
+    if (cells) *cells = cu;
+}
+
+int ensure_prepared(crt_ctx *c, const crt_params *prm);
+
+// ---------------------------------------------------------------------------------------------- the run
+// Executes the units (already carrying pair_base) in batches bounded by a workspace budget.
+// If paths are requested, they are copied back per batch into host vectors (descending order as walked).
+struct PathSink {
+    bool want = false;
+    std::vector<std::vector<int>> a1, a2;   // per pair, ascending residue order
+};
+
+size_t env_budget()
+{
+    const char *e = getenv("CARETTA_B200_WORKSPACE_MB");
+    size_t mb = e ? (size_t)atoll(e) : 8192;
+    if (mb < 64) mb = 64;
+    return mb << 20;
+}
+
+int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, long long n_pairs, PathSink *sink)
+{
+    const int prec = prm->precision;
+    const bool f32 = prec == CRT_FP32;
+    const size_t tsz = f32 ? 4 : 8;
+    const size_t row2sz = f32 ? 16 : 32;
+    const int rs32 = ((c->D + 2 + 3) / 4) * 4;
+    int rc;
+    if ((rc = c->score.ensure((size_t)n_pairs + 1))) return rc;
+    if ((rc = c->score1.ensure((size_t)n_pairs + 1))) return rc;
+    if ((rc = c->rmsd.ensure((size_t)n_pairs + 1))) return rc;
+    if ((rc = c->tm.ensure((size_t)n_pairs + 1))) return rc;
+    if ((rc = c->ncommon.ensure((size_t)n_pairs + 1))) return rc;
+    if ((rc = c->status.ensure((size_t)n_pairs + 1))) return rc;
+    if ((rc = c->pair_istar.ensure((size_t)n_pairs + 1))) return rc;
+    if ((rc = c->pair_zflag.ensure((size_t)n_pairs + 1))) return rc;
+    if ((rc = c->path_len.ensure((size_t)n_pairs + 1))) return rc;
+    if (sink && sink->want) { sink->a1.assign((size_t)n_pairs, {}); sink->a2.assign((size_t)n_pairs, {}); }
+
+    // group by kernel variant so that each launch is homogeneous; inside a group keep the (j, i0) order
+    std::stable_sort(units.begin(), units.end(), [](const HostUnit &a, const HostUnit &b) {
+        if (a.multi != b.multi) return a.multi < b.multi;
+        return a.C < b.C;
+    });
+
+    const size_t budget = env_budget();
+    c->launches = 0;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    size_t pos = 0;
+    std::vector<Unit> hu;
+    while (pos < units.size()) {
+        // ---- carve a batch: same (C, multi), bounded workspace
+        const int C = units[pos].C, multi = units[pos].multi;
+        size_t tb_n = 0, rows2_n = 0, bnd_n = 0, path_n = 0, end = pos;
+        hu.clear();
+        while (end < units.size() && units[end].C == C && units[end].multi == multi) {
+            HostUnit &h = units[end];
+            size_t tb_u = (size_t)h.u.n_strips * h.u.tchunks * 32;
+            size_t rows_u = (size_t)h.u.G;
+            size_t path_u = (size_t)h.u.n_pairs * h.u.path_stride;
+            size_t bnd_u = multi ? (size_t)h.u.G : 0;
+            size_t bytes = (tb_n + tb_u) * 16 + (rows2_n + rows_u) * row2sz + (path_n + path_u) * 4 + (bnd_n + bnd_u) * tsz;
+            if (end > pos && bytes > budget) break;
+            h.u.tb_base = (long long)tb_n; h.u.rows2_base = (long long)rows2_n;
+            h.u.path_base = (long long)path_n; h.u.bnd_base = (long long)bnd_n;
+            tb_n += tb_u; rows2_n += rows_u; path_n += path_u; bnd_n += bnd_u;
+            hu.push_back(h.u);
+            ++end;
+        }
+        const int nu = (int)hu.size();
+        if ((rc = c->d_units.ensure(nu))) return rc;
+        if ((rc = c->tb.ensure(tb_n))) return rc;
+        if ((rc = c->rows2.ensure((rows2_n + 2 * ROW_PAD) * row2sz))) return rc;
+        if ((rc = c->path.ensure(path_n + 1))) return rc;
+        if ((rc = c->bnd.ensure(bnd_n * tsz + 16))) return rc;
+        CU(cudaMemcpyAsync(c->d_units.p, hu.data(), sizeof(Unit) * nu, cudaMemcpyHostToDevice, c->stream));
+
+        FillOut fo{};
+        fo.tb = c->tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
+        fo.pair_score = c->score1.p; fo.bnd = c->bnd.p;
+        // ---- stage 1
+        if (f32) {
+            Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
+            if (c->D == 10) rc = launch_fill1_f32<10>(C, multi, c->d_units.p, nu, a, fo, c->stream);
+            else rc = launch_fill1_f32<16>(C, multi, c->d_units.p, nu, a, fo, c->stream);
+        } else {
+            if (c->D == 10) { P1F64<10>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; rc = launch_fill_c<P1F64<10>, false, true, 4>(C, multi, c->d_units.p, nu, a, fo, c->stream); }
+            else { P1F64<16>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; rc = launch_fill_c<P1F64<16>, false, true, 3>(C, multi, c->d_units.p, nu, a, fo, c->stream); }
+        }
+        if (rc) return rc;
+        // ---- traceback + Kabsch + stage-2 rows
+        TraceArgs ta{};
+        ta.units = c->d_units.p; ta.tb = c->tb.p; ta.pair_istar = c->pair_istar.p; ta.pair_zflag = c->pair_zflag.p;
+        ta.offsets = c->d_offsets.p; ta.coords = c->coords.p; ta.centroid = c->centroid.p;
+        ta.path = c->path.p; ta.path_len = c->path_len.p; ta.rmsd = c->rmsd.p; ta.tm = c->tm.p;
+        ta.ncommon = c->ncommon.p; ta.status = c->status.p; ta.rot = nullptr; ta.rows2 = c->rows2.p + (size_t)ROW_PAD * row2sz;
+        ta.rec32 = c->rec32.p + (size_t)ROW_PAD * rs32; ta.rs32 = rs32; ta.d32 = c->D;
+        ta.rec64 = c->rec64.p; ta.d64 = c->D; ta.neg_gamma_t = -prm->gamma_tensor;
+        ta.C = C; ta.scale2 = (float)std::sqrt(prm->gamma_coords * 1.4426950408889634);
+        ta.precision = prec;
+        k_trace<<<nu, 32, 0, c->stream>>>(ta);
+        CU(cudaGetLastError());
+        // ---- stage 2
+        fo.pair_score = c->score.p;
+        if (f32) {
+            Fill2Args a{reinterpret_cast<const float4 *>(c->rows2.p) + ROW_PAD, c->cols2.p};
+            rc = launch_fill2_f32(C, multi, c->d_units.p, nu, a, fo, c->stream);
+        } else {
+            P2F64::Args a{reinterpret_cast<const double *>(c->rows2.p) + (size_t)ROW_PAD * 4, c->coords.p, -prm->gamma_coords};
+            rc = launch_fill_c<P2F64, false, false, 4>(C, multi, c->d_units.p, nu, a, fo, c->stream);
+        }
+        if (rc) return rc;
+        c->launches += 3;
+
+        if (sink && sink->want) {
+            std::vector<short2> hp(path_n);
+            std::vector<int> hl((size_t)n_pairs);
+            CU(cudaMemcpyAsync(hp.data(), c->path.p, path_n * sizeof(short2), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(hl.data(), c->path_len.p, (size_t)n_pairs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            for (const Unit &u : hu)
+                for (int q = 0; q < u.n_pairs; ++q) {
+                    const int pidx = u.pair_base + q, len = hl[pidx];
+                    const short2 *pp = hp.data() + u.path_base + (size_t)q * u.path_stride;
+                    auto &v1 = sink->a1[pidx];
+                    auto &v2 = sink->a2[pidx];
+                    v1.resize(len); v2.resize(len);
+                    for (int k = 0; k < len; ++k) { v1[k] = pp[len - 1 - k].x; v2[k] = pp[len - 1 - k].y; }
+                }
+        }
+        pos = end;
+    }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->elapsed_ms = ms;
+    c->run_pairs = n_pairs;
+    return 0;
+}
+
+int check_params(const crt_ctx *c, const crt_params *prm)
+{
+    if (!c) return fail(CRT_E_ARG, "null context");
+    if (!prm) return fail(CRT_E_ARG, "null params");
+    if (c->N <= 0) return fail(CRT_E_STATE, "crt_set_chains has not been called");
+    if (prm->precision != CRT_FP64 && prm->precision != CRT_FP32) return fail(CRT_E_ARG, "precision must be CRT_FP64 or CRT_FP32");
+    if (prm->sw_gap != 0.0) return fail(CRT_E_ARG, "sw_gap != 0 is not on the reference's pair path (multiple_alignment.py:335, :164)");
+    if (!(prm->gamma_tensor >= 0) || !(prm->gamma_coords >= 0)) return fail(CRT_E_ARG, "gamma must be >= 0");
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char *crt_last_error(void) { return g_err.c_str(); }
+int crt_version(void) { return 100; }
+
+int crt_create(int device, crt_ctx **out)
+{
+    if (!out) return fail(CRT_E_ARG, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(CRT_E_CUDA, "no CUDA device: %s (this engine has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= n) return fail(CRT_E_ARG, "device %d out of range (%d devices)", device, n);
+    CU(cudaSetDevice(device));
+    crt_ctx *c = new crt_ctx();
+    c->device = device;
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    c->sm_count = p.multiProcessorCount;
+    c->clock_khz = p.clockRate;
+    c->mem_total = p.totalGlobalMem;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+int crt_destroy(crt_ctx *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->coords.release(); c->tensors.release(); c->centroid.release(); c->rec64.release(); c->d_offsets.release();
+    c->chain_of.release(); c->meta.release(); c->rec32.release(); c->cols2.release(); c->d_units.release();
+    c->tb.release(); c->rows2.release(); c->bnd.release(); c->path.release(); c->path_len.release();
+    c->pair_istar.release(); c->pair_zflag.release(); c->ncommon.release(); c->status.release();
+    c->score.release(); c->score1.release(); c->rmsd.release(); c->tm.release(); c->f32tmp.release();
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int crt_device_info(crt_ctx *c, int32_t *sm_count, int32_t *clock_khz, int64_t *mem_bytes)
+{
+    if (!c) return fail(CRT_E_ARG, "null context");
+    if (sm_count) *sm_count = c->sm_count;
+    if (clock_khz) *clock_khz = c->clock_khz;
+    if (mem_bytes) *mem_bytes = (int64_t)c->mem_total;
+    return 0;
+}
+
+int crt_set_chains(crt_ctx *c, const double *coords, const double *tensors, const int64_t *offsets, int32_t n_chains, int32_t d)
+{
+    if (!c || !coords || !tensors || !offsets) return fail(CRT_E_ARG, "null argument");
+    if (n_chains <= 0) return fail(CRT_E_ARG, "n_chains must be > 0");
+    const int D = pad_dim(d);
+    if (d <= 0 || D < 0) return fail(CRT_E_ARG, "tensor width d=%d unsupported (1..16)", d);
+    if (offsets[0] != 0) return fail(CRT_E_ARG, "offsets[0] must be 0");
+    int max_len = 0;
+    for (int p = 0; p < n_chains; ++p) {
+        long long l = offsets[p + 1] - offsets[p];
+        if (l <= 0) return fail(CRT_E_ARG, "chain %d is empty (the reference cannot align an empty chain)", p);
+        if (l > 32000) return fail(CRT_E_ARG, "chain %d has %lld residues; the path buffer is 16-bit (max 32000)", p, l);
+        max_len = std::max<int>(max_len, (int)l);
+    }
+    const long long total = offsets[n_chains];
+    if (total >= (1ll << 31) - 64) return fail(CRT_E_ARG, "too many residues");
+    CU(cudaSetDevice(c->device));
+    c->N = 0;
+    int rc;
+    if ((rc = c->coords.ensure((size_t)total * 3))) return rc;
+    if ((rc = c->tensors.ensure((size_t)total * d))) return rc;
+    if ((rc = c->d_offsets.ensure((size_t)n_chains + 1))) return rc;
+    if ((rc = c->chain_of.ensure((size_t)total))) return rc;
+    if ((rc = c->meta.ensure((size_t)total + 2 * ROW_PAD))) return rc;
+    if ((rc = c->centroid.ensure((size_t)n_chains * 3))) return rc;
+    if ((rc = c->rec64.ensure((size_t)total * D))) return rc;
+    if ((rc = c->rec32.ensure(((size_t)total + 2 * ROW_PAD) * (((D + 2 + 3) / 4) * 4)))) return rc;
+    CU(cudaMemsetAsync(c->meta.p, 0, sizeof(int) * ((size_t)total + 2 * ROW_PAD), c->stream));
+    CU(cudaMemsetAsync(c->rec32.p, 0, sizeof(float) * ((size_t)total + 2 * ROW_PAD) * (((D + 2 + 3) / 4) * 4), c->stream));
+    if ((rc = c->cols2.ensure((size_t)total))) return rc;
+    c->offsets.assign(offsets, offsets + n_chains + 1);
+    std::vector<int> chain_of((size_t)total);
+    for (int p = 0; p < n_chains; ++p)
+        for (long long r = offsets[p]; r < offsets[p + 1]; ++r) chain_of[(size_t)r] = p;
+    // global tensor mean (the Gaussian is translation invariant; centring keeps the fp32 dot-product form accurate)
+    for (int k = 0; k < 32; ++k) c->mean[k] = 0.0;
+    bool finite = true;
+    for (long long r = 0; r < total; ++r)
+        for (int k = 0; k < d; ++k) { double v = tensors[r * d + k]; c->mean[k] += v; finite &= std::isfinite(v); }
+    for (long long r = 0; r < total * 3; ++r) finite &= std::isfinite(coords[r]);
+    if (!finite) return fail(CRT_E_ARG, "non-finite value in coords/tensors");
+    for (int k = 0; k < d; ++k) c->mean[k] /= (double)total;
+    CU(cudaMemcpyAsync(c->coords.p, coords, sizeof(double) * (size_t)total * 3, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->tensors.p, tensors, sizeof(double) * (size_t)total * d, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_offsets.p, c->offsets.data(), sizeof(long long) * ((size_t)n_chains + 1), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->chain_of.p, chain_of.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));     // chain_of is a local vector
+    c->N = n_chains; c->d = d; c->D = D; c->total = total; c->max_len = max_len;
+    c->prep_gamma_t = c->prep_gamma_c = -1;
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+int ensure_prepared(crt_ctx *c, const crt_params *prm)
+{
+    if (c->prep_gamma_t == prm->gamma_tensor && c->prep_gamma_c == prm->gamma_coords) return 0;
+    PrepArgs a{};
+    a.coords = c->coords.p; a.tensors = c->tensors.p; a.offsets = c->d_offsets.p; a.chain_of = c->chain_of.p;
+    a.n_chains = c->N; a.d = c->d; a.total = c->total;
+    for (int k = 0; k < 32; ++k) a.mean[k] = c->mean[k];
+    a.g2 = prm->gamma_tensor * 1.4426950408889634;
+    a.scale2 = std::sqrt(prm->gamma_coords * 1.4426950408889634);
+    a.rs32 = ((c->D + 2 + 3) / 4) * 4; a.d32 = c->D; a.rec32 = c->rec32.p + (size_t)ROW_PAD * a.rs32;
+    a.rec64 = c->rec64.p; a.d64 = c->D;
+    a.meta = c->meta.p + ROW_PAD; a.cols2 = c->cols2.p; a.centroid = c->centroid.p;
+    k_centroid<<<(c->N + 127) / 128, 128, 0, c->stream>>>(a);
+    CU(cudaGetLastError());
+    k_prep<<<(unsigned)((c->total + 127) / 128), 128, 0, c->stream>>>(a);
+    CU(cudaGetLastError());
+    c->prep_gamma_t = prm->gamma_tensor; c->prep_gamma_c = prm->gamma_coords;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crt_pairwise_shard(crt_ctx *c, const crt_params *prm, int32_t rank, int32_t world)
+{
+    int rc = check_params(c, prm);
+    if (rc) return rc;
+    if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world %d/%d", rank, world);
+    CU(cudaSetDevice(c->device));
+    if ((rc = ensure_prepared(c, prm))) return rc;
+    std::vector<HostUnit> units;
+    build_all_units(c, prm->precision, units);
+    shard_units(units, rank, world);
+    long long np = 0;
+    assign_pairs(units, &c->run_pi, &c->run_pj, &np, &c->cell_updates, c);
+    if (np == 0) { c->run_pairs = 0; c->elapsed_ms = 0; c->launches = 0; return 0; }
+    return run_units(c, prm, units, np, nullptr);
+}
+
+int64_t crt_shard_size(crt_ctx *c, int32_t rank, int32_t world)
+{
+    if (!c || c->N <= 0) return fail(CRT_E_STATE, "no chains");
+    if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world");
+    std::vector<HostUnit> units;
+    build_all_units(c, CRT_FP32, units);     // the enumeration does not depend on the precision
+    shard_units(units, rank, world);
+    long long np = 0;
+    assign_pairs(units, nullptr, nullptr, &np, nullptr, c);
+    return np;
+}
+
+int crt_shard_pairs(crt_ctx *c, int32_t rank, int32_t world, int32_t *pair_i, int32_t *pair_j)
+{
+    if (!c || c->N <= 0) return fail(CRT_E_STATE, "no chains");
+    if (!pair_i || !pair_j) return fail(CRT_E_ARG, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world");
+    std::vector<HostUnit> units;
+    build_all_units(c, CRT_FP32, units);
+    shard_units(units, rank, world);
+    std::vector<int> pi, pj;
+    long long np = 0;
+    assign_pairs(units, &pi, &pj, &np, nullptr, c);
+    std::memcpy(pair_i, pi.data(), sizeof(int) * (size_t)np);
+    std::memcpy(pair_j, pj.data(), sizeof(int) * (size_t)np);
+    return 0;
+}
+
+int crt_fetch(crt_ctx *c, double *score, double *rmsd, double *tm, int32_t *ncommon, int32_t *status)
+{
+    if (!c) return fail(CRT_E_ARG, "null context");
+    const size_t n = (size_t)c->run_pairs;
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    if (score) CU(cudaMemcpyAsync(score, c->score.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (rmsd) CU(cudaMemcpyAsync(rmsd, c->rmsd.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (tm) CU(cudaMemcpyAsync(tm, c->tm.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (ncommon) CU(cudaMemcpyAsync(ncommon, c->ncommon.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (status) CU(cudaMemcpyAsync(status, c->status.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+__global__ void k_d2f(const double *a, float *o, long long n)
+{
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) o[q] = (float)a[q];
+}
+}  // namespace
+
+extern "C" {
+
+int crt_fetch_device(crt_ctx *c, void *d_score, void *d_rmsd, void *d_tm, int64_t n)
+{
+    if (!c) return fail(CRT_E_ARG, "null context");
+    if (n < c->run_pairs) return fail(CRT_E_ARG, "destination holds %lld elements, run produced %lld", (long long)n, c->run_pairs);
+    const long long np = c->run_pairs;
+    if (np == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    const unsigned grid = (unsigned)((np + 255) / 256);
+    if (d_score) k_d2f<<<grid, 256, 0, c->stream>>>(c->score.p, (float *)d_score, np);
+    if (d_rmsd) k_d2f<<<grid, 256, 0, c->stream>>>(c->rmsd.p, (float *)d_rmsd, np);
+    if (d_tm) k_d2f<<<grid, 256, 0, c->stream>>>(c->tm.p, (float *)d_tm, np);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+double crt_last_elapsed_ms(crt_ctx *c) { return c ? c->elapsed_ms : -1.0; }
+int64_t crt_last_launches(crt_ctx *c) { return c ? c->launches : -1; }
+double crt_last_cell_updates(crt_ctx *c) { return c ? c->cell_updates : -1.0; }
+
+int crt_pairwise_all(crt_ctx *c, const crt_params *prm, double *out_score, double *out_rmsd, double *out_tm)
+{
+    if (!out_score) return fail(CRT_E_ARG, "null out_score");
+    int rc = crt_pairwise_shard(c, prm, 0, 1);
+    if (rc) return rc;
+    const size_t N = (size_t)c->N, np = (size_t)c->run_pairs;
+    std::vector<double> s(np + 1), r(np + 1), t(np + 1);
+    if ((rc = crt_fetch(c, s.data(), out_rmsd ? r.data() : nullptr, out_tm ? t.data() : nullptr, nullptr, nullptr))) return rc;
+    for (size_t q = 0; q < N * N; ++q) {
+        out_score[q] = 0.0;
+        if (out_rmsd) out_rmsd[q] = 0.0;
+        if (out_tm) out_tm[q] = 0.0;
+    }
+    if (out_tm) for (size_t q = 0; q < N; ++q) out_tm[q * N + q] = 1.0;
+    for (size_t q = 0; q < np; ++q) {
+        const size_t i = (size_t)c->run_pi[q], j = (size_t)c->run_pj[q];
+        out_score[i * N + j] = out_score[j * N + i] = s[q];       // symmetric fill, multiple_alignment.py:164
+        if (out_rmsd) out_rmsd[i * N + j] = out_rmsd[j * N + i] = r[q];
+        if (out_tm) out_tm[i * N + j] = out_tm[j * N + i] = t[q];
+    }
+    return 0;
+}
+
+int crt_pairwise_list(crt_ctx *c, const crt_params *prm, const int32_t *pair_i, const int32_t *pair_j, int64_t n_pairs,
+                      double *score, double *rmsd, double *tm, int32_t *ncommon, int32_t *status,
+                      int32_t *aln1, int32_t *aln2, int64_t *aln_off, int64_t aln_cap)
+{
+    int rc = check_params(c, prm);
+    if (rc) return rc;
+    if (n_pairs < 0 || (n_pairs > 0 && (!pair_i || !pair_j))) return fail(CRT_E_ARG, "bad pair list");
+    const bool want_paths = aln1 || aln2 || aln_off;
+    if (want_paths && !(aln1 && aln2 && aln_off)) return fail(CRT_E_ARG, "aln1, aln2 and aln_off must be given together");
+    if (n_pairs == 0) { if (aln_off) aln_off[0] = 0; c->run_pairs = 0; return 0; }
+    for (int64_t q = 0; q < n_pairs; ++q)
+        if (pair_i[q] < 0 || pair_i[q] >= c->N || pair_j[q] < 0 || pair_j[q] >= c->N)
+            return fail(CRT_E_ARG, "pair %lld = (%d, %d) out of range", (long long)q, pair_i[q], pair_j[q]);
+    CU(cudaSetDevice(c->device));
+    if ((rc = ensure_prepared(c, prm))) return rc;
+    // sort by (column chain, row chain); runs of consecutive row chains become units
+    std::vector<long long> order((size_t)n_pairs);
+    for (int64_t q = 0; q < n_pairs; ++q) order[(size_t)q] = q;
+    std::stable_sort(order.begin(), order.end(), [&](long long a, long long b) {
+        if (pair_j[a] != pair_j[b]) return pair_j[a] < pair_j[b];
+        return pair_i[a] < pair_i[b];
+    });
+    std::vector<HostUnit> units;
+    std::vector<long long> slot_of((size_t)n_pairs);      // caller index -> result slot
+    long long slot = 0;
+    size_t q = 0;
+    while (q < order.size()) {
+        HostUnit h{};
+        const int j = pair_j[order[q]];
+        const int i = pair_i[order[q]];
+        h.u.row_chain0 = i; h.u.row_base = c->offsets[i];
+        h.u.col_chain = j; h.u.col_base = (int)c->offsets[j]; h.u.m = (int)(c->offsets[j + 1] - c->offsets[j]);
+        h.u.pair_base = (int)slot;
+        int cnt = 0, maxn = 0;
+        long long G = 0;
+        while (q < order.size() && pair_j[order[q]] == j) {
+            const int ii = pair_i[order[q]];
+            if (cnt > 0 && ii == i + cnt - 1) { slot_of[(size_t)order[q]] = slot - 1; ++q; continue; }   // duplicate pair
+            if (ii != i + cnt || cnt >= MAX_PAIRS_PER_UNIT) break;
+            const int n = (int)(c->offsets[ii + 1] - c->offsets[ii]);
+            if (cnt > 0 && G + n > TARGET_ROWS_PER_UNIT) break;
+            G += n; maxn = std::max(maxn, n);
+            slot_of[(size_t)order[q]] = slot++;
+            ++cnt; ++q;
+        }
+        h.u.G = (int)G; h.u.n_pairs = cnt; h.u.path_stride = maxn + h.u.m;
+        finish_unit(c, h, prm->precision);
+        units.push_back(h);
+    }
+    double cu = 0;
+    for (auto &h : units) cu += 2.0 * (double)h.u.G * (double)h.u.m;
+    c->cell_updates = cu;
+    c->run_pi.clear(); c->run_pj.clear();
+    PathSink sink;
+    sink.want = want_paths;
+    if ((rc = run_units(c, prm, units, slot, &sink))) return rc;
+    const size_t np = (size_t)slot;
+    std::vector<double> s(np), r(np), t(np);
+    std::vector<int> nc(np), st(np);
+    if ((rc = crt_fetch(c, s.data(), r.data(), t.data(), nc.data(), st.data()))) return rc;
+    int64_t off = 0;
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        const size_t sl = (size_t)slot_of[(size_t)k];
+        if (score) score[k] = s[sl];
+        if (rmsd) rmsd[k] = r[sl];
+        if (tm) tm[k] = t[sl];
+        if (ncommon) ncommon[k] = nc[sl];
+        if (status) status[k] = st[sl];
+        if (want_paths) {
+            const auto &v1 = sink.a1[sl];
+            const auto &v2 = sink.a2[sl];
+            aln_off[k] = off;
+            if (off + (int64_t)v1.size() > aln_cap) return fail(CRT_E_ARG, "aln_cap too small");
+            for (size_t x = 0; x < v1.size(); ++x) { aln1[off + x] = v1[x]; aln2[off + x] = v2[x]; }
+            off += (int64_t)v1.size();
+        }
+    }
+    if (want_paths) aln_off[n_pairs] = off;
+    return 0;
+}
+
+int crt_sw_align_batch(crt_ctx *, const double *, const int64_t *, const int32_t *, const int32_t *, int32_t, double,
+                       int32_t *, int32_t *, int64_t *, int64_t, double *, int32_t *)
+{
+    return fail(CRT_E_STATE, "crt_sw_align_batch: not built yet");
+}
+
+int crt_dtw_align_batch(crt_ctx *, const double *, const int64_t *, const int32_t *, const int32_t *, int32_t, double,
+                        double, int32_t *, int32_t *, int64_t *, int64_t, double *)
+{
+    return fail(CRT_E_STATE, "crt_dtw_align_batch: not built yet");
+}
+
+int crt_rmsd_cov_tm(crt_ctx *, const int64_t *, int64_t, double *, double *, double *, int32_t *)
+{
+    return fail(CRT_E_STATE, "crt_rmsd_cov_tm: not built yet");
+}
+
+int crt_fp32_peak(crt_ctx *c, double *ffma_per_s, double *elapsed_ms)
+{
+    if (!c || !ffma_per_s) return fail(CRT_E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = c->f32tmp.ensure(64))) return rc;
+    const int iters = 4096, block = 256, grid = c->sm_count * 8;
+    k_ffma_peak<<<grid, block, 0, c->stream>>>(c->f32tmp.p, 64);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(cudaEventRecord(c->ev0, c->stream));
+        k_ffma_peak<<<grid, block, 0, c->stream>>>(c->f32tmp.p, iters);
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        best = std::min(best, ms);
+    }
+    const double ops = (double)grid * block * (double)iters * 16.0 * 8.0;
+    *ffma_per_s = ops / (best * 1e-3);
+    if (elapsed_ms) *elapsed_ms = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,630 @@
+// crt_kernels.cuh -- device side of the caretta pair path for sm_100a.
+//
+// Data-parallel structure (DESIGN.md has the long form):
+//   * a UNIT is one column chain j (the reference's seq2, multiple_alignment.py:164-169) and a run of consecutive
+//     row chains i0..i1 (seq1).  One warp owns a unit.  Lane l keeps C consecutive columns of chain j in
+//     REGISTERS (their feature vectors and the previous DP row), rows stream through the 32 lanes as a systolic
+//     array: at step t lane l works on row t-l, the value crossing the strip boundary moves to lane l+1 with one
+//     warp shuffle.  Row chains are streamed back to back, so the anti-diagonal wavefront never drains inside a unit.
+//   * the Gaussian score S[a,b] (score_functions.py:6-11) is computed on the fly from the row record and the
+//     lane's column registers; no n x m matrix ever exists in memory.
+//   * stage 1 (Smith-Waterman on shape tensors + traceback, dynamic_time_warping.py:225-278) writes 2 bits per
+//     cell -- (h != diag+S, h != left) -- as one coalesced 128-bit store per lane per 4 rows.
+//   * k_trace walks those bits per pair (first row-major maximum, diag > left > up priority), accumulates the
+//     Kabsch sums on the matched residues (superposition_functions.py:6-35), does the 3x3 Jacobi SVD with the
+//     reflection fix, and writes the transformed row coordinates for stage 2.
+//   * stage 2 (smith_waterman_score on superposed CA coordinates, dynamic_time_warping.py:204-222) is the same
+//     systolic fill without traceback.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace crt {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS_PER_CTA = 4;
+
+struct Unit {
+    long long row_base;    // packed residue index of the first row of the stream
+    long long tb_base;     // traceback buffer, uint4 index
+    long long rows2_base;  // stage-2 row records (batch-local index)
+    long long bnd_base;    // strip boundary buffer (elements), multi-strip units only
+    long long path_base;   // path buffer, short2 index
+    int G;                 // rows in the stream (sum of the row chains' lengths)
+    int m;                 // columns (length of chain j)
+    int col_base;          // packed residue index of chain j
+    int col_chain;         // j
+    int row_chain0;        // i0
+    int n_pairs;           // number of row chains
+    int pair_base;         // index of pair (i0, j) in the run's result arrays
+    int n_strips;          // ceil(m / (32*C))
+    int path_stride;       // path entries reserved per pair
+    int tchunks;           // 128-bit traceback chunks per lane per strip = ceil((G + 31) / 4)
+};
+
+// per-residue row meta: bit0 = first residue of its chain, bit1 = last, bits 2.. = chain index
+__host__ __device__ inline int make_meta(int chain, bool first, bool last) { return (chain << 2) | (last ? 2 : 0) | (first ? 1 : 0); }
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Score policies.  Row = what a lane loads every step, Col = what it keeps in registers per owned column.
+// ------------------------------------------------------------------------------------------------------------
+
+// stage 1, fp64 parity: the reference's arithmetic, score_functions.py:11 -- strict left-to-right sum of
+// (a-b)*(a-b) with separate roundings (no FMA), then exp((-gamma) * acc).  Records: D doubles, zero padded
+// beyond d (adds exact zeros), meta in a separate int array.
+template <int D_>
+struct P1F64 {
+    typedef double T;
+    static constexpr bool ROWS2 = false;
+    static constexpr int D = D_;
+    struct Row { double a[D]; int meta; };
+    struct Col { double b[D]; };
+    struct Args { const double *rec; const int *meta; double neg_gamma; };
+    __device__ static __forceinline__ Row load_row(const Args &g, long long idx)
+    {
+        Row r;
+        const double2 *p = reinterpret_cast<const double2 *>(g.rec + idx * D);
+#pragma unroll
+        for (int q = 0; q < D / 2; ++q) { double2 v = __ldg(p + q); r.a[2 * q] = v.x; r.a[2 * q + 1] = v.y; }
+        r.meta = __ldg(g.meta + idx);
+        return r;
+    }
+    __device__ static __forceinline__ Col load_col(const Args &g, long long idx)
+    {
+        Col c;
+#pragma unroll
+        for (int k = 0; k < D; ++k) c.b[k] = g.rec[idx * D + k];
+        return c;
+    }
+    __device__ static __forceinline__ Col pad_col()
+    {
+        Col c;
+#pragma unroll
+        for (int k = 0; k < D; ++k) c.b[k] = 1e300;      // (a - 1e300)^2 = inf, exp(-inf) = 0
+        return c;
+    }
+    __device__ static __forceinline__ double score(const Args &g, const Row &r, const Col &c)
+    {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double t = __dsub_rn(r.a[k], c.b[k]);
+            acc = __dadd_rn(acc, __dmul_rn(t, t));
+        }
+        return exp(__dmul_rn(g.neg_gamma, acc));
+    }
+};
+
+// stage 2, fp64 parity: rows = (a - mean(common_1)) R^T + mean(common_2), columns = raw coordinates.
+struct P2F64 {
+    typedef double T;
+    static constexpr bool ROWS2 = true;
+    struct Row { double x, y, z; int meta; };
+    struct Col { double x, y, z; };
+    struct Args { const double *rows; const double *cols; double neg_gamma; };
+    __device__ static __forceinline__ Row load_row(const Args &g, long long idx)
+    {
+        const double2 *p = reinterpret_cast<const double2 *>(g.rows + idx * 4);
+        double2 v0 = __ldg(p), v1 = __ldg(p + 1);
+        Row r; r.x = v0.x; r.y = v0.y; r.z = v1.x; r.meta = (int)__double_as_longlong(v1.y);
+        return r;
+    }
+    __device__ static __forceinline__ Col load_col(const Args &g, long long idx)
+    {
+        Col c; c.x = g.cols[idx * 3]; c.y = g.cols[idx * 3 + 1]; c.z = g.cols[idx * 3 + 2];
+        return c;
+    }
+    __device__ static __forceinline__ Col pad_col() { Col c; c.x = c.y = c.z = 1e300; return c; }
+    __device__ static __forceinline__ double score(const Args &g, const Row &r, const Col &c)
+    {
+        double dx = __dsub_rn(r.x, c.x), dy = __dsub_rn(r.y, c.y), dz = __dsub_rn(r.z, c.z);
+        double acc = __dmul_rn(dx, dx);
+        acc = __dadd_rn(acc, __dmul_rn(dy, dy));
+        acc = __dadd_rn(acc, __dmul_rn(dz, dz));
+        return exp(__dmul_rn(g.neg_gamma, acc));
+    }
+};
+
+template <typename T> __device__ __forceinline__ T max3(T a, T b, T c);
+template <> __device__ __forceinline__ float max3<float>(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+template <> __device__ __forceinline__ double max3<double>(double a, double b, double c)
+{
+    double t = a > b ? a : b;     // all operands are finite and >= 0 on this path
+    return t > c ? t : c;
+}
+__device__ __forceinline__ float shfl_up1(float v) { return __shfl_up_sync(FULL, v, 1); }
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(FULL, v, 1); }
+
+struct FillOut {
+    uint4 *tb;           // traceback bits (stage 1)
+    int *pair_istar;     // 1-based row of the first row-major maximum (0 = no positive cell)
+    int *pair_zflag;     // 1 if S[0][0] == 0 (a zero region exists, k_trace handles the stop state)
+    double *pair_score;  // stage 1: H[n][m] of the tensor SW; stage 2: the pair score
+    void *bnd;           // strip boundary values
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Systolic Smith-Waterman fill, gap = 0.
+//   DIFF = false: absolute form  h = max(H[i-1][j-1] + S, H[i][j-1], H[i-1][j])       (the reference's expression)
+//   DIFF = true : difference form d = max(S, a, b), u' = d - a, v' = d - b with a = H[i][j-1]-H[i-1][j-1] (vertical
+//                 difference of the left neighbour) and b = H[i-1][j]-H[i-1][j-1] (horizontal difference of the upper
+//                 neighbour).  Every quantity stays in [0, 1], so fp32 keeps ~100x more absolute resolution than
+//                 the absolute form; the decisions d==S / d==a are the same decisions in exact arithmetic.
+//   CODES: emit the 2-bit traceback codes and the start row (stage 1).
+// ------------------------------------------------------------------------------------------------------------
+template <typename P, int C, bool DIFF, bool CODES, bool MULTI>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_fill(const Unit *__restrict__ units, int n_units, typename P::Args args, FillOut out)
+{
+    typedef typename P::T T;
+    const int lane = threadIdx.x & 31;
+    const int uidx = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (uidx >= n_units) return;
+    const Unit u = units[uidx];
+    const int G = u.G;
+    const int steps4 = u.tchunks * 4;           // >= G + 31
+    const long long rbase = P::ROWS2 ? u.rows2_base : u.row_base;
+    T *bnd = MULTI ? reinterpret_cast<T *>(out.bnd) + u.bnd_base : nullptr;
+
+    for (int strip = 0; strip < (MULTI ? u.n_strips : 1); ++strip) {
+        typename P::Col col[C];
+        const int c0 = (strip * 32 + lane) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            col[c] = (c0 + c < u.m) ? P::load_col(args, (long long)u.col_base + c0 + c) : P::pad_col();
+        const bool last_strip = !MULTI || strip == u.n_strips - 1;
+
+        T prev[C];                 // DIFF: horizontal differences u[i-1][j]; else H[i-1][j]
+#pragma unroll
+        for (int c = 0; c < C; ++c) prev[c] = T(0);
+        T carry = T(0);            // value handed to lane+1: DIFF: v[i][cend]; else H[i][cend]
+        T dsave = T(0);            // abs form: H[i-1][c0-1]
+        T acc = T(0);              // DIFF: running H[i][m] on the last lane
+        int istar = 0, r = 0;
+        uint4 *tbp = CODES ? out.tb + u.tb_base + (long long)strip * u.tchunks * 32 + lane : nullptr;
+
+        for (int t0 = 0; t0 < steps4; t0 += 4) {
+            unsigned w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int g = t0 + q - lane;
+                const bool valid = (unsigned)g < (unsigned)G;
+                const int gc = min(max(g, 0), G - 1);
+                const typename P::Row row = P::load_row(args, rbase + gc);
+                T in = shfl_up1(carry);
+                if (lane == 0) {
+                    in = T(0);
+                    if (MULTI && strip > 0) in = bnd[gc];
+                }
+                const bool first = valid && (row.meta & 1);
+                if (first) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) prev[c] = T(0);
+                    dsave = T(0); acc = T(0); istar = 0; r = 0;
+                }
+                unsigned word = 0;
+                T left = in;           // DIFF: a
+                T diag = dsave;
+                T s0 = T(0);
+                bool grew = false;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const T s = P::score(args, row, col[c]);
+                    if (c == 0) s0 = s;
+                    if (DIFF) {
+                        const T b = prev[c];
+                        const T d = max3<T>(s, left, b);
+                        if (CODES) word |= ((d != s ? 2u : 0u) | (d != left ? 1u : 0u)) << (2 * (C - 1 - c));
+                        prev[c] = d - left;
+                        left = d - b;
+                    } else {
+                        const T up = prev[c];
+                        const T dg = diag + s;
+                        const T h = max3<T>(dg, left, up);
+                        if (CODES) word |= ((h != dg ? 2u : 0u) | (h != left ? 1u : 0u)) << (2 * (C - 1 - c));
+                        if (c == C - 1) grew = h > up;
+                        diag = up;
+                        prev[c] = h;
+                        left = h;
+                    }
+                }
+                carry = left;
+                dsave = in;
+                ++r;
+                if (DIFF) { grew = left > T(0); acc += left; }
+                if (CODES && grew) istar = r;          // last row whose H[i][m] exceeds H[i-1][m] (meaningful on lane 31)
+                w[q] = word;
+                if (valid) {
+                    if (MULTI && !last_strip && lane == 31) bnd[g] = carry;
+                    if (CODES && lane == 0 && strip == 0 && (row.meta & 1))
+                        out.pair_zflag[u.pair_base + (row.meta >> 2) - u.row_chain0] = (s0 == T(0)) ? 1 : 0;
+                    if (last_strip && lane == 31 && (row.meta & 2)) {
+                        const int pidx = u.pair_base + (row.meta >> 2) - u.row_chain0;
+                        out.pair_score[pidx] = DIFF ? (double)acc : (double)carry;
+                        if (CODES) out.pair_istar[pidx] = istar;
+                    }
+                }
+            }
+            if (CODES) tbp[(long long)(t0 >> 2) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (MULTI) __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 3x3 SVD by one-sided Jacobi in fp64 and the Kabsch rotation with the reference's reflection fix
+// (superposition_functions.py:27-33): R = U diag(1,1,sign) Vt for C = X2c^T X1c, row-vector convention x2 R ~ x1.
+// ------------------------------------------------------------------------------------------------------------
+__device__ inline void kabsch_rotation(const double Cm[9], double R[9])
+{
+    double W[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int q = 0; q < 9; ++q) W[q] = Cm[q];
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
+            double al = 0, be = 0, ga = 0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                al += W[r * 3 + p] * W[r * 3 + p];
+                be += W[r * 3 + q] * W[r * 3 + q];
+                ga += W[r * 3 + p] * W[r * 3 + q];
+            }
+            const double lim = sqrt(al * be);
+            if (ga == 0.0 || fabs(ga) <= 1e-300 || fabs(ga) <= 2.2e-16 * lim) continue;
+            off = fmax(off, fabs(ga) / (lim > 0 ? lim : 1.0));
+            const double zeta = (be - al) / (2.0 * ga);
+            const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double wp = W[r * 3 + p], wq = W[r * 3 + q];
+                W[r * 3 + p] = cs * wp - sn * wq; W[r * 3 + q] = sn * wp + cs * wq;
+                const double vp = V[r * 3 + p], vq = V[r * 3 + q];
+                V[r * 3 + p] = cs * vp - sn * vq; V[r * 3 + q] = sn * vp + cs * vq;
+            }
+        }
+        if (off == 0.0) break;
+    }
+    double nrm[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) nrm[q] = sqrt(W[q] * W[q] + W[3 + q] * W[3 + q] + W[6 + q] * W[6 + q]);
+    // order columns by decreasing singular value (o0, o1, o2)
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (nrm[o1] > nrm[o0]) { int t = o0; o0 = o1; o1 = t; }
+    if (nrm[o2] > nrm[o0]) { int t = o0; o0 = o2; o2 = t; }
+    if (nrm[o2] > nrm[o1]) { int t = o1; o1 = o2; o2 = t; }
+    double U[3][3], Vc[3][3];      // U[q] = q-th left singular vector, Vc[q] = q-th right singular vector
+    const int ord[3] = {o0, o1, o2};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int o = ord[q];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            Vc[q][r] = V[r * 3 + o];
+            U[q][r] = nrm[o] > 0 ? W[r * 3 + o] / nrm[o] : 0.0;
+        }
+    }
+    const double s0 = nrm[o0], s1 = nrm[o1], s2 = nrm[o2];
+    const double tiny = 1e-14 * (s0 > 0 ? s0 : 1.0);
+    if (!(s2 > tiny)) {
+        if (!(s1 > tiny)) {
+            if (!(s0 > 0)) { U[0][0] = 1; U[0][1] = 0; U[0][2] = 0; }
+            int mn = 0;
+            if (fabs(U[0][1]) < fabs(U[0][mn])) mn = 1;
+            if (fabs(U[0][2]) < fabs(U[0][mn])) mn = 2;
+            double ax[3] = {0, 0, 0};
+            ax[mn] = 1.0;
+            const double dp = U[0][mn];
+            double nn = 0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { U[1][r] = ax[r] - dp * U[0][r]; nn += U[1][r] * U[1][r]; }
+            nn = sqrt(nn);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) U[1][r] /= nn;
+        }
+        U[2][0] = U[0][1] * U[1][2] - U[0][2] * U[1][1];
+        U[2][1] = U[0][2] * U[1][0] - U[0][0] * U[1][2];
+        U[2][2] = U[0][0] * U[1][1] - U[0][1] * U[1][0];
+    }
+    // det of the matrices whose COLUMNS are U[q] (resp. rows of Vt are Vc[q]); det is transpose invariant
+    const double detU = U[0][0] * (U[1][1] * U[2][2] - U[1][2] * U[2][1]) - U[0][1] * (U[1][0] * U[2][2] - U[1][2] * U[2][0])
+                      + U[0][2] * (U[1][0] * U[2][1] - U[1][1] * U[2][0]);
+    const double detV = Vc[0][0] * (Vc[1][1] * Vc[2][2] - Vc[1][2] * Vc[2][1]) - Vc[0][1] * (Vc[1][0] * Vc[2][2] - Vc[1][2] * Vc[2][0])
+                      + Vc[0][2] * (Vc[1][0] * Vc[2][1] - Vc[1][1] * Vc[2][0]);
+    const double sg = (detU * detV < 0) ? -1.0 : 1.0;
+    // R[a][b] = sum_q Umat[a][q] * Vt[q][b] = sum_q U[q][a] * Vc[q][b], last term sign-flipped on reflection
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+            R[a * 3 + b] = U[0][a] * Vc[0][b] + U[1][a] * Vc[1][b] + sg * U[2][a] * Vc[2][b];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_trace: one thread per pair.  Start cell = first row-major maximum (dynamic_time_warping.py:241-247), walk with
+// priority diag > left > up (:255-277), common positions (helper.py:12-42), Kabsch (superposition_functions.py:6-60),
+// by-products RMSD / TM (score_functions.py:14-19, multiple_alignment.py:59-70), stage-2 row records.
+// ------------------------------------------------------------------------------------------------------------
+struct TraceArgs {
+    const Unit *units;
+    const uint4 *tb;
+    const int *pair_istar;
+    const int *pair_zflag;
+    const long long *offsets;     // [N+1]
+    const double *coords;         // raw CA coordinates [sumL,3]
+    const double *centroid;       // per-chain centroid [N,3] (fp32 records are relative to it)
+    short2 *path;
+    int *path_len;                // per pair
+    double *rmsd, *tm;
+    int *ncommon, *status;
+    double *rot;                  // optional [pairs, 12]: R (9) then t (3); may be null
+    void *rows2;                  // float4[] (fp32) or double[4][] (fp64)
+    // for the exact zero-region test (stop state of the reference traceback)
+    const float *rec32; int rs32; int d32;
+    const double *rec64; int d64; double neg_gamma_t;
+    int C;                        // columns per lane used by the stage-1 fill of these units
+    float scale2;                 // sqrt(gamma_c * log2 e) (fp32 only)
+    int precision;                // 0 fp64, 1 fp32
+};
+
+__device__ inline bool s1_is_zero(const TraceArgs &a, long long ri, long long ci)
+{
+    if (a.precision == 1) {
+        // same operation order as k_fill1_f32: even terms in the .x lane, odd terms in the .y lane of the FFMA2 chain,
+        // the last pair is (A_row * 1, 1 * A_col)
+        const float *x = a.rec32 + ri * a.rs32, *y = a.rec32 + ci * a.rs32;
+        float ex = x[0] * y[0], ey = x[1] * y[1];
+        for (int k = 2; k < a.d32; k += 2) { ex = __fmaf_rn(x[k], y[k], ex); ey = __fmaf_rn(x[k + 1], y[k + 1], ey); }
+        ex = __fmaf_rn(x[a.d32], 1.0f, ex);
+        ey = __fmaf_rn(1.0f, y[a.d32], ey);
+        return ex2_approx(ex + ey) == 0.f;
+    }
+    const double *x = a.rec64 + ri * a.d64, *y = a.rec64 + ci * a.d64;
+    double acc = 0.0;
+    for (int k = 0; k < a.d64; ++k) { double t = __dsub_rn(x[k], y[k]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
+    return exp(__dmul_rn(a.neg_gamma_t, acc)) == 0.0;
+}
+
+__global__ void __launch_bounds__(32) k_trace(TraceArgs a)
+{
+    const Unit u = a.units[blockIdx.x];
+    const int tid = threadIdx.x;
+    if (tid >= u.n_pairs) return;
+    const int ci = u.row_chain0 + tid;
+    const int pair = u.pair_base + tid;
+    const long long ro = a.offsets[ci];
+    const int n = (int)(a.offsets[ci + 1] - ro), m = u.m;
+    const int g0 = (int)(ro - u.row_base);
+    const double *A = a.coords + ro * 3;
+    const double *B = a.coords + (long long)u.col_base * 3;
+    short2 *path = a.path + u.path_base + (long long)tid * u.path_stride;
+    const int C = a.C, SW = 32 * C;
+
+    long long cidx = -1;
+    uint4 cw = make_uint4(0, 0, 0, 0);
+    auto code = [&](int i, int j) -> unsigned {           // 1-based cell -> (nA << 1) | nB
+        const int c = j - 1;
+        const int strip = c / SW, cc = c - strip * SW;
+        const int l = cc / C, k = cc - l * C;
+        const int t = g0 + (i - 1) + l;
+        const long long idx = u.tb_base + ((long long)strip * u.tchunks + (t >> 2)) * 32 + l;
+        if (idx != cidx) { cw = a.tb[idx]; cidx = idx; }
+        const int q = t & 3;
+        const unsigned w = q == 0 ? cw.x : (q == 1 ? cw.y : (q == 2 ? cw.z : cw.w));
+        return (w >> (2 * (C - 1 - k))) & 3u;
+    };
+
+    // exact stop-state emulation: H[i][j] == 0 iff every S in [1..i] x [1..j] is 0; only possible when S[1][1] == 0
+    const bool zreg = a.pair_zflag[pair] != 0;
+    int wi = 0, wj = 0;               // witness: a nonzero S at (wi, wj) (1-based), 0 = none known
+    auto is_zero_cell = [&](int i, int j) -> bool {
+        if (!zreg) return false;
+        if (wi > 0 && wi <= i && wj <= j) return false;
+        for (int ii = 1; ii <= i; ++ii)
+            for (int jj = 1; jj <= j; ++jj)
+                if (!s1_is_zero(a, ro + ii - 1, (long long)u.col_base + jj - 1)) { wi = ii; wj = jj; return false; }
+        return true;
+    };
+
+    int i = a.pair_istar[pair], j = m;
+    int st = 0, len = 0, c = 0;
+    double sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0};
+    if (i <= 0) {
+        st |= 2;                      // CRT_ST_NO_POSITIVE
+    } else {
+        while (j > 1 && (code(i, j) & 1u) == 0u) --j;      // first column of row i* that attains the maximum
+        while (i > 0 && j > 0) {
+            if (is_zero_cell(i, j)) break;
+            const unsigned cd = code(i, j);
+            if ((cd & 2u) == 0u) {
+                --i; --j;
+                path[len++] = make_short2((short)i, (short)j);
+                ++c;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sa[k] += A[i * 3 + k]; sb[k] += B[j * 3 + k]; }
+            } else if ((cd & 1u) == 0u) {
+                --j;
+                path[len++] = make_short2((short)-1, (short)j);
+            } else {
+                --i;
+                path[len++] = make_short2((short)i, (short)-1);
+            }
+        }
+    }
+    a.path_len[pair] = len;
+    a.ncommon[pair] = c;
+
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
+    const bool superpose = c > 3;
+    if (!superpose) st |= 1;          // CRT_ST_FEW_COMMON: multiple_alignment.py:337-342
+    if (superpose) {
+        // the reference's means are sequential sums over ascending residue order (helper.py:45-53); the path is
+        // stored in descending order, so walk it backwards to add in the same order
+        for (int k = 0; k < 3; ++k) { sa[k] = 0; sb[k] = 0; }
+        for (int q = len - 1; q >= 0; --q) {
+            const short2 e = path[q];
+            if (e.x >= 0 && e.y >= 0)
+                for (int k = 0; k < 3; ++k) { sa[k] += A[e.x * 3 + k]; sb[k] += B[e.y * 3 + k]; }
+        }
+        for (int k = 0; k < 3; ++k) { m1[k] = sa[k] / (double)c; m2[k] = sb[k] / (double)c; }
+        double Cm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q = len - 1; q >= 0; --q) {
+            const short2 e = path[q];
+            if (e.x < 0 || e.y < 0) continue;
+            double x1[3], x2[3];
+            for (int k = 0; k < 3; ++k) { x1[k] = A[e.x * 3 + k] - m1[k]; x2[k] = B[e.y * 3 + k] - m2[k]; }
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Cm[p * 3 + k] += x2[p] * x1[k];
+        }
+        kabsch_rotation(Cm, R);
+    }
+    // translation of apply_rotran: t = m1 - m2 R
+    double tr[3];
+    for (int b = 0; b < 3; ++b) tr[b] = m1[b] - (m2[0] * R[b] + m2[1] * R[3 + b] + m2[2] * R[6 + b]);
+    if (a.rot) {
+        for (int q = 0; q < 9; ++q) a.rot[(long long)pair * 12 + q] = R[q];
+        for (int q = 0; q < 3; ++q) a.rot[(long long)pair * 12 + 9 + q] = tr[q];
+    }
+    // by-products over the matched residues
+    double rmsd = 0.0, tm = 0.0;
+    if (c >= 1) {
+        const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
+        double ss = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int q = len - 1; q >= 0; --q) {
+            const short2 e = path[q];
+            if (e.x < 0 || e.y < 0) continue;
+            double sm = 0.0;
+            for (int b = 0; b < 3; ++b) {
+                const double *y = B + e.y * 3;
+                const double yr = superpose ? (y[0] * R[b] + y[1] * R[3 + b] + y[2] * R[6 + b]) + tr[b] : y[b];
+                const double df = A[e.x * 3 + b] - yr;
+                ss += df * df;
+                sm += df;
+            }
+            const double q1 = sm / d1, q2 = sm / d2;
+            t1 += 1 / (1 + q1 * q1);
+            t2 += 1 / (1 + q2 * q2);
+        }
+        rmsd = sqrt(ss / (double)c);
+        t1 = (1.0 / (double)n) * t1;
+        t2 = (1.0 / (double)m) * t2;
+        tm = t1 > t2 ? t1 : t2;
+    }
+    a.rmsd[pair] = rmsd;
+    a.tm[pair] = tm;
+    a.status[pair] = st;
+
+    // stage-2 row records: (x - m1) R^T + m2  == the reference's frame up to a rigid motion of BOTH chains
+    // (superposition_functions.py:57-58 rotates chain 2 instead; the Gaussian only sees distances).
+    const double *cj = a.centroid + (long long)u.col_chain * 3;
+    for (int r = 0; r < n; ++r) {
+        double x[3], y[3];
+        for (int k = 0; k < 3; ++k) x[k] = A[r * 3 + k] - m1[k];
+        for (int k = 0; k < 3; ++k) y[k] = superpose ? (x[0] * R[k * 3] + x[1] * R[k * 3 + 1] + x[2] * R[k * 3 + 2]) + m2[k] : A[r * 3 + k];
+        const int meta = make_meta(ci, r == 0, r == n - 1);
+        const long long idx = u.rows2_base + g0 + r;
+        if (a.precision == 1) {
+            float4 v;
+            v.x = (float)((y[0] - cj[0]) * (double)a.scale2);
+            v.y = (float)((y[1] - cj[1]) * (double)a.scale2);
+            v.z = (float)((y[2] - cj[2]) * (double)a.scale2);
+            v.w = __int_as_float(meta);
+            reinterpret_cast<float4 *>(a.rows2)[idx] = v;
+        } else {
+            double *o = reinterpret_cast<double *>(a.rows2) + idx * 4;
+            o[0] = y[0]; o[1] = y[1]; o[2] = y[2]; o[3] = __longlong_as_double((long long)meta);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Preprocessing of the uploaded chains (device side of crt_set_chains).
+// ------------------------------------------------------------------------------------------------------------
+struct PrepArgs {
+    const double *coords, *tensors;
+    const long long *offsets;
+    const int *chain_of;      // [sumL]
+    int n_chains, d;
+    long long total;
+    double mean[32];          // global tensor mean (host computed)
+    double g2;                // gamma_tensor * log2(e)
+    double scale2;            // sqrt(gamma_coords * log2(e))
+    float *rec32; int rs32, d32;
+    double *rec64; int d64;
+    int *meta;
+    float4 *cols2;
+    double *centroid;
+};
+
+__global__ void k_centroid(PrepArgs a)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= a.n_chains) return;
+    double s[3] = {0, 0, 0};
+    const long long b = a.offsets[ch], e = a.offsets[ch + 1];
+    for (long long r = b; r < e; ++r)
+        for (int k = 0; k < 3; ++k) s[k] += a.coords[r * 3 + k];
+    const double inv = e > b ? 1.0 / (double)(e - b) : 0.0;
+    for (int k = 0; k < 3; ++k) a.centroid[(long long)ch * 3 + k] = s[k] * inv;
+}
+
+__global__ void k_prep(PrepArgs a)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.total) return;
+    const int ch = a.chain_of[r];
+    const bool first = r == a.offsets[ch], last = r + 1 == a.offsets[ch + 1];
+    const int meta = make_meta(ch, first, last);
+    a.meta[r] = meta;
+    const double *t = a.tensors + r * a.d;
+    const double sc = sqrt(2.0 * a.g2);
+    double nn = 0.0;
+    float *o = a.rec32 + r * a.rs32;
+    for (int k = 0; k < a.d32; ++k) {
+        const double x = k < a.d ? t[k] - a.mean[k] : 0.0;
+        nn += x * x;
+        o[k] = (float)(sc * x);
+    }
+    o[a.d32] = (float)(-a.g2 * nn);
+    o[a.d32 + 1] = 1.0f;
+    for (int k = a.d32 + 2; k < a.rs32; ++k) o[k] = 0.f;
+    double *o64 = a.rec64 + r * a.d64;
+    for (int k = 0; k < a.d64; ++k) o64[k] = k < a.d ? t[k] : 0.0;
+    const double *cen = a.centroid + (long long)ch * 3;
+    float4 v;
+    v.x = (float)((a.coords[r * 3] - cen[0]) * a.scale2);
+    v.y = (float)((a.coords[r * 3 + 1] - cen[1]) * a.scale2);
+    v.z = (float)((a.coords[r * 3 + 2] - cen[2]) * a.scale2);
+    v.w = 0.f;
+    a.cols2[r] = v;
+}
+
+// FP32 FFMA peak probe: 8 independent chains per thread, 148 * k CTAs.
+__global__ void k_ffma_peak(float *out, int iters)
+{
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    const float a = 0.999f, b = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+            x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+        }
+    }
+    if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 12345.678f) out[0] = x0;
+}
+
+}  // namespace crt

@@ -1,0 +1,209 @@
+"""ctypes binding of the C ABI in include/caretta_b200.h -- the only door between the Python host code and the
+CUDA engine.  There is no CPU fallback: if the shared library is missing or no CUDA device is present, creating
+an Engine raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcaretta_b200.so")
+
+FP64, FP32 = 0, 1
+ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE = 1, 2, 4
+
+EXPORTS = [
+    "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
+    "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_fetch", "crt_fetch_device",
+    "crt_last_elapsed_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
+    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak",
+]
+
+
+class CrtError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("gamma_tensor", C.c_double), ("gamma_coords", C.c_double), ("sw_gap", C.c_double),
+                ("precision", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libcaretta_b200.so; raises if it has not been built (python -m caretta_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CrtError(f"{LIB_PATH} is missing: build it with `python -m caretta_b200.build` "
+                       "(the engine has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.crt_last_error.restype = C.c_char_p
+    L.crt_version.restype = C.c_int
+    L.crt_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.crt_destroy.argtypes = [vp]
+    L.crt_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
+    L.crt_set_chains.argtypes = [vp, vp, vp, vp, i32, i32]
+    L.crt_pairwise_shard.argtypes = [vp, C.POINTER(Params), i32, i32]
+    L.crt_shard_size.argtypes = [vp, i32, i32]
+    L.crt_shard_size.restype = i64
+    L.crt_shard_pairs.argtypes = [vp, i32, i32, vp, vp]
+    L.crt_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.crt_fetch_device.argtypes = [vp, vp, vp, vp, i64]
+    L.crt_last_elapsed_ms.argtypes = [vp]
+    L.crt_last_elapsed_ms.restype = dbl
+    L.crt_last_launches.argtypes = [vp]
+    L.crt_last_launches.restype = i64
+    L.crt_last_cell_updates.argtypes = [vp]
+    L.crt_last_cell_updates.restype = dbl
+    L.crt_pairwise_all.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
+    L.crt_pairwise_list.argtypes = [vp, C.POINTER(Params), vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64]
+    L.crt_sw_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, dbl, vp, vp, vp, i64, vp, vp]
+    L.crt_dtw_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, dbl, dbl, vp, vp, vp, i64, vp]
+    L.crt_rmsd_cov_tm.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(i32)]
+    L.crt_fp32_peak.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("crt_version",):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One CUDA device.  Mirrors the life cycle the reference's driver has implicitly: hold the chains
+    (MultipleAlignment.sequences), score all pairs (make_pairwise_matrix)."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.crt_create(int(device), C.byref(h))
+        if rc != 0:
+            raise CrtError(f"crt_create failed ({rc}): {self.lib.crt_last_error().decode()}")
+        self.h = h
+        self.n_chains = 0
+        self._offsets = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.crt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise CrtError(f"{what} failed ({rc}): {self.lib.crt_last_error().decode()}")
+
+    def device_info(self):
+        sm, clk, mem = C.c_int32(), C.c_int32(), C.c_int64()
+        self._check(self.lib.crt_device_info(self.h, C.byref(sm), C.byref(clk), C.byref(mem)), "crt_device_info")
+        return dict(sm_count=sm.value, clock_khz=clk.value, mem_bytes=mem.value)
+
+    @staticmethod
+    def params(gamma_tensor=7.0, gamma_coords=0.03, precision=FP32, sw_gap=0.0) -> Params:
+        return Params(float(gamma_tensor), float(gamma_coords), float(sw_gap), int(precision), 0)
+
+    def set_chains(self, coords, tensors, offsets):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        tensors = np.ascontiguousarray(tensors, dtype=np.float64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        if coords.ndim != 2 or coords.shape[1] != 3 or tensors.ndim != 2 or coords.shape[0] != tensors.shape[0] \
+                or offsets[-1] != coords.shape[0]:
+            raise ValueError("coords [sumL,3], tensors [sumL,d], offsets [N+1] expected")
+        self._check(self.lib.crt_set_chains(self.h, _p(coords), _p(tensors), _p(offsets), n, tensors.shape[1]),
+                    "crt_set_chains")
+        self.n_chains = n
+        self._offsets = offsets.copy()
+
+    # ------------------------------------------------------------------------------------------------ all-vs-all
+    def pairwise_all(self, prm: Params, want_rmsd_tm: bool = False):
+        n = self.n_chains
+        score = np.empty((n, n))
+        rm = np.empty((n, n)) if want_rmsd_tm else None
+        tm = np.empty((n, n)) if want_rmsd_tm else None
+        self._check(self.lib.crt_pairwise_all(self.h, C.byref(prm), _p(score), _p(rm), _p(tm)), "crt_pairwise_all")
+        return (score, rm, tm) if want_rmsd_tm else score
+
+    def pairwise_shard(self, prm: Params, rank: int = 0, world: int = 1):
+        self._check(self.lib.crt_pairwise_shard(self.h, C.byref(prm), rank, world), "crt_pairwise_shard")
+
+    def shard_size(self, rank: int, world: int) -> int:
+        n = int(self.lib.crt_shard_size(self.h, rank, world))
+        if n < 0:
+            raise CrtError(f"crt_shard_size failed: {self.lib.crt_last_error().decode()}")
+        return n
+
+    def shard_pairs(self, rank: int, world: int):
+        n = self.shard_size(rank, world)
+        pi = np.empty(max(n, 1), np.int32)
+        pj = np.empty(max(n, 1), np.int32)
+        self._check(self.lib.crt_shard_pairs(self.h, rank, world, _p(pi), _p(pj)), "crt_shard_pairs")
+        return pi[:n], pj[:n]
+
+    def fetch(self, n: int, extras: bool = True):
+        score = np.empty(max(n, 1))
+        rm = np.empty(max(n, 1)) if extras else None
+        tm = np.empty(max(n, 1)) if extras else None
+        nc = np.empty(max(n, 1), np.int32) if extras else None
+        st = np.empty(max(n, 1), np.int32) if extras else None
+        self._check(self.lib.crt_fetch(self.h, _p(score), _p(rm), _p(tm), _p(nc), _p(st)), "crt_fetch")
+        out = dict(score=score[:n])
+        if extras:
+            out.update(rmsd=rm[:n], tm=tm[:n], ncommon=nc[:n], status=st[:n])
+        return out
+
+    def fetch_device(self, d_score: int, d_rmsd: int, d_tm: int, n: int):
+        self._check(self.lib.crt_fetch_device(self.h, C.c_void_p(d_score), C.c_void_p(d_rmsd), C.c_void_p(d_tm), n),
+                    "crt_fetch_device")
+
+    def last_elapsed_ms(self) -> float:
+        return float(self.lib.crt_last_elapsed_ms(self.h))
+
+    def last_launches(self) -> int:
+        return int(self.lib.crt_last_launches(self.h))
+
+    def last_cell_updates(self) -> float:
+        return float(self.lib.crt_last_cell_updates(self.h))
+
+    # ------------------------------------------------------------------------------------------------ pair list
+    def pairwise_list(self, prm: Params, pi, pj, want_paths: bool = False):
+        pi = np.ascontiguousarray(pi, dtype=np.int32)
+        pj = np.ascontiguousarray(pj, dtype=np.int32)
+        n = len(pi)
+        score, rm, tm = np.empty(max(n, 1)), np.empty(max(n, 1)), np.empty(max(n, 1))
+        nc, st = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
+        a1 = a2 = off = None
+        cap = 0
+        if want_paths:
+            lens = np.diff(self._offsets)
+            cap = int((lens[pi] + lens[pj]).sum()) + 1
+            a1, a2 = np.empty(cap, np.int32), np.empty(cap, np.int32)
+            off = np.zeros(n + 1, np.int64)
+        self._check(self.lib.crt_pairwise_list(self.h, C.byref(prm), _p(pi), _p(pj), n, _p(score), _p(rm), _p(tm),
+                                               _p(nc), _p(st), _p(a1), _p(a2), _p(off), cap), "crt_pairwise_list")
+        out = dict(score=score[:n], rmsd=rm[:n], tm=tm[:n], ncommon=nc[:n], status=st[:n])
+        if want_paths:
+            out.update(aln1=a1, aln2=a2, aln_off=off)
+        return out
+
+    def fp32_peak(self):
+        v, ms = C.c_double(), C.c_double()
+        self._check(self.lib.crt_fp32_peak(self.h, C.byref(v), C.byref(ms)), "crt_fp32_peak")
+        return v.value, ms.value

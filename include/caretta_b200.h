@@ -1,0 +1,130 @@
+/*
+ * caretta_b200.h -- C ABI of the B200-native engine for caretta's all-vs-all pair path.
+ *
+ * The reference (TurtleTools/caretta 0.2.0, pure Python + numba) has no FFI layer; these entry points are what a
+ * ctypes binding placed behind the reference's own Python seams binds (INTEGRATION.md shows the stub):
+ *
+ *   crt_set_chains            <- the List[Protein] held by MultipleAlignment.sequences
+ *                                (caretta/multiple_alignment.py:148-156, Protein :312-319: tensors f64[L,d],
+ *                                coordinates f64[L,3]), packed residue-major.
+ *   crt_pairwise_all          <- MultipleAlignment.make_pairwise_matrix        (multiple_alignment.py:158-170)
+ *                                = for i<j: smith_waterman_score(Protein.score_function(...))   (:321-349, :164-169)
+ *   crt_pairwise_list         <- the same per-pair recipe on an explicit pair list (parity tests, sampled baselines);
+ *                                optionally returns the stage-1 smith_waterman paths
+ *                                (caretta/dynamic_time_warping.py:225-278).
+ *   crt_sw_align_batch        <- dtw.smith_waterman / smith_waterman_score on caller-supplied score matrices
+ *                                (dynamic_time_warping.py:204-278)
+ *   crt_dtw_align_batch       <- dtw.dtw_align / dtw_align_score                (dynamic_time_warping.py:7-201)
+ *   crt_rmsd_cov_tm           <- make_rmsd_coverage_tm_matrix(superpose_first=False) (multiple_alignment.py:1000-1055)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller (numpy) owns every host buffer, the library never keeps a host
+ *     pointer past return and never frees caller memory.  Device buffers belong to the context.
+ *   - every function returns 0 on success or a negative CRT_E_* code; crt_last_error() gives the message
+ *     (thread-local).  Nothing throws or exits across the ABI.  There is no CPU fallback: without a CUDA
+ *     device crt_create fails with CRT_E_CUDA.
+ *   - data-dependent degeneracies are not errors; they set bits in out_status[pair]:
+ *       CRT_ST_FEW_COMMON  <= 3 matched residues, superposition skipped exactly like multiple_alignment.py:337-342
+ *       CRT_ST_NO_POSITIVE stage-1 score matrix had no cell > 0 (the reference raises from
+ *                          dynamic_time_warping.py:250); the pair is scored without superposition
+ *   - chain layout: coords[(offsets[p] + r) * 3 + axis], tensors[(offsets[p] + r) * d + k], float64, offsets[N+1].
+ *   - precision: CRT_FP64 reproduces the reference's arithmetic (sequential non-fused RBF sum, equality
+ *     traceback, row-major first maximum): stage-1 paths are identical to the reference's.  CRT_FP32 is the
+ *     production mode (score / RMSD / TM within 1e-4 relative, >= 99.9 % identical aligned columns).
+ *   - calls on one context are serialised by the caller; one context per (process, device).
+ */
+#ifndef CARETTA_B200_H
+#define CARETTA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crt_ctx crt_ctx;
+
+enum { CRT_FP64 = 0, CRT_FP32 = 1 };
+
+enum {
+    CRT_OK = 0,
+    CRT_E_ARG = -1,        /* bad argument (null pointer, negative size, unsupported d / gap / length) */
+    CRT_E_CUDA = -2,       /* CUDA runtime failure (including: no device) */
+    CRT_E_STATE = -3,      /* call order (e.g. pairwise before set_chains) */
+    CRT_E_NOMEM = -4       /* device or host allocation failed */
+};
+
+enum { CRT_ST_FEW_COMMON = 1, CRT_ST_NO_POSITIVE = 2, CRT_ST_NONFINITE = 4 };
+
+/* Parameters of the pair recipe; defaults are the reference's (multiple_alignment.py:490-492, :335). */
+typedef struct crt_params {
+    double gamma_tensor;   /* 7.0  */
+    double gamma_coords;   /* 0.03 */
+    double sw_gap;         /* 0.0 -- the only value the reference uses on this path; others -> CRT_E_ARG */
+    int32_t precision;     /* CRT_FP64 | CRT_FP32 */
+    int32_t reserved;
+} crt_params;
+
+const char *crt_last_error(void);
+int crt_version(void);
+
+/* Context = one CUDA device + its streams and workspaces.  device < 0 -> current device. */
+int crt_create(int device, crt_ctx **out);
+int crt_destroy(crt_ctx *ctx);
+int crt_device_info(crt_ctx *ctx, int32_t *sm_count, int32_t *clock_khz, int64_t *mem_bytes);
+
+/* Upload (and preprocess on the device) the packed chain set.  Replaces any previous set. */
+int crt_set_chains(crt_ctx *ctx, const double *coords, const double *tensors, const int64_t *offsets,
+                   int32_t n_chains, int32_t d);
+
+/* All-vs-all, the shard of `rank` out of `world` (world = 1 -> everything).  Pairs are grouped into units
+ * (one column chain x a run of row chains), units are dealt to ranks by cost; the enumeration is deterministic
+ * so every rank can reconstruct every other rank's pair list with crt_shard_pairs.
+ * Results stay in device memory (packed, in shard order) until fetched; the call returns after the work is
+ * enqueued AND finished (synchronous), timing available from crt_last_elapsed_ms. */
+int crt_pairwise_shard(crt_ctx *ctx, const crt_params *prm, int32_t rank, int32_t world);
+int64_t crt_shard_size(crt_ctx *ctx, int32_t rank, int32_t world);      /* pairs in that shard, <0 on error */
+int crt_shard_pairs(crt_ctx *ctx, int32_t rank, int32_t world, int32_t *pair_i, int32_t *pair_j);
+/* Copy the packed results of the last crt_pairwise_shard / crt_pairwise_list to host (any pointer may be NULL).
+ * score/rmsd/tm are float64 at the boundary in both precisions (the reference returns float64). */
+int crt_fetch(crt_ctx *ctx, double *score, double *rmsd, double *tm, int32_t *ncommon, int32_t *status);
+/* Same, device to device: dst pointers are DEVICE addresses of float32 buffers (e.g. torch tensors used as NCCL
+ * all-gather inputs), n = capacity in elements. */
+int crt_fetch_device(crt_ctx *ctx, void *d_score, void *d_rmsd, void *d_tm, int64_t n);
+double crt_last_elapsed_ms(crt_ctx *ctx);        /* device time of the last run (CUDA events on the run's stream) */
+int64_t crt_last_launches(crt_ctx *ctx);         /* kernels launched by the last run */
+double crt_last_cell_updates(crt_ctx *ctx);      /* sum over pairs of 2 * L1 * L2 */
+
+/* make_pairwise_matrix: dense symmetric float64 [N,N], diagonal 0 (rmsd/tm by-products: diagonal 0 / 1).
+ * Convenience wrapper = crt_pairwise_shard(world=1) + crt_fetch + scatter. out_rmsd/out_tm may be NULL. */
+int crt_pairwise_all(crt_ctx *ctx, const crt_params *prm, double *out_score, double *out_rmsd, double *out_tm);
+
+/* Explicit pair list.  Optional stage-1 paths: aln_off[n_pairs+1] (int64, filled by the library), aln1/aln2 int32
+ * with -1 = gap, ascending residue order like dynamic_time_warping.py:278; capacity aln_cap entries (sum over
+ * pairs of L_i + L_j is always enough).  Pass NULL for all three to skip. */
+int crt_pairwise_list(crt_ctx *ctx, const crt_params *prm, const int32_t *pair_i, const int32_t *pair_j,
+                      int64_t n_pairs, double *score, double *rmsd, double *tm, int32_t *ncommon, int32_t *status,
+                      int32_t *aln1, int32_t *aln2, int64_t *aln_off, int64_t aln_cap);
+
+/* DP in isolation on caller-supplied float64 score matrices, problem p is S[shape_off[p] ...] with
+ * n[p] x m[p] row-major.  aln1/aln2/aln_off as above (may be NULL for score only). */
+int crt_sw_align_batch(crt_ctx *ctx, const double *S, const int64_t *shape_off, const int32_t *n, const int32_t *m,
+                       int32_t n_problems, double gap, int32_t *aln1, int32_t *aln2, int64_t *aln_off,
+                       int64_t aln_cap, double *score, int32_t *status);
+int crt_dtw_align_batch(crt_ctx *ctx, const double *S, const int64_t *shape_off, const int32_t *n, const int32_t *m,
+                        int32_t n_problems, double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2,
+                        int64_t *aln_off, int64_t aln_cap, double *score);
+
+/* make_rmsd_coverage_tm_matrix(superpose_first=False) on the chains of the context: aln int64 [N, A], -1 = gap.
+ * Outputs float64 [N,N] with the reference's diagonals (0 / 1 / 1).  *n_bad = pairs with < 3 common positions
+ * (the reference asserts there); their entries keep the diagonal defaults. */
+int crt_rmsd_cov_tm(crt_ctx *ctx, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm,
+                    int32_t *n_bad);
+
+/* FP32 FFMA micro-benchmark used as the measured roofline denominator: returns lane-FFMA/s. */
+int crt_fp32_peak(crt_ctx *ctx, double *ffma_per_s, double *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

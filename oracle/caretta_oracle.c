@@ -517,45 +517,104 @@ API int crt_o_rmsd_cov_tm(const int64_t *aln, int N, int64_t A, const double *co
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* fp32 model of the production arithmetic (RBF in float, DP in float) used only to study how far an fp32
- * DP can agree with the fp64 reference (tests/test_fp32_model.py).  Not a restatement of reference code. */
+/* fp32 models of the production arithmetic, used only to study how far an fp32 DP can agree with the fp64
+ * reference (tests/test_fp32_model.py).  Not a restatement of reference code.
+ *   variant 0: direct-difference RBF, absolute-value DP   H = max(Hd + S, Hl, Hu)
+ *   variant 1: dot-product RBF (|a|^2 + |b|^2 - 2ab folded into an FMA chain), difference-form DP
+ *              d = max(S, a, b), u = d - a, v = d - b   with a = vertical diff of the left cell, b = horizontal
+ *              diff of the upper cell; all quantities stay in [0, 1] so fp32 keeps ~100x more absolute resolution.
+ * Traceback codes are taken at fill time exactly as the CUDA kernels do (diag if d==S, else left if d==a, else up).
+ */
+static float g_f32_flush = 0.f;   /* model of a flush-to-zero threshold on S (study only) */
+API void crt_o_set_f32_flush(double v) { g_f32_flush = (float)v; }
+
 API int crt_o_pair_f32model(const double *t1, const double *c1, int n, const double *t2, const double *c2,
-                            int m, int d, double gamma_t, double gamma_c,
+                            int m, int d, double gamma_t, double gamma_c, int variant,
                             double *score, int64_t *aln1, int64_t *aln2, int64_t *aln_len)
 {
     (void)c1; (void)c2; (void)gamma_c;
     float *S = (float *)malloc(sizeof(float) * (size_t)n * m);
-    float *H = (float *)calloc((size_t)(n + 1) * (m + 1), sizeof(float));
+    uint8_t *code = (uint8_t *)calloc((size_t)(n + 1) * (m + 1), 1);
     const int W = m + 1;
     const float g2 = (float)(gamma_t * 1.4426950408889634);
-    for (int a = 0; a < n; ++a)
-        for (int b = 0; b < m; ++b) {
-            float acc = 0.f;
-            for (int q = 0; q < d; ++q) {
-                float t = (float)t1[(size_t)a * d + q] - (float)t2[(size_t)b * d + q];
-                acc = fmaf(t, t, acc);
+    if (variant == 0) {
+        for (int a = 0; a < n; ++a)
+            for (int b = 0; b < m; ++b) {
+                float acc = 0.f;
+                for (int q = 0; q < d; ++q) {
+                    float t = (float)t1[(size_t)a * d + q] - (float)t2[(size_t)b * d + q];
+                    acc = fmaf(t, t, acc);
+                }
+                S[(size_t)a * m + b] = exp2f(-g2 * acc);
             }
-            S[(size_t)a * m + b] = exp2f(-g2 * acc);
+    } else {
+        float *ap = (float *)malloc(sizeof(float) * (size_t)(n + m) * (d + 1));
+        float *bp = ap + (size_t)n * (d + 1);
+        for (int a = 0; a < n; ++a) {
+            double nn = 0;
+            for (int q = 0; q < d; ++q) { double v = t1[(size_t)a * d + q]; nn += v * v; ap[(size_t)a * (d + 1) + q] = (float)(2.0 * gamma_t * 1.4426950408889634 * v); }
+            ap[(size_t)a * (d + 1) + d] = (float)(-gamma_t * 1.4426950408889634 * nn);
         }
-    for (int i = 1; i <= n; ++i)
-        for (int j = 1; j <= m; ++j) {
-            float dg = H[(size_t)(i - 1) * W + j - 1] + S[(size_t)(i - 1) * m + j - 1];
-            float lf = H[(size_t)i * W + j - 1], up = H[(size_t)(i - 1) * W + j];
-            float h = dg > lf ? dg : lf;
-            H[(size_t)i * W + j] = h > up ? h : up;
+        for (int b = 0; b < m; ++b) {
+            double nn = 0;
+            for (int q = 0; q < d; ++q) { double v = t2[(size_t)b * d + q]; nn += v * v; bp[(size_t)b * (d + 1) + q] = (float)v; }
+            bp[(size_t)b * (d + 1) + d] = (float)(-gamma_t * 1.4426950408889634 * nn);
         }
-    float best = 0.f; int bi = -1, bj = -1;
-    for (int i = 1; i <= n; ++i)
-        for (int j = 1; j <= m; ++j)
-            if (H[(size_t)i * W + j] > best) { best = H[(size_t)i * W + j]; bi = i; bj = j; }
+        for (int a = 0; a < n; ++a)
+            for (int b = 0; b < m; ++b) {
+                float acc = ap[(size_t)a * (d + 1) + d] + bp[(size_t)b * (d + 1) + d];
+                for (int q = 0; q < d; ++q) acc = fmaf(ap[(size_t)a * (d + 1) + q], bp[(size_t)b * (d + 1) + q], acc);
+                S[(size_t)a * m + b] = exp2f(acc);
+                if (S[(size_t)a * m + b] < g_f32_flush) S[(size_t)a * m + b] = 0.f;
+            }
+        free(ap);
+    }
+    int bi = -1, bj = -1;
+    float best = 0.f;
+    if (variant == 0) {
+        float *H = (float *)calloc((size_t)(n + 1) * W, sizeof(float));
+        for (int i = 1; i <= n; ++i)
+            for (int j = 1; j <= m; ++j) {
+                float dg = H[(size_t)(i - 1) * W + j - 1] + S[(size_t)(i - 1) * m + j - 1];
+                float lf = H[(size_t)i * W + j - 1], up = H[(size_t)(i - 1) * W + j];
+                float h = dg > lf ? dg : lf; h = h > up ? h : up;
+                H[(size_t)i * W + j] = h;
+                code[(size_t)i * W + j] = (h == 0.f) ? 0 : (h == dg ? 1 : (h == lf ? 2 : 3));
+            }
+        for (int i = 1; i <= n; ++i)
+            for (int j = 1; j <= m; ++j)
+                if (H[(size_t)i * W + j] > best) { best = H[(size_t)i * W + j]; bi = i; bj = j; }
+        free(H);
+    } else {
+        float *u = (float *)calloc((size_t)W, sizeof(float));     /* horizontal diffs of the previous row */
+        uint8_t *lefteq = (uint8_t *)calloc((size_t)(n + 1) * W, 1);
+        double hsum = 0.0;
+        int istar = -1;
+        for (int i = 1; i <= n; ++i) {
+            float a = 0.f;                                          /* v[i][0] = 0 */
+            for (int j = 1; j <= m; ++j) {
+                float s = S[(size_t)(i - 1) * m + j - 1], b = u[j];
+                float dd = s > a ? s : a; dd = dd > b ? dd : b;
+                code[(size_t)i * W + j] = (dd == s) ? 1 : (dd == a ? 2 : 3);
+                lefteq[(size_t)i * W + j] = (dd == a);
+                u[j] = dd - a;
+                a = dd - b;
+            }
+            if (a > 0.f) istar = i;                                 /* H[i][m] > H[i-1][m] */
+            hsum += a;
+        }
+        best = (float)hsum;
+        if (istar > 0) { bi = istar; bj = m; while (bj > 1 && lefteq[(size_t)bi * W + bj]) --bj; }
+        free(u); free(lefteq);
+    }
     *score = best; *aln_len = 0;
-    if (bi < 0) { free(S); free(H); return -1; }
+    if (bi < 0) { free(S); free(code); return -1; }
     int i = bi, j = bj; int64_t k = 0;
     while (i > 0 && j > 0) {
-        float h = H[(size_t)i * W + j];
-        if (h == 0.f) break;
-        else if (h == H[(size_t)(i - 1) * W + j - 1] + S[(size_t)(i - 1) * m + j - 1]) { --i; --j; aln1[k] = i; aln2[k] = j; ++k; }
-        else if (h == H[(size_t)i * W + j - 1]) { --j; aln1[k] = -1; aln2[k] = j; ++k; }
+        int cd = code[(size_t)i * W + j];
+        if (cd == 0) break;
+        else if (cd == 1) { --i; --j; aln1[k] = i; aln2[k] = j; ++k; }
+        else if (cd == 2) { --j; aln1[k] = -1; aln2[k] = j; ++k; }
         else { --i; aln1[k] = i; aln2[k] = -1; ++k; }
     }
     for (int64_t a = 0, b = k - 1; a < b; ++a, --b) {
@@ -563,7 +622,7 @@ API int crt_o_pair_f32model(const double *t1, const double *c1, int n, const dou
         x = aln2[a]; aln2[a] = aln2[b]; aln2[b] = x;
     }
     *aln_len = k;
-    free(S); free(H);
+    free(S); free(code);
     return 0;
 }
 

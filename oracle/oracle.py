@@ -61,7 +61,7 @@ def lib():
                                  C.POINTER(C.c_double), _P, _P, _P, _P, _P, _P, _P, _P]
         L.crt_o_pair.restype = C.c_int
         L.crt_o_pair_f32model.argtypes = [_D, _D, C.c_int, _D, _D, C.c_int, C.c_int, C.c_double, C.c_double,
-                                          C.POINTER(C.c_double), _I64, _I64, C.POINTER(C.c_int64)]
+                                          C.c_int, C.POINTER(C.c_double), _I64, _I64, C.POINTER(C.c_int64)]
         L.crt_o_pair_f32model.restype = C.c_int
         L.crt_o_pairwise_list.argtypes = [_D, _D, _I64, C.c_int, _I32, _I32, C.c_int64, C.c_double, C.c_double,
                                           C.c_int, _D, _P, _P, _P, _P]
@@ -177,13 +177,13 @@ def pair(t1, c1, t2, c2, gamma_t: float = 7.0, gamma_c: float = 0.03) -> dict:
                 rmsd=float(rr[0]), tm=float(tt[0]), score1=float(s1[0]), status=int(st))
 
 
-def pair_f32model(t1, c1, t2, c2, gamma_t: float = 7.0, gamma_c: float = 0.03):
+def pair_f32model(t1, c1, t2, c2, gamma_t: float = 7.0, gamma_c: float = 0.03, variant: int = 1):
     t1, c1, t2, c2 = _c(t1), _c(c1), _c(t2), _c(c2)
     n, m, d = t1.shape[0], t2.shape[0], t1.shape[1]
     a1 = np.empty(n + m + 1, np.int64)
     a2 = np.empty(n + m + 1, np.int64)
     ln, sc = C.c_int64(0), C.c_double(0)
-    lib().crt_o_pair_f32model(t1, c1, n, t2, c2, m, d, gamma_t, gamma_c, C.byref(sc), a1, a2, C.byref(ln))
+    lib().crt_o_pair_f32model(t1, c1, n, t2, c2, m, d, gamma_t, gamma_c, variant, C.byref(sc), a1, a2, C.byref(ln))
     return a1[:ln.value].copy(), a2[:ln.value].copy(), sc.value
 
 

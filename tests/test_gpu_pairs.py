@@ -1,0 +1,226 @@
+"""Parity of the CUDA pair path (through the C ABI) against the golden fixtures produced by the unmodified
+reference and against the pinned oracle.  fp64 mode: stage-1 alignment paths bit-identical, scores <= 1e-11
+relative.  fp32 mode: score / RMSD / TM within 1e-4 relative (RMSD/TM atol 1e-4 on values near 0), >= 99.9 %
+identical aligned columns."""
+import os
+
+import numpy as np
+import pytest
+
+from caretta_b200 import engine, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = engine.Engine()
+    yield e
+    e.close()
+
+
+def _cols(a1, a2):
+    return set((int(x), int(y)) for x, y in zip(a1, a2) if x >= 0 and y >= 0)
+
+
+def _paths(res, q):
+    o = res["aln_off"]
+    return res["aln1"][o[q]:o[q + 1]], res["aln2"][o[q]:o[q + 1]]
+
+
+def _check_fp64(res, gold_a1, gold_a2, gold_off, gold, n):
+    for q in range(n):
+        a1, a2 = _paths(res, q)
+        assert a1.tolist() == gold_a1[gold_off[q]:gold_off[q + 1]].tolist(), q
+        assert a2.tolist() == gold_a2[gold_off[q]:gold_off[q + 1]].tolist(), q
+    np.testing.assert_allclose(res["score"], gold["score"], rtol=1e-11)
+    assert np.array_equal(res["ncommon"], gold["ncommon"])
+    np.testing.assert_allclose(res["rmsd"], gold["rmsd"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(res["tm"], gold["tm"], rtol=1e-8, atol=1e-12)
+
+
+def _check_fp32(res, gold_a1, gold_a2, gold_off, gold, n, min_cols=0.999, min_same=0.8):
+    tot = same = 0
+    same_path = np.zeros(n, bool)
+    for q in range(n):
+        a1, a2 = _paths(res, q)
+        cr = _cols(gold_a1[gold_off[q]:gold_off[q + 1]], gold_a2[gold_off[q]:gold_off[q + 1]])
+        cg = _cols(a1, a2)
+        tot += len(cr)
+        same += len(cr & cg)
+        same_path[q] = cr == cg
+    assert same / max(tot, 1) >= min_cols, f"identical aligned columns {same}/{tot}"
+    # the 1e-4 bound is a statement about arithmetic, so it is checked where the stage-1 alignment is the same one
+    # (the fp32 difference-form DP keeps increments the fp64 reference absorbs below 2^-53 * H, so a few low-similarity
+    # pairs legitimately extend their paths by columns whose score is < 1e-16)
+    sp = same_path
+    assert sp.mean() >= min_same
+    # fp32 flushes scores below ~1e-38 to zero (pairs of 1-2 residue chains that do not match at all)
+    np.testing.assert_allclose(res["score"][sp], gold["score"][sp], rtol=1e-4, atol=1e-30)
+    np.testing.assert_allclose(res["rmsd"][sp], gold["rmsd"][sp], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(res["tm"][sp], gold["tm"][sp], rtol=1e-4, atol=1e-6)
+    return same / max(tot, 1), sp.mean()
+
+
+@pytest.fixture(scope="module")
+def small():
+    g = np.load(os.path.join(G, "pairs_small.npz"))
+    ch = synth.make_chains(len(g["lengths"]), g["lengths"], int(g["d"]), seed=int(g["seed"]), family_size=int(g["family_size"]))
+    return g, ch
+
+
+def test_small_fp64_bit_exact_paths(eng, small):
+    g, ch = small
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    res = eng.pairwise_list(eng.params(precision=engine.FP64), g["pi"], g["pj"], want_paths=True)
+    _check_fp64(res, g["aln1"], g["aln2"], g["aln_off"], g, len(g["pi"]))
+    # <= 3 common positions -> superposition skipped, flagged (multiple_alignment.py:337-342)
+    assert np.array_equal((res["status"] & engine.ST_FEW_COMMON) != 0, g["ncommon"] <= 3)
+    assert ((res["status"] & engine.ST_FEW_COMMON) != 0).sum() >= 10
+
+
+def test_small_fp32(eng, small):
+    g, ch = small
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    res = eng.pairwise_list(eng.params(precision=engine.FP32), g["pi"], g["pj"], want_paths=True)
+    _check_fp32(res, g["aln1"], g["aln2"], g["aln_off"], g, len(g["pi"]))
+
+
+@pytest.mark.parametrize("prec", [engine.FP64, engine.FP32])
+def test_pairwise_all_is_the_reference_matrix(eng, small, prec):
+    g, ch = small
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    S, R, T = eng.pairwise_all(eng.params(precision=prec), want_rmsd_tm=True)
+    assert S.dtype == np.float64 and S.shape == (ch.n, ch.n)
+    assert np.array_equal(S, S.T) and np.all(np.diag(S) == 0)          # multiple_alignment.py:161-170
+    np.testing.assert_allclose(S, g["score_matrix"], rtol=1e-11 if prec == engine.FP64 else 1e-4)
+    assert np.all(np.diag(T) == 1) and np.all(np.diag(R) == 0)
+
+
+def test_c1_test_data(eng):
+    g = np.load(os.path.join(G, "c1_test_data.npz"))
+    names = [str(n) for n in g["names"]]
+    coords = np.concatenate([g[f"ca_{n}"] for n in names])
+    tens = np.concatenate([g[f"tensors_{n}"] for n in names])
+    off = np.zeros(4, np.int64)
+    off[1:] = np.cumsum([len(g[f"ca_{n}"]) for n in names])
+    eng.set_chains(coords, tens, off)
+    np.testing.assert_allclose(eng.pairwise_all(eng.params(precision=engine.FP64)), g["score_matrix"], rtol=1e-11)
+    np.testing.assert_allclose(eng.pairwise_all(eng.params(precision=engine.FP32)), g["score_matrix"], rtol=1e-4)
+
+
+def test_c2_all_19900_pairs(eng):
+    """BASELINE config 2 (200 x 80): fp64 paths identical to the reference's for every pair."""
+    g = np.load(os.path.join(G, "c2_full.npz"))
+    ch = synth.config("C2")
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    pi, pj = np.triu_indices(ch.n, 1)
+    res = eng.pairwise_list(eng.params(precision=engine.FP64), pi, pj, want_paths=True)
+    _check_fp64(res, g["aln1"], g["aln2"], g["aln_off"], g, len(pi))
+    res = eng.pairwise_list(eng.params(precision=engine.FP32), pi, pj, want_paths=True)
+    frac, same = _check_fp32(res, g["aln1"], g["aln2"], g["aln_off"], g, len(pi), min_same=0.999)
+    assert frac >= 0.9999
+
+
+def _oracle_compare(eng, ch, pi, pj, prec):
+    res = eng.pairwise_list(eng.params(precision=prec), pi, pj, want_paths=True)
+    ora = [O.pair(*ch.chain(int(i)), *ch.chain(int(j))) for i, j in zip(pi, pj)]
+    a1 = np.concatenate([o["aln1"] for o in ora]); a2 = np.concatenate([o["aln2"] for o in ora])
+    off = np.zeros(len(ora) + 1, np.int64); off[1:] = np.cumsum([len(o["aln1"]) for o in ora])
+    gold = dict(score=np.array([o["score"] for o in ora]), ncommon=np.array([o["ncommon"] for o in ora], np.int32),
+                rmsd=np.array([o["rmsd"] for o in ora]), tm=np.array([o["tm"] for o in ora]))
+    if prec == engine.FP64:
+        _check_fp64(res, a1, a2, off, gold, len(pi))
+    else:
+        _check_fp32(res, a1, a2, off, gold, len(pi))
+    return res
+
+
+@pytest.mark.parametrize("prec", [engine.FP64, engine.FP32])
+def test_ragged_lengths_multi_strip(eng, prec):
+    """Lengths 1 .. 700: exercises every columns-per-lane variant and the multi-strip path (m > 320 / > 128)."""
+    lengths = [1, 2, 7, 33, 64, 65, 96, 97, 128, 129, 160, 200, 257, 300, 320, 321, 400, 513, 700, 90]
+    ch = synth.make_chains(len(lengths), lengths, 10, seed=21, family_size=5)
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    rng = np.random.default_rng(3)
+    pi, pj = np.triu_indices(ch.n, 1)
+    sel = rng.choice(len(pi), 70, replace=False)
+    # both orientations: the row chain may be the longer one
+    pi2 = np.concatenate([pi[sel], pj[sel][:25]]); pj2 = np.concatenate([pj[sel], pi[sel][:25]])
+    _oracle_compare(eng, ch, pi2, pj2, prec)
+
+
+@pytest.mark.parametrize("prec", [engine.FP64, engine.FP32])
+def test_long_chains_1500(eng, prec):
+    """BASELINE config 5 shape (1500 residues: several strips, traceback far beyond shared memory)."""
+    ch = synth.make_chains(3, 1500, 10, seed=5, family_size=2)
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    _oracle_compare(eng, ch, [0, 0, 1], [1, 2, 2], prec)
+
+
+@pytest.mark.parametrize("d", [3, 13, 16])
+def test_other_tensor_widths(eng, d):
+    ch = synth.make_chains(6, [40, 55, 70, 61, 48, 90], d, seed=31, family_size=3)
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    pi, pj = np.triu_indices(ch.n, 1)
+    _oracle_compare(eng, ch, pi, pj, engine.FP64)
+    _oracle_compare(eng, ch, pi, pj, engine.FP32)
+
+
+def test_zero_region_stop_state(eng):
+    """S underflows to exactly 0 in the top-left block: the reference's traceback stops at the first H == 0 cell
+    (dynamic_time_warping.py:260-261); an all-zero matrix makes it raise (:250) -> CRT_ST_NO_POSITIVE."""
+    ch = synth.make_chains(4, [30, 34, 28, 31], 10, seed=41, family_size=4)
+    t = ch.tensors.copy()
+    for p in range(2):                       # chains 0,1: a far-away head of 6 residues
+        s = int(ch.offsets[p])
+        t[s:s + 6] += 40.0 * (p + 1)
+    s2, e2 = int(ch.offsets[2]), int(ch.offsets[3])
+    t[s2:e2] += 1000.0                       # chain 2 is far from everything: every S is 0 against 0,1,3
+    ch2 = synth.Chains(ch.coords, t, ch.offsets)
+    eng.set_chains(ch2.coords, ch2.tensors, ch2.offsets)
+    res = eng.pairwise_list(eng.params(precision=engine.FP64), [0, 0, 1], [1, 3, 3], want_paths=True)
+    for q, (i, j) in enumerate([(0, 1), (0, 3), (1, 3)]):
+        o = O.pair(*ch2.chain(i), *ch2.chain(j))
+        a1, a2 = _paths(res, q)
+        assert a1.tolist() == o["aln1"].tolist() and a2.tolist() == o["aln2"].tolist()
+        np.testing.assert_allclose(res["score"][q], o["score"], rtol=1e-11)
+    res = eng.pairwise_list(eng.params(precision=engine.FP64), [0, 2], [2, 3], want_paths=True)
+    assert np.all(res["status"] & engine.ST_NO_POSITIVE)
+    assert res["aln_off"][-1] == 0 and np.all(res["ncommon"] == 0)
+    with pytest.raises(ValueError):
+        O.smith_waterman(O.rbf_matrix(ch2.chain(0)[0], ch2.chain(2)[0], 7.0))
+
+
+def test_shards_partition_the_pairs(eng):
+    ch = synth.make_chains(37, list(np.random.default_rng(9).integers(20, 120, 37)), 10, seed=9)
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    prm = eng.params(precision=engine.FP32)
+    S = eng.pairwise_all(prm)
+    for world in (2, 3, 8):
+        seen = np.zeros((ch.n, ch.n), int)
+        M = np.zeros((ch.n, ch.n))
+        for rank in range(world):
+            pi, pj = eng.shard_pairs(rank, world)
+            eng.pairwise_shard(prm, rank, world)
+            r = eng.fetch(len(pi))
+            seen[pi, pj] += 1
+            M[pi, pj] = r["score"]; M[pj, pi] = r["score"]
+        assert np.array_equal(seen, np.triu(np.ones((ch.n, ch.n), int), 1))       # every pair exactly once
+        assert np.array_equal(M, S)                                               # bitwise the 1-GPU result
+
+
+def test_argument_errors(eng):
+    ch = synth.make_chains(3, 20, 10, seed=1)
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    with pytest.raises(engine.CrtError):
+        eng.pairwise_list(eng.params(sw_gap=0.5), [0], [1])
+    with pytest.raises(engine.CrtError):
+        eng.pairwise_list(eng.params(), [0], [7])
+    with pytest.raises(engine.CrtError):
+        eng.set_chains(ch.coords, np.zeros((60, 40)), ch.offsets)          # d = 40 unsupported
+    bad = ch.coords.copy(); bad[3, 1] = np.nan
+    with pytest.raises(engine.CrtError):
+        eng.set_chains(bad, ch.tensors, ch.offsets)
