@@ -85,19 +85,30 @@ struct crt_ctx {
     DevBuf<float4> cols2;
     double prep_gamma_t = -1, prep_gamma_c = -1;   // parameters the fp32 records were built with
 
-    // run workspaces
+    // run workspaces: one set per stream so that the batches of a run overlap (the tail of one batch's fill runs
+    // beside the next batch's, and the latency-bound traceback hides under the fills)
+    struct Workspace {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};      // serial mode: phase boundaries of the last batch
+        DevBuf<uint4> tb;
+        DevBuf<unsigned char> rows2, bnd;
+        DevBuf<short2> path;
+    };
+    static constexpr int MAX_WS = 4;
+    Workspace ws[MAX_WS];
+    int n_streams = 3;
     DevBuf<Unit> d_units;
-    DevBuf<uint4> tb;
-    DevBuf<unsigned char> rows2, bnd;
-    DevBuf<short2> path;
     DevBuf<int> path_len, pair_istar, pair_zflag, ncommon, status;
-    DevBuf<double> score, score1, rmsd, tm;
+    DevBuf<double> score, score1, rmsd, tm, xform;
     DevBuf<float> f32tmp;
+    double phase_ms[4] = {0, 0, 0, 0};      // fill1, trace, rows2, fill2 (only meaningful with one stream)
 
     // last run
     long long run_pairs = 0;
     double elapsed_ms = 0, cell_updates = 0;
     long long launches = 0;
+    int last_streams = 1;
     std::vector<int> run_pi, run_pj;     // pair ids in result order
 };
 
@@ -291,10 +302,36 @@ struct PathSink {
 size_t env_budget()
 {
     const char *e = getenv("CARETTA_B200_WORKSPACE_MB");
-    size_t mb = e ? (size_t)atoll(e) : 8192;
-    if (mb < 64) mb = 64;
+    size_t mb = e ? (size_t)atoll(e) : 3072;      // per stream
+    if (mb < 16) mb = 16;
     return mb << 20;
 }
+
+int env_streams()
+{
+    const char *e = getenv("CARETTA_B200_STREAMS");
+    int n = e ? atoi(e) : 3;
+    return std::min(std::max(n, 1), (int)crt_ctx::MAX_WS);
+}
+
+template <int CMAXT>
+int launch_trace(int C, const TraceArgs &ta, int nu, cudaStream_t st)
+{
+    const int grid = (nu + TRACE_WARPS - 1) / TRACE_WARPS;
+    switch (C) {
+    case 2: k_trace<2><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
+    case 3: k_trace<3><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
+    case 4: k_trace<4><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
+    case 6: k_trace<6><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
+    case 8: k_trace<8><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
+    case 10: k_trace<10><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
+    default: return fail(CRT_E_ARG, "no trace kernel for C=%d", C);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+struct Batch { size_t first, count; int C, multi; size_t tb_n, rows2_n, bnd_n, path_n; };
 
 int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, long long n_pairs, PathSink *sink)
 {
@@ -303,6 +340,8 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     const size_t tsz = f32 ? 4 : 8;
     const size_t row2sz = f32 ? 16 : 32;
     const int rs32 = ((c->D + 2 + 3) / 4) * 4;
+    const bool want_paths = sink && sink->want;
+    const int NS = want_paths ? 1 : env_streams();
     int rc;
     if ((rc = c->score.ensure((size_t)n_pairs + 1))) return rc;
     if ((rc = c->score1.ensure((size_t)n_pairs + 1))) return rc;
@@ -313,7 +352,8 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     if ((rc = c->pair_istar.ensure((size_t)n_pairs + 1))) return rc;
     if ((rc = c->pair_zflag.ensure((size_t)n_pairs + 1))) return rc;
     if ((rc = c->path_len.ensure((size_t)n_pairs + 1))) return rc;
-    if (sink && sink->want) { sink->a1.assign((size_t)n_pairs, {}); sink->a2.assign((size_t)n_pairs, {}); }
+    if ((rc = c->xform.ensure(((size_t)n_pairs + 1) * XF))) return rc;
+    if (want_paths) { sink->a1.assign((size_t)n_pairs, {}); sink->a2.assign((size_t)n_pairs, {}); }
 
     // group by kernel variant so that each launch is homogeneous; inside a group keep the (j, i0) order
     std::stable_sort(units.begin(), units.end(), [](const HostUnit &a, const HostUnit &b) {
@@ -321,92 +361,141 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         return a.C < b.C;
     });
 
-    const size_t budget = env_budget();
-    c->launches = 0;
-    CU(cudaEventRecord(c->ev0, c->stream));
+    // ---- carve batches: same (C, multi), bounded workspace; aim for at least 2 batches per stream
+    size_t total_bytes = 0;
+    auto unit_bytes = [&](const HostUnit &h) {
+        return (size_t)h.u.n_strips * h.u.tchunks * 32 * 16 + (size_t)h.u.G * row2sz + (size_t)h.u.n_pairs * h.u.path_stride * 4 +
+               (h.multi ? (size_t)h.u.G * tsz : 0);
+    };
+    for (auto &h : units) total_bytes += unit_bytes(h);
+    size_t budget = env_budget();
+    if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
+    std::vector<Batch> batches;
+    std::vector<Unit> hu(units.size());
     size_t pos = 0;
-    std::vector<Unit> hu;
     while (pos < units.size()) {
-        // ---- carve a batch: same (C, multi), bounded workspace
-        const int C = units[pos].C, multi = units[pos].multi;
-        size_t tb_n = 0, rows2_n = 0, bnd_n = 0, path_n = 0, end = pos;
-        hu.clear();
-        while (end < units.size() && units[end].C == C && units[end].multi == multi) {
+        Batch b{pos, 0, units[pos].C, units[pos].multi, 0, 0, 0, 0};
+        size_t end = pos;
+        while (end < units.size() && units[end].C == b.C && units[end].multi == b.multi) {
             HostUnit &h = units[end];
-            size_t tb_u = (size_t)h.u.n_strips * h.u.tchunks * 32;
-            size_t rows_u = (size_t)h.u.G;
-            size_t path_u = (size_t)h.u.n_pairs * h.u.path_stride;
-            size_t bnd_u = multi ? (size_t)h.u.G : 0;
-            size_t bytes = (tb_n + tb_u) * 16 + (rows2_n + rows_u) * row2sz + (path_n + path_u) * 4 + (bnd_n + bnd_u) * tsz;
+            const size_t tb_u = (size_t)h.u.n_strips * h.u.tchunks * 32, rows_u = (size_t)h.u.G;
+            const size_t path_u = (size_t)h.u.n_pairs * h.u.path_stride, bnd_u = b.multi ? (size_t)h.u.G : 0;
+            const size_t bytes = (b.tb_n + tb_u) * 16 + (b.rows2_n + rows_u) * row2sz + (b.path_n + path_u) * 4 + (b.bnd_n + bnd_u) * tsz;
             if (end > pos && bytes > budget) break;
-            h.u.tb_base = (long long)tb_n; h.u.rows2_base = (long long)rows2_n;
-            h.u.path_base = (long long)path_n; h.u.bnd_base = (long long)bnd_n;
-            tb_n += tb_u; rows2_n += rows_u; path_n += path_u; bnd_n += bnd_u;
-            hu.push_back(h.u);
+            h.u.tb_base = (long long)b.tb_n; h.u.rows2_base = (long long)b.rows2_n;
+            h.u.path_base = (long long)b.path_n; h.u.bnd_base = (long long)b.bnd_n;
+            b.tb_n += tb_u; b.rows2_n += rows_u; b.path_n += path_u; b.bnd_n += bnd_u;
+            hu[end] = h.u;
             ++end;
         }
-        const int nu = (int)hu.size();
-        if ((rc = c->d_units.ensure(nu))) return rc;
-        if ((rc = c->tb.ensure(tb_n))) return rc;
-        if ((rc = c->rows2.ensure((rows2_n + 2 * ROW_PAD) * row2sz))) return rc;
-        if ((rc = c->path.ensure(path_n + 1))) return rc;
-        if ((rc = c->bnd.ensure(bnd_n * tsz + 16))) return rc;
-        CU(cudaMemcpyAsync(c->d_units.p, hu.data(), sizeof(Unit) * nu, cudaMemcpyHostToDevice, c->stream));
+        b.count = end - pos;
+        batches.push_back(b);
+        pos = end;
+    }
+    // ---- size the workspaces once (no allocation inside the timed region after the first run of a shape)
+    for (int w = 0; w < NS; ++w) {
+        crt_ctx::Workspace &ws = c->ws[w];
+        size_t tb_n = 0, rows2_n = 0, bnd_n = 0, path_n = 0;
+        for (size_t k = w; k < batches.size(); k += NS) {
+            tb_n = std::max(tb_n, batches[k].tb_n); rows2_n = std::max(rows2_n, batches[k].rows2_n);
+            bnd_n = std::max(bnd_n, batches[k].bnd_n); path_n = std::max(path_n, batches[k].path_n);
+        }
+        if ((rc = ws.tb.ensure(tb_n + 1))) return rc;
+        if ((rc = ws.rows2.ensure((rows2_n + 2 * ROW_PAD) * row2sz))) return rc;
+        if ((rc = ws.path.ensure(path_n + 1))) return rc;
+        if ((rc = ws.bnd.ensure(bnd_n * tsz + 16))) return rc;
+    }
+    if ((rc = c->d_units.ensure(hu.size()))) return rc;
 
+    c->launches = 0;
+    c->last_streams = NS;
+    for (int k = 0; k < 4; ++k) c->phase_ms[k] = 0;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    CU(cudaMemcpyAsync(c->d_units.p, hu.data(), sizeof(Unit) * hu.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    for (int w = 0; w < NS; ++w) CU(cudaStreamWaitEvent(c->ws[w].stream, c->ev1, 0));
+
+    for (size_t bi = 0; bi < batches.size(); ++bi) {
+        const Batch &b = batches[bi];
+        crt_ctx::Workspace &ws = c->ws[bi % NS];
+        cudaStream_t st = ws.stream;
+        const Unit *du = c->d_units.p + b.first;
+        const int nu = (int)b.count;
+        const bool timed = NS == 1;
         FillOut fo{};
-        fo.tb = c->tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
-        fo.pair_score = c->score1.p; fo.bnd = c->bnd.p;
+        fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
+        fo.pair_score = c->score1.p; fo.bnd = ws.bnd.p;
+        if (timed) CU(cudaEventRecord(ws.ev[0], st));
         // ---- stage 1
         if (f32) {
             Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
-            if (c->D == 10) rc = launch_fill1_f32<10>(C, multi, c->d_units.p, nu, a, fo, c->stream);
-            else rc = launch_fill1_f32<16>(C, multi, c->d_units.p, nu, a, fo, c->stream);
+            if (c->D == 10) rc = launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, st);
+            else rc = launch_fill1_f32<16>(b.C, b.multi, du, nu, a, fo, st);
         } else {
-            if (c->D == 10) { P1F64<10>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; rc = launch_fill_c<P1F64<10>, false, true, 4>(C, multi, c->d_units.p, nu, a, fo, c->stream); }
-            else { P1F64<16>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; rc = launch_fill_c<P1F64<16>, false, true, 3>(C, multi, c->d_units.p, nu, a, fo, c->stream); }
+            if (c->D == 10) { P1F64<10>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; rc = launch_fill_c<P1F64<10>, false, true, 4>(b.C, b.multi, du, nu, a, fo, st); }
+            else { P1F64<16>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; rc = launch_fill_c<P1F64<16>, false, true, 3>(b.C, b.multi, du, nu, a, fo, st); }
         }
         if (rc) return rc;
-        // ---- traceback + Kabsch + stage-2 rows
+        if (timed) CU(cudaEventRecord(ws.ev[1], st));
+        // ---- traceback + Kabsch, then the stage-2 row records
         TraceArgs ta{};
-        ta.units = c->d_units.p; ta.tb = c->tb.p; ta.pair_istar = c->pair_istar.p; ta.pair_zflag = c->pair_zflag.p;
+        ta.units = du; ta.tb = ws.tb.p; ta.pair_istar = c->pair_istar.p; ta.pair_zflag = c->pair_zflag.p;
         ta.offsets = c->d_offsets.p; ta.coords = c->coords.p; ta.centroid = c->centroid.p;
-        ta.path = c->path.p; ta.path_len = c->path_len.p; ta.rmsd = c->rmsd.p; ta.tm = c->tm.p;
-        ta.ncommon = c->ncommon.p; ta.status = c->status.p; ta.rot = nullptr; ta.rows2 = c->rows2.p + (size_t)ROW_PAD * row2sz;
+        ta.path = ws.path.p; ta.path_len = c->path_len.p; ta.rmsd = c->rmsd.p; ta.tm = c->tm.p;
+        ta.ncommon = c->ncommon.p; ta.status = c->status.p; ta.xform = c->xform.p; ta.meta = c->meta.p + ROW_PAD;
+        ta.rows2 = ws.rows2.p + (size_t)ROW_PAD * row2sz;
         ta.rec32 = c->rec32.p + (size_t)ROW_PAD * rs32; ta.rs32 = rs32; ta.d32 = c->D;
         ta.rec64 = c->rec64.p; ta.d64 = c->D; ta.neg_gamma_t = -prm->gamma_tensor;
-        ta.C = C; ta.scale2 = (float)std::sqrt(prm->gamma_coords * 1.4426950408889634);
+        ta.scale2 = (float)std::sqrt(prm->gamma_coords * 1.4426950408889634);
         ta.precision = prec;
-        k_trace<<<nu, 32, 0, c->stream>>>(ta);
+        if ((rc = launch_trace<10>(b.C, ta, nu, st))) return rc;
+        if (timed) CU(cudaEventRecord(ws.ev[2], st));
+        k_rows2<<<nu, 256, 0, st>>>(ta, nu);
         CU(cudaGetLastError());
         // ---- stage 2
         fo.pair_score = c->score.p;
         if (f32) {
-            Fill2Args a{reinterpret_cast<const float4 *>(c->rows2.p) + ROW_PAD, c->cols2.p};
-            rc = launch_fill2_f32(C, multi, c->d_units.p, nu, a, fo, c->stream);
+            Fill2Args a{reinterpret_cast<const float4 *>(ws.rows2.p) + ROW_PAD, c->cols2.p};
+            rc = launch_fill2_f32(b.C, b.multi, du, nu, a, fo, st);
         } else {
-            P2F64::Args a{reinterpret_cast<const double *>(c->rows2.p) + (size_t)ROW_PAD * 4, c->coords.p, -prm->gamma_coords};
-            rc = launch_fill_c<P2F64, false, false, 4>(C, multi, c->d_units.p, nu, a, fo, c->stream);
+            P2F64::Args a{reinterpret_cast<const double *>(ws.rows2.p) + (size_t)ROW_PAD * 4, c->coords.p, -prm->gamma_coords};
+            rc = launch_fill_c<P2F64, false, false, 4>(b.C, b.multi, du, nu, a, fo, st);
         }
         if (rc) return rc;
-        c->launches += 3;
+        if (timed) CU(cudaEventRecord(ws.ev[3], st));
+        c->launches += 4;
 
-        if (sink && sink->want) {
-            std::vector<short2> hp(path_n);
+        if (timed) {
+            // one stream: phase timing (and, for the tests, the paths) per batch
+            CU(cudaStreamSynchronize(st));
+            float m01 = 0, m12 = 0, m23 = 0;
+            CU(cudaEventElapsedTime(&m01, ws.ev[0], ws.ev[1]));
+            CU(cudaEventElapsedTime(&m12, ws.ev[1], ws.ev[2]));
+            CU(cudaEventElapsedTime(&m23, ws.ev[2], ws.ev[3]));
+            c->phase_ms[0] += m01; c->phase_ms[1] += m12; c->phase_ms[3] += m23;
+        }
+        if (want_paths) {
+            std::vector<short2> hp(b.path_n + 1);
             std::vector<int> hl((size_t)n_pairs);
-            CU(cudaMemcpyAsync(hp.data(), c->path.p, path_n * sizeof(short2), cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaMemcpyAsync(hl.data(), c->path_len.p, (size_t)n_pairs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            for (const Unit &u : hu)
+            CU(cudaMemcpyAsync(hp.data(), ws.path.p, b.path_n * sizeof(short2), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(hl.data(), c->path_len.p, (size_t)n_pairs * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (size_t k = b.first; k < b.first + b.count; ++k) {
+                const Unit &u = hu[k];
                 for (int q = 0; q < u.n_pairs; ++q) {
                     const int pidx = u.pair_base + q, len = hl[pidx];
                     const short2 *pp = hp.data() + u.path_base + (size_t)q * u.path_stride;
                     auto &v1 = sink->a1[pidx];
                     auto &v2 = sink->a2[pidx];
                     v1.resize(len); v2.resize(len);
-                    for (int k = 0; k < len; ++k) { v1[k] = pp[len - 1 - k].x; v2[k] = pp[len - 1 - k].y; }
+                    for (int k2 = 0; k2 < len; ++k2) { v1[k2] = pp[len - 1 - k2].x; v2[k2] = pp[len - 1 - k2].y; }
                 }
+            }
         }
-        pos = end;
+    }
+    for (int w = 0; w < NS; ++w) {
+        CU(cudaEventRecord(c->ws[w].done, c->ws[w].stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ws[w].done, 0));
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -457,6 +546,11 @@ int crt_create(int device, crt_ctx **out)
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    for (int w = 0; w < crt_ctx::MAX_WS; ++w) {
+        CU(cudaStreamCreateWithFlags(&c->ws[w].stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ws[w].done, cudaEventDisableTiming));
+        for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&c->ws[w].ev[k]));
+    }
     *out = c;
     return 0;
 }
@@ -468,7 +562,14 @@ int crt_destroy(crt_ctx *c)
     cudaStreamSynchronize(c->stream);
     c->coords.release(); c->tensors.release(); c->centroid.release(); c->rec64.release(); c->d_offsets.release();
     c->chain_of.release(); c->meta.release(); c->rec32.release(); c->cols2.release(); c->d_units.release();
-    c->tb.release(); c->rows2.release(); c->bnd.release(); c->path.release(); c->path_len.release();
+    for (int w = 0; w < crt_ctx::MAX_WS; ++w) {
+        crt_ctx::Workspace &ws = c->ws[w];
+        ws.tb.release(); ws.rows2.release(); ws.bnd.release(); ws.path.release();
+        if (ws.done) cudaEventDestroy(ws.done);
+        for (int k = 0; k < 4; ++k) if (ws.ev[k]) cudaEventDestroy(ws.ev[k]);
+        if (ws.stream) cudaStreamDestroy(ws.stream);
+    }
+    c->xform.release(); c->path_len.release();
     c->pair_istar.release(); c->pair_zflag.release(); c->ncommon.release(); c->status.release();
     c->score.release(); c->score1.release(); c->rmsd.release(); c->tm.release(); c->f32tmp.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -654,6 +755,12 @@ int crt_fetch_device(crt_ctx *c, void *d_score, void *d_rmsd, void *d_tm, int64_
 }
 
 double crt_last_elapsed_ms(crt_ctx *c) { return c ? c->elapsed_ms : -1.0; }
+int crt_last_phase_ms(crt_ctx *c, double *out4)
+{
+    if (!c || !out4) return fail(CRT_E_ARG, "null argument");
+    for (int k = 0; k < 4; ++k) out4[k] = c->last_streams == 1 ? c->phase_ms[k] : -1.0;
+    return 0;
+}
 int64_t crt_last_launches(crt_ctx *c) { return c ? c->launches : -1; }
 double crt_last_cell_updates(crt_ctx *c) { return c ? c->cell_updates : -1.0; }
 

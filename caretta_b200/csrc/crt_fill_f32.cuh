@@ -23,6 +23,23 @@ constexpr int PREFETCH_ROWS = 8;
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// cp.async (LDGSTS): the warp stages the next 32 row records in shared memory one block ahead, so the per-step row
+// reads are fixed-latency LDS and no lane ever waits on L2/HBM for a row nobody has touched yet.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+constexpr int RING = 96;             // rows held in the shared-memory ring (3 blocks of 32)
+constexpr int RING_OFF = 30;
+
 struct Fill1Args {
     const float *rec;        // [ROW_PAD + sumL + ROW_PAD][RS] row/column records, pointer already past the front pad
     const int *meta;         // [ROW_PAD + sumL + ROW_PAD]
@@ -36,17 +53,32 @@ struct Fill1Args {
 // FFMA2 work of row t+1 is issued, and the record of row t+2 is in flight.
 // ------------------------------------------------------------------------------------------------------------
 template <int NP, int RS>
-__device__ __forceinline__ void load_row1(const float *rp, const int *mp, int t, float2 (&row)[NP], int &meta)
+__device__ __forceinline__ void load_row1(const float *srow, const int *smeta, int slot, float2 (&row)[NP], int &meta)
 {
-    const float4 *p4 = reinterpret_cast<const float4 *>(rp + (long long)t * RS);
+    const float4 *p4 = reinterpret_cast<const float4 *>(srow + slot * RS);
 #pragma unroll
     for (int k = 0; k < NP / 2; ++k) {
-        const float4 v = __ldg(p4 + k);
+        const float4 v = p4[k];
         row[2 * k] = make_float2(v.x, v.y);
         row[2 * k + 1] = make_float2(v.z, v.w);
     }
-    if (NP & 1) row[NP - 1] = __ldg(reinterpret_cast<const float2 *>(rp + (long long)t * RS) + (NP - 1));
-    meta = __ldg(mp + t);
+    if (NP & 1) row[NP - 1] = reinterpret_cast<const float2 *>(srow + slot * RS)[NP - 1];
+    meta = smeta[slot];
+}
+
+// Ring addressing: stream row g lives at ring row rr = g + RING_OFF, slot rr % 96.  Block B = ring rows [32B, 32B+32).
+// With RING_OFF = 30 the loads of the window of steps [t0, t0+32) (row t+2-lane at step t) touch only blocks t0/32 and
+// t0/32+1, so block t0/32+2 can be in flight during the whole window.
+template <int RS>
+__device__ __forceinline__ void stage_block1(float *srow, int *smeta, const float *rec_unit, const int *meta_unit, int B, int lane)
+{
+    const int slot0 = (B % 3) * 32;
+    const float *src = rec_unit + (long long)(32 * B - RING_OFF) * RS;  // record of stream row g = 32B - RING_OFF
+    constexpr int CHUNKS = 32 * RS / 4;                                 // 16-byte chunks in a block
+#pragma unroll
+    for (int q = lane; q < CHUNKS; q += 32) cp_async16(srow + slot0 * RS + q * 4, src + q * 4);
+    cp_async4(smeta + slot0 + lane, meta_unit + (32 * B - RING_OFF) + lane);
+    cp_async_commit();
 }
 
 template <int NP, int C>
@@ -62,7 +94,10 @@ __device__ __forceinline__ void rbf_row1(const float2 (&row)[NP], const float2 (
 }
 
 template <int D, int C, bool MULTI>
-__global__ void __launch_bounds__(32) k_fill1_f32(const Unit *__restrict__ units, int n_units, Fill1Args args, FillOut out)
+#ifndef CRT_FILL1_MINB
+#define CRT_FILL1_MINB 1
+#endif
+__global__ void __launch_bounds__(32, CRT_FILL1_MINB) k_fill1_f32(const Unit *__restrict__ units, int n_units, Fill1Args args, FillOut out)
 {
     constexpr int NP = (D + 2) / 2;                 // float2 pairs per record
     constexpr int RS = ((2 * NP + 3) / 4) * 4;      // record stride in floats
@@ -101,17 +136,27 @@ __global__ void __launch_bounds__(32) k_fill1_f32(const Unit *__restrict__ units
         int istar = 0, r = 0;
         unsigned word = 0;
         uint4 *tbp = out.tb + u.tb_base + (long long)strip * u.tchunks * 32 + lane;
-        const float *rp = args.rec + (u.row_base - lane) * RS;       // row of step t is rp + t*RS
-        const int *mp = args.meta + (u.row_base - lane);
+        const float *rec_unit = args.rec + u.row_base * RS;          // record of stream row g is rec_unit + g*RS
+        const int *meta_unit = args.meta + u.row_base;
+        __shared__ __align__(16) float srow[RING * RS];
+        __shared__ int smeta[RING];
+        __syncwarp();
+        stage_block1<RS>(srow, smeta, rec_unit, meta_unit, 0, lane);
+        stage_block1<RS>(srow, smeta, rec_unit, meta_unit, 1, lane);
+        cp_async_wait_all();
+        __syncwarp();
+        stage_block1<RS>(srow, smeta, rec_unit, meta_unit, 2, lane);
+        int slot = RING_OFF + 2 - lane;      // ring slot of the row loaded at step t = 0 (stream row 2 - lane)
 
         float s_cur[C];
         float2 row_nxt[NP];
         int meta_cur, meta_nxt, meta_prev = 0;
         {
             float2 row0[NP];
-            load_row1<NP, RS>(rp, mp, 0, row0, meta_cur);
+            // rows -lane and 1-lane (pipeline fill; lane 31's row -31 is clamped to ring row 0, any record will do)
+            load_row1<NP, RS>(srow, smeta, max(slot - 2, 0), row0, meta_cur);
             rbf_row1<NP, C>(row0, col, s_cur);
-            load_row1<NP, RS>(rp, mp, 1, row_nxt, meta_nxt);
+            load_row1<NP, RS>(srow, smeta, slot - 1, row_nxt, meta_nxt);
         }
 
         for (int t0 = 0; t0 < steps4; t0 += 4) {
@@ -120,10 +165,16 @@ __global__ void __launch_bounds__(32) k_fill1_f32(const Unit *__restrict__ units
             for (int q = 0; q < 4; ++q) {
                 const int t = t0 + q;
                 const int g = t - lane;
+                if (q == 0 && (t0 & 31) == 0 && t0 > 0) {
+                    // rows of block t0/32 + 1 must have landed; refill the slot whose rows nobody needs any more
+                    cp_async_wait_all();
+                    __syncwarp();
+                    stage_block1<RS>(srow, smeta, rec_unit, meta_unit, (t0 >> 5) + 2, lane);
+                }
                 float2 row_ld[NP];
                 int meta_ld;
-                load_row1<NP, RS>(rp, mp, t + 2, row_ld, meta_ld);
-                prefetch_l1(rp + (long long)(t + PREFETCH_ROWS) * RS + RS - 1);
+                load_row1<NP, RS>(srow, smeta, slot, row_ld, meta_ld);
+                slot = (slot == RING - 1) ? 0 : slot + 1;
                 float a = __shfl_up_sync(FULL, carry, 1);
                 if (lane == 0) {
                     a = 0.f;
@@ -217,16 +268,35 @@ __global__ void __launch_bounds__(32) k_fill2_f32(const Unit *__restrict__ units
 #pragma unroll
         for (int c = 0; c < C; ++c) prev[c] = 0.f;
         float carry = 0.f, dsave = 0.f;
-        const float4 *rp = args.rows + (u.rows2_base - lane);
-        float4 rv_nxt = __ldg(rp);
+        // rows staged through a shared-memory ring (see k_fill1_f32); here the load of step t is stream row t+1-lane,
+        // ring row rr = g + 31, so a window of 32 steps touches blocks t0/32 and t0/32+1 only
+        const float4 *rows_unit = args.rows + u.rows2_base;
+        __shared__ float4 srow2[RING];
+        auto stage2 = [&](int B) {
+            cp_async16(&srow2[(B % 3) * 32 + lane], rows_unit + (32 * B - 31) + lane);
+            cp_async_commit();
+        };
+        __syncwarp();
+        stage2(0); stage2(1);
+        cp_async_wait_all();
+        __syncwarp();
+        stage2(2);
+        int slot = 31 - lane;                // ring slot of stream row -lane
+        float4 rv_nxt = srow2[slot];
+        slot += 1;
         int meta_prev = 0;
         const bool emitter = last_strip && lane == 31;
 
         for (int t = 0; t < steps4; ++t) {
             const int g = t - lane;
+            if ((t & 31) == 0 && t > 0) {
+                cp_async_wait_all();
+                __syncwarp();
+                stage2((t >> 5) + 2);
+            }
             const float4 rv = rv_nxt;
-            rv_nxt = __ldg(rp + t + 1);
-            prefetch_l1(rp + t + 2 * PREFETCH_ROWS);
+            rv_nxt = srow2[slot];
+            slot = (slot == RING - 1) ? 0 : slot + 1;
             const int meta = __float_as_int(rv.w);
             float left = __shfl_up_sync(FULL, carry, 1);
             if (lane == 0) {

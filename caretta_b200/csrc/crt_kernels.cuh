@@ -367,12 +367,12 @@ struct TraceArgs {
     int *path_len;                // per pair
     double *rmsd, *tm;
     int *ncommon, *status;
-    double *rot;                  // optional [pairs, 12]: R (9) then t (3); may be null
+    double *xform;                // [pairs, XF]: R (9), mean1 (3), mean2 (3), superpose flag
+    const int *meta;              // per-residue row meta (chain index, first/last flags)
     void *rows2;                  // float4[] (fp32) or double[4][] (fp64)
     // for the exact zero-region test (stop state of the reference traceback)
     const float *rec32; int rs32; int d32;
     const double *rec64; int d64; double neg_gamma_t;
-    int C;                        // columns per lane used by the stage-1 fill of these units
     float scale2;                 // sqrt(gamma_c * log2 e) (fp32 only)
     int precision;                // 0 fp64, 1 fp32
 };
@@ -395,10 +395,16 @@ __device__ inline bool s1_is_zero(const TraceArgs &a, long long ri, long long ci
     return exp(__dmul_rn(a.neg_gamma_t, acc)) == 0.0;
 }
 
-__global__ void __launch_bounds__(32) k_trace(TraceArgs a)
+constexpr int TRACE_WARPS = 4;        // units per CTA of k_trace
+constexpr int XF = 16;                // doubles per pair in the transform array: R[9], m1[3], m2[3], superpose flag
+
+template <int C>
+__global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_units)
 {
-    const Unit u = a.units[blockIdx.x];
-    const int tid = threadIdx.x;
+    const int uidx = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5);
+    if (uidx >= n_units) return;
+    const Unit u = a.units[uidx];
+    const int tid = threadIdx.x & 31;
     if (tid >= u.n_pairs) return;
     const int ci = u.row_chain0 + tid;
     const int pair = u.pair_base + tid;
@@ -407,8 +413,10 @@ __global__ void __launch_bounds__(32) k_trace(TraceArgs a)
     const int g0 = (int)(ro - u.row_base);
     const double *A = a.coords + ro * 3;
     const double *B = a.coords + (long long)u.col_base * 3;
+    const double *ceni = a.centroid + (long long)ci * 3, *cenj = a.centroid + (long long)u.col_chain * 3;
+    const double ca0 = ceni[0], ca1 = ceni[1], ca2 = ceni[2], cb0 = cenj[0], cb1 = cenj[1], cb2 = cenj[2];
     short2 *path = a.path + u.path_base + (long long)tid * u.path_stride;
-    const int C = a.C, SW = 32 * C;
+    constexpr int SW = 32 * C;
 
     long long cidx = -1;
     uint4 cw = make_uint4(0, 0, 0, 0);
@@ -428,7 +436,6 @@ __global__ void __launch_bounds__(32) k_trace(TraceArgs a)
     const bool zreg = a.pair_zflag[pair] != 0;
     int wi = 0, wj = 0;               // witness: a nonzero S at (wi, wj) (1-based), 0 = none known
     auto is_zero_cell = [&](int i, int j) -> bool {
-        if (!zreg) return false;
         if (wi > 0 && wi <= i && wj <= j) return false;
         for (int ii = 1; ii <= i; ++ii)
             for (int jj = 1; jj <= j; ++jj)
@@ -438,20 +445,27 @@ __global__ void __launch_bounds__(32) k_trace(TraceArgs a)
 
     int i = a.pair_istar[pair], j = m;
     int st = 0, len = 0, c = 0;
-    double sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0};
+    // moments of the matched residues, relative to the chains' own centroids (translation does not change the
+    // covariance; it keeps the raw-moment form well conditioned)
+    double s1x = 0, s1y = 0, s1z = 0, s2x = 0, s2y = 0, s2z = 0;
+    double cxx = 0, cxy = 0, cxz = 0, cyx = 0, cyy = 0, cyz = 0, czx = 0, czy = 0, czz = 0;
     if (i <= 0) {
         st |= 2;                      // CRT_ST_NO_POSITIVE
     } else {
         while (j > 1 && (code(i, j) & 1u) == 0u) --j;      // first column of row i* that attains the maximum
         while (i > 0 && j > 0) {
-            if (is_zero_cell(i, j)) break;
+            if (zreg && is_zero_cell(i, j)) break;
             const unsigned cd = code(i, j);
             if ((cd & 2u) == 0u) {
                 --i; --j;
                 path[len++] = make_short2((short)i, (short)j);
                 ++c;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { sa[k] += A[i * 3 + k]; sb[k] += B[j * 3 + k]; }
+                const double x1 = A[i * 3] - ca0, y1 = A[i * 3 + 1] - ca1, z1 = A[i * 3 + 2] - ca2;
+                const double x2 = B[j * 3] - cb0, y2 = B[j * 3 + 1] - cb1, z2 = B[j * 3 + 2] - cb2;
+                s1x += x1; s1y += y1; s1z += z1; s2x += x2; s2y += y2; s2z += z2;
+                cxx += x2 * x1; cxy += x2 * y1; cxz += x2 * z1;
+                cyx += y2 * x1; cyy += y2 * y1; cyz += y2 * z1;
+                czx += z2 * x1; czy += z2 * y1; czz += z2 * z1;
             } else if ((cd & 1u) == 0u) {
                 --j;
                 path[len++] = make_short2((short)-1, (short)j);
@@ -469,36 +483,24 @@ __global__ void __launch_bounds__(32) k_trace(TraceArgs a)
     const bool superpose = c > 3;
     if (!superpose) st |= 1;          // CRT_ST_FEW_COMMON: multiple_alignment.py:337-342
     if (superpose) {
-        // the reference's means are sequential sums over ascending residue order (helper.py:45-53); the path is
-        // stored in descending order, so walk it backwards to add in the same order
-        for (int k = 0; k < 3; ++k) { sa[k] = 0; sb[k] = 0; }
-        for (int q = len - 1; q >= 0; --q) {
-            const short2 e = path[q];
-            if (e.x >= 0 && e.y >= 0)
-                for (int k = 0; k < 3; ++k) { sa[k] += A[e.x * 3 + k]; sb[k] += B[e.y * 3 + k]; }
-        }
-        for (int k = 0; k < 3; ++k) { m1[k] = sa[k] / (double)c; m2[k] = sb[k] / (double)c; }
-        double Cm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int q = len - 1; q >= 0; --q) {
-            const short2 e = path[q];
-            if (e.x < 0 || e.y < 0) continue;
-            double x1[3], x2[3];
-            for (int k = 0; k < 3; ++k) { x1[k] = A[e.x * 3 + k] - m1[k]; x2[k] = B[e.y * 3 + k] - m2[k]; }
-#pragma unroll
-            for (int p = 0; p < 3; ++p)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) Cm[p * 3 + k] += x2[p] * x1[k];
-        }
+        const double inv = 1.0 / (double)c;
+        const double p1[3] = {s1x * inv, s1y * inv, s1z * inv}, p2[3] = {s2x * inv, s2y * inv, s2z * inv};
+        double Cm[9];                 // sum (x2 - mean2)(x1 - mean1)^T = raw moments - c * mean2 mean1^T
+        Cm[0] = cxx - s2x * p1[0]; Cm[1] = cxy - s2x * p1[1]; Cm[2] = cxz - s2x * p1[2];
+        Cm[3] = cyx - s2y * p1[0]; Cm[4] = cyy - s2y * p1[1]; Cm[5] = cyz - s2y * p1[2];
+        Cm[6] = czx - s2z * p1[0]; Cm[7] = czy - s2z * p1[1]; Cm[8] = czz - s2z * p1[2];
         kabsch_rotation(Cm, R);
+        m1[0] = p1[0] + ca0; m1[1] = p1[1] + ca1; m1[2] = p1[2] + ca2;
+        m2[0] = p2[0] + cb0; m2[1] = p2[1] + cb1; m2[2] = p2[2] + cb2;
     }
     // translation of apply_rotran: t = m1 - m2 R
     double tr[3];
     for (int b = 0; b < 3; ++b) tr[b] = m1[b] - (m2[0] * R[b] + m2[1] * R[3 + b] + m2[2] * R[6 + b]);
-    if (a.rot) {
-        for (int q = 0; q < 9; ++q) a.rot[(long long)pair * 12 + q] = R[q];
-        for (int q = 0; q < 3; ++q) a.rot[(long long)pair * 12 + 9 + q] = tr[q];
-    }
-    // by-products over the matched residues
+    double *xf = a.xform + (long long)pair * XF;
+    for (int q = 0; q < 9; ++q) xf[q] = R[q];
+    for (int q = 0; q < 3; ++q) { xf[9 + q] = m1[q]; xf[12 + q] = m2[q]; }
+    xf[15] = superpose ? 1.0 : 0.0;
+    // by-products over the matched residues, ascending residue order like the reference's sums
     double rmsd = 0.0, tm = 0.0;
     if (c >= 1) {
         const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
@@ -507,9 +509,11 @@ __global__ void __launch_bounds__(32) k_trace(TraceArgs a)
             const short2 e = path[q];
             if (e.x < 0 || e.y < 0) continue;
             double sm = 0.0;
+            const double *y = B + e.y * 3;
+            const double y0 = y[0], y1 = y[1], y2 = y[2];
+#pragma unroll
             for (int b = 0; b < 3; ++b) {
-                const double *y = B + e.y * 3;
-                const double yr = superpose ? (y[0] * R[b] + y[1] * R[3 + b] + y[2] * R[6 + b]) + tr[b] : y[b];
+                const double yr = superpose ? (y0 * R[b] + y1 * R[3 + b] + y2 * R[6 + b]) + tr[b] : (b == 0 ? y0 : (b == 1 ? y1 : y2));
                 const double df = A[e.x * 3 + b] - yr;
                 ss += df * df;
                 sm += df;
@@ -526,26 +530,40 @@ __global__ void __launch_bounds__(32) k_trace(TraceArgs a)
     a.rmsd[pair] = rmsd;
     a.tm[pair] = tm;
     a.status[pair] = st;
+}
 
-    // stage-2 row records: (x - m1) R^T + m2  == the reference's frame up to a rigid motion of BOTH chains
-    // (superposition_functions.py:57-58 rotates chain 2 instead; the Gaussian only sees distances).
+// Stage-2 row records, one thread per row of the unit's stream: (x - m1) R^T + m2  == the reference's frame up
+// to a rigid motion of BOTH chains (superposition_functions.py:57-58 rotates chain 2 instead; the Gaussian only
+// sees distances).  fp32: relative to chain j's centroid and scaled by sqrt(gamma_c log2 e).
+__global__ void __launch_bounds__(256) k_rows2(TraceArgs a, int n_units)
+{
+    if ((int)blockIdx.x >= n_units) return;
+    const Unit u = a.units[blockIdx.x];
     const double *cj = a.centroid + (long long)u.col_chain * 3;
-    for (int r = 0; r < n; ++r) {
-        double x[3], y[3];
-        for (int k = 0; k < 3; ++k) x[k] = A[r * 3 + k] - m1[k];
-        for (int k = 0; k < 3; ++k) y[k] = superpose ? (x[0] * R[k * 3] + x[1] * R[k * 3 + 1] + x[2] * R[k * 3 + 2]) + m2[k] : A[r * 3 + k];
-        const int meta = make_meta(ci, r == 0, r == n - 1);
-        const long long idx = u.rows2_base + g0 + r;
+    const double c0 = cj[0], c1 = cj[1], c2 = cj[2];
+    for (int g = threadIdx.x; g < u.G; g += blockDim.x) {
+        const long long r = u.row_base + g;
+        const int meta = a.meta[r];
+        const double *xf = a.xform + (long long)(u.pair_base + (meta >> 2) - u.row_chain0) * XF;
+        const double ax = a.coords[r * 3], ay = a.coords[r * 3 + 1], az = a.coords[r * 3 + 2];
+        double y0 = ax, y1 = ay, y2 = az;
+        if (xf[15] != 0.0) {
+            const double x0 = ax - xf[9], x1 = ay - xf[10], x2 = az - xf[11];
+            y0 = (x0 * xf[0] + x1 * xf[1] + x2 * xf[2]) + xf[12];
+            y1 = (x0 * xf[3] + x1 * xf[4] + x2 * xf[5]) + xf[13];
+            y2 = (x0 * xf[6] + x1 * xf[7] + x2 * xf[8]) + xf[14];
+        }
+        const long long idx = u.rows2_base + g;
         if (a.precision == 1) {
             float4 v;
-            v.x = (float)((y[0] - cj[0]) * (double)a.scale2);
-            v.y = (float)((y[1] - cj[1]) * (double)a.scale2);
-            v.z = (float)((y[2] - cj[2]) * (double)a.scale2);
+            v.x = (float)((y0 - c0) * (double)a.scale2);
+            v.y = (float)((y1 - c1) * (double)a.scale2);
+            v.z = (float)((y2 - c2) * (double)a.scale2);
             v.w = __int_as_float(meta);
             reinterpret_cast<float4 *>(a.rows2)[idx] = v;
         } else {
             double *o = reinterpret_cast<double *>(a.rows2) + idx * 4;
-            o[0] = y[0]; o[1] = y[1]; o[2] = y[2]; o[3] = __longlong_as_double((long long)meta);
+            o[0] = y0; o[1] = y1; o[2] = y2; o[3] = __longlong_as_double((long long)meta);
         }
     }
 }

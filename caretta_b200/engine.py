@@ -10,7 +10,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcaretta_b200.so")
+LIB_PATH = os.environ.get("CARETTA_B200_LIB") or os.path.join(_HERE, "libcaretta_b200.so")   # env override: A/B builds
 
 FP64, FP32 = 0, 1
 ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE = 1, 2, 4
@@ -18,7 +18,7 @@ ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE = 1, 2, 4
 EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_fetch", "crt_fetch_device",
-    "crt_last_elapsed_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
+    "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak",
 ]
 
@@ -59,6 +59,7 @@ def load_library():
     L.crt_fetch_device.argtypes = [vp, vp, vp, vp, i64]
     L.crt_last_elapsed_ms.argtypes = [vp]
     L.crt_last_elapsed_ms.restype = dbl
+    L.crt_last_phase_ms.argtypes = [vp, vp]
     L.crt_last_launches.argtypes = [vp]
     L.crt_last_launches.restype = i64
     L.crt_last_cell_updates.argtypes = [vp]
@@ -175,6 +176,11 @@ class Engine:
 
     def last_elapsed_ms(self) -> float:
         return float(self.lib.crt_last_elapsed_ms(self.h))
+
+    def last_phase_ms(self):
+        out = np.zeros(4)
+        self._check(self.lib.crt_last_phase_ms(self.h, _p(out)), "crt_last_phase_ms")
+        return dict(fill1=out[0], trace=out[1], fill2=out[3])
 
     def last_launches(self) -> int:
         return int(self.lib.crt_last_launches(self.h))

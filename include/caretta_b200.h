@@ -92,6 +92,10 @@ int crt_fetch(crt_ctx *ctx, double *score, double *rmsd, double *tm, int32_t *nc
  * all-gather inputs), n = capacity in elements. */
 int crt_fetch_device(crt_ctx *ctx, void *d_score, void *d_rmsd, void *d_tm, int64_t n);
 double crt_last_elapsed_ms(crt_ctx *ctx);        /* device time of the last run (CUDA events on the run's stream) */
+/* Per-phase device time of the last run: out4 = {stage-1 fill, traceback+Kabsch, (unused), stage-2 rows + fill}.
+ * Only measured when the run used ONE stream (environment CARETTA_B200_STREAMS=1, or a path-returning call);
+ * otherwise the phases of different batches overlap and every entry is -1. */
+int crt_last_phase_ms(crt_ctx *ctx, double *out4);
 int64_t crt_last_launches(crt_ctx *ctx);         /* kernels launched by the last run */
 double crt_last_cell_updates(crt_ctx *ctx);      /* sum over pairs of 2 * L1 * L2 */
 
