@@ -1,0 +1,163 @@
+"""Host-side mirror of the reference's interface for the all-vs-all pair path (names, argument meaning and error
+behaviour follow caretta/multiple_alignment.py of TurtleTools/caretta 0.2.0), backed by the CUDA engine through
+the C ABI (caretta_b200.engine).  Nothing here computes the path on the CPU.
+
+    reference                                                        here
+    ---------------------------------------------------------------  --------------------------------------------
+    Protein(name, tensors, coordinates, sequence)        :312-319    Protein (same fields, same __len__/__str__)
+    MultipleAlignment(sequences)                         :148-156    MultipleAlignment
+      .make_pairwise_matrix(score_function_params)       :158-170    same signature, float64 [N,N], symmetric, diag 0
+    make_rmsd_coverage_tm_matrix(alignment, proteins,    :1000-1055  same signature (superpose_first=False only,
+                                 superpose_first)                    the reference's own call site, :571-572)
+    dtw.dtw_align / smith_waterman / smith_waterman_score            dtw_align / smith_waterman / smith_waterman_score
+      (dynamic_time_warping.py:147-278)                              (batched: *_batch)
+    StructureMultiple (name used by the CLI help and the legacy API) StructureMultiple facade
+
+``install(reference_module)`` swaps the reference's own methods for these, so that an unmodified
+``align_from_structure_files`` / ``caretta-cli`` run uses the GPU for the pair loop.
+"""
+from __future__ import annotations
+
+import os
+import typing
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import engine as _engine
+
+DEFAULT_SCORE_PARAMS = dict(flexible=False, gamma_tensor=7.0, gamma_coords=0.03)     # multiple_alignment.py:490-492
+
+
+def _precision_from_env() -> int:
+    v = os.environ.get("CARETTA_B200_PRECISION", "fp32").lower()
+    if v in ("fp64", "f64", "double", "parity"):
+        return _engine.FP64
+    if v in ("fp32", "f32", "float"):
+        return _engine.FP32
+    raise ValueError(f"CARETTA_B200_PRECISION={v!r}: expected fp32 or fp64")
+
+
+@dataclass
+class Protein:
+    """Same fields as the reference's Protein (multiple_alignment.py:312-319)."""
+    name: str
+    tensors: np.ndarray
+    coordinates: np.ndarray = None
+    sequence: str = ""
+
+    def __len__(self) -> int:
+        return self.tensors.shape[0]
+
+    def __str__(self) -> str:
+        return self.sequence
+
+
+def pack_sequences(sequences) -> typing.Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """List of Protein-like objects (anything with .tensors [L,d] and .coordinates [L,3]) -> packed chain set."""
+    if len(sequences) == 0:
+        raise ValueError("no sequences")
+    d = int(np.asarray(sequences[0].tensors).shape[1])
+    lens = []
+    for s in sequences:
+        t = np.asarray(s.tensors)
+        c = np.asarray(s.coordinates)
+        if t.ndim != 2 or t.shape[1] != d:
+            raise ValueError(f"{getattr(s, 'name', '?')}: tensors must be [L,{d}]")
+        if c.ndim != 2 or c.shape[1] != 3 or c.shape[0] != t.shape[0]:
+            raise ValueError(f"{getattr(s, 'name', '?')}: coordinates must be [L,3] with the same L as tensors")
+        lens.append(t.shape[0])
+    offsets = np.zeros(len(sequences) + 1, np.int64)
+    offsets[1:] = np.cumsum(lens)
+    coords = np.concatenate([np.asarray(s.coordinates, dtype=np.float64) for s in sequences])
+    tensors = np.concatenate([np.asarray(s.tensors, dtype=np.float64) for s in sequences])
+    return coords, tensors, offsets
+
+
+_shared_engine: typing.Optional[_engine.Engine] = None
+
+
+def get_engine() -> _engine.Engine:
+    """One engine (context) per process, on the current CUDA device (LOCAL_RANK when launched by torchrun)."""
+    global _shared_engine
+    if _shared_engine is None:
+        dev = int(os.environ.get("CARETTA_B200_DEVICE", os.environ.get("LOCAL_RANK", "-1")))
+        _shared_engine = _engine.Engine(dev)
+    return _shared_engine
+
+
+@dataclass
+class MultipleAlignment:
+    """The part of the reference's MultipleAlignment that sits on the hot path (multiple_alignment.py:148-170)."""
+    sequences: typing.List[typing.Any]
+    tree: typing.Optional[np.ndarray] = None
+    branch_lengths: typing.Optional[np.ndarray] = None
+    alignment: typing.Optional[typing.Dict[str, np.ndarray]] = None
+    precision: typing.Optional[int] = None
+    last_status: typing.Optional[np.ndarray] = field(default=None, repr=False)
+
+    def _params(self, score_function_params) -> _engine.Params:
+        p = dict(DEFAULT_SCORE_PARAMS)
+        # the reference's Protein.score_function defaults (gamma_tensor=0.03) apply when the caller passes nothing
+        # (:321-322); align_from_structure_files always passes 7.0 / 0.03 (:490-492)
+        if score_function_params is None:
+            p.update(gamma_tensor=0.03, gamma_coords=0.03)
+        else:
+            unknown = set(score_function_params) - {"flexible", "gamma_tensor", "gamma_coords", "verbose"}
+            if unknown:
+                raise TypeError(f"score_function() got unexpected keyword arguments {sorted(unknown)}")
+            if "gamma_tensor" not in score_function_params:
+                p["gamma_tensor"] = 0.03
+            if "gamma_coords" not in score_function_params:
+                p["gamma_coords"] = 0.03
+            p.update(score_function_params)
+        if p.get("flexible", False):
+            raise NotImplementedError("flexible=True (tensor-only scoring, multiple_alignment.py:323-326) is not on the "
+                                      "all-vs-all path and is not accelerated")
+        prec = self.precision if self.precision is not None else _precision_from_env()
+        return _engine.Engine.params(p["gamma_tensor"], p["gamma_coords"], prec)
+
+    def make_pairwise_matrix(self, score_function_params=None) -> np.ndarray:
+        """float64 [N,N] similarity, symmetric, zero diagonal (the caller turns it into max - S, :501)."""
+        eng = get_engine()
+        eng.set_chains(*pack_sequences(self.sequences))
+        prm = self._params(score_function_params)
+        n = len(self.sequences)
+        if n < 2:
+            return np.zeros((n, n))
+        return eng.pairwise_all(prm)
+
+    def make_pairwise_matrices(self, score_function_params=None):
+        """Engine by-product: (score, rmsd, tm) over the stage-1 matched residues, each float64 [N,N]."""
+        eng = get_engine()
+        eng.set_chains(*pack_sequences(self.sequences))
+        return eng.pairwise_all(self._params(score_function_params), want_rmsd_tm=True)
+
+
+class StructureMultiple(MultipleAlignment):
+    """Name kept for the legacy API / the CLI help text (bin/caretta-cli:84)."""
+
+    @classmethod
+    def from_arrays(cls, names, tensors_list, coords_list, sequences=None):
+        seqs = sequences or ["" for _ in names]
+        return cls([Protein(n, np.asarray(t, np.float64), np.asarray(c, np.float64), s)
+                    for n, t, c, s in zip(names, tensors_list, coords_list, seqs)])
+
+    @classmethod
+    def from_chains(cls, chains):
+        return cls([Protein(f"s{p}", *chains.chain(p), "") for p in range(chains.n)])
+
+    def make_pairwise_score_matrix(self, **score_function_params):
+        return self.make_pairwise_matrix(score_function_params or dict(DEFAULT_SCORE_PARAMS))
+
+
+def install(reference_multiple_alignment_module) -> None:
+    """Monkey-patches the reference module in place: its MultipleAlignment.make_pairwise_matrix (the all-vs-all
+    loop, :158-170) is replaced by the GPU path.  Everything else (neighbor joining, progressive alignment,
+    writers, CLI flags) stays the reference's code."""
+    ref = reference_multiple_alignment_module
+
+    def make_pairwise_matrix(self, score_function_params=None):
+        return MultipleAlignment(self.sequences).make_pairwise_matrix(score_function_params)
+
+    ref.MultipleAlignment.make_pairwise_matrix = make_pairwise_matrix
