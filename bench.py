@@ -122,13 +122,13 @@ def run_reference(args):
         return
     ch, n, L = workload(args.gpus, args.chains, args.length)
     cores = os.cpu_count() or 1
-    rate0, _, _ = cpu_port_rate(ch, 64)
+    rate0, _, _ = cpu_port_rate(ch, 64, nthreads=cores)
     sample = int(max(64, min(20000, rate0 * 4.0)))          # ~4 s per step
     for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_port_rate(ch, max(64, sample // 4))
+        cpu_port_rate(ch, max(64, sample // 4), nthreads=cores)
     rates, t0 = [], time.perf_counter()
     for k in range(args.steps):
-        r, dt, thr = cpu_port_rate(ch, sample, seed=k + 1)
+        r, dt, thr = cpu_port_rate(ch, sample, nthreads=cores, seed=k + 1)
         rates.append(r)
     total = time.perf_counter() - t0
     value = float(np.mean(rates))
@@ -303,10 +303,11 @@ def main():
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, bounded sample)
     cpu = None
-    if not args.no_cpu_baseline:
-        rate0, _, _ = cpu_port_rate(ch, 64)
+    if not args.no_cpu_baseline and world == 1:
+        ncpu = os.cpu_count() or 1
+        rate0, _, _ = cpu_port_rate(ch, 64, nthreads=ncpu)
         sample = int(max(64, min(40000, rate0 * 12.0)))      # ~12 s of all-core CPU work
-        rate, dt, thr = cpu_port_rate(ch, sample, seed=7)
+        rate, dt, thr = cpu_port_rate(ch, sample, nthreads=ncpu, seed=7)
         cpu = {"value": rate, "unit": "pairs/s", "cores": thr, "kind": "port",
                "sample": f"{sample} random pairs of the same {n}x{L} workload in {dt:.1f} s, oracle/caretta_oracle.c with OpenMP over pairs"}
 

@@ -711,6 +711,43 @@ int crt_shard_pairs(crt_ctx *c, int32_t rank, int32_t world, int32_t *pair_i, in
     return 0;
 }
 
+// Host-only planning (no device needed): the same deterministic enumeration crt_pairwise_shard uses.
+static int plan_units(const int64_t *offsets, int32_t n_chains, int32_t rank, int32_t world, std::vector<HostUnit> &units)
+{
+    if (!offsets || n_chains <= 0) return fail(CRT_E_ARG, "bad offsets / n_chains");
+    if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world %d/%d", rank, world);
+    crt_ctx tmp;
+    tmp.N = n_chains; tmp.D = 10;
+    tmp.offsets.assign(offsets, offsets + n_chains + 1);
+    build_all_units(&tmp, CRT_FP32, units);
+    shard_units(units, rank, world);
+    return 0;
+}
+
+int64_t crt_plan_shard_size(const int64_t *offsets, int32_t n_chains, int32_t rank, int32_t world)
+{
+    std::vector<HostUnit> units;
+    int rc = plan_units(offsets, n_chains, rank, world, units);
+    if (rc) return rc;
+    long long np = 0;
+    assign_pairs(units, nullptr, nullptr, &np, nullptr, nullptr);
+    return np;
+}
+
+int crt_plan_shard_pairs(const int64_t *offsets, int32_t n_chains, int32_t rank, int32_t world, int32_t *pair_i, int32_t *pair_j)
+{
+    if (!pair_i || !pair_j) return fail(CRT_E_ARG, "null argument");
+    std::vector<HostUnit> units;
+    int rc = plan_units(offsets, n_chains, rank, world, units);
+    if (rc) return rc;
+    std::vector<int> pi, pj;
+    long long np = 0;
+    assign_pairs(units, &pi, &pj, &np, nullptr, nullptr);
+    std::memcpy(pair_i, pi.data(), sizeof(int) * (size_t)np);
+    std::memcpy(pair_j, pj.data(), sizeof(int) * (size_t)np);
+    return 0;
+}
+
 int crt_fetch(crt_ctx *c, double *score, double *rmsd, double *tm, int32_t *ncommon, int32_t *status)
 {
     if (!c) return fail(CRT_E_ARG, "null context");

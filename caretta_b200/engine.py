@@ -17,7 +17,7 @@ ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE = 1, 2, 4
 
 EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
-    "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_fetch", "crt_fetch_device",
+    "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak",
 ]
@@ -55,6 +55,9 @@ def load_library():
     L.crt_shard_size.argtypes = [vp, i32, i32]
     L.crt_shard_size.restype = i64
     L.crt_shard_pairs.argtypes = [vp, i32, i32, vp, vp]
+    L.crt_plan_shard_size.argtypes = [vp, i32, i32, i32]
+    L.crt_plan_shard_size.restype = i64
+    L.crt_plan_shard_pairs.argtypes = [vp, i32, i32, i32, vp, vp]
     L.crt_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
     L.crt_fetch_device.argtypes = [vp, vp, vp, vp, i64]
     L.crt_last_elapsed_ms.argtypes = [vp]
@@ -80,6 +83,22 @@ def load_library():
 
 def _p(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def plan_shard(offsets, rank: int, world: int):
+    """Pairs (i, j) of one rank's shard, in result order, computed on the host (no device needed)."""
+    L = load_library()
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    np_ = int(L.crt_plan_shard_size(_p(offsets), n, rank, world))
+    if np_ < 0:
+        raise CrtError(f"crt_plan_shard_size failed: {L.crt_last_error().decode()}")
+    pi = np.empty(max(np_, 1), np.int32)
+    pj = np.empty(max(np_, 1), np.int32)
+    rc = L.crt_plan_shard_pairs(_p(offsets), n, rank, world, _p(pi), _p(pj))
+    if rc != 0:
+        raise CrtError(f"crt_plan_shard_pairs failed: {L.crt_last_error().decode()}")
+    return pi[:np_], pj[:np_]
 
 
 class Engine:

@@ -85,6 +85,10 @@ int crt_set_chains(crt_ctx *ctx, const double *coords, const double *tensors, co
 int crt_pairwise_shard(crt_ctx *ctx, const crt_params *prm, int32_t rank, int32_t world);
 int64_t crt_shard_size(crt_ctx *ctx, int32_t rank, int32_t world);      /* pairs in that shard, <0 on error */
 int crt_shard_pairs(crt_ctx *ctx, int32_t rank, int32_t world, int32_t *pair_i, int32_t *pair_j);
+/* The same enumeration without a context or a device (host-side planning: sizes of the all-gather, scatter maps). */
+int64_t crt_plan_shard_size(const int64_t *offsets, int32_t n_chains, int32_t rank, int32_t world);
+int crt_plan_shard_pairs(const int64_t *offsets, int32_t n_chains, int32_t rank, int32_t world, int32_t *pair_i,
+                         int32_t *pair_j);
 /* Copy the packed results of the last crt_pairwise_shard / crt_pairwise_list to host (any pointer may be NULL).
  * score/rmsd/tm are float64 at the boundary in both precisions (the reference returns float64). */
 int crt_fetch(crt_ctx *ctx, double *score, double *rmsd, double *tm, int32_t *ncommon, int32_t *status);
