@@ -3,6 +3,7 @@
 #include "../../include/caretta_b200.h"
 #include "crt_kernels.cuh"
 #include "crt_fill_f32.cuh"
+#include "crt_dp_batch.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -645,6 +646,7 @@ namespace {
 
 int ensure_prepared(crt_ctx *c, const crt_params *prm)
 {
+    if (!prm) return 0;
     if (c->prep_gamma_t == prm->gamma_tensor && c->prep_gamma_c == prm->gamma_coords) return 0;
     PrepArgs a{};
     a.coords = c->coords.p; a.tensors = c->tensors.p; a.offsets = c->d_offsets.p; a.chain_of = c->chain_of.p;
@@ -905,21 +907,146 @@ int crt_pairwise_list(crt_ctx *c, const crt_params *prm, const int32_t *pair_i, 
     return 0;
 }
 
-int crt_sw_align_batch(crt_ctx *, const double *, const int64_t *, const int32_t *, const int32_t *, int32_t, double,
-                       int32_t *, int32_t *, int64_t *, int64_t, double *, int32_t *)
+}  // extern "C"
+
+namespace {
+
+// Shared host driver of the two DP-in-isolation entry points.
+int dp_batch(crt_ctx *c, bool affine, const double *S, const int64_t *shape_off, const int32_t *n, const int32_t *m,
+             int32_t n_problems, double p0, double p1, int32_t *aln1, int32_t *aln2, int64_t *aln_off, int64_t aln_cap,
+             double *score, int32_t *status)
 {
-    return fail(CRT_E_STATE, "crt_sw_align_batch: not built yet");
+    if (!c) return fail(CRT_E_ARG, "null context");
+    if (n_problems < 0 || (n_problems > 0 && (!S || !shape_off || !n || !m || !score))) return fail(CRT_E_ARG, "null argument");
+    const bool want_paths = aln1 || aln2 || aln_off;
+    if (want_paths && !(aln1 && aln2 && aln_off)) return fail(CRT_E_ARG, "aln1, aln2 and aln_off must be given together");
+    if (affine && !want_paths && false) return 0;
+    if (n_problems == 0) { if (aln_off) aln_off[0] = 0; return 0; }
+    CU(cudaSetDevice(c->device));
+    std::vector<DpProblem> probs((size_t)n_problems);
+    long long cells = 0, rows = 0, alen = 0, s_end = 0;
+    for (int p = 0; p < n_problems; ++p) {
+        if (n[p] <= 0 || m[p] <= 0) return fail(CRT_E_ARG, "problem %d has an empty dimension (%d x %d)", p, n[p], m[p]);
+        probs[p].s_off = shape_off[p]; probs[p].b_off = cells; probs[p].bnd_off = rows; probs[p].aln_off = alen;
+        probs[p].n = n[p]; probs[p].m = m[p];
+        cells += (long long)n[p] * m[p]; rows += n[p]; alen += (long long)n[p] + m[p] + 1;
+        s_end = std::max<long long>(s_end, shape_off[p] + (long long)n[p] * m[p]);
+    }
+    DevBuf<double> dS, dW, dBnd, dF, dScore;
+    DevBuf<unsigned char> dB;
+    DevBuf<DpProblem> dP;
+    DevBuf<int> dA1, dA2, dLen, dSt;
+    DevBuf<long long> dIdx;
+    int rc = 0;
+    auto cleanup = [&]() { dS.release(); dW.release(); dBnd.release(); dF.release(); dScore.release(); dB.release(); dP.release();
+                           dA1.release(); dA2.release(); dLen.release(); dSt.release(); dIdx.release(); };
+#define TRY(x) do { if ((rc = (x))) { cleanup(); return rc; } } while (0)
+#define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(CRT_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    TRY(dS.ensure((size_t)s_end)); TRY(dP.ensure((size_t)n_problems)); TRY(dBnd.ensure((size_t)rows * 2 + 2));
+    TRY(dScore.ensure((size_t)n_problems)); TRY(dLen.ensure((size_t)n_problems)); TRY(dSt.ensure((size_t)n_problems));
+    TRY(dA1.ensure((size_t)alen)); TRY(dA2.ensure((size_t)alen));
+    if (affine) { TRY(dB.ensure((size_t)cells)); TRY(dF.ensure((size_t)n_problems * 3)); }
+    else { TRY(dW.ensure((size_t)cells)); TRY(dF.ensure((size_t)n_problems)); TRY(dIdx.ensure((size_t)n_problems)); }
+    cudaStream_t st = c->stream;
+    CUT(cudaMemcpyAsync(dS.p, S, sizeof(double) * (size_t)s_end, cudaMemcpyHostToDevice, st));
+    CUT(cudaMemcpyAsync(dP.p, probs.data(), sizeof(DpProblem) * (size_t)n_problems, cudaMemcpyHostToDevice, st));
+    const int tb = 64, tg = (n_problems + tb - 1) / tb;
+    if (affine) {
+        k_dtw_fill<<<n_problems, 32, 0, st>>>(dP.p, n_problems, dS.p, dB.p, dBnd.p, dF.p, p0, p1);
+        k_dtw_trace<<<tg, tb, 0, st>>>(dP.p, n_problems, dB.p, dF.p, dA1.p, dA2.p, dLen.p, dScore.p);
+    } else {
+        k_sw_fill<<<n_problems, 32, 0, st>>>(dP.p, n_problems, dS.p, dW.p, dBnd.p, dF.p, dIdx.p, p0);
+        k_sw_trace<<<tg, tb, 0, st>>>(dP.p, n_problems, dS.p, dW.p, dF.p, dIdx.p, dA1.p, dA2.p, dLen.p, dScore.p, dSt.p, p0, want_paths ? 1 : 0);
+    }
+    CUT(cudaGetLastError());
+    std::vector<int> h1, h2, hl((size_t)n_problems), hs((size_t)n_problems);
+    CUT(cudaMemcpyAsync(score, dScore.p, sizeof(double) * (size_t)n_problems, cudaMemcpyDeviceToHost, st));
+    CUT(cudaMemcpyAsync(hl.data(), dLen.p, sizeof(int) * (size_t)n_problems, cudaMemcpyDeviceToHost, st));
+    if (!affine) CUT(cudaMemcpyAsync(hs.data(), dSt.p, sizeof(int) * (size_t)n_problems, cudaMemcpyDeviceToHost, st));
+    if (want_paths) {
+        h1.resize((size_t)alen); h2.resize((size_t)alen);
+        CUT(cudaMemcpyAsync(h1.data(), dA1.p, sizeof(int) * (size_t)alen, cudaMemcpyDeviceToHost, st));
+        CUT(cudaMemcpyAsync(h2.data(), dA2.p, sizeof(int) * (size_t)alen, cudaMemcpyDeviceToHost, st));
+    }
+    CUT(cudaStreamSynchronize(st));
+    if (status) for (int p = 0; p < n_problems; ++p) status[p] = affine ? 0 : hs[p];
+    if (want_paths) {
+        int64_t off = 0;
+        for (int p = 0; p < n_problems; ++p) {
+            aln_off[p] = off;
+            if (off + hl[p] > aln_cap) { cleanup(); return fail(CRT_E_ARG, "aln_cap too small"); }
+            std::memcpy(aln1 + off, h1.data() + probs[p].aln_off, sizeof(int) * (size_t)hl[p]);
+            std::memcpy(aln2 + off, h2.data() + probs[p].aln_off, sizeof(int) * (size_t)hl[p]);
+            off += hl[p];
+        }
+        aln_off[n_problems] = off;
+    }
+    cleanup();
+#undef TRY
+#undef CUT
+    return 0;
 }
 
-int crt_dtw_align_batch(crt_ctx *, const double *, const int64_t *, const int32_t *, const int32_t *, int32_t, double,
-                        double, int32_t *, int32_t *, int64_t *, int64_t, double *)
+}  // namespace
+
+extern "C" {
+
+int crt_sw_align_batch(crt_ctx *c, const double *S, const int64_t *shape_off, const int32_t *n, const int32_t *m,
+                       int32_t n_problems, double gap, int32_t *aln1, int32_t *aln2, int64_t *aln_off, int64_t aln_cap,
+                       double *score, int32_t *status)
 {
-    return fail(CRT_E_STATE, "crt_dtw_align_batch: not built yet");
+    if (!(gap >= 0.0)) return fail(CRT_E_ARG, "gap must be >= 0");
+    return dp_batch(c, false, S, shape_off, n, m, n_problems, gap, 0.0, aln1, aln2, aln_off, aln_cap, score, status);
 }
 
-int crt_rmsd_cov_tm(crt_ctx *, const int64_t *, int64_t, double *, double *, double *, int32_t *)
+int crt_dtw_align_batch(crt_ctx *c, const double *S, const int64_t *shape_off, const int32_t *n, const int32_t *m,
+                        int32_t n_problems, double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2,
+                        int64_t *aln_off, int64_t aln_cap, double *score)
 {
-    return fail(CRT_E_STATE, "crt_rmsd_cov_tm: not built yet");
+    return dp_batch(c, true, S, shape_off, n, m, n_problems, gap_open, gap_extend, aln1, aln2, aln_off, aln_cap, score, nullptr);
+}
+
+int crt_rmsd_cov_tm(crt_ctx *c, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm, int32_t *n_bad)
+{
+    if (!c || !aln || !rmsd || !cov || !tm) return fail(CRT_E_ARG, "null argument");
+    if (c->N <= 0) return fail(CRT_E_STATE, "crt_set_chains has not been called");
+    if (A <= 0) return fail(CRT_E_ARG, "alignment length must be > 0");
+    CU(cudaSetDevice(c->device));
+    const int N = c->N;
+    for (int p = 0; p < N; ++p) {
+        const long long L = c->offsets[p + 1] - c->offsets[p];
+        for (int64_t k = 0; k < A; ++k) {
+            const long long v = aln[(size_t)p * A + k];
+            if (v < -1 || v >= L) return fail(CRT_E_ARG, "aln[%d][%lld] = %lld out of range for a chain of %lld residues", p, (long long)k, v, L);
+        }
+    }
+    // centroids are produced by the prep kernels; make sure they exist (parameters are irrelevant for them)
+    crt_params prm{7.0, 0.03, 0.0, CRT_FP32, 0};
+    int rc = ensure_prepared(c, c->prep_gamma_t >= 0 ? nullptr : &prm);
+    if (rc) return rc;
+    DevBuf<long long> dAln;
+    DevBuf<double> dR, dC, dT;
+    DevBuf<int> dBad;
+    auto cleanup = [&]() { dAln.release(); dR.release(); dC.release(); dT.release(); dBad.release(); };
+    const size_t NN = (size_t)N * N;
+    if ((rc = dAln.ensure((size_t)N * A)) || (rc = dR.ensure(NN)) || (rc = dC.ensure(NN)) || (rc = dT.ensure(NN)) || (rc = dBad.ensure(1))) { cleanup(); return rc; }
+    cudaStream_t st = c->stream;
+    cudaMemcpyAsync(dAln.p, aln, sizeof(long long) * (size_t)N * A, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(dBad.p, 0, sizeof(int), st);
+    k_fill_diag<<<(unsigned)((NN + 255) / 256), 256, 0, st>>>(dR.p, dC.p, dT.p, N);
+    const long long np = (long long)N * (N - 1) / 2;
+    if (np > 0)
+        k_rmsd_cov_tm<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(dAln.p, N, A, c->coords.p, c->d_offsets.p, c->centroid.p, dR.p, dC.p, dT.p, dBad.p);
+    int bad = 0;
+    cudaMemcpyAsync(rmsd, dR.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(cov, dC.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(tm, dT.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&bad, dBad.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail(CRT_E_CUDA, "crt_rmsd_cov_tm: %s", cudaGetErrorString(e));
+    if (n_bad) *n_bad = bad;
+    return 0;
 }
 
 int crt_fp32_peak(crt_ctx *c, double *ffma_per_s, double *elapsed_ms)

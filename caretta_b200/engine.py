@@ -228,6 +228,64 @@ class Engine:
             out.update(aln1=a1, aln2=a2, aln_off=off)
         return out
 
+    # ------------------------------------------------------------------------------------------------ DP in isolation
+    @staticmethod
+    def _pack_matrices(mats):
+        mats = [np.ascontiguousarray(m, dtype=np.float64) for m in mats]
+        for m in mats:
+            if m.ndim != 2:
+                raise ValueError("score matrices must be 2-D")
+        n = np.array([m.shape[0] for m in mats], np.int32)
+        mm = np.array([m.shape[1] for m in mats], np.int32)
+        off = np.zeros(len(mats) + 1, np.int64)
+        off[1:] = np.cumsum(n.astype(np.int64) * mm)
+        flat = np.concatenate([m.ravel() for m in mats]) if mats else np.zeros(0)
+        return flat, off, n, mm
+
+    def _split(self, a1, a2, off, k):
+        return [(a1[off[q]:off[q + 1]].astype(np.int64), a2[off[q]:off[q + 1]].astype(np.int64)) for q in range(k)]
+
+    def dtw_align_batch(self, mats, gap_open: float, gap_extend: float):
+        """[(aln1, aln2, score)] for each score matrix -- dtw.dtw_align (dynamic_time_warping.py:147-184)."""
+        flat, off, n, m = self._pack_matrices(mats)
+        k = len(mats)
+        cap = int((n.astype(np.int64) + m + 1).sum()) + 1
+        a1, a2 = np.empty(cap, np.int32), np.empty(cap, np.int32)
+        aoff = np.zeros(k + 1, np.int64)
+        score = np.empty(max(k, 1))
+        self._check(self.lib.crt_dtw_align_batch(self.h, _p(flat), _p(off), _p(n), _p(m), k, float(gap_open),
+                                                 float(gap_extend), _p(a1), _p(a2), _p(aoff), cap, _p(score)),
+                    "crt_dtw_align_batch")
+        return [(x, y, float(score[q])) for q, (x, y) in enumerate(self._split(a1, a2, aoff, k))]
+
+    def sw_align_batch(self, mats, gap: float = 0.0, want_paths: bool = True):
+        """[(aln1, aln2, score, status)] -- dtw.smith_waterman / smith_waterman_score (:204-278)."""
+        flat, off, n, m = self._pack_matrices(mats)
+        k = len(mats)
+        cap = int((n.astype(np.int64) + m + 1).sum()) + 1
+        a1 = np.empty(cap, np.int32) if want_paths else None
+        a2 = np.empty(cap, np.int32) if want_paths else None
+        aoff = np.zeros(k + 1, np.int64) if want_paths else None
+        score = np.empty(max(k, 1))
+        st = np.zeros(max(k, 1), np.int32)
+        self._check(self.lib.crt_sw_align_batch(self.h, _p(flat), _p(off), _p(n), _p(m), k, float(gap), _p(a1), _p(a2),
+                                                _p(aoff), cap, _p(score), _p(st)), "crt_sw_align_batch")
+        if not want_paths:
+            return [(None, None, float(score[q]), int(st[q])) for q in range(k)]
+        return [(x, y, float(score[q]), int(st[q])) for q, (x, y) in enumerate(self._split(a1, a2, aoff, k))]
+
+    def rmsd_cov_tm(self, aln):
+        """make_rmsd_coverage_tm_matrix(superpose_first=False) on the chains of this engine; aln int64 [N, A]."""
+        aln = np.ascontiguousarray(aln, dtype=np.int64)
+        if aln.ndim != 2 or aln.shape[0] != self.n_chains:
+            raise ValueError("aln must be [n_chains, A]")
+        n = self.n_chains
+        r, c, t = np.empty((n, n)), np.empty((n, n)), np.empty((n, n))
+        bad = C.c_int32(0)
+        self._check(self.lib.crt_rmsd_cov_tm(self.h, _p(aln), aln.shape[1], _p(r), _p(c), _p(t), C.byref(bad)),
+                    "crt_rmsd_cov_tm")
+        return r, c, t, int(bad.value)
+
     def fp32_peak(self):
         v, ms = C.c_double(), C.c_double()
         self._check(self.lib.crt_fp32_peak(self.h, C.byref(v), C.byref(ms)), "crt_fp32_peak")

@@ -151,6 +151,61 @@ class StructureMultiple(MultipleAlignment):
         return self.make_pairwise_matrix(score_function_params or dict(DEFAULT_SCORE_PARAMS))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# The DPs in isolation, with the reference's signatures (dynamic_time_warping.py:147-278).  seq1/seq2 must be the
+# identity index arrays the reference always passes on this path (np.arange(n), np.arange(m)).
+# ---------------------------------------------------------------------------------------------------------------
+def _check_arange(seq, n, what):
+    seq = np.asarray(seq)
+    if len(seq) != n or (n and not np.array_equal(seq, np.arange(n))):
+        raise NotImplementedError(f"{what}: only the identity indexing np.arange({n}) used on caretta's pair path is accelerated")
+
+
+def dtw_align(seq1, seq2, score_matrix, gap_open_penalty: float = 0.0, gap_extend_penalty: float = 0.0):
+    score_matrix = np.asarray(score_matrix, dtype=np.float64)
+    _check_arange(seq1, score_matrix.shape[0], "dtw_align")
+    _check_arange(seq2, score_matrix.shape[1], "dtw_align")
+    a1, a2, sc = get_engine().dtw_align_batch([score_matrix], gap_open_penalty, gap_extend_penalty)[0]
+    return a1, a2, sc
+
+
+def dtw_align_score(seq1, seq2, score_matrix, gap_open_penalty: float = 0.0, gap_extend_penalty: float = 0.0):
+    return dtw_align(seq1, seq2, score_matrix, gap_open_penalty, gap_extend_penalty)[2]
+
+
+def smith_waterman(seq1, seq2, score_matrix, gap: float = 0.0):
+    score_matrix = np.asarray(score_matrix, dtype=np.float64)
+    _check_arange(seq1, score_matrix.shape[0], "smith_waterman")
+    _check_arange(seq2, score_matrix.shape[1], "smith_waterman")
+    a1, a2, sc, st = get_engine().sw_align_batch([score_matrix], gap)[0]
+    if st & _engine.ST_NO_POSITIVE:
+        # the reference fails here too (max_pos is None -> TypeError inside numba, dynamic_time_warping.py:250)
+        raise TypeError("smith_waterman: no cell of the score matrix is positive")
+    return a1, a2, sc
+
+
+def smith_waterman_score(seq1, seq2, matrix, gap: float = 0.0):
+    matrix = np.asarray(matrix, dtype=np.float64)
+    _check_arange(seq1, matrix.shape[0], "smith_waterman_score")
+    _check_arange(seq2, matrix.shape[1], "smith_waterman_score")
+    return get_engine().sw_align_batch([matrix], gap, want_paths=False)[0][2]
+
+
+def make_rmsd_coverage_tm_matrix(alignment, proteins, superpose_first: bool = True):
+    """multiple_alignment.py:1000-1055.  Only superpose_first=False (the reference's own call site, :571-572) is
+    accelerated; alignment is {name: int64[A]} with -1 gaps, proteins the matching list of Protein-like objects."""
+    if superpose_first:
+        raise NotImplementedError("superpose_first=True goes through superpose() (reference/core selection, "
+                                  "multiple_alignment.py:596-852), which is outside the accelerated path")
+    names = [p.name for p in proteins]
+    aln = np.array([np.asarray(alignment[n], dtype=np.int64) for n in names])
+    eng = get_engine()
+    eng.set_chains(*pack_sequences(proteins))
+    r, c, t, bad = eng.rmsd_cov_tm(aln)
+    assert bad == 0, "a pair has fewer than 3 common positions (the reference asserts here, :1034)"
+    return r, c, t
+
+
 def install(reference_multiple_alignment_module) -> None:
     """Monkey-patches the reference module in place: its MultipleAlignment.make_pairwise_matrix (the all-vs-all
     loop, :158-170) is replaced by the GPU path.  Everything else (neighbor joining, progressive alignment,
