@@ -64,6 +64,8 @@ struct HostUnit {
     double cost;    // G * m
 };
 
+struct Batch { size_t first, count; int C, multi; size_t tb_n, rows2_n, bnd_n, path_n; };
+
 }  // namespace
 
 struct crt_ctx {
@@ -104,6 +106,19 @@ struct crt_ctx {
     DevBuf<double> score, score1, rmsd, tm, xform;
     DevBuf<float> f32tmp;
     double phase_ms[4] = {0, 0, 0, 0};      // fill1, trace, rows2, fill2 (only meaningful with one stream)
+
+    // plan cache of the all-vs-all shard: the unit list, batches and device copy depend only on the chain lengths
+    struct PlanCache {
+        bool valid = false;
+        unsigned long long offsets_hash = 0;
+        int rank = -1, world = -1, prec = -1, ns = -1;
+        size_t budget = 0;
+        std::vector<Batch> batches;
+        std::vector<Unit> hu;
+        long long n_pairs = 0;
+        double cells = 0;
+    } plan;
+    unsigned long long offsets_hash = 0;
 
     // last run
     long long run_pairs = 0;
@@ -332,9 +347,8 @@ int launch_trace(int C, const TraceArgs &ta, int nu, cudaStream_t st)
     return 0;
 }
 
-struct Batch { size_t first, count; int C, multi; size_t tb_n, rows2_n, bnd_n, path_n; };
-
-int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, long long n_pairs, PathSink *sink)
+int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, long long n_pairs, PathSink *sink,
+              bool use_cached_plan = false, bool store_plan = false)
 {
     const int prec = prm->precision;
     const bool f32 = prec == CRT_FP32;
@@ -356,6 +370,12 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     if ((rc = c->xform.ensure(((size_t)n_pairs + 1) * XF))) return rc;
     if (want_paths) { sink->a1.assign((size_t)n_pairs, {}); sink->a2.assign((size_t)n_pairs, {}); }
 
+    std::vector<Batch> batches;
+    std::vector<Unit> hu;
+    if (use_cached_plan) {
+        batches = c->plan.batches;
+        hu = c->plan.hu;
+    } else {
     // group by kernel variant so that each launch is homogeneous; inside a group keep the (j, i0) order
     std::stable_sort(units.begin(), units.end(), [](const HostUnit &a, const HostUnit &b) {
         if (a.multi != b.multi) return a.multi < b.multi;
@@ -371,8 +391,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     for (auto &h : units) total_bytes += unit_bytes(h);
     size_t budget = env_budget();
     if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
-    std::vector<Batch> batches;
-    std::vector<Unit> hu(units.size());
+    hu.resize(units.size());
     size_t pos = 0;
     while (pos < units.size()) {
         Batch b{pos, 0, units[pos].C, units[pos].multi, 0, 0, 0, 0};
@@ -393,6 +412,8 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         batches.push_back(b);
         pos = end;
     }
+    if (store_plan) { c->plan.batches = batches; c->plan.hu = hu; }
+    }
     // ---- size the workspaces once (no allocation inside the timed region after the first run of a shape)
     for (int w = 0; w < NS; ++w) {
         crt_ctx::Workspace &ws = c->ws[w];
@@ -412,7 +433,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     c->last_streams = NS;
     for (int k = 0; k < 4; ++k) c->phase_ms[k] = 0;
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(cudaMemcpyAsync(c->d_units.p, hu.data(), sizeof(Unit) * hu.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!use_cached_plan) CU(cudaMemcpyAsync(c->d_units.p, hu.data(), sizeof(Unit) * hu.size(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
     for (int w = 0; w < NS; ++w) CU(cudaStreamWaitEvent(c->ws[w].stream, c->ev1, 0));
 
@@ -635,6 +656,12 @@ int crt_set_chains(crt_ctx *c, const double *coords, const double *tensors, cons
     CU(cudaMemcpyAsync(c->d_offsets.p, c->offsets.data(), sizeof(long long) * ((size_t)n_chains + 1), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->chain_of.p, chain_of.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));     // chain_of is a local vector
+    {
+        unsigned long long h = 1469598103934665603ull;
+        for (int p = 0; p <= n_chains; ++p) { h ^= (unsigned long long)offsets[p]; h *= 1099511628211ull; }
+        h ^= (unsigned long long)D; h *= 1099511628211ull;
+        c->offsets_hash = h;
+    }
     c->N = n_chains; c->d = d; c->D = D; c->total = total; c->max_len = max_len;
     c->prep_gamma_t = c->prep_gamma_c = -1;
     return 0;
@@ -676,13 +703,29 @@ int crt_pairwise_shard(crt_ctx *c, const crt_params *prm, int32_t rank, int32_t 
     if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world %d/%d", rank, world);
     CU(cudaSetDevice(c->device));
     if ((rc = ensure_prepared(c, prm))) return rc;
+    const int ns = env_streams();
+    const size_t budget = env_budget();
+    crt_ctx::PlanCache &pc = c->plan;
+    if (pc.valid && pc.offsets_hash == c->offsets_hash && pc.rank == rank && pc.world == world && pc.prec == prm->precision &&
+        pc.ns == ns && pc.budget == budget) {
+        std::vector<HostUnit> none;
+        c->cell_updates = pc.cells;
+        if (pc.n_pairs == 0) { c->run_pairs = 0; c->elapsed_ms = 0; c->launches = 0; return 0; }
+        return run_units(c, prm, none, pc.n_pairs, nullptr, true, false);
+    }
     std::vector<HostUnit> units;
     build_all_units(c, prm->precision, units);
     shard_units(units, rank, world);
     long long np = 0;
     assign_pairs(units, &c->run_pi, &c->run_pj, &np, &c->cell_updates, c);
+    pc.valid = false;
     if (np == 0) { c->run_pairs = 0; c->elapsed_ms = 0; c->launches = 0; return 0; }
-    return run_units(c, prm, units, np, nullptr);
+    rc = run_units(c, prm, units, np, nullptr, false, true);
+    if (rc == 0) {
+        pc.valid = true; pc.offsets_hash = c->offsets_hash; pc.rank = rank; pc.world = world; pc.prec = prm->precision;
+        pc.ns = ns; pc.budget = budget; pc.n_pairs = np; pc.cells = c->cell_updates;
+    }
+    return rc;
 }
 
 int64_t crt_shard_size(crt_ctx *c, int32_t rank, int32_t world)
@@ -881,6 +924,7 @@ int crt_pairwise_list(crt_ctx *c, const crt_params *prm, const int32_t *pair_i, 
     c->run_pi.clear(); c->run_pj.clear();
     PathSink sink;
     sink.want = want_paths;
+    c->plan.valid = false;
     if ((rc = run_units(c, prm, units, slot, &sink))) return rc;
     const size_t np = (size_t)slot;
     std::vector<double> s(np), r(np), t(np);

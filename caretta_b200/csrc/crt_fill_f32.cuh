@@ -52,32 +52,38 @@ struct Fill1Args {
 // Software pipeline inside one basic block per step: the serial max/add chain of row t runs while the independent
 // FFMA2 work of row t+1 is issued, and the record of row t+2 is in flight.
 // ------------------------------------------------------------------------------------------------------------
+// Shared-memory ring row: the RS floats of the record, the row meta (int bits) at [RS], padded to RS + 8 floats.
+// The stride (80 B for d <= 10, 112 B for d <= 16) keeps the lanes' 128-bit LDS of consecutive rows on distinct banks.
 template <int NP, int RS>
-__device__ __forceinline__ void load_row1(const float *srow, const int *smeta, int slot, float2 (&row)[NP], int &meta)
+__device__ __forceinline__ void load_row1(const float *ring_row, float2 (&row)[NP], int &meta)
 {
-    const float4 *p4 = reinterpret_cast<const float4 *>(srow + slot * RS);
+    const float4 *p4 = reinterpret_cast<const float4 *>(ring_row);
 #pragma unroll
     for (int k = 0; k < NP / 2; ++k) {
         const float4 v = p4[k];
         row[2 * k] = make_float2(v.x, v.y);
         row[2 * k + 1] = make_float2(v.z, v.w);
     }
-    if (NP & 1) row[NP - 1] = reinterpret_cast<const float2 *>(srow + slot * RS)[NP - 1];
-    meta = smeta[slot];
+    if (NP & 1) row[NP - 1] = reinterpret_cast<const float2 *>(ring_row)[NP - 1];
+    meta = __float_as_int(ring_row[RS]);
 }
 
 // Ring addressing: stream row g lives at ring row rr = g + RING_OFF, slot rr % 96.  Block B = ring rows [32B, 32B+32).
 // With RING_OFF = 30 the loads of the window of steps [t0, t0+32) (row t+2-lane at step t) touch only blocks t0/32 and
 // t0/32+1, so block t0/32+2 can be in flight during the whole window.
 template <int RS>
-__device__ __forceinline__ void stage_block1(float *srow, int *smeta, const float *rec_unit, const int *meta_unit, int B, int lane)
+__device__ __forceinline__ void stage_block1(float *srow, const float *rec_unit, const int *meta_unit, int B, int lane)
 {
+    constexpr int SROW = RS + 8;
     const int slot0 = (B % 3) * 32;
     const float *src = rec_unit + (long long)(32 * B - RING_OFF) * RS;  // record of stream row g = 32B - RING_OFF
-    constexpr int CHUNKS = 32 * RS / 4;                                 // 16-byte chunks in a block
+    constexpr int CPR = RS / 4;                                         // 16-byte chunks per record
 #pragma unroll
-    for (int q = lane; q < CHUNKS; q += 32) cp_async16(srow + slot0 * RS + q * 4, src + q * 4);
-    cp_async4(smeta + slot0 + lane, meta_unit + (32 * B - RING_OFF) + lane);
+    for (int q = lane; q < 32 * CPR; q += 32) {
+        const int row = q / CPR, part = q - row * CPR;
+        cp_async16(srow + (slot0 + row) * SROW + part * 4, src + q * 4);
+    }
+    cp_async4(srow + (slot0 + lane) * SROW + RS, meta_unit + (32 * B - RING_OFF) + lane);
     cp_async_commit();
 }
 
@@ -138,15 +144,16 @@ __global__ void __launch_bounds__(32, CRT_FILL1_MINB) k_fill1_f32(const Unit *__
         uint4 *tbp = out.tb + u.tb_base + (long long)strip * u.tchunks * 32 + lane;
         const float *rec_unit = args.rec + u.row_base * RS;          // record of stream row g is rec_unit + g*RS
         const int *meta_unit = args.meta + u.row_base;
-        __shared__ __align__(16) float srow[RING * RS];
-        __shared__ int smeta[RING];
+        constexpr int SROW = RS + 8;
+        __shared__ __align__(16) float srow[RING * SROW];
         __syncwarp();
-        stage_block1<RS>(srow, smeta, rec_unit, meta_unit, 0, lane);
-        stage_block1<RS>(srow, smeta, rec_unit, meta_unit, 1, lane);
+        stage_block1<RS>(srow, rec_unit, meta_unit, 0, lane);
+        stage_block1<RS>(srow, rec_unit, meta_unit, 1, lane);
         cp_async_wait_all();
         __syncwarp();
-        stage_block1<RS>(srow, smeta, rec_unit, meta_unit, 2, lane);
-        int slot = RING_OFF + 2 - lane;      // ring slot of the row loaded at step t = 0 (stream row 2 - lane)
+        stage_block1<RS>(srow, rec_unit, meta_unit, 2, lane);
+        // float offset in the ring of the row fetched at the end of step t (stream row t + 2 - lane): starts at slot 32 - lane
+        int roff = (RING_OFF + 2 - lane) * SROW;
 
         float s_cur[C];
         float2 row_nxt[NP];
@@ -154,9 +161,9 @@ __global__ void __launch_bounds__(32, CRT_FILL1_MINB) k_fill1_f32(const Unit *__
         {
             float2 row0[NP];
             // rows -lane and 1-lane (pipeline fill; lane 31's row -31 is clamped to ring row 0, any record will do)
-            load_row1<NP, RS>(srow, smeta, max(slot - 2, 0), row0, meta_cur);
+            load_row1<NP, RS>(srow + max(roff - 2 * SROW, 0), row0, meta_cur);
             rbf_row1<NP, C>(row0, col, s_cur);
-            load_row1<NP, RS>(srow, smeta, slot - 1, row_nxt, meta_nxt);
+            load_row1<NP, RS>(srow + roff - SROW, row_nxt, meta_nxt);
         }
 
         for (int t0 = 0; t0 < steps4; t0 += 4) {
@@ -169,12 +176,8 @@ __global__ void __launch_bounds__(32, CRT_FILL1_MINB) k_fill1_f32(const Unit *__
                     // rows of block t0/32 + 1 must have landed; refill the slot whose rows nobody needs any more
                     cp_async_wait_all();
                     __syncwarp();
-                    stage_block1<RS>(srow, smeta, rec_unit, meta_unit, (t0 >> 5) + 2, lane);
+                    stage_block1<RS>(srow, rec_unit, meta_unit, (t0 >> 5) + 2, lane);
                 }
-                float2 row_ld[NP];
-                int meta_ld;
-                load_row1<NP, RS>(srow, smeta, slot, row_ld, meta_ld);
-                slot = (slot == RING - 1) ? 0 : slot + 1;
                 float a = __shfl_up_sync(FULL, carry, 1);
                 if (lane == 0) {
                     a = 0.f;
@@ -216,9 +219,9 @@ __global__ void __launch_bounds__(32, CRT_FILL1_MINB) k_fill1_f32(const Unit *__
                 if (a > 0.f) istar = r;              // last row whose H[i][m] exceeds H[i-1][m] (meaningful on lane 31)
                 w[q] = word;
                 if (MULTI && !last_strip && lane == 31 && (unsigned)g < (unsigned)G) bnd[g] = carry;
-                meta_prev = meta_cur; meta_cur = meta_nxt; meta_nxt = meta_ld;
-#pragma unroll
-                for (int k = 0; k < NP; ++k) row_nxt[k] = row_ld[k];
+                meta_prev = meta_cur; meta_cur = meta_nxt;
+                load_row1<NP, RS>(srow + roff, row_nxt, meta_nxt);      // row t + 2 - lane, consumed by the next step's rbf
+                roff = (roff == (RING - 1) * SROW) ? 0 : roff + SROW;
             }
             tbp[(long long)(t0 >> 2) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
         }

@@ -418,18 +418,29 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_u
     short2 *path = a.path + u.path_base + (long long)tid * u.path_stride;
     constexpr int SW = 32 * C;
 
-    long long cidx = -1;
-    uint4 cw = make_uint4(0, 0, 0, 0);
-    auto code = [&](int i, int j) -> unsigned {           // 1-based cell -> (nA << 1) | nB
+    // Position of the walk in the traceback layout, kept incrementally (no divisions in the loop): cell (i, j) 1-based
+    // -> strip, lane l, column k inside the lane, unit row trow = g0 + i - 1; chunk = (trow + l) >> 2.
+    const uint4 *tbu = a.tb + u.tb_base;
+    int w_strip = 0, w_l = 0, w_k = 0, w_trow = 0;
+    auto seek = [&](int i, int j) {
         const int c = j - 1;
-        const int strip = c / SW, cc = c - strip * SW;
-        const int l = cc / C, k = cc - l * C;
-        const int t = g0 + (i - 1) + l;
-        const long long idx = u.tb_base + ((long long)strip * u.tchunks + (t >> 2)) * 32 + l;
-        if (idx != cidx) { cw = a.tb[idx]; cidx = idx; }
+        w_strip = c / SW;
+        const int cc = c - w_strip * SW;
+        w_l = cc / C; w_k = cc - w_l * C;
+        w_trow = g0 + i - 1;
+    };
+    auto col_left = [&]() {
+        if (--w_k < 0) { w_k = C - 1; if (--w_l < 0) { w_l = 31; --w_strip; } }
+    };
+    int cidx = -1;
+    uint4 cw = make_uint4(0, 0, 0, 0);
+    auto code = [&]() -> unsigned {                       // (nA << 1) | nB of the current cell
+        const int t = w_trow + w_l;
+        const int idx = (w_strip * u.tchunks + (t >> 2)) * 32 + w_l;
+        if (idx != cidx) { cw = tbu[idx]; cidx = idx; }
         const int q = t & 3;
         const unsigned w = q == 0 ? cw.x : (q == 1 ? cw.y : (q == 2 ? cw.z : cw.w));
-        return (w >> (2 * (C - 1 - k))) & 3u;
+        return (w >> (2 * (C - 1 - w_k))) & 3u;
     };
 
     // exact stop-state emulation: H[i][j] == 0 iff every S in [1..i] x [1..j] is 0; only possible when S[1][1] == 0
@@ -452,12 +463,13 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_u
     if (i <= 0) {
         st |= 2;                      // CRT_ST_NO_POSITIVE
     } else {
-        while (j > 1 && (code(i, j) & 1u) == 0u) --j;      // first column of row i* that attains the maximum
+        seek(i, j);
+        while (j > 1 && (code() & 1u) == 0u) { --j; col_left(); }      // first column of row i* that attains the maximum
         while (i > 0 && j > 0) {
             if (zreg && is_zero_cell(i, j)) break;
-            const unsigned cd = code(i, j);
+            const unsigned cd = code();
             if ((cd & 2u) == 0u) {
-                --i; --j;
+                --i; --j; --w_trow; col_left();
                 path[len++] = make_short2((short)i, (short)j);
                 ++c;
                 const double x1 = A[i * 3] - ca0, y1 = A[i * 3 + 1] - ca1, z1 = A[i * 3 + 2] - ca2;
@@ -467,10 +479,10 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_u
                 cyx += y2 * x1; cyy += y2 * y1; cyz += y2 * z1;
                 czx += z2 * x1; czy += z2 * y1; czz += z2 * z1;
             } else if ((cd & 1u) == 0u) {
-                --j;
+                --j; col_left();
                 path[len++] = make_short2((short)-1, (short)j);
             } else {
-                --i;
+                --i; --w_trow;
                 path[len++] = make_short2((short)i, (short)-1);
             }
         }
