@@ -3,6 +3,7 @@
 #include "../../include/caretta_b200.h"
 #include "crt_kernels.cuh"
 #include "crt_fill_f32.cuh"
+#include "crt_fill1_v2.cuh"
 #include "crt_dp_batch.cuh"
 
 #include <algorithm>
@@ -177,14 +178,20 @@ int launch_fill_c(int C, bool multi, const Unit *units, int n, typename P::Args 
     return 0;
 }
 
+// stage-1 fp32 kernel: k_fill1_v2 (two columns per packed FMA); -DCRT_FILL1_V1 selects the first schedule for A/B runs
+#ifdef CRT_FILL1_V1
+#define CRT_FILL1_KERNEL k_fill1_f32
+#else
+#define CRT_FILL1_KERNEL k_fill1_v2
+#endif
 template <int D>
 int launch_fill1_f32(int C, bool multi, const Unit *units, int n, Fill1Args args, FillOut out, cudaStream_t st)
 {
 #define CRT_CASE(CC)                                                                         \
     case CC:                                                                                 \
         if constexpr (CC * D <= 100) {                                                       \
-            if (multi) k_fill1_f32<D, CC, true><<<n, 32, 0, st>>>(units, n, args, out);       \
-            else k_fill1_f32<D, CC, false><<<n, 32, 0, st>>>(units, n, args, out);           \
+            if (multi) CRT_FILL1_KERNEL<D, CC, true><<<n, 32, 0, st>>>(units, n, args, out);  \
+            else CRT_FILL1_KERNEL<D, CC, false><<<n, 32, 0, st>>>(units, n, args, out);      \
             break;                                                                           \
         } else return fail(CRT_E_ARG, "no fp32 stage-1 kernel for C=%d D=%d", C, D);
     switch (C) {
