@@ -65,7 +65,7 @@ struct HostUnit {
     double cost;    // G * m
 };
 
-struct Batch { size_t first, count; int C, multi; size_t tb_n, rows2_n, bnd_n, path_n; };
+struct Batch { size_t first, count; int C, multi; size_t tb_n, rows2_n, bnd_n, path_n; int n_dense; };
 
 }  // namespace
 
@@ -96,9 +96,13 @@ struct crt_ctx {
         cudaEvent_t done = nullptr;
         cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};      // serial mode: phase boundaries of the last batch
         DevBuf<uint4> tb;
-        DevBuf<unsigned char> rows2, bnd;
-        DevBuf<short2> path;
+        DevBuf<unsigned char> rows2, bnd, bnd2;      // bnd: stage-1 strip boundaries, bnd2: stage-2 (the two fills of
+        DevBuf<short2> path;                         // different batches run concurrently in pipeline mode)
+        cudaEvent_t e_f1 = nullptr, e_t = nullptr, e_f2 = nullptr;   // pipeline mode: stage completion of the last batch here
     };
+    // pipeline mode: one stream per stage, so that stage 1 of batch k+1, the traceback of batch k and stage 2 of
+    // batch k-1 are resident together (the light stage-2 and traceback warps fill the registers stage 1 leaves free)
+    cudaStream_t s_f1 = nullptr, s_tr = nullptr, s_f2 = nullptr;
     static constexpr int MAX_WS = 4;
     Workspace ws[MAX_WS];
     int n_streams = 3;
@@ -226,9 +230,21 @@ int pad_dim(int d)
     return -1;
 }
 
+bool env_pipe();
+int env_batches();
+int env_streams();
+size_t env_budget();
+
 // ---------------------------------------------------------------------------------------------- unit building
 constexpr int MAX_PAIRS_PER_UNIT = 32;
-constexpr int TARGET_ROWS_PER_UNIT = 6144;
+// rows streamed by one unit (tuning knob CARETTA_B200_UNIT_ROWS): longer units amortise the 31-step pipeline drain,
+// shorter units shorten the tail of a launch
+int env_unit_rows()
+{
+    const char *e = getenv("CARETTA_B200_UNIT_ROWS");
+    int n = e ? atoi(e) : 6144;
+    return std::min(std::max(n, 64), 1 << 20);
+}
 
 void finish_unit(const crt_ctx *c, HostUnit &h, int precision)
 {
@@ -244,6 +260,7 @@ void finish_unit(const crt_ctx *c, HostUnit &h, int precision)
 // all-vs-all units in a deterministic order: column chain j ascending, runs of row chains ascending
 void build_all_units(const crt_ctx *c, int precision, std::vector<HostUnit> &out)
 {
+    const int TARGET_ROWS_PER_UNIT = env_unit_rows();
     out.clear();
     for (int j = 1; j < c->N; ++j) {
         int i = 0;
@@ -337,17 +354,31 @@ int env_streams()
     return std::min(std::max(n, 1), (int)crt_ctx::MAX_WS);
 }
 
-template <int CMAXT>
-int launch_trace(int C, const TraceArgs &ta, int nu, cudaStream_t st)
+// CARETTA_B200_PIPE=0 selects the older "one stream per batch" schedule (A/B runs); default is the stage pipeline
+bool env_pipe()
 {
-    const int grid = (nu + TRACE_WARPS - 1) / TRACE_WARPS;
+    const char *e = getenv("CARETTA_B200_PIPE");
+    return e ? atoi(e) != 0 : true;
+}
+
+int env_batches()
+{
+    const char *e = getenv("CARETTA_B200_BATCHES");
+    int n = e ? atoi(e) : 8;
+    return std::min(std::max(n, 1), 256);
+}
+
+template <int CMAXT>
+int launch_trace(int C, const TraceArgs &ta, int nu, int n_dense, cudaStream_t st)
+{
+    const int grid = (n_dense + TRACE_THREADS - 1) / TRACE_THREADS;
     switch (C) {
-    case 2: k_trace<2><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
-    case 3: k_trace<3><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
-    case 4: k_trace<4><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
-    case 6: k_trace<6><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
-    case 8: k_trace<8><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
-    case 10: k_trace<10><<<grid, TRACE_WARPS * 32, 0, st>>>(ta, nu); break;
+    case 2: k_trace<2><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
+    case 3: k_trace<3><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
+    case 4: k_trace<4><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
+    case 6: k_trace<6><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
+    case 8: k_trace<8><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
+    case 10: k_trace<10><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
     default: return fail(CRT_E_ARG, "no trace kernel for C=%d", C);
     }
     CU(cudaGetLastError());
@@ -364,6 +395,8 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     const int rs32 = ((c->D + 2 + 3) / 4) * 4;
     const bool want_paths = sink && sink->want;
     const int NS = want_paths ? 1 : env_streams();
+    const bool pipe = !want_paths && NS > 1 && env_pipe();
+    const int NW = pipe ? 3 : NS;                 // workspace sets in flight
     int rc;
     if ((rc = c->score.ensure((size_t)n_pairs + 1))) return rc;
     if ((rc = c->score1.ensure((size_t)n_pairs + 1))) return rc;
@@ -389,7 +422,8 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         return a.C < b.C;
     });
 
-    // ---- carve batches: same (C, multi), bounded workspace; aim for at least 2 batches per stream
+    // ---- carve batches: same (C, multi), bounded workspace; pipeline mode aims at env_batches() batches, the
+    //      stream-per-batch mode at two batches per stream
     size_t total_bytes = 0;
     auto unit_bytes = [&](const HostUnit &h) {
         return (size_t)h.u.n_strips * h.u.tchunks * 32 * 16 + (size_t)h.u.G * row2sz + (size_t)h.u.n_pairs * h.u.path_stride * 4 +
@@ -397,11 +431,12 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     };
     for (auto &h : units) total_bytes += unit_bytes(h);
     size_t budget = env_budget();
-    if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
+    if (pipe) budget = std::min(budget, std::max<size_t>(total_bytes / env_batches() + 1, (size_t)64 << 20));
+    else if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
     hu.resize(units.size());
     size_t pos = 0;
     while (pos < units.size()) {
-        Batch b{pos, 0, units[pos].C, units[pos].multi, 0, 0, 0, 0};
+        Batch b{pos, 0, units[pos].C, units[pos].multi, 0, 0, 0, 0, 0};
         size_t end = pos;
         while (end < units.size() && units[end].C == b.C && units[end].multi == b.multi) {
             HostUnit &h = units[end];
@@ -411,6 +446,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             if (end > pos && bytes > budget) break;
             h.u.tb_base = (long long)b.tb_n; h.u.rows2_base = (long long)b.rows2_n;
             h.u.path_base = (long long)b.path_n; h.u.bnd_base = (long long)b.bnd_n;
+            h.u.dense_base = b.n_dense; b.n_dense += h.u.n_pairs;
             b.tb_n += tb_u; b.rows2_n += rows_u; b.path_n += path_u; b.bnd_n += bnd_u;
             hu[end] = h.u;
             ++end;
@@ -422,10 +458,10 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     if (store_plan) { c->plan.batches = batches; c->plan.hu = hu; }
     }
     // ---- size the workspaces once (no allocation inside the timed region after the first run of a shape)
-    for (int w = 0; w < NS; ++w) {
+    for (int w = 0; w < NW; ++w) {
         crt_ctx::Workspace &ws = c->ws[w];
         size_t tb_n = 0, rows2_n = 0, bnd_n = 0, path_n = 0;
-        for (size_t k = w; k < batches.size(); k += NS) {
+        for (size_t k = w; k < batches.size(); k += NW) {
             tb_n = std::max(tb_n, batches[k].tb_n); rows2_n = std::max(rows2_n, batches[k].rows2_n);
             bnd_n = std::max(bnd_n, batches[k].bnd_n); path_n = std::max(path_n, batches[k].path_n);
         }
@@ -433,6 +469,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         if ((rc = ws.rows2.ensure((rows2_n + 2 * ROW_PAD) * row2sz))) return rc;
         if ((rc = ws.path.ensure(path_n + 1))) return rc;
         if ((rc = ws.bnd.ensure(bnd_n * tsz + 16))) return rc;
+        if ((rc = ws.bnd2.ensure(bnd_n * tsz + 16))) return rc;
     }
     if ((rc = c->d_units.ensure(hu.size()))) return rc;
 
@@ -442,31 +479,27 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     CU(cudaEventRecord(c->ev0, c->stream));
     if (!use_cached_plan) CU(cudaMemcpyAsync(c->d_units.p, hu.data(), sizeof(Unit) * hu.size(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
-    for (int w = 0; w < NS; ++w) CU(cudaStreamWaitEvent(c->ws[w].stream, c->ev1, 0));
 
-    for (size_t bi = 0; bi < batches.size(); ++bi) {
-        const Batch &b = batches[bi];
-        crt_ctx::Workspace &ws = c->ws[bi % NS];
-        cudaStream_t st = ws.stream;
+    // ---- the three stages of one batch
+    auto stage1 = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st) -> int {
         const Unit *du = c->d_units.p + b.first;
         const int nu = (int)b.count;
-        const bool timed = NS == 1;
         FillOut fo{};
         fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
         fo.pair_score = c->score1.p; fo.bnd = ws.bnd.p;
-        if (timed) CU(cudaEventRecord(ws.ev[0], st));
-        // ---- stage 1
         if (f32) {
             Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
-            if (c->D == 10) rc = launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, st);
-            else rc = launch_fill1_f32<16>(b.C, b.multi, du, nu, a, fo, st);
-        } else {
-            if (c->D == 10) { P1F64<10>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; rc = launch_fill_c<P1F64<10>, false, true, 4>(b.C, b.multi, du, nu, a, fo, st); }
-            else { P1F64<16>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; rc = launch_fill_c<P1F64<16>, false, true, 3>(b.C, b.multi, du, nu, a, fo, st); }
+            if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, st);
+            return launch_fill1_f32<16>(b.C, b.multi, du, nu, a, fo, st);
         }
-        if (rc) return rc;
-        if (timed) CU(cudaEventRecord(ws.ev[1], st));
-        // ---- traceback + Kabsch, then the stage-2 row records
+        if (c->D == 10) { P1F64<10>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; return launch_fill_c<P1F64<10>, false, true, 4>(b.C, b.multi, du, nu, a, fo, st); }
+        P1F64<16>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor};
+        return launch_fill_c<P1F64<16>, false, true, 3>(b.C, b.multi, du, nu, a, fo, st);
+    };
+    // traceback + Kabsch, then the stage-2 row records
+    auto stage_trace = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st, cudaEvent_t mid) -> int {
+        const Unit *du = c->d_units.p + b.first;
+        const int nu = (int)b.count;
         TraceArgs ta{};
         ta.units = du; ta.tb = ws.tb.p; ta.pair_istar = c->pair_istar.p; ta.pair_zflag = c->pair_zflag.p;
         ta.offsets = c->d_offsets.p; ta.coords = c->coords.p; ta.centroid = c->centroid.p;
@@ -477,20 +510,96 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         ta.rec64 = c->rec64.p; ta.d64 = c->D; ta.neg_gamma_t = -prm->gamma_tensor;
         ta.scale2 = (float)std::sqrt(prm->gamma_coords * 1.4426950408889634);
         ta.precision = prec;
-        if ((rc = launch_trace<10>(b.C, ta, nu, st))) return rc;
-        if (timed) CU(cudaEventRecord(ws.ev[2], st));
+        int r2;
+        if ((r2 = launch_trace<10>(b.C, ta, nu, b.n_dense, st))) return r2;
+        if (mid) CU(cudaEventRecord(mid, st));
         k_rows2<<<nu, 256, 0, st>>>(ta, nu);
         CU(cudaGetLastError());
-        // ---- stage 2
-        fo.pair_score = c->score.p;
+        return 0;
+    };
+    auto stage2 = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st) -> int {
+        const Unit *du = c->d_units.p + b.first;
+        const int nu = (int)b.count;
+        FillOut fo{};
+        fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
+        fo.pair_score = c->score.p; fo.bnd = pipe ? ws.bnd2.p : ws.bnd.p;
         if (f32) {
             Fill2Args a{reinterpret_cast<const float4 *>(ws.rows2.p) + ROW_PAD, c->cols2.p};
-            rc = launch_fill2_f32(b.C, b.multi, du, nu, a, fo, st);
-        } else {
-            P2F64::Args a{reinterpret_cast<const double *>(ws.rows2.p) + (size_t)ROW_PAD * 4, c->coords.p, -prm->gamma_coords};
-            rc = launch_fill_c<P2F64, false, false, 4>(b.C, b.multi, du, nu, a, fo, st);
+            return launch_fill2_f32(b.C, b.multi, du, nu, a, fo, st);
         }
-        if (rc) return rc;
+        P2F64::Args a{reinterpret_cast<const double *>(ws.rows2.p) + (size_t)ROW_PAD * 4, c->coords.p, -prm->gamma_coords};
+        return launch_fill_c<P2F64, false, false, 4>(b.C, b.multi, du, nu, a, fo, st);
+    };
+
+    if (pipe) {
+        // ---- stage pipeline: s_f1 runs the stage-1 fills back to back, s_tr (high priority) the tracebacks, s_f2 the
+        //      stage-2 fills.  Workspace set w = k % NW is reused by batch k + NW:
+        //        fill1(k)  needs tb[w] consumed            -> waits for trace(k - NW)
+        //        trace(k)  needs fill1(k), rows2/path free  -> waits for fill1(k), fill2(k - NW)
+        //        fill2(k)  needs trace(k)
+        CU(cudaStreamWaitEvent(c->s_f1, c->ev1, 0));
+        CU(cudaStreamWaitEvent(c->s_tr, c->ev1, 0));
+        CU(cudaStreamWaitEvent(c->s_f2, c->ev1, 0));
+        // CARETTA_B200_TIMELINE=1: bracket every kernel with timing events and print the schedule (debug)
+        const bool timeline = getenv("CARETTA_B200_TIMELINE") && atoi(getenv("CARETTA_B200_TIMELINE")) != 0;
+        struct Mark { const char *what; size_t batch; cudaEvent_t e0, e1; };
+        std::vector<Mark> marks;
+        auto mark0 = [&](const char *what, size_t bi, cudaStream_t st) {
+            if (!timeline) return;
+            Mark mk{what, bi, nullptr, nullptr};
+            cudaEventCreate(&mk.e0); cudaEventCreate(&mk.e1);
+            cudaEventRecord(mk.e0, st);
+            marks.push_back(mk);
+        };
+        auto mark1 = [&](cudaStream_t st) { if (timeline) cudaEventRecord(marks.back().e1, st); };
+        for (size_t bi = 0; bi < batches.size(); ++bi) {
+            const Batch &b = batches[bi];
+            crt_ctx::Workspace &ws = c->ws[bi % NW];
+            if (bi >= (size_t)NW) CU(cudaStreamWaitEvent(c->s_f1, ws.e_t, 0));
+            mark0("fill1", bi, c->s_f1);
+            if ((rc = stage1(b, ws, c->s_f1))) return rc;
+            mark1(c->s_f1);
+            CU(cudaEventRecord(ws.e_f1, c->s_f1));
+            CU(cudaStreamWaitEvent(c->s_tr, ws.e_f1, 0));
+            if (bi >= (size_t)NW) CU(cudaStreamWaitEvent(c->s_tr, ws.e_f2, 0));
+            mark0("trace", bi, c->s_tr);
+            if ((rc = stage_trace(b, ws, c->s_tr, nullptr))) return rc;
+            mark1(c->s_tr);
+            CU(cudaEventRecord(ws.e_t, c->s_tr));
+            CU(cudaStreamWaitEvent(c->s_f2, ws.e_t, 0));
+            mark0("fill2", bi, c->s_f2);
+            if ((rc = stage2(b, ws, c->s_f2))) return rc;
+            mark1(c->s_f2);
+            CU(cudaEventRecord(ws.e_f2, c->s_f2));
+            c->launches += 4;
+        }
+        if (timeline) {
+            CU(cudaDeviceSynchronize());
+            for (auto &mk : marks) {
+                float t0 = 0, t1 = 0;
+                cudaEventElapsedTime(&t0, c->ev0, mk.e0); cudaEventElapsedTime(&t1, c->ev0, mk.e1);
+                fprintf(stderr, "[timeline] %-6s batch %2zu  %8.3f -> %8.3f ms  (%7.3f)\n", mk.what, mk.batch, t0, t1, t1 - t0);
+                cudaEventDestroy(mk.e0); cudaEventDestroy(mk.e1);
+            }
+        }
+        CU(cudaEventRecord(c->ws[0].done, c->s_f2));          // the last fill2 is the last kernel of the run
+        CU(cudaStreamWaitEvent(c->stream, c->ws[0].done, 0));
+        CU(cudaEventRecord(c->ws[1].done, c->s_tr));
+        CU(cudaStreamWaitEvent(c->stream, c->ws[1].done, 0));
+        CU(cudaEventRecord(c->ws[2].done, c->s_f1));
+        CU(cudaStreamWaitEvent(c->stream, c->ws[2].done, 0));
+    } else {
+    for (int w = 0; w < NS; ++w) CU(cudaStreamWaitEvent(c->ws[w].stream, c->ev1, 0));
+    for (size_t bi = 0; bi < batches.size(); ++bi) {
+        const Batch &b = batches[bi];
+        crt_ctx::Workspace &ws = c->ws[bi % NS];
+        cudaStream_t st = ws.stream;
+        const bool timed = NS == 1;
+        if (timed) CU(cudaEventRecord(ws.ev[0], st));
+        if ((rc = stage1(b, ws, st))) return rc;
+        if (timed) CU(cudaEventRecord(ws.ev[1], st));
+        if ((rc = stage_trace(b, ws, st, timed ? ws.ev[2] : nullptr))) return rc;
+        if ((rc = stage2(b, ws, st))) return rc;
         if (timed) CU(cudaEventRecord(ws.ev[3], st));
         c->launches += 4;
 
@@ -525,6 +634,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     for (int w = 0; w < NS; ++w) {
         CU(cudaEventRecord(c->ws[w].done, c->ws[w].stream));
         CU(cudaStreamWaitEvent(c->stream, c->ws[w].done, 0));
+    }
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -579,7 +689,15 @@ int crt_create(int device, crt_ctx **out)
         CU(cudaStreamCreateWithFlags(&c->ws[w].stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ws[w].done, cudaEventDisableTiming));
         for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&c->ws[w].ev[k]));
+        CU(cudaEventCreateWithFlags(&c->ws[w].e_f1, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ws[w].e_t, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ws[w].e_f2, cudaEventDisableTiming));
     }
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&c->s_f1, cudaStreamNonBlocking, prio_lo));
+    CU(cudaStreamCreateWithPriority(&c->s_f2, cudaStreamNonBlocking, prio_lo));
+    CU(cudaStreamCreateWithPriority(&c->s_tr, cudaStreamNonBlocking, prio_hi));     // short latency-bound kernels go first
     *out = c;
     return 0;
 }
@@ -593,8 +711,11 @@ int crt_destroy(crt_ctx *c)
     c->chain_of.release(); c->meta.release(); c->rec32.release(); c->cols2.release(); c->d_units.release();
     for (int w = 0; w < crt_ctx::MAX_WS; ++w) {
         crt_ctx::Workspace &ws = c->ws[w];
-        ws.tb.release(); ws.rows2.release(); ws.bnd.release(); ws.path.release();
+        ws.tb.release(); ws.rows2.release(); ws.bnd.release(); ws.bnd2.release(); ws.path.release();
         if (ws.done) cudaEventDestroy(ws.done);
+        if (ws.e_f1) cudaEventDestroy(ws.e_f1);
+        if (ws.e_t) cudaEventDestroy(ws.e_t);
+        if (ws.e_f2) cudaEventDestroy(ws.e_f2);
         for (int k = 0; k < 4; ++k) if (ws.ev[k]) cudaEventDestroy(ws.ev[k]);
         if (ws.stream) cudaStreamDestroy(ws.stream);
     }
@@ -602,6 +723,9 @@ int crt_destroy(crt_ctx *c)
     c->pair_istar.release(); c->pair_zflag.release(); c->ncommon.release(); c->status.release();
     c->score.release(); c->score1.release(); c->rmsd.release(); c->tm.release(); c->f32tmp.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->s_f1) cudaStreamDestroy(c->s_f1);
+    if (c->s_f2) cudaStreamDestroy(c->s_f2);
+    if (c->s_tr) cudaStreamDestroy(c->s_tr);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -710,7 +834,7 @@ int crt_pairwise_shard(crt_ctx *c, const crt_params *prm, int32_t rank, int32_t 
     if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world %d/%d", rank, world);
     CU(cudaSetDevice(c->device));
     if ((rc = ensure_prepared(c, prm))) return rc;
-    const int ns = env_streams();
+    const int ns = env_streams() + 100 * (env_pipe() ? 1 : 0) + 1000 * env_batches() + 100000 * (env_unit_rows() / 64);
     const size_t budget = env_budget();
     crt_ctx::PlanCache &pc = c->plan;
     if (pc.valid && pc.offsets_hash == c->offsets_hash && pc.rank == rank && pc.world == world && pc.prec == prm->precision &&
@@ -916,7 +1040,7 @@ int crt_pairwise_list(crt_ctx *c, const crt_params *prm, const int32_t *pair_i, 
             if (cnt > 0 && ii == i + cnt - 1) { slot_of[(size_t)order[q]] = slot - 1; ++q; continue; }   // duplicate pair
             if (ii != i + cnt || cnt >= MAX_PAIRS_PER_UNIT) break;
             const int n = (int)(c->offsets[ii + 1] - c->offsets[ii]);
-            if (cnt > 0 && G + n > TARGET_ROWS_PER_UNIT) break;
+            if (cnt > 0 && G + n > env_unit_rows()) break;
             G += n; maxn = std::max(maxn, n);
             slot_of[(size_t)order[q]] = slot++;
             ++cnt; ++q;

@@ -40,6 +40,7 @@ struct Unit {
     int n_strips;          // ceil(m / (32*C))
     int path_stride;       // path entries reserved per pair
     int tchunks;           // 128-bit traceback chunks per lane per strip = ceil((G + 31) / 4)
+    int dense_base;        // pairs of the batch's earlier units (k_trace maps threads densely onto pairs)
 };
 
 // per-residue row meta: bit0 = first residue of its chain, bit1 = last, bits 2.. = chain index
@@ -403,17 +404,33 @@ __device__ inline bool s1_is_zero(const TraceArgs &a, long long ri, long long ci
     return exp(__dmul_rn(a.neg_gamma_t, acc)) == 0.0;
 }
 
-constexpr int TRACE_WARPS = 4;        // units per CTA of k_trace
+#ifndef CRT_TRACE_MINB
+#define CRT_TRACE_MINB 6
+#endif
+constexpr int TRACE_THREADS = 128;    // threads (= pairs) per CTA of k_trace
 constexpr int XF = 16;                // doubles per pair in the transform array: R[9], m1[3], m2[3], superpose flag
 
+__device__ __forceinline__ void prefetch_tb(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// One thread per pair, pairs mapped densely onto threads (Unit::dense_base is the batch-local prefix of n_pairs; the
+// thread finds its unit by bisection).  Three passes per pair:
+//   1. the walk: only the dependent chain  traceback word -> code -> next cell  and the path store; the words the walk
+//      will need next (one and two chunk rows up, same lane and the lane to the left) are prefetched when a new chunk
+//      is entered, so most dependent loads hit L1/L2 instead of HBM;
+//   2. Kabsch moments over the matched residues, read back from the path (independent loads, unrolled);
+//   3. the by-products (RMSD, TM) with the rotation applied.
 template <int C>
-__global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_units)
+__global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceArgs a, int n_units, int n_dense)
 {
-    const int uidx = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5);
-    if (uidx >= n_units) return;
-    const Unit u = a.units[uidx];
-    const int tid = threadIdx.x & 31;
-    if (tid >= u.n_pairs) return;
+    const int gid = blockIdx.x * TRACE_THREADS + threadIdx.x;
+    if (gid >= n_dense) return;
+    int lo = 0, hi = n_units - 1;             // last unit with dense_base <= gid
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.units[mid].dense_base <= gid) lo = mid; else hi = mid - 1;
+    }
+    const Unit u = a.units[lo];
+    const int tid = gid - u.dense_base;
     const int ci = u.row_chain0 + tid;
     const int pair = u.pair_base + tid;
     const long long ro = a.offsets[ci];
@@ -445,7 +462,13 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_u
     auto code = [&]() -> unsigned {                       // (nA << 1) | nB of the current cell
         const int t = w_trow + w_l;
         const int idx = (w_strip * u.tchunks + (t >> 2)) * 32 + w_l;
-        if (idx != cidx) { cw = tbu[idx]; cidx = idx; }
+        if (idx != cidx) {
+            cw = tbu[idx]; cidx = idx;
+            if ((t >> 2) >= 2) {                          // the walk moves up and to the left
+                prefetch_tb(tbu + idx - 64);
+                if (w_l > 0) { prefetch_tb(tbu + idx - 33); prefetch_tb(tbu + idx - 65); }
+            }
+        }
         const int q = t & 3;
         const unsigned w = q == 0 ? cw.x : (q == 1 ? cw.y : (q == 2 ? cw.z : cw.w));
         return (w >> (2 * (C - 1 - w_k))) & 3u;
@@ -462,16 +485,18 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_u
         return true;
     };
 
+    // ---- pass 1: the walk
     int i = a.pair_istar[pair], j = m;
     int st = 0, len = 0, c = 0;
-    // moments of the matched residues, relative to the chains' own centroids (translation does not change the
-    // covariance; it keeps the raw-moment form well conditioned)
-    double s1x = 0, s1y = 0, s1z = 0, s2x = 0, s2y = 0, s2z = 0;
-    double cxx = 0, cxy = 0, cxz = 0, cyx = 0, cyy = 0, cyz = 0, czx = 0, czy = 0, czz = 0;
     if (i <= 0) {
         st |= 2;                      // CRT_ST_NO_POSITIVE
     } else {
         seek(i, j);
+        {   // first chunk: also fetch the row above it (the general prefetch reaches two rows up)
+            const int t = w_trow + w_l;
+            const int idx = (w_strip * u.tchunks + (t >> 2)) * 32 + w_l;
+            if ((t >> 2) >= 1) { prefetch_tb(tbu + idx - 32); if (w_l > 0) prefetch_tb(tbu + idx - 33); }
+        }
         while (j > 1 && (code() & 1u) == 0u) { --j; col_left(); }      // first column of row i* that attains the maximum
         while (i > 0 && j > 0) {
             if (zreg && is_zero_cell(i, j)) break;
@@ -480,12 +505,6 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_u
                 --i; --j; --w_trow; col_left();
                 path[len++] = make_short2((short)i, (short)j);
                 ++c;
-                const double x1 = A[i * 3] - ca0, y1 = A[i * 3 + 1] - ca1, z1 = A[i * 3 + 2] - ca2;
-                const double x2 = B[j * 3] - cb0, y2 = B[j * 3 + 1] - cb1, z2 = B[j * 3 + 2] - cb2;
-                s1x += x1; s1y += y1; s1z += z1; s2x += x2; s2y += y2; s2z += z2;
-                cxx += x2 * x1; cxy += x2 * y1; cxz += x2 * z1;
-                cyx += y2 * x1; cyy += y2 * y1; cyz += y2 * z1;
-                czx += z2 * x1; czy += z2 * y1; czz += z2 * z1;
             } else if ((cd & 1u) == 0u) {
                 --j; col_left();
                 path[len++] = make_short2((short)-1, (short)j);
@@ -498,9 +517,27 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_u
     a.path_len[pair] = len;
     a.ncommon[pair] = c;
 
+    // ---- pass 2: moments of the matched residues, relative to the chains' own centroids (translation does not change
+    // the covariance; it keeps the raw-moment form well conditioned).  Same summation order as the walk (descending).
+    double s1x = 0, s1y = 0, s1z = 0, s2x = 0, s2y = 0, s2z = 0;
+    double cxx = 0, cxy = 0, cxz = 0, cyx = 0, cyy = 0, cyz = 0, czx = 0, czy = 0, czz = 0;
+    const bool superpose = c > 3;
+    if (superpose) {
+#pragma unroll 4
+        for (int q = 0; q < len; ++q) {
+            const short2 e = path[q];
+            if (e.x < 0 || e.y < 0) continue;
+            const double x1 = A[e.x * 3] - ca0, y1 = A[e.x * 3 + 1] - ca1, z1 = A[e.x * 3 + 2] - ca2;
+            const double x2 = B[e.y * 3] - cb0, y2 = B[e.y * 3 + 1] - cb1, z2 = B[e.y * 3 + 2] - cb2;
+            s1x += x1; s1y += y1; s1z += z1; s2x += x2; s2y += y2; s2z += z2;
+            cxx += x2 * x1; cxy += x2 * y1; cxz += x2 * z1;
+            cyx += y2 * x1; cyy += y2 * y1; cyz += y2 * z1;
+            czx += z2 * x1; czy += z2 * y1; czz += z2 * z1;
+        }
+    }
+
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
-    const bool superpose = c > 3;
     if (!superpose) st |= 1;          // CRT_ST_FEW_COMMON: multiple_alignment.py:337-342
     if (superpose) {
         const double inv = 1.0 / (double)c;
@@ -520,11 +557,12 @@ __global__ void __launch_bounds__(TRACE_WARPS * 32) k_trace(TraceArgs a, int n_u
     for (int q = 0; q < 9; ++q) xf[q] = R[q];
     for (int q = 0; q < 3; ++q) { xf[9 + q] = m1[q]; xf[12 + q] = m2[q]; }
     xf[15] = superpose ? 1.0 : 0.0;
-    // by-products over the matched residues, ascending residue order like the reference's sums
+    // ---- pass 3: by-products over the matched residues, ascending residue order like the reference's sums
     double rmsd = 0.0, tm = 0.0;
     if (c >= 1) {
         const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
         double ss = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll 2
         for (int q = len - 1; q >= 0; --q) {
             const short2 e = path[q];
             if (e.x < 0 || e.y < 0) continue;
