@@ -182,21 +182,16 @@ int launch_fill_c(int C, bool multi, const Unit *units, int n, typename P::Args 
     return 0;
 }
 
-// stage-1 fp32 kernel: k_fill1_v2 (two columns per packed FMA); -DCRT_FILL1_V1 selects the first schedule for A/B runs
-#ifdef CRT_FILL1_V1
-#define CRT_FILL1_KERNEL k_fill1_f32
-#else
-#define CRT_FILL1_KERNEL k_fill1_v2
-#endif
+// stage-1 fp32 kernel: k_fill1_v3 (two columns per packed FMA, fast/checked row groups)
 template <int D>
-int launch_fill1_f32(int C, bool multi, const Unit *units, int n, Fill1Args args, FillOut out, cudaStream_t st)
+int launch_fill1_f32(int C, bool multi, const Unit *units, int n, Fill1Args args, FillOut out, const long long *offsets, cudaStream_t st)
 {
-#define CRT_CASE(CC)                                                                         \
-    case CC:                                                                                 \
-        if constexpr (CC * D <= 100) {                                                       \
-            if (multi) CRT_FILL1_KERNEL<D, CC, true><<<n, 32, 0, st>>>(units, n, args, out);  \
-            else CRT_FILL1_KERNEL<D, CC, false><<<n, 32, 0, st>>>(units, n, args, out);      \
-            break;                                                                           \
+#define CRT_CASE(CC)                                                                                  \
+    case CC:                                                                                          \
+        if constexpr (CC * D <= 100) {                                                                \
+            if (multi) k_fill1_v3<D, CC, true><<<n, 32, 0, st>>>(units, n, args, out, offsets);        \
+            else k_fill1_v3<D, CC, false><<<n, 32, 0, st>>>(units, n, args, out, offsets);            \
+            break;                                                                                    \
         } else return fail(CRT_E_ARG, "no fp32 stage-1 kernel for C=%d D=%d", C, D);
     switch (C) {
         CRT_CASE(2) CRT_CASE(4) CRT_CASE(6) CRT_CASE(8) CRT_CASE(10)
@@ -489,8 +484,8 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         fo.pair_score = c->score1.p; fo.bnd = ws.bnd.p;
         if (f32) {
             Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
-            if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, st);
-            return launch_fill1_f32<16>(b.C, b.multi, du, nu, a, fo, st);
+            if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
+            return launch_fill1_f32<16>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
         }
         if (c->D == 10) { P1F64<10>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; return launch_fill_c<P1F64<10>, false, true, 4>(b.C, b.multi, du, nu, a, fo, st); }
         P1F64<16>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor};

@@ -182,4 +182,235 @@ __global__ void __launch_bounds__(32, 1) k_fill1_v2(const Unit *__restrict__ uni
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// k_fill1_v3: same arithmetic as k_fill1_v2, leaner control.
+//   * rows are processed in groups of four; a group takes the CHECKED body (chain-boundary test, emission, reset: the
+//     v2 body) only when some lane of the warp can meet a chain boundary inside it, which a warp-uniform comparison
+//     against the next boundary step decides.  Between boundaries (~9 of 10 groups at 300-residue chains) the FAST body
+//     runs: no meta loads, no per-row branch.
+//   * the row ring (96 rows = 3 blocks of 32, as in v2) carries 3 mirror rows behind it, so a group's four rows never
+//     wrap and are read with immediate offsets from one base advanced once per group.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int RING3 = RING;          // 96
+constexpr int RING3_OFF = RING_OFF;  // ring row of stream row g is (g + 30) mod 96 (see stage_block1 for the block timing)
+
+template <int RS>
+__device__ __forceinline__ void stage_block3(float *srow, const float *rec_unit, const int *meta_unit, int B, int lane)
+{
+    constexpr int SROW = RS + 8;
+    const int slot0 = (B % 3) * 32;
+    const float *src = rec_unit + (long long)(32 * B - RING3_OFF) * RS;     // record of stream row g = 32B - RING3_OFF
+    constexpr int CPR = RS / 4;
+#pragma unroll
+    for (int q = lane; q < 32 * CPR; q += 32) {
+        const int row = q / CPR, part = q - row * CPR;
+        cp_async16(srow + (slot0 + row) * SROW + part * 4, src + q * 4);
+    }
+    cp_async4(srow + (slot0 + lane) * SROW + RS, meta_unit + (32 * B - RING3_OFF) + lane);
+    if (slot0 == 0) {                                                       // mirror rows 0..2 behind the ring
+        if (lane < 3 * CPR) {
+            const int row = lane / CPR, part = lane - row * CPR;
+            cp_async16(srow + (RING3 + row) * SROW + part * 4, src + lane * 4);
+        }
+        if (lane < 3) cp_async4(srow + (RING3 + lane) * SROW + RS, meta_unit + (32 * B - RING3_OFF) + lane);
+    }
+    cp_async_commit();
+}
+
+template <int D, int C, bool MULTI>
+__global__ void __launch_bounds__(32, 1) k_fill1_v3(const Unit *__restrict__ units, int n_units, Fill1Args args, FillOut out,
+                                                    const long long *__restrict__ offsets)
+{
+    constexpr int CP = C / 2;
+    constexpr int RS = ((D + 2 + 3) / 4) * 4;
+    constexpr int SROW = RS + 8;
+    static_assert(C % 2 == 0, "C must be even");
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_units) return;
+    const Unit u = units[blockIdx.x];
+    const int G = u.G;
+    const int steps4 = u.tchunks * 4;
+    float *bnd = MULTI ? reinterpret_cast<float *>(out.bnd) + u.bnd_base : nullptr;
+    __shared__ __align__(16) float srow[(RING3 + 3) * SROW];
+
+    for (int strip = 0; strip < (MULTI ? u.n_strips : 1); ++strip) {
+        float2 colp[CP][D], bp[CP];
+        const int c0 = (strip * 32 + lane) * C;
+#pragma unroll
+        for (int p = 0; p < CP; ++p) {
+            float v0[D + 1], v1[D + 1];
+#pragma unroll
+            for (int k = 0; k <= D; ++k) { v0[k] = 0.f; v1[k] = 0.f; }
+            v0[D] = -INFINITY; v1[D] = -INFINITY;           // padded column: 2^-inf = 0, H[i][m] passes through
+            if (c0 + 2 * p < u.m) {
+                const float *q = args.rec + ((long long)u.col_base + c0 + 2 * p) * RS;
+#pragma unroll
+                for (int k = 0; k <= D; ++k) v0[k] = q[k];
+            }
+            if (c0 + 2 * p + 1 < u.m) {
+                const float *q = args.rec + ((long long)u.col_base + c0 + 2 * p + 1) * RS;
+#pragma unroll
+                for (int k = 0; k <= D; ++k) v1[k] = q[k];
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) colp[p][k] = make_float2(v0[k], v1[k]);
+            bp[p] = make_float2(v0[D], v1[D]);
+        }
+        const bool last_strip = !MULTI || strip == u.n_strips - 1;
+        const bool emitter = last_strip && lane == 31;
+        float nprev[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) nprev[c] = 0.f;
+        float carry = 0.f, acc = 0.f;
+        int istar_t = -1, start_t = 0;       // step of the last growth of H[i][m] / step of the chain's first row (this lane)
+        unsigned word = 0;
+        uint4 *tbp = out.tb + u.tb_base + (long long)strip * u.tchunks * 32 + lane;
+        const float *rec_unit = args.rec + u.row_base * RS;
+        const int *meta_unit = args.meta + u.row_base;
+        __syncwarp();
+        stage_block3<RS>(srow, rec_unit, meta_unit, 0, lane);
+        stage_block3<RS>(srow, rec_unit, meta_unit, 1, lane);
+        cp_async_wait_all();
+        __syncwarp();
+        stage_block3<RS>(srow, rec_unit, meta_unit, 2, lane);
+
+        // chain boundaries of the unit's row stream, as steps of lane 0: B_k = offsets[row_chain0 + k] - row_base.
+        // Lane l meets boundary B at step B + l; the row before it (last of its chain) at step B - 1 + l.
+        int kb = 0;
+        int nextB = 0;                        // boundary whose window [nextB - 1, nextB + 31] is not yet behind t0
+
+        float s_cur[C];
+        float row_nxt[D + 1];
+        int meta_cur = 0, meta_nxt = 0, meta_prev = 0;
+        {
+            float row0[D + 1];
+            // rows -lane and 1-lane (pipeline fill; lane 31's row -31 is clamped to ring row 0, any record will do)
+            load_row_v2<D, RS>(srow + max(RING3_OFF - lane, 0) * SROW, row0, meta_cur);
+            rbf_row_v2<D, CP>(row0, colp, bp, s_cur);
+            load_row_v2<D, RS>(srow + (RING3_OFF + 1 - lane) * SROW, row_nxt, meta_nxt);
+        }
+
+        int roff = (RING3_OFF + 2 - lane) * SROW;          // float offset of stream row t0 + 2 - lane, t0 = 0
+
+        for (int t0 = 0; t0 < steps4; t0 += 4) {
+            if ((t0 & 31) == 0 && t0 > 0) {
+                // rows of block t0/32 + 1 have landed; refill the block whose rows nobody needs any more
+                cp_async_wait_all();
+                __syncwarp();
+                stage_block3<RS>(srow, rec_unit, meta_unit, (t0 >> 5) + 2, lane);
+            }
+            // ring base of the row fetched at the end of step t0 (stream row t0 + 2 - lane); the group reads base + q rows
+            const float *gb = srow + roff;
+            roff += 4 * SROW;
+            if (roff >= RING3 * SROW) roff -= RING3 * SROW;
+            const bool checked = t0 + 4 >= nextB;            // warp-uniform
+            unsigned w[4];
+            if (checked) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = t0 + q;
+                    const int g = t - lane;
+                    float a = __shfl_up_sync(FULL, carry, 1);
+                    if (lane == 0) {
+                        a = 0.f;
+                        if (MULTI && strip > 0) a = bnd[min(max(g, 0), G - 1)];
+                    }
+                    if (((meta_prev & 2) | (meta_cur & 1)) != 0) {
+                        if ((meta_prev & 2) && emitter && (unsigned)(g - 1) < (unsigned)G) {
+                            const int pidx = u.pair_base + (meta_prev >> 2) - u.row_chain0;
+                            out.pair_score[pidx] = (double)acc;
+                            out.pair_istar[pidx] = istar_t >= start_t ? istar_t - start_t + 1 : 0;
+                        }
+                        if (meta_cur & 1) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) nprev[c] = 0.f;
+                            acc = 0.f; start_t = t; istar_t = t - 1;
+                            if (lane == 0 && strip == 0 && (unsigned)g < (unsigned)G)
+                                out.pair_zflag[u.pair_base + (meta_cur >> 2) - u.row_chain0] = (s_cur[0] == 0.f) ? 1 : 0;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float s = s_cur[c];
+                        const float nb = nprev[c];
+                        const float d = fmaxf(fmaxf(s, a), -nb);
+                        const int sd = __float_as_int(s) - __float_as_int(d);
+                        const float nu = a - d;
+                        word = __funnelshift_l((unsigned)sd, word, 1);
+                        word = __funnelshift_l(__float_as_uint(nu), word, 1);
+                        nprev[c] = nu;
+                        a = d + nb;
+                    }
+                    rbf_row_v2<D, CP>(row_nxt, colp, bp, s_cur);
+                    carry = a;
+                    acc += a;
+                    if (a > 0.f) istar_t = t;
+                    w[q] = word;
+                    if (MULTI && !last_strip && lane == 31 && (unsigned)g < (unsigned)G) bnd[g] = carry;
+                    meta_prev = meta_cur; meta_cur = meta_nxt;
+                    load_row_v2<D, RS>(gb + q * SROW, row_nxt, meta_nxt);
+                }
+                // boundaries whose window is behind the next group
+                while (kb <= u.n_pairs && nextB + 31 < t0 + 4) {
+                    ++kb;
+                    nextB = kb <= u.n_pairs ? (int)(offsets[u.row_chain0 + kb] - u.row_base) : 0x3fffffff;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = t0 + q;
+                    float a = __shfl_up_sync(FULL, carry, 1);
+                    if (lane == 0) {
+                        a = 0.f;
+                        if (MULTI && strip > 0) a = bnd[min(max(t, 0), G - 1)];
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float s = s_cur[c];
+                        const float nb = nprev[c];
+                        const float d = fmaxf(fmaxf(s, a), -nb);
+                        const int sd = __float_as_int(s) - __float_as_int(d);
+                        const float nu = a - d;
+                        word = __funnelshift_l((unsigned)sd, word, 1);
+                        word = __funnelshift_l(__float_as_uint(nu), word, 1);
+                        nprev[c] = nu;
+                        a = d + nb;
+                    }
+                    rbf_row_v2<D, CP>(row_nxt, colp, bp, s_cur);
+                    carry = a;
+                    acc += a;
+                    if (a > 0.f) istar_t = t;
+                    w[q] = word;
+                    if (MULTI && !last_strip && lane == 31 && (unsigned)(t - 31) < (unsigned)G) bnd[t - 31] = carry;
+                    // row t + 2 - lane; its meta is only needed when the NEXT group is a checked one
+                    {
+                        const float4 *p4 = reinterpret_cast<const float4 *>(gb + q * SROW);
+                        float tmp[((D + 1 + 3) / 4) * 4];
+#pragma unroll
+                        for (int k = 0; k < (D + 1 + 3) / 4; ++k) {
+                            const float4 v = p4[k];
+                            tmp[4 * k] = v.x; tmp[4 * k + 1] = v.y; tmp[4 * k + 2] = v.z; tmp[4 * k + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k <= D; ++k) row_nxt[k] = tmp[k];
+                    }
+                }
+                // leaving the fast body: the metas the checked body keeps in registers (rows t0+4-lane, t0+5-lane); the
+                // rows of this group carried no flags, so meta_prev = 0 is exact
+                meta_prev = 0;
+                meta_cur = __float_as_int((gb + 2 * SROW)[RS]);
+                meta_nxt = __float_as_int((gb + 3 * SROW)[RS]);
+            }
+            tbp[(long long)(t0 >> 2) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if ((meta_prev & 2) && emitter && (unsigned)(steps4 - 1 - lane) < (unsigned)G) {
+            const int pidx = u.pair_base + (meta_prev >> 2) - u.row_chain0;
+            out.pair_score[pidx] = (double)acc;
+            out.pair_istar[pidx] = istar_t >= start_t ? istar_t - start_t + 1 : 0;
+        }
+        if (MULTI) __syncwarp();
+    }
+}
+
 }  // namespace crt

@@ -381,22 +381,11 @@ struct TraceArgs {
 __device__ inline bool s1_is_zero(const TraceArgs &a, long long ri, long long ci)
 {
     if (a.precision == 1) {
-#ifdef CRT_FILL1_V1
-        // same operation order as k_fill1_f32: even terms in the .x lane, odd terms in the .y lane of the FFMA2 chain,
-        // the last pair is (A_row * 1, 1 * A_col)
-        const float *x = a.rec32 + ri * a.rs32, *y = a.rec32 + ci * a.rs32;
-        float ex = x[0] * y[0], ey = x[1] * y[1];
-        for (int k = 2; k < a.d32; k += 2) { ex = __fmaf_rn(x[k], y[k], ex); ey = __fmaf_rn(x[k + 1], y[k + 1], ey); }
-        ex = __fmaf_rn(x[a.d32], 1.0f, ex);
-        ey = __fmaf_rn(1.0f, y[a.d32], ey);
-        return ex2_approx(ex + ey) == 0.f;
-#else
-        // same operation order as k_fill1_v2: e = A_col; e = fma(r_k, c_k, e) for k = 0..D-1; e += A_row
+        // same operation order as the stage-1 fill (rbf_row_v2): e = A_col; e = fma(r_k, c_k, e) for k = 0..D-1; e += A_row
         const float *x = a.rec32 + ri * a.rs32, *y = a.rec32 + ci * a.rs32;
         float e = y[a.d32];
         for (int k = 0; k < a.d32; ++k) e = __fmaf_rn(x[k], y[k], e);
         return ex2_approx(__fadd_rn(e, x[a.d32])) == 0.f;
-#endif
     }
     const double *x = a.rec64 + ri * a.d64, *y = a.rec64 + ci * a.d64;
     double acc = 0.0;

@@ -55,7 +55,7 @@ int main(int argc, char **argv)
 {
     const int L = argc > 1 ? atoi(argv[1]) : 300;
     const int chains_per_unit = argc > 2 ? atoi(argv[2]) : 10;
-    const char *which = argc > 3 ? argv[3] : "all";          // all | v1 | v2 | c6 | f2
+    const char *which = argc > 3 ? argv[3] : "all";          // all | v1 | v2 | v3 | c6 | f2
     const int only_k = argc > 4 ? atoi(argv[4]) : 0;         // 0 = sweep the resident-warp counts
     auto want = [&](const char *name) { return !strcmp(which, "all") || !strcmp(which, name); };
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
@@ -95,6 +95,9 @@ int main(int argc, char **argv)
     float *bnd; CK(cudaMalloc(&bnd, (size_t)max_units * d.G * 4));
     CK(cudaMalloc(&d.units, (size_t)max_units * sizeof(Unit)));
 
+    std::vector<long long> h_off(d.nchains + 1);
+    for (int q = 0; q <= d.nchains; ++q) h_off[q] = (long long)q * L;
+    long long *d_offsets; CK(cudaMalloc(&d_offsets, h_off.size() * 8)); CK(cudaMemcpy(d_offsets, h_off.data(), h_off.size() * 8, cudaMemcpyHostToDevice));
     auto make_units = [&](int n_units, int C, int nstrips) {
         std::vector<Unit> hu(n_units);
         for (int q = 0; q < n_units; ++q) {
@@ -127,6 +130,13 @@ int main(int argc, char **argv)
         make_units(n, 10, 1);
         float ms = time_kernel([&] { k_fill1_v2<10, 10, false><<<n, 32>>>(d.units, n, a1, fo); });
         report("fill1_v2<10,10>", 10, 1, n, d, ms, L);
+    }
+    if (want("v3")) for (int k : per_sm) {
+        if (k > 16 || (only_k && k != only_k)) continue;
+        const int n = g_sms * k;
+        make_units(n, 10, 1);
+        float ms = time_kernel([&] { k_fill1_v3<10, 10, false><<<n, 32>>>(d.units, n, a1, fo, d_offsets); });
+        report("fill1_v3<10,10>", 10, 1, n, d, ms, L);
     }
 #endif
     if (want("c6")) for (int k : per_sm) {
