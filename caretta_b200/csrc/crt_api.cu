@@ -4,6 +4,7 @@
 #include "crt_kernels.cuh"
 #include "crt_fill_f32.cuh"
 #include "crt_fill1_v2.cuh"
+#include "crt_fill2_v3.cuh"
 #include "crt_dp_batch.cuh"
 
 #include <algorithm>
@@ -202,12 +203,12 @@ int launch_fill1_f32(int C, bool multi, const Unit *units, int n, Fill1Args args
     return 0;
 }
 
-int launch_fill2_f32(int C, bool multi, const Unit *units, int n, Fill2Args args, FillOut out, cudaStream_t st)
+int launch_fill2_f32(int C, bool multi, const Unit *units, int n, Fill2Args args, FillOut out, const long long *offsets, cudaStream_t st)
 {
-#define CRT_CASE(CC)                                                                     \
-    case CC:                                                                             \
-        if (multi) k_fill2_f32<CC, true><<<n, 32, 0, st>>>(units, n, args, out);          \
-        else k_fill2_f32<CC, false><<<n, 32, 0, st>>>(units, n, args, out);              \
+#define CRT_CASE(CC)                                                                              \
+    case CC:                                                                                      \
+        if (multi) k_fill2_v3<CC, true><<<n, 32, 0, st>>>(units, n, args, out, offsets);           \
+        else k_fill2_v3<CC, false><<<n, 32, 0, st>>>(units, n, args, out, offsets);               \
         break;
     switch (C) {
         CRT_CASE(2) CRT_CASE(4) CRT_CASE(6) CRT_CASE(8) CRT_CASE(10)
@@ -520,7 +521,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         fo.pair_score = c->score.p; fo.bnd = pipe ? ws.bnd2.p : ws.bnd.p;
         if (f32) {
             Fill2Args a{reinterpret_cast<const float4 *>(ws.rows2.p) + ROW_PAD, c->cols2.p};
-            return launch_fill2_f32(b.C, b.multi, du, nu, a, fo, st);
+            return launch_fill2_f32(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
         }
         P2F64::Args a{reinterpret_cast<const double *>(ws.rows2.p) + (size_t)ROW_PAD * 4, c->coords.p, -prm->gamma_coords};
         return launch_fill_c<P2F64, false, false, 4>(b.C, b.multi, du, nu, a, fo, st);

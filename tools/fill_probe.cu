@@ -10,6 +10,7 @@
 #include "crt_fill_f32.cuh"
 #ifdef PROBE_V2
 #include "crt_fill1_v2.cuh"
+#include "crt_fill2_v3.cuh"
 #endif
 
 using namespace crt;
@@ -155,5 +156,14 @@ int main(int argc, char **argv)
         float ms = time_kernel([&] { k_fill2_f32<10, false><<<n, 32>>>(d.units, n, a2, fo); });
         report("fill2<10>", 10, 1, n, d, ms, L);
     }
+#ifdef PROBE_V2
+    if (want("f23")) for (int k : per_sm) {
+        if (only_k && k != only_k) continue;
+        const int n = g_sms * k;
+        make_units(n, 10, 1);
+        float ms = time_kernel([&] { k_fill2_v3<10, false><<<n, 32>>>(d.units, n, a2, fo, d_offsets); });
+        report("fill2_v3<10>", 10, 1, n, d, ms, L);
+    }
+#endif
     return 0;
 }
