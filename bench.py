@@ -241,22 +241,28 @@ def main():
     cells_per_step = 2.0 * L * L * total_pairs          # DP cell updates: two SW fills per residue pair
 
     # ------------------------------------------------------------------ e2e: host buffers in, host results out
-    pin_c = torch.from_numpy(ch.coords).pin_memory()
-    pin_t = torch.from_numpy(ch.tensors).pin_memory()
-    pin_o = torch.from_numpy(ch.offsets).pin_memory()
+    # N = 1: the reference-facing call (make_pairwise_matrix -> crt_set_chains + crt_pairwise_all): packed float64
+    # chains in page-locked host memory in, dense float64 [N,N] score / RMSD / TM matrices in page-locked host memory out.
+    # N > 1: upload, shard, all-gather of the packed float32 vectors, one D2H of the gathered buffer per rank.
+    pin_c, pin_t, pin_o = engine.pinned_like(ch.coords), engine.pinned_like(ch.tensors), engine.pinned_like(ch.offsets)
     h_all = torch.empty(world * 3 * pad, dtype=torch.float32).pin_memory() if world > 1 else None
+    dense = tuple(engine.pinned_empty((n, n)) for _ in range(3)) if world == 1 else None
     e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(1):                                                          # untimed: first-touch of the new buffers
+        eng.set_chains(pin_c, pin_t, pin_o)
+        if world == 1:
+            eng.pairwise_all(prm, want_rmsd_tm=True, out=dense)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.set_chains(pin_c.numpy(), pin_t.numpy(), pin_o.numpy())            # H2D of this step's inputs
-        eng.pairwise_shard(prm, rank, world)
+        eng.set_chains(pin_c, pin_t, pin_o)                                     # H2D of this step's inputs
         if world > 1:
+            eng.pairwise_shard(prm, rank, world)
             eng.fetch_device(d_mine.data_ptr(), d_mine.data_ptr() + 4 * pad, d_mine.data_ptr() + 8 * pad, pad)
             dist.all_gather_into_tensor(d_all, d_mine)
             h_all.copy_(d_all, non_blocking=False)                              # D2H of the gathered matrices
         else:
-            res = eng.fetch(my_pairs)                                           # D2H: score, rmsd, tm, ncommon, status
+            eng.pairwise_all(prm, want_rmsd_tm=True, out=dense)                 # D2H: three dense [N,N] float64 matrices
     sync_all()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -264,7 +270,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     h2d = ch.coords.nbytes + ch.tensors.nbytes + ch.offsets.nbytes
-    d2h = (world * 3 * pad * 4) if world > 1 else my_pairs * (3 * 8 + 2 * 4)
+    d2h = (world * 3 * pad * 4) if world > 1 else 3 * n * n * 8
 
     if rank != 0:
         if world > 1:

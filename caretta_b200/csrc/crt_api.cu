@@ -82,8 +82,8 @@ struct crt_ctx {
     long long total = 0;
     std::vector<long long> offsets;      // host copy
     int max_len = 0;
-    double mean[32];
-    DevBuf<double> coords, tensors, centroid, rec64;
+    DevBuf<double> coords, tensors, centroid, rec64, stats;      // stats: [STATS_BLOCKS][32] partial sums, [32] mean
+    DevBuf<int> flag;
     DevBuf<long long> d_offsets;
     DevBuf<int> chain_of, meta;
     DevBuf<float> rec32;
@@ -109,6 +109,8 @@ struct crt_ctx {
     int n_streams = 3;
     DevBuf<Unit> d_units;
     DevBuf<int> path_len, pair_istar, pair_zflag, ncommon, status;
+    DevBuf<int> d_pi, d_pj;              // pair ids of the cached all-vs-all plan, result order (device copy for the dense scatter)
+    DevBuf<double> dense;                // [1 or 3][N][N] dense matrices of crt_pairwise_all
     DevBuf<double> score, score1, rmsd, tm, xform;
     DevBuf<float> f32tmp;
     double phase_ms[4] = {0, 0, 0, 0};      // fill1, trace, rows2, fill2 (only meaningful with one stream)
@@ -704,7 +706,7 @@ int crt_destroy(crt_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->coords.release(); c->tensors.release(); c->centroid.release(); c->rec64.release(); c->d_offsets.release();
-    c->chain_of.release(); c->meta.release(); c->rec32.release(); c->cols2.release(); c->d_units.release();
+    c->chain_of.release(); c->stats.release(); c->flag.release(); c->meta.release(); c->rec32.release(); c->cols2.release(); c->d_units.release();
     for (int w = 0; w < crt_ctx::MAX_WS; ++w) {
         crt_ctx::Workspace &ws = c->ws[w];
         ws.tb.release(); ws.rows2.release(); ws.bnd.release(); ws.bnd2.release(); ws.path.release();
@@ -715,7 +717,7 @@ int crt_destroy(crt_ctx *c)
         for (int k = 0; k < 4; ++k) if (ws.ev[k]) cudaEventDestroy(ws.ev[k]);
         if (ws.stream) cudaStreamDestroy(ws.stream);
     }
-    c->xform.release(); c->path_len.release();
+    c->xform.release(); c->path_len.release(); c->d_pi.release(); c->d_pj.release(); c->dense.release();
     c->pair_istar.release(); c->pair_zflag.release(); c->ncommon.release(); c->status.release();
     c->score.release(); c->score1.release(); c->rmsd.release(); c->tm.release(); c->f32tmp.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -766,23 +768,29 @@ int crt_set_chains(crt_ctx *c, const double *coords, const double *tensors, cons
     CU(cudaMemsetAsync(c->meta.p, 0, sizeof(int) * ((size_t)total + 2 * ROW_PAD), c->stream));
     CU(cudaMemsetAsync(c->rec32.p, 0, sizeof(float) * ((size_t)total + 2 * ROW_PAD) * (((D + 2 + 3) / 4) * 4), c->stream));
     if ((rc = c->cols2.ensure((size_t)total))) return rc;
+    if ((rc = c->stats.ensure((size_t)(STATS_BLOCKS + 1) * 32))) return rc;
+    if ((rc = c->flag.ensure(1))) return rc;
     c->offsets.assign(offsets, offsets + n_chains + 1);
-    std::vector<int> chain_of((size_t)total);
-    for (int p = 0; p < n_chains; ++p)
-        for (long long r = offsets[p]; r < offsets[p + 1]; ++r) chain_of[(size_t)r] = p;
-    // global tensor mean (the Gaussian is translation invariant; centring keeps the fp32 dot-product form accurate)
-    for (int k = 0; k < 32; ++k) c->mean[k] = 0.0;
-    bool finite = true;
-    for (long long r = 0; r < total; ++r)
-        for (int k = 0; k < d; ++k) { double v = tensors[r * d + k]; c->mean[k] += v; finite &= std::isfinite(v); }
-    for (long long r = 0; r < total * 3; ++r) finite &= std::isfinite(coords[r]);
-    if (!finite) return fail(CRT_E_ARG, "non-finite value in coords/tensors");
-    for (int k = 0; k < d; ++k) c->mean[k] /= (double)total;
+    CU(cudaMemsetAsync(c->flag.p, 0, sizeof(int), c->stream));
     CU(cudaMemcpyAsync(c->coords.p, coords, sizeof(double) * (size_t)total * 3, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->tensors.p, tensors, sizeof(double) * (size_t)total * d, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_offsets.p, c->offsets.data(), sizeof(long long) * ((size_t)n_chains + 1), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->chain_of.p, chain_of.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));     // chain_of is a local vector
+    // chain index table, global tensor mean (the Gaussian is translation invariant; centring keeps the fp32 dot-product
+    // form accurate) and the finiteness check run on the device; the only host wait is for the 4-byte flag
+    {
+        PrepArgs a{};
+        a.offsets = c->d_offsets.p; a.chain_of = c->chain_of.p; a.n_chains = n_chains; a.total = total;
+        k_chain_of<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(a);
+        CU(cudaGetLastError());
+        k_tensor_stats<<<STATS_BLOCKS, STATS_THREADS, 0, c->stream>>>(c->tensors.p, c->coords.p, total, d, c->stats.p, c->flag.p);
+        CU(cudaGetLastError());
+        k_tensor_mean<<<1, 32, 0, c->stream>>>(c->stats.p, total, d, c->stats.p + (size_t)STATS_BLOCKS * 32);
+        CU(cudaGetLastError());
+    }
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, c->flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (bad) return fail(CRT_E_ARG, "non-finite value in coords/tensors");
     {
         unsigned long long h = 1469598103934665603ull;
         for (int p = 0; p <= n_chains; ++p) { h ^= (unsigned long long)offsets[p]; h *= 1099511628211ull; }
@@ -805,7 +813,7 @@ int ensure_prepared(crt_ctx *c, const crt_params *prm)
     PrepArgs a{};
     a.coords = c->coords.p; a.tensors = c->tensors.p; a.offsets = c->d_offsets.p; a.chain_of = c->chain_of.p;
     a.n_chains = c->N; a.d = c->d; a.total = c->total;
-    for (int k = 0; k < 32; ++k) a.mean[k] = c->mean[k];
+    a.mean = c->stats.p + (size_t)STATS_BLOCKS * 32;
     a.g2 = prm->gamma_tensor * 1.4426950408889634;
     a.scale2 = std::sqrt(prm->gamma_coords * 1.4426950408889634);
     a.rs32 = ((c->D + 2 + 3) / 4) * 4; a.d32 = c->D; a.rec32 = c->rec32.p + (size_t)ROW_PAD * a.rs32;
@@ -847,6 +855,10 @@ int crt_pairwise_shard(crt_ctx *c, const crt_params *prm, int32_t rank, int32_t 
     assign_pairs(units, &c->run_pi, &c->run_pj, &np, &c->cell_updates, c);
     pc.valid = false;
     if (np == 0) { c->run_pairs = 0; c->elapsed_ms = 0; c->launches = 0; return 0; }
+    if ((rc = c->d_pi.ensure((size_t)np))) return rc;
+    if ((rc = c->d_pj.ensure((size_t)np))) return rc;
+    CU(cudaMemcpyAsync(c->d_pi.p, c->run_pi.data(), sizeof(int) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_pj.p, c->run_pj.data(), sizeof(int) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
     rc = run_units(c, prm, units, np, nullptr, false, true);
     if (rc == 0) {
         pc.valid = true; pc.offsets_hash = c->offsets_hash; pc.rank = rank; pc.world = world; pc.prec = prm->precision;
@@ -938,6 +950,19 @@ int crt_fetch(crt_ctx *c, double *score, double *rmsd, double *tm, int32_t *ncom
 }  // extern "C"
 
 namespace {
+// dense symmetric matrices from the packed per-pair results: out[i][j] = out[j][i] = v; TM diagonal 1
+__global__ void k_scatter_dense(const int *pi, const int *pj, const double *s, const double *r, const double *t,
+                                double *S, double *R, double *T, long long np, int N)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (T && q < N) T[q * N + q] = 1.0;
+    if (q >= np) return;
+    const long long i = pi[q], j = pj[q];
+    S[i * N + j] = S[j * N + i] = s[q];
+    if (R) R[i * N + j] = R[j * N + i] = r[q];
+    if (T) T[i * N + j] = T[j * N + i] = t[q];
+}
+
 __global__ void k_d2f(const double *a, float *o, long long n)
 {
     long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -978,21 +1003,38 @@ int crt_pairwise_all(crt_ctx *c, const crt_params *prm, double *out_score, doubl
     if (!out_score) return fail(CRT_E_ARG, "null out_score");
     int rc = crt_pairwise_shard(c, prm, 0, 1);
     if (rc) return rc;
+    // symmetric fill on the device (multiple_alignment.py:164), then one copy per requested matrix
     const size_t N = (size_t)c->N, np = (size_t)c->run_pairs;
-    std::vector<double> s(np + 1), r(np + 1), t(np + 1);
-    if ((rc = crt_fetch(c, s.data(), out_rmsd ? r.data() : nullptr, out_tm ? t.data() : nullptr, nullptr, nullptr))) return rc;
-    for (size_t q = 0; q < N * N; ++q) {
-        out_score[q] = 0.0;
-        if (out_rmsd) out_rmsd[q] = 0.0;
-        if (out_tm) out_tm[q] = 0.0;
+    const int nm = 1 + (out_rmsd ? 1 : 0) + (out_tm ? 1 : 0);
+    if ((rc = c->dense.ensure(N * N * (size_t)nm))) return rc;
+    double *dS = c->dense.p, *dR = out_rmsd ? dS + N * N : nullptr, *dT = out_tm ? dS + N * N * (size_t)(out_rmsd ? 2 : 1) : nullptr;
+    CU(cudaMemsetAsync(c->dense.p, 0, sizeof(double) * N * N * (size_t)nm, c->stream));
+    if (np > 0 || dT) {
+        const long long work = (long long)std::max(np, N);
+        k_scatter_dense<<<(unsigned)((work + 255) / 256), 256, 0, c->stream>>>(c->d_pi.p, c->d_pj.p, c->score.p, c->rmsd.p, c->tm.p,
+                                                                                dS, dR, dT, (long long)np, (int)N);
+        CU(cudaGetLastError());
     }
-    if (out_tm) for (size_t q = 0; q < N; ++q) out_tm[q * N + q] = 1.0;
-    for (size_t q = 0; q < np; ++q) {
-        const size_t i = (size_t)c->run_pi[q], j = (size_t)c->run_pj[q];
-        out_score[i * N + j] = out_score[j * N + i] = s[q];       // symmetric fill, multiple_alignment.py:164
-        if (out_rmsd) out_rmsd[i * N + j] = out_rmsd[j * N + i] = r[q];
-        if (out_tm) out_tm[i * N + j] = out_tm[j * N + i] = t[q];
-    }
+    CU(cudaMemcpyAsync(out_score, dS, sizeof(double) * N * N, cudaMemcpyDeviceToHost, c->stream));
+    if (out_rmsd) CU(cudaMemcpyAsync(out_rmsd, dR, sizeof(double) * N * N, cudaMemcpyDeviceToHost, c->stream));
+    if (out_tm) CU(cudaMemcpyAsync(out_tm, dT, sizeof(double) * N * N, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+/* Page-locked host memory for the caller's input/output arrays (copies to and from it run at full PCIe rate). */
+int crt_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(CRT_E_ARG, "null out pointer");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(CRT_E_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+
+int crt_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
     return 0;
 }
 

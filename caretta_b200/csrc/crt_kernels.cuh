@@ -621,10 +621,10 @@ __global__ void __launch_bounds__(256) k_rows2(TraceArgs a, int n_units)
 struct PrepArgs {
     const double *coords, *tensors;
     const long long *offsets;
-    const int *chain_of;      // [sumL]
+    int *chain_of;            // [sumL], written by k_chain_of
     int n_chains, d;
     long long total;
-    double mean[32];          // global tensor mean (host computed)
+    const double *mean;       // [32] global tensor mean (k_tensor_stats / k_tensor_mean)
     double g2;                // gamma_tensor * log2(e)
     double scale2;            // sqrt(gamma_coords * log2(e))
     float *rec32; int rs32, d32;
@@ -633,6 +633,60 @@ struct PrepArgs {
     float4 *cols2;
     double *centroid;
 };
+
+// chain index of every residue (bisection over the offsets), one thread per residue
+__global__ void k_chain_of(PrepArgs a)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.total) return;
+    int lo = 0, hi = a.n_chains - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.offsets[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    a.chain_of[r] = lo;
+}
+
+// Global tensor mean and the finiteness check of the uploaded arrays, deterministic for a given input: block b sums a
+// fixed contiguous slice in a fixed order (thread-strided sums, then a fixed shared-memory tree), k_tensor_mean adds the
+// block partials in block order.  partial: [STATS_BLOCKS][32], flag: nonzero if any coordinate/tensor value is not finite.
+constexpr int STATS_BLOCKS = 128, STATS_THREADS = 256;
+__global__ void __launch_bounds__(STATS_THREADS) k_tensor_stats(const double *tensors, const double *coords, long long total, int d,
+                                                                 double *partial, int *flag)
+{
+    __shared__ double sh[STATS_THREADS];
+    const long long per = (total + STATS_BLOCKS - 1) / STATS_BLOCKS;
+    const long long r0 = (long long)blockIdx.x * per, r1 = min(total, r0 + per);
+    bool bad = false;
+    for (int k = 0; k < d; ++k) {
+        double acc = 0.0;
+        for (long long r = r0 + threadIdx.x; r < r1; r += STATS_THREADS) {
+            const double v = tensors[r * d + k];
+            acc += v;
+            bad |= !isfinite(v);
+        }
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int w = STATS_THREADS / 2; w > 0; w >>= 1) {
+            if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partial[blockIdx.x * 32 + k] = sh[0];
+        __syncthreads();
+    }
+    for (long long q = r0 * 3 + threadIdx.x; q < r1 * 3; q += STATS_THREADS) bad |= !isfinite(coords[q]);
+    if (bad) atomicOr(flag, 1);
+}
+
+__global__ void k_tensor_mean(const double *partial, long long total, int d, double *mean)
+{
+    const int k = threadIdx.x;
+    if (k >= 32) return;
+    double acc = 0.0;
+    if (k < d)
+        for (int b = 0; b < STATS_BLOCKS; ++b) acc += partial[b * 32 + k];
+    mean[k] = k < d ? acc / (double)total : 0.0;
+}
 
 __global__ void k_centroid(PrepArgs a)
 {

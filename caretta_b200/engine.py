@@ -19,7 +19,7 @@ EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
-    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak",
+    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak", "crt_host_alloc", "crt_host_free",
 ]
 
 
@@ -73,6 +73,8 @@ def load_library():
     L.crt_dtw_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, dbl, dbl, vp, vp, vp, i64, vp]
     L.crt_rmsd_cov_tm.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(i32)]
     L.crt_fp32_peak.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
+    L.crt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.crt_host_free.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("crt_version",):
@@ -83,6 +85,42 @@ def load_library():
 
 def _p(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _PinnedBlock:
+    """Owner of one crt_host_alloc block; freed when the last numpy view of it dies."""
+
+    def __init__(self, nbytes: int):
+        L = load_library()
+        p = C.c_void_p()
+        rc = L.crt_host_alloc(int(nbytes), C.byref(p))
+        if rc != 0:
+            raise CrtError(f"crt_host_alloc failed ({rc}): {L.crt_last_error().decode()}")
+        self.ptr, self.nbytes, self._lib = p, int(nbytes), L
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.crt_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array in page-locked host memory (crt_host_alloc): host<->device copies of it run at full PCIe rate."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    blk = _PinnedBlock(n * dtype.itemsize)
+    buf = (C.c_char * max(blk.nbytes, 1)).from_address(blk.ptr.value)
+    buf._crt_owner = blk            # array.base -> buf -> blk: the block lives as long as any view of the array
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def pinned_like(a: np.ndarray) -> np.ndarray:
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
 
 
 def plan_shard(offsets, rank: int, world: int):
@@ -153,11 +191,21 @@ class Engine:
         self._offsets = offsets.copy()
 
     # ------------------------------------------------------------------------------------------------ all-vs-all
-    def pairwise_all(self, prm: Params, want_rmsd_tm: bool = False):
+    def pairwise_all(self, prm: Params, want_rmsd_tm: bool = False, out=None):
+        """Dense symmetric float64 [N,N] score matrix (and RMSD / TM by-products).  ``out``: optional preallocated
+        C-contiguous float64 arrays (score,) or (score, rmsd, tm), e.g. from pinned_empty, filled in place."""
         n = self.n_chains
-        score = np.empty((n, n))
-        rm = np.empty((n, n)) if want_rmsd_tm else None
-        tm = np.empty((n, n)) if want_rmsd_tm else None
+        if out is not None:
+            out = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+            for a in out:
+                if a.dtype != np.float64 or a.shape != (n, n) or not a.flags.c_contiguous:
+                    raise ValueError("out arrays must be C-contiguous float64 [N,N]")
+            score = out[0]
+            rm, tm = (out[1], out[2]) if want_rmsd_tm else (None, None)
+        else:
+            score = np.empty((n, n))
+            rm = np.empty((n, n)) if want_rmsd_tm else None
+            tm = np.empty((n, n)) if want_rmsd_tm else None
         self._check(self.lib.crt_pairwise_all(self.h, C.byref(prm), _p(score), _p(rm), _p(tm)), "crt_pairwise_all")
         return (score, rm, tm) if want_rmsd_tm else score
 

@@ -36,6 +36,7 @@
 #ifndef CARETTA_B200_H
 #define CARETTA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -106,6 +107,9 @@ double crt_last_cell_updates(crt_ctx *ctx);      /* sum over pairs of 2 * L1 * L
 /* make_pairwise_matrix: dense symmetric float64 [N,N], diagonal 0 (rmsd/tm by-products: diagonal 0 / 1).
  * Convenience wrapper = crt_pairwise_shard(world=1) + crt_fetch + scatter. out_rmsd/out_tm may be NULL. */
 int crt_pairwise_all(crt_ctx *ctx, const crt_params *prm, double *out_score, double *out_rmsd, double *out_tm);
+/* Page-locked host buffers for inputs/outputs of the calls above (optional; pageable memory works, slower). */
+int crt_host_alloc(size_t bytes, void **out);
+int crt_host_free(void *p);
 
 /* Explicit pair list.  Optional stage-1 paths: aln_off[n_pairs+1] (int64, filled by the library), aln1/aln2 int32
  * with -1 = gap, ascending residue order like dynamic_time_warping.py:278; capacity aln_cap entries (sum over
