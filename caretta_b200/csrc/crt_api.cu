@@ -425,7 +425,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     size_t total_bytes = 0;
     auto unit_bytes = [&](const HostUnit &h) {
         return (size_t)h.u.n_strips * h.u.tchunks * 32 * 16 + (size_t)h.u.G * row2sz + (size_t)h.u.n_pairs * h.u.path_stride * 4 +
-               (h.multi ? (size_t)h.u.G * tsz : 0);
+               (h.multi ? ((size_t)h.u.tchunks * 4 + 8) * tsz : 0);
     };
     for (auto &h : units) total_bytes += unit_bytes(h);
     size_t budget = env_budget();
@@ -439,7 +439,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         while (end < units.size() && units[end].C == b.C && units[end].multi == b.multi) {
             HostUnit &h = units[end];
             const size_t tb_u = (size_t)h.u.n_strips * h.u.tchunks * 32, rows_u = (size_t)h.u.G;
-            const size_t path_u = (size_t)h.u.n_pairs * h.u.path_stride, bnd_u = b.multi ? (size_t)h.u.G : 0;
+            const size_t path_u = (size_t)h.u.n_pairs * h.u.path_stride, bnd_u = b.multi ? (size_t)h.u.tchunks * 4 + 8 : 0;
             const size_t bytes = (b.tb_n + tb_u) * 16 + (b.rows2_n + rows_u) * row2sz + (b.path_n + path_u) * 4 + (b.bnd_n + bnd_u) * tsz;
             if (end > pos && bytes > budget) break;
             h.u.tb_base = (long long)b.tb_n; h.u.rows2_base = (long long)b.rows2_n;

@@ -292,8 +292,16 @@ __global__ void __launch_bounds__(32, 1) k_fill1_v3(const Unit *__restrict__ uni
         }
 
         int roff = (RING3_OFF + 2 - lane) * SROW;          // float offset of stream row t0 + 2 - lane, t0 = 0
+        // lane 0's inputs from the previous strip (bnd[g], g = t for lane 0): one 128-bit load per group, issued one
+        // group ahead so the L2 latency never sits in front of the row's dependent chain (bnd is padded to steps4 + 4)
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), bq_nxt = bq;
+        if (MULTI && strip > 0 && lane == 0) bq_nxt = *reinterpret_cast<const float4 *>(bnd);
 
         for (int t0 = 0; t0 < steps4; t0 += 4) {
+            if (MULTI && strip > 0) {
+                bq = bq_nxt;
+                if (lane == 0) bq_nxt = *reinterpret_cast<const float4 *>(bnd + t0 + 4);
+            }
             if ((t0 & 31) == 0 && t0 > 0) {
                 // rows of block t0/32 + 1 have landed; refill the block whose rows nobody needs any more
                 cp_async_wait_all();
@@ -312,10 +320,7 @@ __global__ void __launch_bounds__(32, 1) k_fill1_v3(const Unit *__restrict__ uni
                     const int t = t0 + q;
                     const int g = t - lane;
                     float a = __shfl_up_sync(FULL, carry, 1);
-                    if (lane == 0) {
-                        a = 0.f;
-                        if (MULTI && strip > 0) a = bnd[min(max(g, 0), G - 1)];
-                    }
+                    if (lane == 0) a = (MULTI && strip > 0) ? (q == 0 ? bq.x : q == 1 ? bq.y : q == 2 ? bq.z : bq.w) : 0.f;
                     if (((meta_prev & 2) | (meta_cur & 1)) != 0) {
                         if ((meta_prev & 2) && emitter && (unsigned)(g - 1) < (unsigned)G) {
                             const int pidx = u.pair_base + (meta_prev >> 2) - u.row_chain0;
@@ -361,10 +366,7 @@ __global__ void __launch_bounds__(32, 1) k_fill1_v3(const Unit *__restrict__ uni
                 for (int q = 0; q < 4; ++q) {
                     const int t = t0 + q;
                     float a = __shfl_up_sync(FULL, carry, 1);
-                    if (lane == 0) {
-                        a = 0.f;
-                        if (MULTI && strip > 0) a = bnd[min(max(t, 0), G - 1)];
-                    }
+                    if (lane == 0) a = (MULTI && strip > 0) ? (q == 0 ? bq.x : q == 1 ? bq.y : q == 2 ? bq.z : bq.w) : 0.f;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const float s = s_cur[c];

@@ -39,7 +39,7 @@ __device__ __forceinline__ void rbf_row2(const float4 rv, const float2 (&nx)[CP]
 }
 
 template <int C, bool MULTI>
-__global__ void __launch_bounds__(32, CRT_FILL2_MINB) k_fill2_v3(const Unit *__restrict__ units, int n_units, Fill2Args args, FillOut out,
+__global__ void __launch_bounds__(32, MULTI ? 1 : CRT_FILL2_MINB) k_fill2_v3(const Unit *__restrict__ units, int n_units, Fill2Args args, FillOut out,
                                                  const long long *__restrict__ offsets)
 {
     static_assert(C % 2 == 0, "C must be even");
@@ -89,7 +89,15 @@ __global__ void __launch_bounds__(32, CRT_FILL2_MINB) k_fill2_v3(const Unit *__r
             meta_nxt = __float_as_int(rv_nxt.w);
         }
 
+        // lane 0's inputs from the previous strip, one 128-bit load per group issued one group ahead (see k_fill1_v3)
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), bq_nxt = bq;
+        if (MULTI && strip > 0 && lane == 0) bq_nxt = *reinterpret_cast<const float4 *>(bnd);
+
         for (int t0 = 0; t0 < steps4; t0 += 4) {
+            if (MULTI && strip > 0) {
+                bq = bq_nxt;
+                if (lane == 0) bq_nxt = *reinterpret_cast<const float4 *>(bnd + t0 + 4);
+            }
             if ((t0 & 31) == 0 && t0 > 0) {
                 cp_async_wait_all();
                 __syncwarp();
@@ -104,10 +112,7 @@ __global__ void __launch_bounds__(32, CRT_FILL2_MINB) k_fill2_v3(const Unit *__r
                 for (int q = 0; q < 4; ++q) {
                     const int g = t0 + q - lane;
                     float left = __shfl_up_sync(FULL, carry, 1);
-                    if (lane == 0) {
-                        left = 0.f;
-                        if (MULTI && strip > 0) left = bnd[min(max(g, 0), G - 1)];
-                    }
+                    if (lane == 0) left = (MULTI && strip > 0) ? (q == 0 ? bq.x : q == 1 ? bq.y : q == 2 ? bq.z : bq.w) : 0.f;
                     if (((meta_prev & 2) | (meta_cur & 1)) != 0) {
                         if ((meta_prev & 2) && emitter && (unsigned)(g - 1) < (unsigned)G)
                             out.pair_score[u.pair_base + (meta_prev >> 2) - u.row_chain0] = (double)carry;
@@ -143,10 +148,7 @@ __global__ void __launch_bounds__(32, CRT_FILL2_MINB) k_fill2_v3(const Unit *__r
                 for (int q = 0; q < 4; ++q) {
                     const int t = t0 + q;
                     float left = __shfl_up_sync(FULL, carry, 1);
-                    if (lane == 0) {
-                        left = 0.f;
-                        if (MULTI && strip > 0) left = bnd[min(max(t, 0), G - 1)];
-                    }
+                    if (lane == 0) left = (MULTI && strip > 0) ? (q == 0 ? bq.x : q == 1 ? bq.y : q == 2 ? bq.z : bq.w) : 0.f;
                     const float in = left;
                     float diag = dsave;
 #pragma unroll
