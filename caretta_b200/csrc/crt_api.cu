@@ -103,7 +103,8 @@ struct crt_ctx {
     };
     // pipeline mode: one stream per stage, so that stage 1 of batch k+1, the traceback of batch k and stage 2 of
     // batch k-1 are resident together (the light stage-2 and traceback warps fill the registers stage 1 leaves free)
-    cudaStream_t s_f1 = nullptr, s_tr = nullptr, s_f2 = nullptr;
+    cudaStream_t s_f1[2] = {nullptr, nullptr}, s_tr = nullptr, s_f2[2] = {nullptr, nullptr};   // fills alternate between two
+                                                                                              // streams: the tail of one launch overlaps the head of the next
     static constexpr int MAX_WS = 4;
     Workspace ws[MAX_WS];
     int n_streams = 3;
@@ -340,7 +341,7 @@ struct PathSink {
 size_t env_budget()
 {
     const char *e = getenv("CARETTA_B200_WORKSPACE_MB");
-    size_t mb = e ? (size_t)atoll(e) : 3072;      // per stream
+    size_t mb = e ? (size_t)atoll(e) : 8192;      // per workspace set (up to 4 sets in flight); B200 has 180 GB
     if (mb < 16) mb = 16;
     return mb << 20;
 }
@@ -394,7 +395,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     const bool want_paths = sink && sink->want;
     const int NS = want_paths ? 1 : env_streams();
     const bool pipe = !want_paths && NS > 1 && env_pipe();
-    const int NW = pipe ? 3 : NS;                 // workspace sets in flight
+    const int NW = pipe ? 4 : NS;                 // workspace sets in flight
     int rc;
     if ((rc = c->score.ensure((size_t)n_pairs + 1))) return rc;
     if ((rc = c->score1.ensure((size_t)n_pairs + 1))) return rc;
@@ -429,6 +430,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     };
     for (auto &h : units) total_bytes += unit_bytes(h);
     size_t budget = env_budget();
+    budget = std::min(budget, std::max<size_t>(c->mem_total / 20, (size_t)64 << 20));
     if (pipe) budget = std::min(budget, std::max<size_t>(total_bytes / env_batches() + 1, (size_t)64 << 20));
     else if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
     hu.resize(units.size());
@@ -530,14 +532,16 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     };
 
     if (pipe) {
-        // ---- stage pipeline: s_f1 runs the stage-1 fills back to back, s_tr (high priority) the tracebacks, s_f2 the
-        //      stage-2 fills.  Workspace set w = k % NW is reused by batch k + NW:
+        // ---- stage pipeline: s_f1[] run the stage-1 fills (alternating, so consecutive launches overlap at their
+        //      tails), s_tr (high priority) the tracebacks, s_f2[] the stage-2 fills.  Workspace set w = k % NW is reused by batch k + NW:
         //        fill1(k)  needs tb[w] consumed            -> waits for trace(k - NW)
         //        trace(k)  needs fill1(k), rows2/path free  -> waits for fill1(k), fill2(k - NW)
         //        fill2(k)  needs trace(k)
-        CU(cudaStreamWaitEvent(c->s_f1, c->ev1, 0));
+        for (int k = 0; k < 2; ++k) {
+            CU(cudaStreamWaitEvent(c->s_f1[k], c->ev1, 0));
+            CU(cudaStreamWaitEvent(c->s_f2[k], c->ev1, 0));
+        }
         CU(cudaStreamWaitEvent(c->s_tr, c->ev1, 0));
-        CU(cudaStreamWaitEvent(c->s_f2, c->ev1, 0));
         // CARETTA_B200_TIMELINE=1: bracket every kernel with timing events and print the schedule (debug)
         const bool timeline = getenv("CARETTA_B200_TIMELINE") && atoi(getenv("CARETTA_B200_TIMELINE")) != 0;
         struct Mark { const char *what; size_t batch; cudaEvent_t e0, e1; };
@@ -553,22 +557,23 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         for (size_t bi = 0; bi < batches.size(); ++bi) {
             const Batch &b = batches[bi];
             crt_ctx::Workspace &ws = c->ws[bi % NW];
-            if (bi >= (size_t)NW) CU(cudaStreamWaitEvent(c->s_f1, ws.e_t, 0));
-            mark0("fill1", bi, c->s_f1);
-            if ((rc = stage1(b, ws, c->s_f1))) return rc;
-            mark1(c->s_f1);
-            CU(cudaEventRecord(ws.e_f1, c->s_f1));
+            cudaStream_t sf1 = c->s_f1[bi & 1], sf2 = c->s_f2[bi & 1];
+            if (bi >= (size_t)NW) CU(cudaStreamWaitEvent(sf1, ws.e_t, 0));
+            mark0("fill1", bi, sf1);
+            if ((rc = stage1(b, ws, sf1))) return rc;
+            mark1(sf1);
+            CU(cudaEventRecord(ws.e_f1, sf1));
             CU(cudaStreamWaitEvent(c->s_tr, ws.e_f1, 0));
             if (bi >= (size_t)NW) CU(cudaStreamWaitEvent(c->s_tr, ws.e_f2, 0));
             mark0("trace", bi, c->s_tr);
             if ((rc = stage_trace(b, ws, c->s_tr, nullptr))) return rc;
             mark1(c->s_tr);
             CU(cudaEventRecord(ws.e_t, c->s_tr));
-            CU(cudaStreamWaitEvent(c->s_f2, ws.e_t, 0));
-            mark0("fill2", bi, c->s_f2);
-            if ((rc = stage2(b, ws, c->s_f2))) return rc;
-            mark1(c->s_f2);
-            CU(cudaEventRecord(ws.e_f2, c->s_f2));
+            CU(cudaStreamWaitEvent(sf2, ws.e_t, 0));
+            mark0("fill2", bi, sf2);
+            if ((rc = stage2(b, ws, sf2))) return rc;
+            mark1(sf2);
+            CU(cudaEventRecord(ws.e_f2, sf2));
             c->launches += 4;
         }
         if (timeline) {
@@ -576,16 +581,19 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             for (auto &mk : marks) {
                 float t0 = 0, t1 = 0;
                 cudaEventElapsedTime(&t0, c->ev0, mk.e0); cudaEventElapsedTime(&t1, c->ev0, mk.e1);
-                fprintf(stderr, "[timeline] %-6s batch %2zu  %8.3f -> %8.3f ms  (%7.3f)\n", mk.what, mk.batch, t0, t1, t1 - t0);
+                const Batch &bb = batches[mk.batch];
+                double cells = 0;
+                for (size_t k = bb.first; k < bb.first + bb.count; ++k) cells += (double)hu[k].G * hu[k].m;
+                fprintf(stderr, "[timeline] %-6s batch %3zu C=%2d multi=%d units=%6zu Mcells=%9.1f  %9.3f -> %9.3f ms  (%7.3f)\n", mk.what, mk.batch,
+                        bb.C, bb.multi, bb.count, cells * 1e-6, t0, t1, t1 - t0);
                 cudaEventDestroy(mk.e0); cudaEventDestroy(mk.e1);
             }
         }
-        CU(cudaEventRecord(c->ws[0].done, c->s_f2));          // the last fill2 is the last kernel of the run
-        CU(cudaStreamWaitEvent(c->stream, c->ws[0].done, 0));
-        CU(cudaEventRecord(c->ws[1].done, c->s_tr));
-        CU(cudaStreamWaitEvent(c->stream, c->ws[1].done, 0));
-        CU(cudaEventRecord(c->ws[2].done, c->s_f1));
-        CU(cudaStreamWaitEvent(c->stream, c->ws[2].done, 0));
+        cudaStream_t all5[5] = {c->s_f1[0], c->s_f1[1], c->s_f2[0], c->s_f2[1], c->s_tr};
+        for (int k = 0; k < 5; ++k) {
+            CU(cudaEventRecord(c->ws[k % crt_ctx::MAX_WS].ev[k / crt_ctx::MAX_WS], all5[k]));
+            CU(cudaStreamWaitEvent(c->stream, c->ws[k % crt_ctx::MAX_WS].ev[k / crt_ctx::MAX_WS], 0));
+        }
     } else {
     for (int w = 0; w < NS; ++w) CU(cudaStreamWaitEvent(c->ws[w].stream, c->ev1, 0));
     for (size_t bi = 0; bi < batches.size(); ++bi) {
@@ -693,8 +701,10 @@ int crt_create(int device, crt_ctx **out)
     }
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    CU(cudaStreamCreateWithPriority(&c->s_f1, cudaStreamNonBlocking, prio_lo));
-    CU(cudaStreamCreateWithPriority(&c->s_f2, cudaStreamNonBlocking, prio_lo));
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaStreamCreateWithPriority(&c->s_f1[k], cudaStreamNonBlocking, prio_lo));
+        CU(cudaStreamCreateWithPriority(&c->s_f2[k], cudaStreamNonBlocking, prio_lo));
+    }
     CU(cudaStreamCreateWithPriority(&c->s_tr, cudaStreamNonBlocking, prio_hi));     // short latency-bound kernels go first
     *out = c;
     return 0;
@@ -721,8 +731,10 @@ int crt_destroy(crt_ctx *c)
     c->pair_istar.release(); c->pair_zflag.release(); c->ncommon.release(); c->status.release();
     c->score.release(); c->score1.release(); c->rmsd.release(); c->tm.release(); c->f32tmp.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    if (c->s_f1) cudaStreamDestroy(c->s_f1);
-    if (c->s_f2) cudaStreamDestroy(c->s_f2);
+    for (int k = 0; k < 2; ++k) {
+        if (c->s_f1[k]) cudaStreamDestroy(c->s_f1[k]);
+        if (c->s_f2[k]) cudaStreamDestroy(c->s_f2[k]);
+    }
     if (c->s_tr) cudaStreamDestroy(c->s_tr);
     cudaStreamDestroy(c->stream);
     delete c;
