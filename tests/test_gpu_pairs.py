@@ -224,3 +224,60 @@ def test_argument_errors(eng):
     bad = ch.coords.copy(); bad[3, 1] = np.nan
     with pytest.raises(engine.CrtError):
         eng.set_chains(bad, ch.tensors, ch.offsets)
+
+
+@pytest.mark.parametrize("prec", [engine.FP64, engine.FP32])
+def test_short_chains_many_boundaries_per_unit(eng, prec):
+    """Chains of 1 .. 40 residues all-vs-all: one unit streams many row chains, so several chain boundaries fall inside
+    one 32-step window of the systolic array (the checked/fast row groups of the fp32 fills must agree with the
+    oracle for every pair), mixed with a few longer chains so that several columns-per-lane variants share a run."""
+    lengths = [1, 2, 3, 5, 8, 13, 21, 31, 32, 33, 40, 4, 6, 9, 17, 29, 35, 2, 1, 12, 75, 130, 7, 3, 330, 36, 11, 5, 64, 65]
+    ch = synth.make_chains(len(lengths), lengths, 10, seed=77, family_size=6)
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    want = O.pairwise_all(ch.coords, ch.tensors, ch.offsets)
+    S, R, T = eng.pairwise_all(eng.params(precision=prec), want_rmsd_tm=True)
+    assert np.array_equal(S, S.T) and np.all(np.diag(S) == 0) and np.all(np.diag(T) == 1) and np.all(np.diag(R) == 0)
+    if prec == engine.FP64:
+        np.testing.assert_allclose(S, want, rtol=1e-11, atol=0)
+    else:
+        # pairs whose fp32 stage-1 alignment differs from the fp64 one are compared through the paths below
+        pi, pj = np.triu_indices(ch.n, 1)
+        res = eng.pairwise_list(eng.params(precision=prec), pi, pj, want_paths=True)
+        np.testing.assert_array_equal(res["score"], S[pi, pj])          # the list path and the all-vs-all path agree bitwise
+    # the all-vs-all unit layout (many chains per unit) against the per-pair oracle, paths included
+    pi, pj = np.triu_indices(ch.n, 1)
+    _oracle_compare(eng, ch, pi, pj, prec)
+
+
+def test_zero_region_fp32(eng):
+    """The fp32 fill and k_trace's exact zero test must evaluate the exponent in the same operation order: a far-away
+    head makes S underflow to 0 in the top-left block, the traceback has to stop where the reference's does."""
+    ch = synth.make_chains(4, [30, 34, 28, 31], 10, seed=41, family_size=4)
+    t = ch.tensors.copy()
+    for p in range(2):
+        s = int(ch.offsets[p])
+        t[s:s + 6] += 40.0 * (p + 1)
+    ch2 = synth.Chains(ch.coords, t, ch.offsets)
+    eng.set_chains(ch2.coords, ch2.tensors, ch2.offsets)
+    res = eng.pairwise_list(eng.params(precision=engine.FP32), [0, 0, 1], [1, 3, 3], want_paths=True)
+    for q, (i, j) in enumerate([(0, 1), (0, 3), (1, 3)]):
+        o = O.pair(*ch2.chain(i), *ch2.chain(j))
+        a1, a2 = _paths(res, q)
+        assert _cols(a1, a2) == _cols(o["aln1"], o["aln2"])
+        np.testing.assert_allclose(res["score"][q], o["score"], rtol=1e-4)
+
+
+def test_pinned_buffers_and_out_arrays(eng, small):
+    """crt_host_alloc-backed numpy arrays as inputs and as the dense outputs of crt_pairwise_all."""
+    g, ch = small
+    pc, pt, po = engine.pinned_like(ch.coords), engine.pinned_like(ch.tensors), engine.pinned_like(ch.offsets)
+    eng.set_chains(pc, pt, po)
+    out = tuple(engine.pinned_empty((ch.n, ch.n)) for _ in range(3))
+    S, R, T = eng.pairwise_all(eng.params(precision=engine.FP64), want_rmsd_tm=True, out=out)
+    assert S is out[0] and T is out[2]
+    np.testing.assert_allclose(S, g["score_matrix"], rtol=1e-11)
+    S2 = eng.pairwise_all(eng.params(precision=engine.FP64))             # pageable output, same numbers
+    assert np.array_equal(S, S2)
+    with pytest.raises(ValueError):
+        eng.pairwise_all(eng.params(), out=np.zeros((ch.n, ch.n), np.float32))
+    del out, S, R, T                                                     # frees the pinned blocks
