@@ -13,8 +13,9 @@ Pairs are sharded by cost over the ranks (no data-path collective); at N > 1 the
 all-gather of the packed score / RMSD / TM vectors.
 
 The JSON line: value = pairs/s with the chains resident in HBM, device-timed (CUDA events on the engine's stream,
-max over ranks); e2e = the same through the Python API with pinned HOST buffers (H2D of the chains and D2H of the
-results inside the timed region); roofline = the dominant kernel (stage-1 fill) against the FP32 FFMA peak measured
+max over ranks); e2e = the same through the reference-facing call (crt_set_chains + crt_pairwise_all behind
+make_pairwise_matrix) with page-locked HOST buffers: H2D of the packed float64 chains and D2H of the dense float64
+[N,N] score / RMSD / TM matrices inside the timed region; roofline = the dominant kernel (stage-1 fill) against the FP32 FFMA peak measured
 in the same run; cpu_baseline = the oracle port on the host cores on a bounded sample of the same workload.
 """
 import argparse
@@ -243,26 +244,27 @@ def main():
     # ------------------------------------------------------------------ e2e: host buffers in, host results out
     # N = 1: the reference-facing call (make_pairwise_matrix -> crt_set_chains + crt_pairwise_all): packed float64
     # chains in page-locked host memory in, dense float64 [N,N] score / RMSD / TM matrices in page-locked host memory out.
-    # N > 1: upload, shard, all-gather of the packed float32 vectors, one D2H of the gathered buffer per rank.
+    # N > 1: upload, shard, all-gather of the packed float32 vectors, scatter into the dense matrices on the GPU, D2H of
+    # the three dense [N,N] float64 matrices on every rank (caretta_b200.distributed.all_vs_all).
     pin_c, pin_t, pin_o = engine.pinned_like(ch.coords), engine.pinned_like(ch.tensors), engine.pinned_like(ch.offsets)
-    h_all = torch.empty(world * 3 * pad, dtype=torch.float32).pin_memory() if world > 1 else None
     dense = tuple(engine.pinned_empty((n, n)) for _ in range(3)) if world == 1 else None
+    h_dense = torch.empty(3, n, n, dtype=torch.float64).pin_memory() if world > 1 else None
+    if world > 1:
+        from caretta_b200 import distributed as D
     e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(1):                                                          # untimed: first-touch of the new buffers
-        eng.set_chains(pin_c, pin_t, pin_o)
-        if world == 1:
-            eng.pairwise_all(prm, want_rmsd_tm=True, out=dense)
+
+    def e2e_step():
+        eng.set_chains(pin_c, pin_t, pin_o)                                     # H2D of this step's inputs
+        if world > 1:
+            D.all_vs_all(eng, prm, rank, world, out=h_dense)                    # shard, all-gather, device scatter, D2H
+        else:
+            eng.pairwise_all(prm, want_rmsd_tm=True, out=dense)                 # D2H: three dense [N,N] float64 matrices
+
+    e2e_step()                                                                  # untimed: first touch of the new buffers
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.set_chains(pin_c, pin_t, pin_o)                                     # H2D of this step's inputs
-        if world > 1:
-            eng.pairwise_shard(prm, rank, world)
-            eng.fetch_device(d_mine.data_ptr(), d_mine.data_ptr() + 4 * pad, d_mine.data_ptr() + 8 * pad, pad)
-            dist.all_gather_into_tensor(d_all, d_mine)
-            h_all.copy_(d_all, non_blocking=False)                              # D2H of the gathered matrices
-        else:
-            eng.pairwise_all(prm, want_rmsd_tm=True, out=dense)                 # D2H: three dense [N,N] float64 matrices
+        e2e_step()
     sync_all()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -270,7 +272,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     h2d = ch.coords.nbytes + ch.tensors.nbytes + ch.offsets.nbytes
-    d2h = (world * 3 * pad * 4) if world > 1 else 3 * n * n * 8
+    d2h = 3 * n * n * 8                      # per rank: every rank ends with the dense score / RMSD / TM matrices on its host
 
     if rank != 0:
         if world > 1:
@@ -295,7 +297,7 @@ def main():
     peak = peak_ffma / 1e12
     sm_clock = clocks.get("sm_mhz") or 0.0
     roofline = {
-        "bound": "fp32", "kernel": "k_fill1_f32 (stage-1 Smith-Waterman fill + traceback bits)",
+        "bound": "fp32", "kernel": "k_fill1_v3 (stage-1 Smith-Waterman fill + traceback bits)",
         "achieved": achieved, "peak": peak, "unit": "T lane-instr/s", "frac": achieved / peak,
         "peak_source": "FFMA micro-benchmark in this run (crt_fp32_peak); MEASURED_PEAKS.json has no FP32-pipe entry; "
                        "nominal 148 SM x 128 lanes x 1.965 GHz = 37.2",
@@ -303,8 +305,12 @@ def main():
         "avg_launch_ms": ph["fill1"] / max(n_batches, 1),
         "serial_step_ms": serial_ms, "phase_ms": ph,
         "whole_step_frac": (my_cells * W_ALL / (ms_per_step * 1e-3)) / peak_ffma,
-        "traffic": None,
-        "hbm": {"peak_gbs": _measured_hbm(), "note": "path is FP32-pipe bound; HBM traffic is the 0.4 B/cell traceback stream (profiles/)"},
+        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel: 2.422 GB for a launch of
+        # 5.740e9 residue pairs (profiles/r01_ncu_summary.md, r1d) = 0.422 B per residue pair, scaled to this run's launches
+        "traffic": 0.422 * my_cells / max(n_batches, 1),
+        "traffic_unit": "bytes per launch (ncu-measured bytes per residue pair x residue pairs per launch)",
+        "hbm": {"peak_gbs": _measured_hbm(), "achieved_gbs": 0.422 * my_cells / fill1_s / 1e9,
+                "note": "path is FP32-issue bound; HBM traffic is the 0.4 B/cell traceback stream, equal to the algorithmic bytes"},
     }
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, bounded sample)

@@ -236,13 +236,38 @@ size_t env_budget();
 
 // ---------------------------------------------------------------------------------------------- unit building
 constexpr int MAX_PAIRS_PER_UNIT = 32;
-// rows streamed by one unit (tuning knob CARETTA_B200_UNIT_ROWS): longer units amortise the 31-step pipeline drain,
-// shorter units shorten the tail of a launch
+// Rows streamed by one unit.  Longer units amortise the 31-step pipeline fill of the systolic array, shorter units give
+// the block scheduler more, finer work items (a short run sharded over 8 GPUs must not end on a few long stragglers).
+// Default: about 24 units per resident-warp slot of the rank's shard, between one chain and 3072 rows; the rule depends
+// on (offsets, world) only, so the host-side planner and every precision enumerate the same units.
+// CARETTA_B200_UNIT_ROWS overrides it (tuning).
 int env_unit_rows()
 {
     const char *e = getenv("CARETTA_B200_UNIT_ROWS");
-    int n = e ? atoi(e) : 6144;
-    return std::min(std::max(n, 64), 1 << 20);
+    int n = e ? atoi(e) : 0;
+    return n <= 0 ? 0 : std::min(std::max(n, 64), 1 << 20);
+}
+
+constexpr int UNIT_ROWS_MIN = 512, UNIT_ROWS_MAX = 3072, NOMINAL_STRIP_COLS = 320, RESIDENT_SLOTS = 148 * 8, UNITS_PER_SLOT = 24;
+
+// row-steps (rows x nominal strips) one unit should stream, for this shard
+double unit_rowsteps_target(const std::vector<long long> &offsets, int N, int world)
+{
+    double total = 0.0, rows_before = 0.0;
+    for (int j = 0; j < N; ++j) {
+        const double len = (double)(offsets[j + 1] - offsets[j]);
+        total += rows_before * std::ceil(len / NOMINAL_STRIP_COLS);
+        rows_before += len;
+    }
+    return total / std::max(world, 1) / ((double)RESIDENT_SLOTS * UNITS_PER_SLOT);
+}
+
+int unit_rows_cap(double target_rowsteps, int m)
+{
+    if (const int forced = env_unit_rows()) return forced;
+    const double strips = std::ceil((double)m / NOMINAL_STRIP_COLS);
+    const double r = target_rowsteps / std::max(strips, 1.0);
+    return (int)std::min<double>(std::max<double>(r, UNIT_ROWS_MIN), UNIT_ROWS_MAX);
 }
 
 void finish_unit(const crt_ctx *c, HostUnit &h, int precision)
@@ -257,11 +282,12 @@ void finish_unit(const crt_ctx *c, HostUnit &h, int precision)
 }
 
 // all-vs-all units in a deterministic order: column chain j ascending, runs of row chains ascending
-void build_all_units(const crt_ctx *c, int precision, std::vector<HostUnit> &out)
+void build_all_units(const crt_ctx *c, int precision, int world, std::vector<HostUnit> &out)
 {
-    const int TARGET_ROWS_PER_UNIT = env_unit_rows();
+    const double target = unit_rowsteps_target(c->offsets, c->N, world);
     out.clear();
     for (int j = 1; j < c->N; ++j) {
+        const int TARGET_ROWS_PER_UNIT = unit_rows_cap(target, (int)(c->offsets[j + 1] - c->offsets[j]));
         int i = 0;
         while (i < j) {
             HostUnit h{};
@@ -861,7 +887,7 @@ int crt_pairwise_shard(crt_ctx *c, const crt_params *prm, int32_t rank, int32_t 
         return run_units(c, prm, none, pc.n_pairs, nullptr, true, false);
     }
     std::vector<HostUnit> units;
-    build_all_units(c, prm->precision, units);
+    build_all_units(c, prm->precision, world, units);
     shard_units(units, rank, world);
     long long np = 0;
     assign_pairs(units, &c->run_pi, &c->run_pj, &np, &c->cell_updates, c);
@@ -884,7 +910,7 @@ int64_t crt_shard_size(crt_ctx *c, int32_t rank, int32_t world)
     if (!c || c->N <= 0) return fail(CRT_E_STATE, "no chains");
     if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world");
     std::vector<HostUnit> units;
-    build_all_units(c, CRT_FP32, units);     // the enumeration does not depend on the precision
+    build_all_units(c, CRT_FP32, world, units);     // the enumeration does not depend on the precision
     shard_units(units, rank, world);
     long long np = 0;
     assign_pairs(units, nullptr, nullptr, &np, nullptr, c);
@@ -897,7 +923,7 @@ int crt_shard_pairs(crt_ctx *c, int32_t rank, int32_t world, int32_t *pair_i, in
     if (!pair_i || !pair_j) return fail(CRT_E_ARG, "null argument");
     if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world");
     std::vector<HostUnit> units;
-    build_all_units(c, CRT_FP32, units);
+    build_all_units(c, CRT_FP32, world, units);
     shard_units(units, rank, world);
     std::vector<int> pi, pj;
     long long np = 0;
@@ -915,7 +941,7 @@ static int plan_units(const int64_t *offsets, int32_t n_chains, int32_t rank, in
     crt_ctx tmp;
     tmp.N = n_chains; tmp.D = 10;
     tmp.offsets.assign(offsets, offsets + n_chains + 1);
-    build_all_units(&tmp, CRT_FP32, units);
+    build_all_units(&tmp, CRT_FP32, world, units);
     shard_units(units, rank, world);
     return 0;
 }
@@ -1090,7 +1116,7 @@ int crt_pairwise_list(crt_ctx *c, const crt_params *prm, const int32_t *pair_i, 
             if (cnt > 0 && ii == i + cnt - 1) { slot_of[(size_t)order[q]] = slot - 1; ++q; continue; }   // duplicate pair
             if (ii != i + cnt || cnt >= MAX_PAIRS_PER_UNIT) break;
             const int n = (int)(c->offsets[ii + 1] - c->offsets[ii]);
-            if (cnt > 0 && G + n > env_unit_rows()) break;
+            if (cnt > 0 && G + n > (env_unit_rows() ? env_unit_rows() : UNIT_ROWS_MAX)) break;
             G += n; maxn = std::max(maxn, n);
             slot_of[(size_t)order[q]] = slot++;
             ++cnt; ++q;
