@@ -6,6 +6,7 @@
 #include "crt_fill1_v2.cuh"
 #include "crt_fill2_v3.cuh"
 #include "crt_dp_batch.cuh"
+#include "crt_nj.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1297,6 +1298,63 @@ int crt_rmsd_cov_tm(crt_ctx *c, const int64_t *aln, int64_t A, double *rmsd, dou
     cleanup();
     if (e != cudaSuccess) return fail(CRT_E_CUDA, "crt_rmsd_cov_tm: %s", cudaGetErrorString(e));
     if (n_bad) *n_bad = bad;
+    return 0;
+}
+
+/* neighbor_joining.py:17-99 on the device: guide tree (node_1, node_2) rows + branch lengths, bit-identical to the
+ * reference for any float64 input (symmetric or not).  tree: [2N-3][2] uint64, branch_lengths: [2N-3] float64. */
+int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, uint64_t *tree, double *branch_lengths, int64_t *n_rows)
+{
+    if (!c || !distance_matrix || !tree || !branch_lengths) return fail(CRT_E_ARG, "null argument");
+    if (N < 3) return fail(CRT_E_ARG, "neighbor joining needs at least 3 nodes (the reference indexes out of range below that)");
+    CU(cudaSetDevice(c->device));
+    const size_t NN = (size_t)N * N, rows_max = (size_t)2 * N - 3;
+    const int max_part = 1024;
+    double *A = nullptr, *B = nullptr, *S0 = nullptr, *S1 = nullptr, *pq = nullptr, *d_bl = nullptr;
+    long long *t0 = nullptr, *t1 = nullptr, *plin = nullptr;
+    unsigned long long *d_tree = nullptr;
+    NjSel *sel = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(A); cudaFree(B); cudaFree(S0); cudaFree(S1); cudaFree(pq); cudaFree(d_bl); cudaFree(t0); cudaFree(t1); cudaFree(plin);
+        cudaFree(d_tree); cudaFree(sel);
+    };
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return e == cudaSuccess; };
+    std::vector<long long> ident((size_t)N);
+    for (int q = 0; q < N; ++q) ident[(size_t)q] = q;
+    cudaStream_t st = c->stream;
+    if (ok(cudaMalloc(&A, NN * 8)) && ok(cudaMalloc(&B, NN * 8)) && ok(cudaMalloc(&S0, (size_t)N * 8)) && ok(cudaMalloc(&S1, (size_t)N * 8)) &&
+        ok(cudaMalloc(&pq, max_part * 8)) && ok(cudaMalloc(&plin, max_part * 8)) && ok(cudaMalloc(&t0, (size_t)N * 8)) &&
+        ok(cudaMalloc(&t1, (size_t)N * 8)) && ok(cudaMalloc(&d_tree, rows_max * 16)) && ok(cudaMalloc(&d_bl, rows_max * 8)) &&
+        ok(cudaMalloc(&sel, sizeof(NjSel)))) {
+        ok(cudaMemcpyAsync(A, distance_matrix, NN * 8, cudaMemcpyHostToDevice, st));
+        ok(cudaMemcpyAsync(t0, ident.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+        ok(cudaMemsetAsync(sel, 0, sizeof(NjSel), st));
+        CU(cudaEventRecord(c->ev0, st));
+        k_nj_rowsums<<<(unsigned)(((size_t)N * 32 + 255) / 256), 256, 0, st>>>(A, N, S0);
+        int n = N;
+        while (n > 3 && e == cudaSuccess) {
+            const long long total = (long long)n * n;
+            const int n_part = (int)std::min<long long>(max_part, (total + NJ_ARGMIN_THREADS * 8 - 1) / (NJ_ARGMIN_THREADS * 8));
+            k_nj_argmin<<<n_part, NJ_ARGMIN_THREADS, 0, st>>>(A, S0, n, pq, plin);
+            k_nj_select<<<1, NJ_ARGMIN_THREADS, 0, st>>>(A, S0, n, N, pq, plin, n_part, t0, sel, d_tree, d_bl);
+            k_nj_rebuild<<<(unsigned)(((size_t)(n - 1) * 32 + 255) / 256), 256, 0, st>>>(A, n, sel, N, t0, t1, B, S1);
+            std::swap(A, B); std::swap(S0, S1); std::swap(t0, t1);
+            --n;
+            if ((n & 255) == 0) ok(cudaGetLastError());
+        }
+        k_nj_last3<<<1, 32, 0, st>>>(A, S0, N, t0, sel, d_tree, d_bl);
+        ok(cudaGetLastError());
+        CU(cudaEventRecord(c->ev1, st));
+        ok(cudaMemcpyAsync(tree, d_tree, rows_max * 16, cudaMemcpyDeviceToHost, st));
+        ok(cudaMemcpyAsync(branch_lengths, d_bl, rows_max * 8, cudaMemcpyDeviceToHost, st));
+        ok(cudaStreamSynchronize(st));
+        float ms = 0;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->elapsed_ms = ms;
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(CRT_E_CUDA, "crt_neighbor_joining: %s", cudaGetErrorString(e));
+    if (n_rows) *n_rows = (int64_t)rows_max;
     return 0;
 }
 

@@ -19,7 +19,7 @@ EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
-    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak", "crt_host_alloc", "crt_host_free",
+    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining",
 ]
 
 
@@ -73,6 +73,7 @@ def load_library():
     L.crt_dtw_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, dbl, dbl, vp, vp, vp, i64, vp]
     L.crt_rmsd_cov_tm.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(i32)]
     L.crt_fp32_peak.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
+    L.crt_neighbor_joining.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i64)]
     L.crt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.crt_host_free.argtypes = [vp]
     for name in EXPORTS:
@@ -333,6 +334,20 @@ class Engine:
         self._check(self.lib.crt_rmsd_cov_tm(self.h, _p(aln), aln.shape[1], _p(r), _p(c), _p(t), C.byref(bad)),
                     "crt_rmsd_cov_tm")
         return r, c, t, int(bad.value)
+
+    def neighbor_joining(self, distance_matrix):
+        """caretta/neighbor_joining.py:17-99 on the device: (tree uint64 [2N-3, 2], branch_lengths float64 [2N-3, 1])."""
+        D = np.ascontiguousarray(distance_matrix, dtype=np.float64)
+        if D.ndim != 2 or D.shape[0] != D.shape[1]:
+            raise ValueError("square distance matrix expected")
+        n = D.shape[0]
+        if n < 3:
+            raise IndexError("neighbor_joining needs at least 3 nodes (the reference indexes out of range below that)")
+        tree = np.zeros((2 * n - 3, 2), np.uint64)
+        bl = np.zeros((2 * n - 3, 1))
+        k = C.c_int64()
+        self._check(self.lib.crt_neighbor_joining(self.h, _p(D), n, _p(tree), _p(bl), C.byref(k)), "crt_neighbor_joining")
+        return tree[:k.value], bl[:k.value]
 
     def fp32_peak(self):
         v, ms = C.c_double(), C.c_double()

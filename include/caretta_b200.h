@@ -133,6 +133,14 @@ int crt_dtw_align_batch(crt_ctx *ctx, const double *S, const int64_t *shape_off,
 int crt_rmsd_cov_tm(crt_ctx *ctx, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm,
                     int32_t *n_bad);
 
+/* Neighbor joining on the device: replaces caretta/neighbor_joining.py:17-99 (`neighbor_joining(distance_matrix)`, called
+ * at multiple_alignment.py:277 on max(S) - S of the pairwise matrix).  distance_matrix: float64 [N,N] row-major (host),
+ * N >= 3.  tree: uint64 [2N-3][2] rows (node_1, node_2), node ids >= N are intermediate nodes in creation order;
+ * branch_lengths: float64 [2N-3].  Bit-identical to the reference: sequential float64 row sums, Q in the reference's
+ * operation order, first strict minimum in row-major order, new node at index 0.  crt_last_elapsed_ms = device time. */
+int crt_neighbor_joining(crt_ctx *ctx, const double *distance_matrix, int32_t N, uint64_t *tree, double *branch_lengths,
+                         int64_t *n_rows);
+
 /* FP32 FFMA micro-benchmark used as the measured roofline denominator: returns lane-FFMA/s. */
 int crt_fp32_peak(crt_ctx *ctx, double *ffma_per_s, double *elapsed_ms);
 

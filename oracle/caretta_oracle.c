@@ -28,6 +28,7 @@
  *   crt_o_pair                  multiple_alignment.py:321-349 + :164-169
  *   crt_o_pairwise_all/_list    multiple_alignment.py:158-170
  *   crt_o_rmsd_cov_tm           multiple_alignment.py:1000-1055 (superpose_first=False)
+ *   crt_o_neighbor_joining      neighbor_joining.py:17-157
  */
 #include <math.h>
 #include <float.h>
@@ -514,6 +515,73 @@ API int crt_o_rmsd_cov_tm(const int64_t *aln, int N, int64_t A, const double *co
         }
     free(p1); free(k1);
     return bad;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* neighbor_joining.py:17-157.  The reference recomputes np.sum(distance_matrix[i, :]) inside the O(n^2) scan of
+ * _find_join_nodes (:118-125); numba's np.sum is a plain left-to-right loop, so caching the n row sums per iteration
+ * gives the identical values.  Q is evaluated in the reference's order ((n-2)*d - sum_i) - sum_j, the minimum is the
+ * first strict minimum in row-major order starting from +inf (:127-129), the matrix is rebuilt with the new node at
+ * index 0 and the remaining nodes in their previous order (:59-77).  tree: [2N-3][2] uint64, bl: [2N-3] float64.
+ * Returns the number of rows written, or -1 if N < 3 (the reference indexes out of range there). */
+API int64_t crt_o_neighbor_joining(const double *D0, int N, uint64_t *tree, double *bl)
+{
+    if (N < 3) return -1;
+    int n = N;
+    double *D = (double *)malloc(sizeof(double) * (size_t)N * N), *Dn = (double *)malloc(sizeof(double) * (size_t)N * N);
+    double *S = (double *)malloc(sizeof(double) * (size_t)N);
+    int64_t *ti = (int64_t *)malloc(sizeof(int64_t) * (size_t)N), *tn = (int64_t *)malloc(sizeof(int64_t) * (size_t)N);
+    int *idx = (int *)malloc(sizeof(int) * (size_t)N);
+    memcpy(D, D0, sizeof(double) * (size_t)N * N);
+    for (int i = 0; i < N; ++i) ti[i] = i;
+    int64_t index = 0, n_inter = 0;
+    while (n > 3) {
+        for (int i = 0; i < n; ++i) { double acc = 0.0; for (int j = 0; j < n; ++j) acc = acc + D[(size_t)i * n + j]; S[i] = acc; }
+        int mi = 0, mj = 0;
+        double min_q = INFINITY;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j)
+                if (i != j) {
+                    const double q = ((double)(n - 2) * D[(size_t)i * n + j] - S[i]) - S[j];
+                    if (q < min_q) { mi = i; mj = j; min_q = q; }
+                }
+        const double dij = D[(size_t)mi * n + mj];
+        const double di = 0.5 * dij + (0.5 / (double)(n - 2)) * (S[mi] - S[mj]);      /* _find_branch_length :137-157 */
+        const double dj = dij - di;
+        const int64_t node = n_inter + N;
+        ++n_inter;
+        tree[2 * index] = (uint64_t)ti[mi]; tree[2 * index + 1] = (uint64_t)node; bl[index] = di; ++index;
+        tree[2 * index] = (uint64_t)ti[mj]; tree[2 * index + 1] = (uint64_t)node; bl[index] = dj; ++index;
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) if (i != mi && i != mj) idx[cnt++] = i;
+        const int nn = n - 1;
+        Dn[0] = 0.0;
+        for (int a = 0; a < cnt; ++a)
+            for (int b = 0; b < cnt; ++b) Dn[(size_t)(a + 1) * nn + (b + 1)] = D[(size_t)idx[a] * n + idx[b]];
+        for (int a = 0; a < cnt; ++a) {
+            const double v = 0.5 * ((D[(size_t)mi * n + idx[a]] + D[(size_t)mj * n + idx[a]]) - dij);
+            Dn[a + 1] = v; Dn[(size_t)(a + 1) * nn] = v;
+        }
+        tn[0] = node;
+        for (int a = 0; a < cnt; ++a) tn[a + 1] = ti[idx[a]];
+        { double *t = D; D = Dn; Dn = t; }
+        { int64_t *t = ti; ti = tn; tn = t; }
+        n = nn;
+    }
+    {   /* last three nodes, :80-98 */
+        double s1 = 0.0, s2 = 0.0;
+        for (int j = 0; j < n; ++j) { s1 = s1 + D[(size_t)1 * n + j]; s2 = s2 + D[(size_t)2 * n + j]; }
+        const double d12 = D[(size_t)1 * n + 2];
+        const double di = 0.5 * d12 + (0.5 / (double)(n - 2)) * (s1 - s2);
+        const double dj = d12 - di;
+        const int64_t node = n_inter + N;
+        tree[2 * index] = (uint64_t)ti[1]; tree[2 * index + 1] = (uint64_t)node; bl[index] = di; ++index;
+        tree[2 * index] = (uint64_t)ti[2]; tree[2 * index + 1] = (uint64_t)node; bl[index] = dj; ++index;
+        tree[2 * index] = (uint64_t)ti[0]; tree[2 * index + 1] = (uint64_t)node;
+        bl[index] = 0.5 * ((D[(size_t)1 * n + 0] + D[(size_t)2 * n + 0]) - D[(size_t)1 * n + 2]); ++index;
+    }
+    free(D); free(Dn); free(S); free(ti); free(tn); free(idx);
+    return index;
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -71,6 +71,8 @@ def lib():
         L.crt_o_rmsd_cov_tm.argtypes = [_I64, C.c_int, C.c_int64, _D, _I64, _D, _D, _D]
         L.crt_o_rmsd_cov_tm.restype = C.c_int
         L.crt_o_num_threads.restype = C.c_int
+        L.crt_o_neighbor_joining.argtypes = [_D, C.c_int, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"), _D]
+        L.crt_o_neighbor_joining.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -219,6 +221,20 @@ def rmsd_cov_tm(aln, coords, offsets):
     r, c, t = np.empty((N, N)), np.empty((N, N)), np.empty((N, N))
     bad = lib().crt_o_rmsd_cov_tm(aln, N, A, coords, offsets, r, c, t)
     return r, c, t, bad
+
+
+def neighbor_joining(distance_matrix) -> Tuple[np.ndarray, np.ndarray]:
+    """neighbor_joining.py:17-99: (tree uint64 [2N-3, 2], branch_lengths float64 [2N-3, 1])."""
+    D = _c(distance_matrix)
+    n = D.shape[0]
+    if D.ndim != 2 or D.shape[1] != n:
+        raise ValueError("square distance matrix expected")
+    tree = np.zeros((max(2 * n - 3, 1), 2), np.uint64)
+    bl = np.zeros(max(2 * n - 3, 1))
+    k = int(lib().crt_o_neighbor_joining(D, n, tree, bl))
+    if k < 0:
+        raise IndexError("neighbor_joining needs at least 3 nodes (the reference indexes out of range)")
+    return tree[:k], bl[:k].reshape(-1, 1)
 
 
 def num_threads() -> int:

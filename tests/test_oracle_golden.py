@@ -195,3 +195,14 @@ def test_c2_full_paths_bit_exact():
         r = O.pair(*ch.chain(int(pi[q])), *ch.chain(int(pj[q])))
         assert r["aln1"].tolist() == g["aln1"][off[q]:off[q + 1]].tolist()
         assert r["aln2"].tolist() == g["aln2"][off[q]:off[q + 1]].tolist()
+
+
+def test_nj_golden():
+    """neighbor_joining.py:17-157 restated in C (crt_o_neighbor_joining) against the reference's own output."""
+    g = np.load(os.path.join(G, "nj.npz"))
+    for name in [str(n) for n in g["names"]]:
+        tree, bl = O.neighbor_joining(g[f"{name}_D"])
+        assert np.array_equal(tree, g[f"{name}_tree"]), name
+        assert np.array_equal(bl, g[f"{name}_bl"]), name
+    with pytest.raises(IndexError):
+        O.neighbor_joining(np.zeros((2, 2)))
