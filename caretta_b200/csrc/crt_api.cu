@@ -7,6 +7,7 @@
 #include "crt_fill2_v3.cuh"
 #include "crt_dp_batch.cuh"
 #include "crt_nj.cuh"
+#include "crt_node.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -129,6 +130,13 @@ struct crt_ctx {
         double cells = 0;
     } plan;
     unsigned long long offsets_hash = 0;
+
+    // progressive-alignment nodes (crt_progressive_node): a private context for the stage-1 pair run of the two
+    // consensus sequences, and grow-only device buffers
+    crt_ctx *node_ctx = nullptr;
+    DevBuf<double> nd_w, nd_S, nd_bnd, nd_f, nd_score, nd_xf2, nd_t, nd_c, nd_wm;
+    DevBuf<unsigned char> nd_B;
+    DevBuf<int> nd_a1, nd_a2, nd_len;
 
     // last run
     long long run_pairs = 0;
@@ -757,6 +765,9 @@ int crt_destroy(crt_ctx *c)
     c->xform.release(); c->path_len.release(); c->d_pi.release(); c->d_pj.release(); c->dense.release();
     c->pair_istar.release(); c->pair_zflag.release(); c->ncommon.release(); c->status.release();
     c->score.release(); c->score1.release(); c->rmsd.release(); c->tm.release(); c->f32tmp.release();
+    if (c->node_ctx) { crt_destroy(c->node_ctx); c->node_ctx = nullptr; }
+    c->nd_w.release(); c->nd_S.release(); c->nd_bnd.release(); c->nd_f.release(); c->nd_score.release(); c->nd_xf2.release();
+    c->nd_t.release(); c->nd_c.release(); c->nd_wm.release(); c->nd_B.release(); c->nd_a1.release(); c->nd_a2.release(); c->nd_len.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) {
         if (c->s_f1[k]) cudaStreamDestroy(c->s_f1[k]);
@@ -1298,6 +1309,89 @@ int crt_rmsd_cov_tm(crt_ctx *c, const int64_t *aln, int64_t A, double *rmsd, dou
     cleanup();
     if (e != cudaSuccess) return fail(CRT_E_CUDA, "crt_rmsd_cov_tm: %s", cudaGetErrorString(e));
     if (n_bad) *n_bad = bad;
+    return 0;
+}
+
+/* One node of progressive_align (multiple_alignment.py:195-234): score_function + weight Gaussian -> dtw_align ->
+ * mean_function + get_mean_weights, all on the device in float64.  Inputs are host arrays of the two (consensus)
+ * sequences; outputs: the alignment (int32, -1 = gap, length *aln_len <= n + m) and the intermediate node. */
+int crt_progressive_node(crt_ctx *c, const double *tensors1, const double *coords1, const double *weights1, int32_t n,
+                         const double *tensors2, const double *coords2, const double *weights2, int32_t m, int32_t d,
+                         double mult1, double mult2, double gamma_tensor, double gamma_coords, double gamma_weight,
+                         double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2, int32_t *aln_len,
+                         double *tensors_mean, double *coords_mean, double *weights_mean, double *score, int32_t *status)
+{
+    if (!c || !tensors1 || !coords1 || !weights1 || !tensors2 || !coords2 || !weights2 || !aln1 || !aln2 || !aln_len ||
+        !tensors_mean || !coords_mean || !weights_mean)
+        return fail(CRT_E_ARG, "null argument");
+    if (n <= 0 || m <= 0) return fail(CRT_E_ARG, "empty sequence (%d x %d)", n, m);
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if (!c->node_ctx && (rc = crt_create(c->device, &c->node_ctx))) return rc;
+    crt_ctx *nc = c->node_ctx;
+    // ---- stage 1 of score_function on the two sequences: the fp64 pair kernels, pair (0, 1)
+    std::vector<double> pc((size_t)(n + m) * 3), pt((size_t)(n + m) * d);
+    std::memcpy(pc.data(), coords1, sizeof(double) * (size_t)n * 3);
+    std::memcpy(pc.data() + (size_t)n * 3, coords2, sizeof(double) * (size_t)m * 3);
+    std::memcpy(pt.data(), tensors1, sizeof(double) * (size_t)n * d);
+    std::memcpy(pt.data() + (size_t)n * d, tensors2, sizeof(double) * (size_t)m * d);
+    const int64_t off[3] = {0, n, (int64_t)n + m};
+    if ((rc = crt_set_chains(nc, pc.data(), pt.data(), off, 2, d))) return rc;
+    crt_params prm{};
+    prm.gamma_tensor = gamma_tensor; prm.gamma_coords = gamma_coords; prm.sw_gap = 0.0; prm.precision = CRT_FP64;
+    const int32_t pi = 0, pj = 1;
+    double sc1 = 0, rm = 0, tm = 0;
+    int32_t ncm = 0, st1 = 0;
+    if ((rc = crt_pairwise_list(nc, &prm, &pi, &pj, 1, &sc1, &rm, &tm, &ncm, &st1, nullptr, nullptr, nullptr, 0))) return rc;
+    // ---- score matrix, affine DTW, intermediate node
+    const size_t cells = (size_t)n * m, alen = (size_t)n + m + 1;
+    if ((rc = c->nd_w.ensure((size_t)n + m))) return rc;
+    if ((rc = c->nd_S.ensure(cells))) return rc;
+    if ((rc = c->nd_B.ensure(cells))) return rc;
+    if ((rc = c->nd_bnd.ensure((size_t)n * 2 + 2))) return rc;
+    if ((rc = c->nd_f.ensure(3))) return rc;
+    if ((rc = c->nd_score.ensure(1))) return rc;
+    if ((rc = c->nd_xf2.ensure(XF))) return rc;
+    if ((rc = c->nd_a1.ensure(alen))) return rc;
+    if ((rc = c->nd_a2.ensure(alen))) return rc;
+    if ((rc = c->nd_len.ensure(1))) return rc;
+    if ((rc = c->nd_t.ensure(alen * (size_t)d))) return rc;
+    if ((rc = c->nd_c.ensure(alen * 3))) return rc;
+    if ((rc = c->nd_wm.ensure(alen))) return rc;
+    if ((rc = c->d_units.ensure(1))) return rc;                      // one DpProblem record fits in a Unit slot
+    static_assert(sizeof(DpProblem) <= sizeof(Unit), "DpProblem must fit in the unit buffer");
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->nd_w.p, weights1, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->nd_w.p + n, weights2, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, st));
+    DpProblem pr{};
+    pr.s_off = 0; pr.b_off = 0; pr.bnd_off = 0; pr.aln_off = 0; pr.n = n; pr.m = m;
+    DpProblem *d_pr = reinterpret_cast<DpProblem *>(c->d_units.p);
+    CU(cudaMemcpyAsync(d_pr, &pr, sizeof(pr), cudaMemcpyHostToDevice, st));
+    const double *dc1 = nc->coords.p, *dc2 = nc->coords.p + (size_t)n * 3;          // the node context holds the packed chains
+    const double *dt1 = nc->tensors.p, *dt2 = nc->tensors.p + (size_t)n * d;
+    k_node_score<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(dc1, n, dc2, m, nc->xform.p, c->nd_w.p, c->nd_w.p + n, mult1, mult2,
+                                                                 -gamma_coords, -gamma_weight, c->nd_S.p);
+    k_dtw_fill<<<1, 32, 0, st>>>(d_pr, 1, c->nd_S.p, c->nd_B.p, c->nd_bnd.p, c->nd_f.p, gap_open, gap_extend);
+    k_dtw_trace<<<1, 64, 0, st>>>(d_pr, 1, c->nd_B.p, c->nd_f.p, c->nd_a1.p, c->nd_a2.p, c->nd_len.p, c->nd_score.p);
+    k_node_kabsch<<<1, 32, 0, st>>>(dc1, dc2, c->nd_a1.p, c->nd_a2.p, c->nd_len.p, c->nd_xf2.p);
+    k_node_mean<<<(unsigned)((alen + 127) / 128), 128, 0, st>>>(dt1, dc1, c->nd_w.p, dt2, dc2, c->nd_w.p + n, d, c->nd_a1.p, c->nd_a2.p,
+                                                                c->nd_len.p, c->nd_xf2.p, c->nd_t.p, c->nd_c.p, c->nd_wm.p);
+    CU(cudaGetLastError());
+    int len = 0;
+    double sc = 0;
+    CU(cudaMemcpyAsync(&len, c->nd_len.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&sc, c->nd_score.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (len < 0 || (size_t)len > alen) return fail(CRT_E_STATE, "alignment length %d out of range", len);
+    CU(cudaMemcpyAsync(aln1, c->nd_a1.p, sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(aln2, c->nd_a2.p, sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tensors_mean, c->nd_t.p, sizeof(double) * (size_t)len * d, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(coords_mean, c->nd_c.p, sizeof(double) * (size_t)len * 3, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(weights_mean, c->nd_wm.p, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *aln_len = len;
+    if (score) *score = sc;
+    if (status) *status = st1;
     return 0;
 }
 

@@ -1,0 +1,115 @@
+// crt_node.cuh -- one node of the progressive alignment on the device, all float64.
+//
+// Reference: MultipleAlignment.progressive_align / make_intermediate_node, multiple_alignment.py:172-253:
+//   score_matrix  = Protein.score_function(n1, n2)                       (:203-205, :321-349; stage 1 = the pair kernels)
+//   score_matrix += make_score_matrix(w1 * mult1, w2 * mult2, gaussian, gamma_weight)              (:206-210)
+//   aln_1, aln_2  = dtw_align(arange, arange, score_matrix, gap_open, gap_extend)   (:211-214; k_dtw_fill / k_dtw_trace)
+//   intermediate  = Protein.mean_function(n1, n2, aln_1, aln_2)          (:215-216, :351-383)
+//   weights       = get_mean_weights(w1, w2, aln_1, aln_2)                (:217, :73-82)
+#pragma once
+#include "crt_kernels.cuh"
+
+namespace crt {
+
+// S[a][b] = exp(-gamma_c |c1'[a] - c2'[b]|^2) + exp(-gamma_w (w1[a] mult1 - w2[b] mult2)^2), with the chains in the frame of
+// paired_svd_superpose_with_subset (superposition_functions.py:38-60): c1' = c1 - mean(common_1),
+// c2' = (c2 - mean(common_2)) R; raw coordinates when the stage-1 alignment has <= 3 common positions (:337-342).
+// xf = k_trace's transform record of the pair: R[9], mean_1[3], mean_2[3], superpose flag.
+__global__ void __launch_bounds__(256) k_node_score(const double *c1, int n, const double *c2, int m, const double *xf,
+                                                    const double *w1, const double *w2, double mult1, double mult2,
+                                                    double neg_gamma_c, double neg_gamma_w, double *S)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)n * m) return;
+    const int a = (int)(q / m), b = (int)(q - (long long)a * m);
+    double x0 = c1[a * 3], x1 = c1[a * 3 + 1], x2 = c1[a * 3 + 2];
+    double y0 = c2[b * 3], y1 = c2[b * 3 + 1], y2 = c2[b * 3 + 2];
+    if (xf[15] != 0.0) {
+        x0 = __dsub_rn(x0, xf[9]); x1 = __dsub_rn(x1, xf[10]); x2 = __dsub_rn(x2, xf[11]);
+        const double u0 = __dsub_rn(y0, xf[12]), u1 = __dsub_rn(y1, xf[13]), u2 = __dsub_rn(y2, xf[14]);
+        y0 = __dadd_rn(__dadd_rn(__dmul_rn(u0, xf[0]), __dmul_rn(u1, xf[3])), __dmul_rn(u2, xf[6]));
+        y1 = __dadd_rn(__dadd_rn(__dmul_rn(u0, xf[1]), __dmul_rn(u1, xf[4])), __dmul_rn(u2, xf[7]));
+        y2 = __dadd_rn(__dadd_rn(__dmul_rn(u0, xf[2]), __dmul_rn(u1, xf[5])), __dmul_rn(u2, xf[8]));
+    }
+    // score_functions.py:11: sequential sum of (x - y)^2 with separate roundings, exp((-gamma) * acc)
+    double t = __dsub_rn(x0, y0), acc = __dmul_rn(t, t);
+    t = __dsub_rn(x1, y1); acc = __dadd_rn(acc, __dmul_rn(t, t));
+    t = __dsub_rn(x2, y2); acc = __dadd_rn(acc, __dmul_rn(t, t));
+    const double sc = exp(__dmul_rn(neg_gamma_c, acc));
+    double sw = 0.0;                              // neg_gamma_w > 0 (gamma_weight < 0): no weight term (two-structure case, :263-275)
+    if (!(neg_gamma_w > 0.0)) {
+        const double dw = __dsub_rn(__dmul_rn(w1[a], mult1), __dmul_rn(w2[b], mult2));
+        sw = exp(__dmul_rn(neg_gamma_w, __dmul_rn(dw, dw)));
+    }
+    S[q] = __dadd_rn(sc, sw);
+}
+
+// Superposition of mean_function (multiple_alignment.py:362-372) over the common positions of the DTW alignment.
+// One thread: the sums run in alignment order like helper.nb_mean_axis_0 (helper.py:45-53).  xf2: same record layout as xf.
+__global__ void k_node_kabsch(const double *c1, const double *c2, const int *aln1, const int *aln2, const int *len_p, double *xf2)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int len = *len_p;
+    int c = 0;
+    double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+    for (int q = 0; q < len; ++q) {
+        const int x = aln1[q], y = aln2[q];
+        if (x < 0 || y < 0) continue;
+        ++c;
+        for (int k = 0; k < 3; ++k) { s1[k] += c1[x * 3 + k]; s2[k] += c2[y * 3 + k]; }
+    }
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
+    const bool superpose = c > 3;
+    if (superpose) {
+        for (int k = 0; k < 3; ++k) { m1[k] = s1[k] / (double)c; m2[k] = s2[k] / (double)c; }
+        double Cm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < len; ++q) {
+            const int x = aln1[q], y = aln2[q];
+            if (x < 0 || y < 0) continue;
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b)
+                    Cm[a * 3 + b] = __dadd_rn(Cm[a * 3 + b], __dmul_rn(__dsub_rn(c2[y * 3 + a], m2[a]), __dsub_rn(c1[x * 3 + b], m1[b])));
+        }
+        kabsch_rotation(Cm, R);
+    }
+    for (int q = 0; q < 9; ++q) xf2[q] = R[q];
+    for (int q = 0; q < 3; ++q) { xf2[9 + q] = m1[q]; xf2[12 + q] = m2[q]; }
+    xf2[15] = superpose ? 1.0 : 0.0;
+}
+
+// Intermediate node: tensors_mean [len, d], coordinates_mean [len, 3], mean weights [len]; one thread per alignment column.
+__global__ void __launch_bounds__(128) k_node_mean(const double *t1, const double *c1, const double *w1, const double *t2,
+                                                   const double *c2, const double *w2, int d, const int *aln1, const int *aln2,
+                                                   const int *len_p, const double *xf2, double *t_out, double *c_out, double *w_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *len_p) return;
+    const int x = aln1[i], y = aln2[i];
+    for (int k = 0; k < d; ++k) {
+        double v;
+        if (x < 0) v = t2[(size_t)y * d + k];
+        else if (y < 0) v = t1[(size_t)x * d + k];
+        else v = __dadd_rn(t1[(size_t)x * d + k], t2[(size_t)y * d + k]) / 2;
+        t_out[(size_t)i * d + k] = v;
+    }
+    const bool sp = xf2[15] != 0.0;
+    double p[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+    if (x >= 0)
+        for (int k = 0; k < 3; ++k) p[k] = sp ? __dsub_rn(c1[x * 3 + k], xf2[9 + k]) : c1[x * 3 + k];
+    if (y >= 0) {
+        if (sp) {
+            const double u0 = __dsub_rn(c2[y * 3], xf2[12]), u1 = __dsub_rn(c2[y * 3 + 1], xf2[13]), u2 = __dsub_rn(c2[y * 3 + 2], xf2[14]);
+            for (int k = 0; k < 3; ++k)
+                r[k] = __dadd_rn(__dadd_rn(__dmul_rn(u0, xf2[k]), __dmul_rn(u1, xf2[3 + k])), __dmul_rn(u2, xf2[6 + k]));
+        } else {
+            for (int k = 0; k < 3; ++k) r[k] = c2[y * 3 + k];
+        }
+    }
+    for (int k = 0; k < 3; ++k) c_out[i * 3 + k] = x < 0 ? r[k] : (y < 0 ? p[k] : __dadd_rn(p[k], r[k]) / 2);
+    double w = 0.0;                                                  // get_mean_weights, multiple_alignment.py:73-82
+    if (x >= 0) w = __dadd_rn(w, w1[x]);
+    if (y >= 0) w = __dadd_rn(w, w2[y]);
+    w_out[i] = w;
+}
+
+}  // namespace crt

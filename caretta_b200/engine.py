@@ -19,7 +19,7 @@ EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
-    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining",
+    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node",
 ]
 
 
@@ -74,6 +74,8 @@ def load_library():
     L.crt_rmsd_cov_tm.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(i32)]
     L.crt_fp32_peak.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
     L.crt_neighbor_joining.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i64)]
+    L.crt_progressive_node.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, dbl,
+                                       vp, vp, C.POINTER(i32), vp, vp, vp, C.POINTER(dbl), C.POINTER(i32)]
     L.crt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.crt_host_free.argtypes = [vp]
     for name in EXPORTS:
@@ -348,6 +350,29 @@ class Engine:
         k = C.c_int64()
         self._check(self.lib.crt_neighbor_joining(self.h, _p(D), n, _p(tree), _p(bl), C.byref(k)), "crt_neighbor_joining")
         return tree[:k.value], bl[:k.value]
+
+    def progressive_node(self, t1, c1, w1, t2, c2, w2, mult1, mult2, gamma_tensor=7.0, gamma_coords=0.03, gamma_weight=0.03,
+                         gap_open=1.0, gap_extend=0.01):
+        """One node of progressive_align (multiple_alignment.py:195-234) on the device, float64.  Returns
+        (aln_1 int64[k], aln_2 int64[k], tensors_mean [k,d], coordinates_mean [k,3], weights_mean [k,1], dtw_score, status)."""
+        t1, c1, t2, c2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (t1, c1, t2, c2))
+        w1 = np.ascontiguousarray(np.asarray(w1, dtype=np.float64).reshape(-1))
+        w2 = np.ascontiguousarray(np.asarray(w2, dtype=np.float64).reshape(-1))
+        n, m, d = t1.shape[0], t2.shape[0], t1.shape[1]
+        if c1.shape != (n, 3) or c2.shape != (m, 3) or t2.shape[1] != d or len(w1) != n or len(w2) != m:
+            raise ValueError("tensors [L,d], coordinates [L,3], weights [L] expected for both sequences")
+        cap = n + m + 1
+        a1, a2 = np.empty(cap, np.int32), np.empty(cap, np.int32)
+        tm, cm, wm = np.empty((cap, d)), np.empty((cap, 3)), np.empty(cap)
+        k, sc, st = C.c_int32(), C.c_double(), C.c_int32()
+        self._check(self.lib.crt_progressive_node(self.h, _p(t1), _p(c1), _p(w1), n, _p(t2), _p(c2), _p(w2), m, d,
+                                                  float(mult1), float(mult2), float(gamma_tensor), float(gamma_coords),
+                                                  float(gamma_weight), float(gap_open), float(gap_extend), _p(a1), _p(a2),
+                                                  C.byref(k), _p(tm), _p(cm), _p(wm), C.byref(sc), C.byref(st)),
+                    "crt_progressive_node")
+        k = k.value
+        return (a1[:k].astype(np.int64), a2[:k].astype(np.int64), tm[:k].copy(), cm[:k].copy(), wm[:k].reshape(-1, 1).copy(),
+                sc.value, st.value)
 
     def fp32_peak(self):
         v, ms = C.c_double(), C.c_double()

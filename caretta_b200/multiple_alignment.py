@@ -95,6 +95,9 @@ class MultipleAlignment:
     alignment: typing.Optional[typing.Dict[str, np.ndarray]] = None
     precision: typing.Optional[int] = None
     last_status: typing.Optional[np.ndarray] = field(default=None, repr=False)
+    final_consensus_weights: typing.Optional[list] = field(default=None, repr=False)
+    final_alignments: typing.Optional[dict] = field(default=None, repr=False)
+    final_sequences: typing.Optional[list] = field(default=None, repr=False)
 
     def _params(self, score_function_params) -> _engine.Params:
         p = dict(DEFAULT_SCORE_PARAMS)
@@ -126,6 +129,70 @@ class MultipleAlignment:
         if n < 2:
             return np.zeros((n, n))
         return eng.pairwise_all(prm)
+
+    # ------------------------------------------------------------------ guide tree + progressive alignment
+    def progressive_align(self, tree, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight,
+                          score_function_params=None, mean_function_params=None) -> typing.Dict[str, np.ndarray]:
+        """MultipleAlignment.progressive_align (multiple_alignment.py:172-253): same bookkeeping, every node's score matrix,
+        affine DTW and intermediate node computed on the device by crt_progressive_node."""
+        p = dict(score_function_params or {})
+        if p.get("flexible", False) or (mean_function_params or {}).get("flexible", False):
+            raise NotImplementedError("flexible=True is not accelerated")
+        gt, gc = p.get("gamma_tensor", 0.03), p.get("gamma_coords", 0.03)          # Protein.score_function defaults, :321-322
+        eng = get_engine()
+        final_sequences = [s for s in self.sequences]
+        final_alignments = {s.name: {s.name: np.arange(len(s))} for s in final_sequences}
+        final_consensus_weights = [np.full((len(s), 1), consensus_weight, dtype=np.float64) for s in final_sequences]
+        statuses = []
+
+        def make_intermediate_node(n1, n2, n_int):
+            s1, s2 = final_sequences[n1], final_sequences[n2]
+            l1, l2 = len(final_alignments[s1.name]), len(final_alignments[s2.name])
+            multiplier_n1, multiplier_n2 = l2 / (2 * (l1 + l2)), l1 / (2 * (l1 + l2))
+            aln_1, aln_2, tm, cm, wm, _, st = eng.progressive_node(
+                s1.tensors, s1.coordinates, final_consensus_weights[n1], s2.tensors, s2.coordinates, final_consensus_weights[n2],
+                multiplier_n1, multiplier_n2, gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty)
+            statuses.append(st)
+            name_int = f"int-{n_int}"
+            final_alignments[s1.name] = {name: np.where(aln_1 != -1, seq[np.maximum(aln_1, 0)], -1)
+                                         for name, seq in final_alignments[s1.name].items()}
+            final_alignments[s2.name] = {name: np.where(aln_2 != -1, seq[np.maximum(aln_2, 0)], -1)
+                                         for name, seq in final_alignments[s2.name].items()}
+            final_alignments[name_int] = {**final_alignments[s1.name], **final_alignments[s2.name]}
+            final_sequences.append(Protein(name_int, tm, cm))
+            final_consensus_weights.append(wm)
+
+        tree = np.asarray(tree)
+        for x in range(0, tree.shape[0] - 1, 2):
+            node_1, node_2, node_int = int(tree[x, 0]), int(tree[x + 1, 0]), int(tree[x, 1])
+            assert int(tree[x + 1, 1]) == node_int
+            make_intermediate_node(node_1, node_2, node_int)
+        node_1, node_2 = int(tree[-1, 0]), int(tree[-1, 1])
+        make_intermediate_node(node_1, node_2, "final")
+        alignment = {**final_alignments[final_sequences[node_1].name], **final_alignments[final_sequences[node_2].name]}
+        self.final_consensus_weights = final_consensus_weights
+        self.final_alignments = final_alignments
+        self.final_sequences = final_sequences
+        self.last_status = np.array(statuses, np.int32)
+        return alignment
+
+    def multiple_align(self, pairwise_distance_matrix, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight,
+                       score_function_params=None, mean_function_params=None) -> typing.Dict[str, np.ndarray]:
+        """MultipleAlignment.multiple_align (multiple_alignment.py:255-285): neighbor joining + progressive alignment."""
+        from . import neighbor_joining as _nj
+        if len(self.sequences) == 2:
+            p = dict(score_function_params or {})
+            s1, s2 = self.sequences
+            # two structures: dtw_align on the plain score matrix (:263-275); gamma_weight < 0 switches the weight term off
+            aln_1, aln_2, *_ = get_engine().progressive_node(
+                s1.tensors, s1.coordinates, np.zeros(len(s1)), s2.tensors, s2.coordinates, np.zeros(len(s2)), 0.0, 0.0,
+                p.get("gamma_tensor", 0.03), p.get("gamma_coords", 0.03), -1.0, gap_open_penalty, gap_extend_penalty)
+            self.alignment = {s1.name: aln_1, s2.name: aln_2}
+            return self.alignment
+        self.tree, self.branch_lengths = _nj.neighbor_joining(pairwise_distance_matrix)
+        self.alignment = self.progressive_align(self.tree, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight,
+                                                score_function_params, mean_function_params)
+        return self.alignment
 
     def make_pairwise_matrices(self, score_function_params=None):
         """Engine by-product: (score, rmsd, tm) over the stage-1 matched residues, each float64 [N,N]."""
@@ -216,3 +283,20 @@ def install(reference_multiple_alignment_module) -> None:
         return MultipleAlignment(self.sequences).make_pairwise_matrix(score_function_params)
 
     ref.MultipleAlignment.make_pairwise_matrix = make_pairwise_matrix
+
+    if os.environ.get("CARETTA_B200_TREE", "1") != "0":
+        # the guide tree and the progressive alignment as well (CARETTA_B200_TREE=0 keeps the reference's)
+        from . import neighbor_joining as _nj
+        if hasattr(ref, "nj"):
+            _nj.install(ref.nj)
+
+        def progressive_align(self, tree, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight,
+                              score_function_params=None, mean_function_params=None):
+            m = MultipleAlignment(self.sequences)
+            aln = m.progressive_align(tree, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight,
+                                      score_function_params, mean_function_params)
+            self.final_consensus_weights, self.final_alignments = m.final_consensus_weights, m.final_alignments
+            self.final_sequences = [ref.Protein(s.name, s.tensors, s.coordinates, getattr(s, "sequence", "")) for s in m.final_sequences]
+            return aln
+
+        ref.MultipleAlignment.progressive_align = progressive_align

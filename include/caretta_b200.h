@@ -133,6 +133,19 @@ int crt_dtw_align_batch(crt_ctx *ctx, const double *S, const int64_t *shape_off,
 int crt_rmsd_cov_tm(crt_ctx *ctx, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm,
                     int32_t *n_bad);
 
+/* One node of the progressive alignment: replaces make_intermediate_node of MultipleAlignment.progressive_align
+ * (multiple_alignment.py:195-234): score_matrix = Protein.score_function(n1, n2) (:321-349) + Gaussian of the scaled
+ * consensus weights (:206-210), dtw_align with affine gaps (:211-214), Protein.mean_function (:351-383) and
+ * get_mean_weights (:73-82).  All float64.  tensors: [n,d] / [m,d], coords: [n,3] / [m,3], weights: [n] / [m] (host).
+ * Outputs: aln1/aln2 int32 with -1 = gap (capacity n + m), *aln_len, the intermediate node tensors_mean [len,d],
+ * coords_mean [len,3], weights_mean [len]; *score = the DTW score; *status = status bits of the stage-1 pair run.
+ * gamma_weight < 0 leaves the weight term out (multiple_align with two structures, :263-275). */
+int crt_progressive_node(crt_ctx *ctx, const double *tensors1, const double *coords1, const double *weights1, int32_t n,
+                         const double *tensors2, const double *coords2, const double *weights2, int32_t m, int32_t d,
+                         double mult1, double mult2, double gamma_tensor, double gamma_coords, double gamma_weight,
+                         double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2, int32_t *aln_len,
+                         double *tensors_mean, double *coords_mean, double *weights_mean, double *score, int32_t *status);
+
 /* Neighbor joining on the device: replaces caretta/neighbor_joining.py:17-99 (`neighbor_joining(distance_matrix)`, called
  * at multiple_alignment.py:277 on max(S) - S of the pairwise matrix).  distance_matrix: float64 [N,N] row-major (host),
  * N >= 3.  tree: uint64 [2N-3][2] rows (node_1, node_2), node ids >= N are intermediate nodes in creation order;

@@ -29,6 +29,7 @@
  *   crt_o_pairwise_all/_list    multiple_alignment.py:158-170
  *   crt_o_rmsd_cov_tm           multiple_alignment.py:1000-1055 (superpose_first=False)
  *   crt_o_neighbor_joining      neighbor_joining.py:17-157
+ *   crt_o_score_matrix          multiple_alignment.py:321-349 (full matrix; progressive_align, section 8f rank 2)
  */
 #include <math.h>
 #include <float.h>
@@ -439,6 +440,35 @@ API int crt_o_pair(const double *t1, const double *c1, int n, const double *t2, 
     if (R_out) memcpy(R_out, R, sizeof(R));
     if (score1) *score1 = sc1;
     free(S); free(a1); free(w1);
+    return status;
+}
+
+/* Protein.score_function(flexible=False), multiple_alignment.py:321-349: the full n x m coordinate score matrix of a pair
+ * (what progressive_align feeds to dtw_align, :203-214).  Returns the status bits of crt_o_pair. */
+API int crt_o_score_matrix(const double *t1, const double *c1, int n, const double *t2, const double *c2, int m,
+                           int d, double gamma_t, double gamma_c, double *S_out)
+{
+    int status = 0;
+    int64_t *a1 = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + m + 1) * 4);
+    int64_t *a2 = a1 + (n + m + 1), *p1 = a2 + (n + m + 1), *p2 = p1 + (n + m + 1);
+    double *w1 = (double *)malloc(sizeof(double) * (size_t)(n + m) * 3 * 2);
+    double *w2 = w1 + (size_t)n * 3, *k1 = w2 + (size_t)m * 3, *k2 = k1 + (size_t)(n < m ? n : m) * 3;
+    int64_t len = 0, c = 0;
+    double sc1 = 0.0;
+    crt_o_rbf_matrix(t1, t2, n, m, d, gamma_t, S_out);
+    if (crt_o_smith_waterman(S_out, n, m, 0.0, a1, a2, &len, &sc1) != 0) status |= 2;
+    c = crt_o_common_positions(a1, a2, len, p1, p2);
+    for (int64_t q = 0; q < c; ++q)
+        for (int a = 0; a < 3; ++a) { k1[q * 3 + a] = c1[p1[q] * 3 + a]; k2[q * 3 + a] = c2[p2[q] * 3 + a]; }
+    if (c <= 3) {
+        status |= 1;
+        memcpy(w1, c1, sizeof(double) * (size_t)n * 3);
+        memcpy(w2, c2, sizeof(double) * (size_t)m * 3);
+    } else {
+        crt_o_superpose_with_subset(c1, n, c2, m, k1, k2, c, w1, w2, NULL);
+    }
+    crt_o_rbf_matrix(w1, w2, n, m, 3, gamma_c, S_out);
+    free(a1); free(w1);
     return status;
 }
 

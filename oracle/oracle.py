@@ -71,6 +71,8 @@ def lib():
         L.crt_o_rmsd_cov_tm.argtypes = [_I64, C.c_int, C.c_int64, _D, _I64, _D, _D, _D]
         L.crt_o_rmsd_cov_tm.restype = C.c_int
         L.crt_o_num_threads.restype = C.c_int
+        L.crt_o_score_matrix.argtypes = [_D, _D, C.c_int, _D, _D, C.c_int, C.c_int, C.c_double, C.c_double, _D]
+        L.crt_o_score_matrix.restype = C.c_int
         L.crt_o_neighbor_joining.argtypes = [_D, C.c_int, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"), _D]
         L.crt_o_neighbor_joining.restype = C.c_int64
         _lib = L
@@ -235,6 +237,78 @@ def neighbor_joining(distance_matrix) -> Tuple[np.ndarray, np.ndarray]:
     if k < 0:
         raise IndexError("neighbor_joining needs at least 3 nodes (the reference indexes out of range)")
     return tree[:k], bl[:k].reshape(-1, 1)
+
+
+def score_matrix(t1, c1, t2, c2, gamma_t=7.0, gamma_c=0.03) -> np.ndarray:
+    """Protein.score_function(flexible=False), multiple_alignment.py:321-349: the full n x m matrix."""
+    t1, c1, t2, c2 = _c(t1), _c(c1), _c(t2), _c(c2)
+    S = np.empty((t1.shape[0], t2.shape[0]))
+    lib().crt_o_score_matrix(t1, c1, t1.shape[0], t2, c2, t2.shape[0], t1.shape[1], gamma_t, gamma_c, S)
+    return S
+
+
+def mean_function(t1, c1, t2, c2, aln_1, aln_2):
+    """Protein.mean_function(flexible=False), multiple_alignment.py:351-383 -> (tensors_mean, coordinates_mean)."""
+    k = len(aln_1)
+    tm = np.zeros((k, t1.shape[1]))
+    for i, (x, y) in enumerate(zip(aln_1, aln_2)):
+        tm[i] = t2[y] if x == -1 else (t1[x] if y == -1 else (t1[x] + t2[y]) / 2)
+    p1, p2 = common_positions(aln_1, aln_2)
+    if len(p1) <= 3:
+        k1, k2 = np.array(c1), np.array(c2)
+    else:
+        k1, k2, _ = superpose_with_subset(c1, c2, c1[p1], c2[p2])
+    cm = np.zeros((k, 3))
+    for i, (x, y) in enumerate(zip(aln_1, aln_2)):
+        cm[i] = k2[y] if x == -1 else (k1[x] if y == -1 else (k1[x] + k2[y]) / 2)
+    return tm, cm
+
+
+def mean_weights(w1, w2, aln_1, aln_2) -> np.ndarray:
+    """get_mean_weights, multiple_alignment.py:73-82."""
+    out = np.zeros((len(aln_1), 1))
+    for i, (x, y) in enumerate(zip(aln_1, aln_2)):
+        if x != -1:
+            out[i] += w1[x]
+        if y != -1:
+            out[i] += w2[y]
+    return out
+
+
+def progressive_align(seqs, tree, gap_open=1.0, gap_extend=0.01, consensus_weight=1.0, gamma_weight=0.03,
+                      gamma_t=7.0, gamma_c=0.03):
+    """MultipleAlignment.progressive_align, multiple_alignment.py:172-253, on [(name, tensors, coords)] (small cases:
+    Python loops).  Returns (alignment {name: int64[A]}, final_sequences [(name, tensors, coords)], final_weights)."""
+    fs = [(n, _c(t), _c(c)) for n, t, c in seqs]
+    fa = {n: {n: np.arange(len(t))} for n, t, _ in fs}
+    fw = [np.full((len(t), 1), consensus_weight, dtype=np.float64) for _, t, _ in fs]
+
+    def node(n1, n2, n_int):
+        (name_1, t1, c1), (name_2, t2, c2) = fs[n1], fs[n2]
+        w1, w2 = fw[n1], fw[n2]
+        l1, l2 = len(fa[name_1]), len(fa[name_2])
+        mult1, mult2 = l2 / (2 * (l1 + l2)), l1 / (2 * (l1 + l2))
+        name_int = f"int-{n_int}"
+        S = score_matrix(t1, c1, t2, c2, gamma_t, gamma_c)
+        S += rbf_matrix(w1 * mult1, w2 * mult2, gamma_weight)
+        a1, a2, _ = dtw_align(S, gap_open, gap_extend)
+        tmn, cmn = mean_function(t1, c1, t2, c2, a1, a2)
+        wmn = mean_weights(w1, w2, a1, a2)
+        fa[name_1] = {k: np.array([v[i] if i != -1 else -1 for i in a1]) for k, v in fa[name_1].items()}
+        fa[name_2] = {k: np.array([v[i] if i != -1 else -1 for i in a2]) for k, v in fa[name_2].items()}
+        fa[name_int] = {**fa[name_1], **fa[name_2]}
+        fs.append((name_int, tmn, cmn))
+        fw.append(wmn)
+
+    tree = np.asarray(tree)
+    for x in range(0, tree.shape[0] - 1, 2):
+        n1, n2, ni = int(tree[x, 0]), int(tree[x + 1, 0]), int(tree[x, 1])
+        assert int(tree[x + 1, 1]) == ni
+        node(n1, n2, ni)
+    n1, n2 = int(tree[-1, 0]), int(tree[-1, 1])
+    node(n1, n2, "final")
+    alignment = {**fa[fs[n1][0]], **fa[fs[n2][0]]}
+    return alignment, fs, fw
 
 
 def num_threads() -> int:

@@ -206,3 +206,21 @@ def test_nj_golden():
         assert np.array_equal(bl, g[f"{name}_bl"]), name
     with pytest.raises(IndexError):
         O.neighbor_joining(np.zeros((2, 2)))
+
+
+def test_progressive_align_golden():
+    """oracle.progressive_align (multiple_alignment.py:172-253 restated on the C primitives) against the reference's
+    multiple_align output: identical final alignment, consensus node within 1e-11."""
+    g = np.load(os.path.join(G, "msa.npz"))
+    for name in ("fam8", "ragged12"):
+        L = g[f"{name}_lengths"]
+        ch = synth.make_chains(len(L), list(L), 10, seed=int(g[f"{name}_seed"]), family_size=int(g[f"{name}_family"]))
+        S = O.pairwise_all(ch.coords, ch.tensors, ch.offsets)
+        np.testing.assert_allclose(S, g[f"{name}_score"], rtol=1e-12)
+        tree, bl = O.neighbor_joining(np.max(g[f"{name}_score"]) - g[f"{name}_score"])
+        assert np.array_equal(tree, g[f"{name}_tree"]) and np.array_equal(bl, g[f"{name}_bl"])
+        aln, fs, fw = O.progressive_align([(f"s{p}",) + ch.chain(p) for p in range(ch.n)], tree)
+        A = np.array([aln[f"s{p}"] for p in range(ch.n)])
+        assert np.array_equal(A, g[f"{name}_aln"])
+        np.testing.assert_allclose(fs[-1][2], g[f"{name}_final_coords"], rtol=0, atol=1e-11)
+        assert np.array_equal(fw[-1], g[f"{name}_final_weights"])
