@@ -8,6 +8,7 @@
 #include "crt_dp_batch.cuh"
 #include "crt_nj.cuh"
 #include "crt_node.cuh"
+#include "crt_consumers.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -137,6 +138,10 @@ struct crt_ctx {
     DevBuf<double> nd_w, nd_S, nd_bnd, nd_f, nd_score, nd_xf2, nd_t, nd_c, nd_wm;
     DevBuf<unsigned char> nd_B;
     DevBuf<int> nd_a1, nd_a2, nd_len;
+
+    // text produced by crt_format_matrix / crt_format_fasta, fetched with crt_text_fetch
+    DevBuf<char> text;
+    long long text_len = 0;
 
     // last run
     long long run_pairs = 0;
@@ -767,7 +772,7 @@ int crt_destroy(crt_ctx *c)
     c->score.release(); c->score1.release(); c->rmsd.release(); c->tm.release(); c->f32tmp.release();
     if (c->node_ctx) { crt_destroy(c->node_ctx); c->node_ctx = nullptr; }
     c->nd_w.release(); c->nd_S.release(); c->nd_bnd.release(); c->nd_f.release(); c->nd_score.release(); c->nd_xf2.release();
-    c->nd_t.release(); c->nd_c.release(); c->nd_wm.release(); c->nd_B.release(); c->nd_a1.release(); c->nd_a2.release(); c->nd_len.release();
+    c->nd_t.release(); c->nd_c.release(); c->nd_wm.release(); c->nd_B.release(); c->nd_a1.release(); c->nd_a2.release(); c->nd_len.release(); c->text.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) {
         if (c->s_f1[k]) cudaStreamDestroy(c->s_f1[k]);
@@ -1269,7 +1274,19 @@ int crt_dtw_align_batch(crt_ctx *c, const double *S, const int64_t *shape_off, c
     return dp_batch(c, true, S, shape_off, n, m, n_problems, gap_open, gap_extend, aln1, aln2, aln_off, aln_cap, score, nullptr);
 }
 
+static int rmsd_cov_tm_impl(crt_ctx *c, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm, int32_t *n_bad, int superpose);
+
 int crt_rmsd_cov_tm(crt_ctx *c, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm, int32_t *n_bad)
+{
+    return rmsd_cov_tm_impl(c, aln, A, rmsd, cov, tm, n_bad, 1);
+}
+
+int crt_rmsd_cov_tm_superposed(crt_ctx *c, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm, int32_t *n_bad)
+{
+    return rmsd_cov_tm_impl(c, aln, A, rmsd, cov, tm, n_bad, 0);
+}
+
+static int rmsd_cov_tm_impl(crt_ctx *c, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm, int32_t *n_bad, int superpose)
 {
     if (!c || !aln || !rmsd || !cov || !tm) return fail(CRT_E_ARG, "null argument");
     if (c->N <= 0) return fail(CRT_E_STATE, "crt_set_chains has not been called");
@@ -1299,7 +1316,7 @@ int crt_rmsd_cov_tm(crt_ctx *c, const int64_t *aln, int64_t A, double *rmsd, dou
     k_fill_diag<<<(unsigned)((NN + 255) / 256), 256, 0, st>>>(dR.p, dC.p, dT.p, N);
     const long long np = (long long)N * (N - 1) / 2;
     if (np > 0)
-        k_rmsd_cov_tm<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(dAln.p, N, A, c->coords.p, c->d_offsets.p, c->centroid.p, dR.p, dC.p, dT.p, dBad.p);
+        k_rmsd_cov_tm<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(dAln.p, N, A, c->coords.p, c->d_offsets.p, c->centroid.p, dR.p, dC.p, dT.p, dBad.p, superpose);
     int bad = 0;
     cudaMemcpyAsync(rmsd, dR.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(cov, dC.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);
@@ -1477,3 +1494,5 @@ int crt_fp32_peak(crt_ctx *c, double *ffma_per_s, double *elapsed_ms)
 }
 
 }  // extern "C"
+
+#include "crt_consumers_api.inl"

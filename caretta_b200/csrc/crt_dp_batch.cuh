@@ -222,7 +222,7 @@ __global__ void k_sw_trace(const DpProblem *probs, int n_probs, const double *S_
 // make_rmsd_coverage_tm_matrix(superpose_first=False): one thread per pair i<j over the A alignment columns.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_rmsd_cov_tm(const long long *aln, int N, long long A, const double *coords, const long long *offsets,
-                              const double *centroid, double *rmsd, double *cov, double *tm, int *n_bad)
+                              const double *centroid, double *rmsd, double *cov, double *tm, int *n_bad, int superpose)
 {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long np = (long long)N * (N - 1) / 2;
@@ -252,8 +252,13 @@ __global__ void k_rmsd_cov_tm(const long long *aln, int N, long long A, const do
     for (int d = 0; d < 3; ++d) { p1[d] = s1[d] * inv; p2[d] = s2[d] * inv; m1[d] = p1[d] + ci[d]; m2[d] = p2[d] + cj[d]; }
     for (int u = 0; u < 3; ++u)
         for (int v = 0; v < 3; ++v) Cm[u * 3 + v] = Cr[u * 3 + v] - s2[u] * p1[v];
-    kabsch_rotation(Cm, R);
-    for (int b = 0; b < 3; ++b) tr[b] = m1[b] - (m2[0] * R[b] + m2[1] * R[3 + b] + m2[2] * R[6 + b]);
+    if (superpose) {
+        kabsch_rotation(Cm, R);
+        for (int b = 0; b < 3; ++b) tr[b] = m1[b] - (m2[0] * R[b] + m2[1] * R[3 + b] + m2[2] * R[6 + b]);
+    } else {                                   // superpose_first=True: the chains were superposed beforehand (:1025-1026, :1037)
+        for (int q = 0; q < 9; ++q) R[q] = (q % 4 == 0) ? 1.0 : 0.0;
+        tr[0] = tr[1] = tr[2] = 0.0;
+    }
     const long long l1 = offsets[i + 1] - offsets[i], l2 = offsets[j + 1] - offsets[j];
     const double d1 = 1.24 * (double)(l1 - 15) / 3 - 1.8, d2 = 1.24 * (double)(l2 - 15) / 3 - 1.8;
     double ss = 0.0, t1 = 0.0, t2 = 0.0;
@@ -263,7 +268,7 @@ __global__ void k_rmsd_cov_tm(const long long *aln, int N, long long A, const do
         const double y0 = Y[b * 3], y1 = Y[b * 3 + 1], y2 = Y[b * 3 + 2];
         double sm = 0.0;
         for (int d = 0; d < 3; ++d) {
-            const double yr = (y0 * R[d] + y1 * R[3 + d] + y2 * R[6 + d]) + tr[d];
+            const double yr = superpose ? (y0 * R[d] + y1 * R[3 + d] + y2 * R[6 + d]) + tr[d] : (d == 0 ? y0 : (d == 1 ? y1 : y2));
             const double df = X[a * 3 + d] - yr;
             ss += df * df;
             sm += df;

@@ -13,13 +13,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CARETTA_B200_LIB") or os.path.join(_HERE, "libcaretta_b200.so")   # env override: A/B builds
 
 FP64, FP32 = 0, 1
+SUP_AUTO, SUP_CORE, SUP_REFERENCE = 0, 1, 2
 ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE = 1, 2, 4
 
 EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
-    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node",
+    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node",
+    "crt_coverage_gap_matrix", "crt_superpose", "crt_superpose_pairs", "crt_format_matrix", "crt_format_fasta", "crt_text_fetch",
 ]
 
 
@@ -72,10 +74,17 @@ def load_library():
     L.crt_sw_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, dbl, vp, vp, vp, i64, vp, vp]
     L.crt_dtw_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, dbl, dbl, vp, vp, vp, i64, vp]
     L.crt_rmsd_cov_tm.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(i32)]
+    L.crt_rmsd_cov_tm_superposed.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(i32)]
     L.crt_fp32_peak.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
     L.crt_neighbor_joining.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i64)]
     L.crt_progressive_node.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, dbl,
                                        vp, vp, C.POINTER(i32), vp, vp, vp, C.POINTER(dbl), C.POINTER(i32)]
+    L.crt_coverage_gap_matrix.argtypes = [vp, vp, i32, i64, vp, vp]
+    L.crt_superpose.argtypes = [vp, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
+    L.crt_superpose_pairs.argtypes = [vp, vp, i64, vp, vp, i64, vp, i32, vp, vp, vp, vp]
+    L.crt_format_matrix.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(i64)]
+    L.crt_format_fasta.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, C.POINTER(i64)]
+    L.crt_text_fetch.argtypes = [vp, vp, i64]
     L.crt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.crt_host_free.argtypes = [vp]
     for name in EXPORTS:
@@ -325,16 +334,17 @@ class Engine:
             return [(None, None, float(score[q]), int(st[q])) for q in range(k)]
         return [(x, y, float(score[q]), int(st[q])) for q, (x, y) in enumerate(self._split(a1, a2, aoff, k))]
 
-    def rmsd_cov_tm(self, aln):
-        """make_rmsd_coverage_tm_matrix(superpose_first=False) on the chains of this engine; aln int64 [N, A]."""
+    def rmsd_cov_tm(self, aln, superpose: bool = True):
+        """make_rmsd_coverage_tm_matrix on the chains of this engine; aln int64 [N, A].  superpose=True: Kabsch per pair
+        (superpose_first=False, the reference's call site); False: the chains are already in one frame (after Engine.superpose)."""
         aln = np.ascontiguousarray(aln, dtype=np.int64)
         if aln.ndim != 2 or aln.shape[0] != self.n_chains:
             raise ValueError("aln must be [n_chains, A]")
         n = self.n_chains
         r, c, t = np.empty((n, n)), np.empty((n, n)), np.empty((n, n))
         bad = C.c_int32(0)
-        self._check(self.lib.crt_rmsd_cov_tm(self.h, _p(aln), aln.shape[1], _p(r), _p(c), _p(t), C.byref(bad)),
-                    "crt_rmsd_cov_tm")
+        fn = self.lib.crt_rmsd_cov_tm if superpose else self.lib.crt_rmsd_cov_tm_superposed
+        self._check(fn(self.h, _p(aln), aln.shape[1], _p(r), _p(c), _p(t), C.byref(bad)), "crt_rmsd_cov_tm")
         return r, c, t, int(bad.value)
 
     def neighbor_joining(self, distance_matrix):
@@ -373,6 +383,89 @@ class Engine:
         k = k.value
         return (a1[:k].astype(np.int64), a2[:k].astype(np.int64), tm[:k].copy(), cm[:k].copy(), wm[:k].reshape(-1, 1).copy(),
                 sc.value, st.value)
+
+    # ------------------------------------------------------------------------------------------------ alignment consumers
+    def _aln(self, aln, need_chains=True):
+        aln = np.ascontiguousarray(aln, dtype=np.int64)
+        if aln.ndim != 2 or (need_chains and aln.shape[0] != self.n_chains):
+            raise ValueError("aln must be int64 [n_chains, A]")
+        return aln
+
+    def coverage_gap_matrix(self, aln):
+        """make_coverage_gap_distance_matrix (multiple_alignment.py:45-56): (distance float64 [N,N], aligning int32 [N,N])."""
+        aln = self._aln(aln, need_chains=False)
+        n = aln.shape[0]
+        dist, al = np.empty((n, n)), np.empty((n, n), np.int32)
+        self._check(self.lib.crt_coverage_gap_matrix(self.h, _p(aln), n, aln.shape[1], _p(dist), _p(al)), "crt_coverage_gap_matrix")
+        return dist, al
+
+    def superpose(self, aln, mode: int = SUP_AUTO, reference: int = -1, core_columns=None):
+        """superpose / superpose_core / superpose_reference (multiple_alignment.py:854-927) on the chains of this engine.
+        Returns dict(coords [sumL,3], rot [N,3,3], tran [N,3], ncommon [N], mode, reference, n_core)."""
+        aln = self._aln(aln)
+        n = self.n_chains
+        coords = np.empty((int(self._offsets[-1]), 3))
+        rot, tran, nc = np.empty((n, 3, 3)), np.empty((n, 3)), np.empty(n, np.int32)
+        m, r, k = C.c_int32(), C.c_int32(), C.c_int64()
+        cc = None if core_columns is None else np.ascontiguousarray(core_columns, dtype=np.int64)
+        if cc is not None and len(cc) == 0:
+            raise IndexError("empty core_indices")
+        self._check(self.lib.crt_superpose(self.h, _p(aln), aln.shape[1], int(mode), int(reference), _p(cc), 0 if cc is None else len(cc),
+                                           _p(coords), _p(rot), _p(tran), _p(nc), C.byref(m), C.byref(r), C.byref(k)), "crt_superpose")
+        return dict(coords=coords, rot=rot, tran=tran, ncommon=nc, mode=m.value, reference=r.value, n_core=k.value)
+
+    def superpose_pairs(self, aln, ref, mem, batch_off):
+        """Sequential batches of (reference, member) superpositions over common alignment columns (superpose_references,
+        multiple_alignment.py:930-950).  Returns dict(coords, rot [P,3,3], tran [P,3], ncommon [P])."""
+        aln = self._aln(aln)
+        ref = np.ascontiguousarray(ref, dtype=np.int32)
+        mem = np.ascontiguousarray(mem, dtype=np.int32)
+        batch_off = np.ascontiguousarray(batch_off, dtype=np.int64)
+        k = len(ref)
+        if len(mem) != k or len(batch_off) < 1:
+            raise ValueError("ref / mem of equal length and batch_off [n_batches + 1] expected")
+        coords = np.empty((int(self._offsets[-1]), 3))
+        rot, tran, nc = np.empty((max(k, 1), 3, 3)), np.empty((max(k, 1), 3)), np.empty(max(k, 1), np.int32)
+        self._check(self.lib.crt_superpose_pairs(self.h, _p(aln), aln.shape[1], _p(ref), _p(mem), k, _p(batch_off), len(batch_off) - 1,
+                                                 _p(coords), _p(rot), _p(tran), _p(nc)), "crt_superpose_pairs")
+        return dict(coords=coords, rot=rot[:k], tran=tran[:k], ncommon=nc[:k])
+
+    @staticmethod
+    def _pack_text(items):
+        enc = [x if isinstance(x, bytes) else str(x).encode("utf-8") for x in items]
+        off = np.zeros(len(enc) + 1, np.int64)
+        if enc:
+            off[1:] = np.cumsum([len(e) for e in enc])
+        blob = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
+        return blob, off
+
+    def _fetch_text(self, n: int) -> bytes:
+        buf = np.empty(max(n, 1), np.uint8)
+        self._check(self.lib.crt_text_fetch(self.h, _p(buf), n), "crt_text_fetch")
+        return buf[:n].tobytes()
+
+    def format_matrix(self, names, matrix) -> bytes:
+        """The bytes helper.write_distance_matrix (helper.py:183-203) writes: header, then 'name v v ...' rows with %.4f values."""
+        M = np.ascontiguousarray(matrix, dtype=np.float64)
+        if M.ndim != 2 or M.shape[0] < len(names):
+            raise IndexError("distance_matrix needs one row per name")
+        M = np.ascontiguousarray(M[:len(names)])
+        blob, off = self._pack_text(names)
+        n = C.c_int64()
+        self._check(self.lib.crt_format_matrix(self.h, _p(M), M.shape[0], M.shape[1], _p(blob), _p(off), C.byref(n)), "crt_format_matrix")
+        return self._fetch_text(n.value)
+
+    def format_fasta(self, names, sequences, aln) -> bytes:
+        """The bytes MultipleAlignment.write_alignment (multiple_alignment.py:299-309) writes for aln int64 [N, A]."""
+        aln = self._aln(aln, need_chains=False)
+        if len(names) != aln.shape[0] or len(sequences) != aln.shape[0]:
+            raise ValueError("one name and one sequence per alignment row expected")
+        nb, noff = self._pack_text(names)
+        sb, soff = self._pack_text(sequences)
+        n = C.c_int64()
+        self._check(self.lib.crt_format_fasta(self.h, _p(aln), aln.shape[0], aln.shape[1], _p(sb), _p(soff), _p(nb), _p(noff), C.byref(n)),
+                    "crt_format_fasta")
+        return self._fetch_text(n.value)
 
     def fp32_peak(self):
         v, ms = C.c_double(), C.c_double()

@@ -7,8 +7,16 @@ the C ABI (caretta_b200.engine).  Nothing here computes the path on the CPU.
     Protein(name, tensors, coordinates, sequence)        :312-319    Protein (same fields, same __len__/__str__)
     MultipleAlignment(sequences)                         :148-156    MultipleAlignment
       .make_pairwise_matrix(score_function_params)       :158-170    same signature, float64 [N,N], symmetric, diag 0
-    make_rmsd_coverage_tm_matrix(alignment, proteins,    :1000-1055  same signature (superpose_first=False only,
-                                 superpose_first)                    the reference's own call site, :571-572)
+    make_rmsd_coverage_tm_matrix(alignment, proteins,    :1000-1055  same signature
+                                 superpose_first)
+    make_coverage_gap_distance_matrix(alignment_array)   :45-56      same signature
+    get_reference_structures(alignment, min_coverage)    :740-784    same signature
+    superpose / superpose_core / superpose_reference /   :854-950    same signatures (coordinates of the given proteins are
+      superpose_references                                           replaced, the list is returned)
+    MultipleAlignment.to_sequence_alignment /            :287-309    same signatures, same bytes
+      write_alignment
+    helper.write_distance_matrix(names, matrix, file)    helper.py   write_distance_matrix, same bytes
+                                                         :183-203
     dtw.dtw_align / smith_waterman / smith_waterman_score            dtw_align / smith_waterman / smith_waterman_score
       (dynamic_time_warping.py:147-278)                              (batched: *_batch)
     StructureMultiple (name used by the CLI help and the legacy API) StructureMultiple facade
@@ -194,6 +202,36 @@ class MultipleAlignment:
                                                 score_function_params, mean_function_params)
         return self.alignment
 
+    # ------------------------------------------------------------------ text writers
+    def _fasta_bytes(self, alignment=None) -> bytes:
+        if alignment is None:
+            alignment = self.alignment
+        names = [p.name for p in self.sequences]
+        aln = np.array([np.asarray(alignment[n], dtype=np.int64) for n in names])
+        seqs = [str(p) for p in self.sequences]
+        for q in seqs:
+            if not q.isascii():
+                raise ValueError("sequences must be ASCII (one byte per residue)")
+        return get_engine().format_fasta(names, seqs, aln)
+
+    def to_sequence_alignment(self, alignment=None) -> typing.Dict[str, str]:
+        """multiple_alignment.py:287-297: {name: aligned amino-acid string with '-' for gaps}; the gather runs on the device."""
+        text = self._fasta_bytes(alignment)
+        out, pos = {}, 0
+        alen = len(next(iter((alignment or self.alignment).values()))) if len(self.sequences) else 0
+        for p in self.sequences:
+            nl = len(p.name.encode("utf-8"))
+            start = pos + 1 + nl + 1
+            out[p.name] = text[start:start + alen].decode("ascii")
+            pos = start + alen + 1
+        return out
+
+    def write_alignment(self, fasta_file, alignment=None) -> None:
+        """multiple_alignment.py:299-309: same bytes as the reference's file."""
+        text = self._fasta_bytes(alignment)
+        with open(fasta_file, "wb") as f:
+            f.write(text)
+
     def make_pairwise_matrices(self, score_function_params=None):
         """Engine by-product: (score, rmsd, tm) over the stage-1 matched residues, each float64 [N,N]."""
         eng = get_engine()
@@ -259,18 +297,143 @@ def smith_waterman_score(seq1, seq2, matrix, gap: float = 0.0):
 
 
 def make_rmsd_coverage_tm_matrix(alignment, proteins, superpose_first: bool = True):
-    """multiple_alignment.py:1000-1055.  Only superpose_first=False (the reference's own call site, :571-572) is
-    accelerated; alignment is {name: int64[A]} with -1 gaps, proteins the matching list of Protein-like objects."""
+    """multiple_alignment.py:1000-1055.  alignment is {name: int64[A]} with -1 gaps, proteins the matching list of Protein-like
+    objects.  superpose_first=True superposes all structures with superpose() first (and, like the reference, leaves the
+    proteins with their new coordinates), then measures every pair in that common frame."""
     if superpose_first:
-        raise NotImplementedError("superpose_first=True goes through superpose() (reference/core selection, "
-                                  "multiple_alignment.py:596-852), which is outside the accelerated path")
+        proteins = superpose(alignment, proteins)
     names = [p.name for p in proteins]
     aln = np.array([np.asarray(alignment[n], dtype=np.int64) for n in names])
     eng = get_engine()
     eng.set_chains(*pack_sequences(proteins))
-    r, c, t, bad = eng.rmsd_cov_tm(aln)
+    r, c, t, bad = eng.rmsd_cov_tm(aln, superpose=not superpose_first)
     assert bad == 0, "a pair has fewer than 3 common positions (the reference asserts here, :1034)"
     return r, c, t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Consumers of the alignment (SURVEY 8f rank 3): coverage matrix, reference selection, superposition.
+# ---------------------------------------------------------------------------------------------------------------
+def _aln_array(alignment, names):
+    return np.array([np.asarray(alignment[n], dtype=np.int64) for n in names])
+
+
+def _check_gap(gap):
+    if gap != -1:
+        raise NotImplementedError("only the reference's gap marker -1 is supported")
+
+
+def make_coverage_gap_distance_matrix(alignment_array):
+    """multiple_alignment.py:45-56: (distance float64 [N,N], matrix_aligning int32 [N,N])."""
+    return get_engine().coverage_gap_matrix(np.asarray(alignment_array))
+
+
+def get_reference_structures(alignment, minimum_coverage=50, gap=-1):
+    """multiple_alignment.py:740-784 with the O(N^2 A) matrix computed on the device; the greedy selection over that matrix is
+    the reference's.  Returns (first reference name, {reference name: [member names]}, [names that align to nobody])."""
+    _check_gap(gap)
+    names = list(alignment.keys())
+    alignment_array = _aln_array(alignment, names)
+    distance_matrix, matrix_aligning = make_coverage_gap_distance_matrix(alignment_array)
+    minimum_coverage = np.array([minimum_coverage * int((alignment_array[i] != gap).sum()) / 100 for i in range(len(names))])
+    reference_structures = {}
+    first_reference_structure = int(np.argmin(np.median(distance_matrix, axis=0)))
+    not_covered = np.where(matrix_aligning[:, first_reference_structure] < minimum_coverage[:])[0]
+    covered = list(np.where(matrix_aligning[:, first_reference_structure] >= minimum_coverage[:])[0])
+    reference_structures[first_reference_structure] = [names[c] for c in covered]
+    problematic = []
+    while len(not_covered) > 0:
+        if len(not_covered) > 1:
+            reference_structure = covered[int(np.argmin(np.median(distance_matrix[not_covered, :][:, covered], axis=0)))]
+        else:
+            reference_structure = covered[int(np.argmin(distance_matrix[not_covered, :][:, covered]))]
+        covered_i = not_covered[np.where(matrix_aligning[not_covered, reference_structure] >= minimum_coverage[not_covered])[0]]
+        if len(covered_i) == 0:
+            problematic += list(not_covered)
+            break
+        not_covered = not_covered[np.where(matrix_aligning[not_covered, reference_structure] < minimum_coverage[not_covered])[0]]
+        reference_structures[reference_structure] = [names[c] for c in covered_i]
+        covered += list(covered_i)
+    no_aligning = []
+    for i in problematic:
+        found = False
+        for j in covered:
+            if matrix_aligning[i, j] >= minimum_coverage[i]:
+                reference_structures[j].append(names[i])
+                found = True
+                break
+        if not found:
+            no_aligning.append(names[i])
+    return names[first_reference_structure], {names[k]: v for k, v in reference_structures.items()}, no_aligning
+
+
+def _superpose_on_device(alignment, proteins, mode, reference_name=None, core_indices=None):
+    names = [p.name for p in proteins]
+    eng = get_engine()
+    eng.set_chains(*pack_sequences(proteins))
+    ref = -1 if reference_name is None else names.index(reference_name)
+    res = eng.superpose(_aln_array(alignment, names), mode, ref, core_indices)
+    off = eng._offsets
+    if res["mode"] == _engine.SUP_REFERENCE:
+        assert int(res["ncommon"].min()) > 3, "a structure has <= 3 positions in common with the reference (the reference asserts, :918)"
+    for p, prot in enumerate(proteins):
+        prot.coordinates = res["coords"][off[p]:off[p + 1]].copy()
+    return proteins, res
+
+
+def superpose(alignment, proteins, gap=-1):
+    """multiple_alignment.py:854-867: core superposition when at least half of the columns are gap-free, else onto the
+    reference structure (the protein with the most aligned residues)."""
+    _check_gap(gap)
+    proteins, res = _superpose_on_device(alignment, proteins, _engine.SUP_AUTO)
+    print("Core indices", res["n_core"])                                   # the reference prints this, :863
+    return proteins
+
+
+def superpose_core(alignment, proteins, reference_name, core_indices: np.ndarray = None, gap=-1):
+    """multiple_alignment.py:869-905."""
+    _check_gap(gap)
+    return _superpose_on_device(alignment, proteins, _engine.SUP_CORE, reference_name, core_indices)[0]
+
+
+def superpose_reference(alignment, proteins, reference_name):
+    """multiple_alignment.py:908-927."""
+    return _superpose_on_device(alignment, proteins, _engine.SUP_REFERENCE, reference_name)[0]
+
+
+def superpose_references(alignment, proteins, minimum_coverage=50):
+    """multiple_alignment.py:930-950: every group of get_reference_structures is superposed onto its reference, group after
+    group (a later reference has already been moved by an earlier group); one device call, one launch per dependency level."""
+    names = [p.name for p in proteins]
+    index = {n: q for q, n in enumerate(names)}
+    first_reference_structure, reference_structures, no_aligning = get_reference_structures(alignment, minimum_coverage)
+    ref, mem, batch_off = [], [], [0]
+    for reference_name, members in reference_structures.items():
+        r = index[reference_name]
+        # members in the reference's loop order; the reference itself (if listed) is replaced on its turn, so the members
+        # before it see the old coordinates and the ones after it the new ones: up to three dependent batches
+        cut = [q for q, n in enumerate(members) if index[n] == r]
+        parts = [members] if not cut else [members[:cut[0]], members[cut[0]:cut[0] + 1], members[cut[0] + 1:]]
+        for part in parts:
+            if part:
+                ref += [r] * len(part)
+                mem += [index[n] for n in part]
+                batch_off.append(len(ref))
+    eng = get_engine()
+    eng.set_chains(*pack_sequences(proteins))
+    res = eng.superpose_pairs(_aln_array(alignment, names), ref, mem, batch_off)
+    assert len(ref) == 0 or int(res["ncommon"].min()) > 3, "a structure has <= 3 positions in common with its reference (:941)"
+    off = eng._offsets
+    for p, prot in enumerate(proteins):
+        prot.coordinates = res["coords"][off[p]:off[p + 1]].copy()
+    return proteins
+
+
+def write_distance_matrix(names, distance_matrix, filename) -> None:
+    """helper.write_distance_matrix (helper.py:183-203): Clustal-style text, '%.4f' values formatted on the device, same bytes."""
+    text = get_engine().format_matrix([str(n) for n in names], np.asarray(distance_matrix, dtype=np.float64))
+    with open(filename, "wb") as f:
+        f.write(text)
 
 
 def install(reference_multiple_alignment_module) -> None:
@@ -300,3 +463,20 @@ def install(reference_multiple_alignment_module) -> None:
             return aln
 
         ref.MultipleAlignment.progressive_align = progressive_align
+
+    if os.environ.get("CARETTA_B200_CONSUMERS", "1") != "0":
+        # what consumes the alignment (CARETTA_B200_CONSUMERS=0 keeps the reference's)
+        for fn in (make_coverage_gap_distance_matrix, get_reference_structures, superpose, superpose_core, superpose_reference,
+                   superpose_references, make_rmsd_coverage_tm_matrix):
+            setattr(ref, fn.__name__, fn)
+
+        def to_sequence_alignment(self, alignment=None):
+            return MultipleAlignment(self.sequences, alignment=self.alignment).to_sequence_alignment(alignment)
+
+        def write_alignment(self, fasta_file, alignment=None):
+            return MultipleAlignment(self.sequences, alignment=self.alignment).write_alignment(fasta_file, alignment)
+
+        ref.MultipleAlignment.to_sequence_alignment = to_sequence_alignment
+        ref.MultipleAlignment.write_alignment = write_alignment
+        if hasattr(ref, "helper"):
+            ref.helper.write_distance_matrix = write_distance_matrix

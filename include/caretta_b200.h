@@ -132,6 +132,10 @@ int crt_dtw_align_batch(crt_ctx *ctx, const double *S, const int64_t *shape_off,
  * (the reference asserts there); their entries keep the diagonal defaults. */
 int crt_rmsd_cov_tm(crt_ctx *ctx, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm,
                     int32_t *n_bad);
+/* make_rmsd_coverage_tm_matrix(superpose_first=True) after crt_superpose: the same matrices on chains that are already in one
+ * frame (no per-pair Kabsch, multiple_alignment.py:1025-1026, :1037). */
+int crt_rmsd_cov_tm_superposed(crt_ctx *ctx, const int64_t *aln, int64_t A, double *rmsd, double *cov, double *tm,
+                               int32_t *n_bad);
 
 /* One node of the progressive alignment: replaces make_intermediate_node of MultipleAlignment.progressive_align
  * (multiple_alignment.py:195-234): score_matrix = Protein.score_function(n1, n2) (:321-349) + Gaussian of the scaled
@@ -153,6 +157,52 @@ int crt_progressive_node(crt_ctx *ctx, const double *tensors1, const double *coo
  * operation order, first strict minimum in row-major order, new node at index 0.  crt_last_elapsed_ms = device time. */
 int crt_neighbor_joining(crt_ctx *ctx, const double *distance_matrix, int32_t N, uint64_t *tree, double *branch_lengths,
                          int64_t *n_rows);
+
+/* ---- consumers of the multiple alignment.  aln: int64 [N, A] row-major, -1 = gap, rows in the
+ * order of the chains of the context (crt_set_chains) where coordinates are involved. ---- */
+
+/* make_coverage_gap_distance_matrix (multiple_alignment.py:45-56), the input of get_reference_structures (:740-784):
+ * distance[i][j] = (# columns where i has a residue and j a gap) / (# residues of i), aligning[i][j] = (# residues of i) minus
+ * that count.  float64 [N,N] / int32 [N,N].  A protein without any residue in the alignment -> CRT_E_ARG (the reference divides
+ * by zero).  Bit-identical to the reference (integer counts, one IEEE division).  Needs no chains. */
+int crt_coverage_gap_matrix(crt_ctx *ctx, const int64_t *aln, int32_t N, int64_t A, double *distance, int32_t *aligning);
+
+enum { CRT_SUP_AUTO = 0, CRT_SUP_CORE = 1, CRT_SUP_REFERENCE = 2 };
+
+/* superpose (multiple_alignment.py:854-867): superpose_core (:869-905) when at least half of the columns are gap-free, else
+ * superpose_reference (:908-927), on the coordinates of the context's chains.  mode: CRT_SUP_AUTO follows the reference's rule,
+ * the other two force one of them.  reference < 0: the first protein with the most residues in the alignment (:855).
+ * Pair p of the outputs is (reference, protein p): out_coords float64 [sum L, 3] (all chains, packed like the input),
+ * out_rot [N,9] / out_tran [N,3] with x' = x R + t (apply_rotran, superposition_functions.py:63-80), out_ncommon [N] = columns
+ * used.  Reference mode: a protein with <= 3 common columns keeps its coordinates (the reference asserts, :918); the caller sees it
+ * in out_ncommon.  Any output except out_coords may be NULL. */
+int crt_superpose(crt_ctx *ctx, const int64_t *aln, int64_t A, int32_t mode, int32_t reference, const int64_t *core_columns,
+                  int64_t n_core_columns, double *out_coords, double *out_rot, double *out_tran, int32_t *out_ncommon,
+                  int32_t *out_mode, int32_t *out_reference, int64_t *out_ncore);
+
+/* The superposition loops of superpose_references (:930-950) and write_superposed_pdbs_reference(s) (:684-737, :787-850): pair q
+ * superposes chain mem[q] onto chain ref[q] over their common alignment columns (helper.get_common_positions, helper.py:12-42) and
+ * replaces mem[q]'s coordinates.  Batches [batch_off[b], batch_off[b+1]) run one after the other (a later batch sees the
+ * coordinates an earlier one produced, like the reference's loop over its reference structures); the pairs of one batch run
+ * concurrently, so inside a batch no chain may be both a member and a reference (a batch of one pair may superpose a chain onto
+ * itself).  Pairs with <= 3 common columns are skipped (out_ncommon). */
+int crt_superpose_pairs(crt_ctx *ctx, const int64_t *aln, int64_t A, const int32_t *ref, const int32_t *mem, int64_t n_pairs,
+                        const int64_t *batch_off, int32_t n_batches, double *out_coords, double *out_rot, double *out_tran,
+                        int32_t *out_ncommon);
+
+/* helper.write_distance_matrix (helper.py:183-203): the text "n_rows\n" + for every row "name v v v ...\n" with each value
+ * formatted like Python's f"{x:.4f}" (correctly rounded decimal expansion, ties to even; "nan", "inf", "-inf", "-0.0000").
+ * matrix: float64 [n_rows, n_cols] (host), names: the row names as packed bytes, name_off [n_rows+1].  The text stays in device
+ * memory; *out_len = its size in bytes, crt_text_fetch copies it out.  Byte-identical to the reference's file. */
+int crt_format_matrix(crt_ctx *ctx, const double *matrix, int32_t n_rows, int32_t n_cols, const char *names, const int64_t *name_off,
+                      int64_t *out_len);
+
+/* MultipleAlignment.write_alignment / to_sequence_alignment (multiple_alignment.py:287-309): for every protein
+ * ">name\n" + (sequence[aln[p][k]] or '-' for a gap, k < A) + "\n".  seqs / names: packed bytes with offsets [N+1].  An index
+ * beyond its sequence -> CRT_E_ARG (the reference raises IndexError). */
+int crt_format_fasta(crt_ctx *ctx, const int64_t *aln, int32_t N, int64_t A, const char *seqs, const int64_t *seq_off, const char *names,
+                     const int64_t *name_off, int64_t *out_len);
+int crt_text_fetch(crt_ctx *ctx, char *out, int64_t cap);        /* the text of the last crt_format_* call */
 
 /* FP32 FFMA micro-benchmark used as the measured roofline denominator: returns lane-FFMA/s. */
 int crt_fp32_peak(crt_ctx *ctx, double *ffma_per_s, double *elapsed_ms);

@@ -732,3 +732,60 @@ API int crt_o_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Consumers of the multiple alignment.                               */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* make_coverage_gap_distance_matrix, multiple_alignment.py:45-56: for every i the columns where i has a residue;
+ * num_gaps(i, j) = how many of them are gaps in j; distance = num_gaps / length_i; aligning = length_i - num_gaps.
+ * Returns -1 when some protein has no residue at all (the reference divides by zero there). */
+API int crt_o_coverage_gap_matrix(const int64_t *aln, int N, int64_t A, double *distance, int32_t *aligning)
+{
+    int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(A > 0 ? A : 1));
+    int rc = 0;
+    for (int i = 0; i < N && rc == 0; ++i) {
+        int64_t len = 0;
+        for (int64_t q = 0; q < A; ++q)
+            if (aln[(size_t)i * A + q] != -1) idx[len++] = q;
+        if (len == 0) { rc = -1; break; }
+        for (int j = 0; j < N; ++j) {
+            int64_t gaps = 0;
+            for (int64_t k = 0; k < len; ++k) gaps += aln[(size_t)j * A + idx[k]] == -1;
+            distance[(size_t)i * N + j] = (double)gaps / (double)len;
+            aligning[(size_t)i * N + j] = (int32_t)(len - gaps);
+        }
+    }
+    free(idx);
+    return rc;
+}
+
+/* helper.write_distance_matrix, helper.py:183-203: f"{len(names)}\n" then f"{name} {' '.join(f'{x:.4f}' ...)}\n".
+ * Python's '.4f' is the correctly rounded decimal expansion, like glibc's printf("%.4f"); the one difference is that
+ * Python prints "nan" for every NaN where printf prints "-nan" when the sign bit is set.
+ * out = NULL: only returns the length.  names: packed bytes, name_off [n_rows + 1]. */
+API int64_t crt_o_format_matrix(const double *M, int n_rows, int n_cols, const char *names, const int64_t *name_off,
+                                char *out)
+{
+    char buf[400];
+    int64_t pos = 0;
+    int n = snprintf(buf, sizeof(buf), "%d\n", n_rows);
+    if (out) memcpy(out + pos, buf, (size_t)n);
+    pos += n;
+    for (int i = 0; i < n_rows; ++i) {
+        int64_t nl = name_off[i + 1] - name_off[i];
+        if (out) { memcpy(out + pos, names + name_off[i], (size_t)nl); out[pos + nl] = ' '; }
+        pos += nl + 1;
+        for (int j = 0; j < n_cols; ++j) {
+            double x = M[(size_t)i * n_cols + j];
+            if (x != x) n = snprintf(buf, sizeof(buf), "nan");
+            else n = snprintf(buf, sizeof(buf), "%.4f", x);
+            if (j) { if (out) out[pos] = ' '; ++pos; }
+            if (out) memcpy(out + pos, buf, (size_t)n);
+            pos += n;
+        }
+        if (out) out[pos] = '\n';
+        ++pos;
+    }
+    return pos;
+}

@@ -75,6 +75,10 @@ def lib():
         L.crt_o_score_matrix.restype = C.c_int
         L.crt_o_neighbor_joining.argtypes = [_D, C.c_int, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"), _D]
         L.crt_o_neighbor_joining.restype = C.c_int64
+        L.crt_o_coverage_gap_matrix.argtypes = [_I64, C.c_int, C.c_int64, _D, _I32]
+        L.crt_o_coverage_gap_matrix.restype = C.c_int
+        L.crt_o_format_matrix.argtypes = [_D, C.c_int, C.c_int, C.c_char_p, _I64, _P]
+        L.crt_o_format_matrix.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -309,6 +313,157 @@ def progressive_align(seqs, tree, gap_open=1.0, gap_extend=0.01, consensus_weigh
     node(n1, n2, "final")
     alignment = {**fa[fs[n1][0]], **fa[fs[n2][0]]}
     return alignment, fs, fw
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Consumers of the multiple alignment: control flow restated in Python over the C primitives.
+# --------------------------------------------------------------------------------------------------------------
+def coverage_gap_matrix(aln):
+    """make_coverage_gap_distance_matrix, multiple_alignment.py:45-56."""
+    aln = _c(aln, np.int64)
+    n = aln.shape[0]
+    dist, al = np.empty((n, n)), np.empty((n, n), np.int32)
+    if lib().crt_o_coverage_gap_matrix(aln, n, aln.shape[1], dist, al) != 0:
+        raise ZeroDivisionError("a protein has no residue in the alignment")
+    return dist, al
+
+
+def _reference_index(aln) -> int:
+    """sorted(names, key=residues in the alignment, reverse=True)[0] -- the first protein with the maximum, :855."""
+    return int(np.argmax((np.asarray(aln) != -1).sum(axis=1)))
+
+
+def core_columns(aln) -> np.ndarray:
+    """Columns where no protein has a gap, multiple_alignment.py:856-862."""
+    return np.nonzero((np.asarray(aln) != -1).all(axis=0))[0]
+
+
+def superpose_core(aln, coords_list, reference: int, core=None):
+    """superpose_core, multiple_alignment.py:869-905.  Returns (new coordinate list, rotations, translations)."""
+    aln = np.asarray(aln)
+    core = core_columns(aln) if core is None else np.asarray(core)
+    ref_core = np.ascontiguousarray(coords_list[reference][aln[reference][core]])
+    cen = _mean_axis0(ref_core)
+    ref_c = ref_core - cen
+    out, rots, trans = [], [], []
+    for i, c in enumerate(coords_list):
+        if i == reference:
+            out.append(c - cen); rots.append(np.eye(3)); trans.append(-cen)
+            continue
+        R, t = kabsch(ref_c, np.ascontiguousarray(c[aln[i][core]]))
+        out.append(apply_rotran(c, R, t)); rots.append(R); trans.append(t)
+    return out, np.array(rots), np.array(trans)
+
+
+def _mean_axis0(x) -> np.ndarray:
+    """helper.nb_mean_axis_0 (helper.py:45-53): np.mean of every column = sequential sum / n."""
+    x = np.asarray(x, dtype=np.float64)
+    out = np.zeros(x.shape[1])
+    for a in range(x.shape[1]):
+        acc = 0.0
+        for v in x[:, a]:
+            acc += float(v)
+        out[a] = acc / x.shape[0]
+    return out
+
+
+def superpose_reference(aln, coords_list, reference: int):
+    """superpose_reference, multiple_alignment.py:908-927 (the loop replaces the reference's own coordinates on its turn)."""
+    aln = np.asarray(aln)
+    cur = [np.array(c, dtype=np.float64) for c in coords_list]
+    rots, trans, ncs = [], [], []
+    for i in range(len(cur)):
+        p1, p2 = common_positions(aln[reference], aln[i])
+        ncs.append(len(p1))
+        assert len(p1) > 3
+        R, t = kabsch(np.ascontiguousarray(cur[reference][p1]), np.ascontiguousarray(cur[i][p2]))
+        cur[i] = apply_rotran(cur[i], R, t)
+        rots.append(R); trans.append(t)
+    return cur, np.array(rots), np.array(trans), np.array(ncs)
+
+
+def superpose(aln, coords_list):
+    """superpose, multiple_alignment.py:854-867.  Returns (mode, reference, new coordinate list)."""
+    aln = np.asarray(aln)
+    ref = _reference_index(aln)
+    core = core_columns(aln)
+    if len(core) < aln.shape[1] // 2:
+        return "reference", ref, superpose_reference(aln, coords_list, ref)[0]
+    return "core", ref, superpose_core(aln, coords_list, ref, core)[0]
+
+
+def get_reference_structures(aln, minimum_coverage=50):
+    """get_reference_structures, multiple_alignment.py:740-784, on indices instead of names.
+    Returns (first reference, {reference: [members]} in insertion order, [not aligning])."""
+    aln = np.asarray(aln)
+    n = aln.shape[0]
+    dist, al = coverage_gap_matrix(aln)
+    mincov = np.array([minimum_coverage * int((aln[i] != -1).sum()) / 100 for i in range(n)])
+    refs = {}
+    first = int(np.argmin(np.median(dist, axis=0)))
+    not_cov = np.where(al[:, first] < mincov[:])[0]
+    covered = list(np.where(al[:, first] >= mincov[:])[0])
+    refs[first] = [int(c) for c in covered]
+    problematic = []
+    while len(not_cov) > 0:
+        if len(not_cov) > 1:
+            r = covered[int(np.argmin(np.median(dist[not_cov, :][:, covered], axis=0)))]
+        else:
+            r = covered[int(np.argmin(dist[not_cov, :][:, covered]))]
+        cov_i = not_cov[np.where(al[not_cov, r] >= mincov[not_cov])[0]]
+        if len(cov_i) == 0:
+            problematic += list(not_cov)
+            break
+        not_cov = not_cov[np.where(al[not_cov, r] < mincov[not_cov])[0]]
+        refs[int(r)] = [int(c) for c in cov_i]
+        covered += list(cov_i)
+    no_aligning = []
+    for i in problematic:
+        found = False
+        for j in covered:
+            if al[i, j] >= mincov[i]:
+                refs[int(j)].append(int(i))
+                found = True
+                break
+        if not found:
+            no_aligning.append(int(i))
+    return first, refs, no_aligning
+
+
+def superpose_references(aln, coords_list, minimum_coverage=50):
+    """superpose_references, multiple_alignment.py:930-950."""
+    aln = np.asarray(aln)
+    cur = [np.array(c, dtype=np.float64) for c in coords_list]
+    first, refs, no_aligning = get_reference_structures(aln, minimum_coverage)
+    for r, members in refs.items():
+        for i in members:
+            p1, p2 = common_positions(aln[r], aln[i])
+            assert len(p1) > 3
+            R, t = kabsch(np.ascontiguousarray(cur[r][p1]), np.ascontiguousarray(cur[i][p2]))
+            cur[i] = apply_rotran(cur[i], R, t)
+    return cur
+
+
+def format_matrix(names, matrix) -> bytes:
+    """The bytes helper.write_distance_matrix writes (helper.py:183-203)."""
+    M = _c(np.asarray(matrix, dtype=np.float64)[:len(names)])
+    enc = [str(x).encode("utf-8") for x in names]
+    off = np.zeros(len(enc) + 1, np.int64)
+    if enc:
+        off[1:] = np.cumsum([len(e) for e in enc])
+    blob = b"".join(enc)
+    n = lib().crt_o_format_matrix(M, M.shape[0], M.shape[1], blob, off, None)
+    buf = C.create_string_buffer(int(n) + 1)
+    lib().crt_o_format_matrix(M, M.shape[0], M.shape[1], blob, off, C.cast(buf, C.c_void_p))
+    return buf.raw[:n]
+
+
+def format_fasta(names, sequences, aln) -> bytes:
+    """MultipleAlignment.write_alignment, multiple_alignment.py:299-309."""
+    out = []
+    for name, seq, row in zip(names, sequences, np.asarray(aln)):
+        out.append(">" + name + "\n" + "".join(seq[int(i)] if i != -1 else "-" for i in row) + "\n")
+    return "".join(out).encode("utf-8")
 
 
 def num_threads() -> int:

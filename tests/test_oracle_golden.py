@@ -224,3 +224,64 @@ def test_progressive_align_golden():
         assert np.array_equal(A, g[f"{name}_aln"])
         np.testing.assert_allclose(fs[-1][2], g[f"{name}_final_coords"], rtol=0, atol=1e-11)
         assert np.array_equal(fw[-1], g[f"{name}_final_weights"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Consumers of the multiple alignment: the oracle restatement against the reference's outputs
+# ------------------------------------------------------------------------------------------------------------------
+from tests import consumer_cases as CC  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cons():
+    return CC.load()
+
+
+@pytest.mark.parametrize("name", CC.CASES)
+def test_consumers_coverage_and_references(cons, name):
+    aln = cons[f"{name}_aln"]
+    dist, al = O.coverage_gap_matrix(aln)
+    assert np.array_equal(dist, cons[f"{name}_cg_distance"])            # integer counts and one division: bit-exact
+    assert np.array_equal(al, cons[f"{name}_cg_aligning"])
+    assert O._reference_index(aln) == int(cons[f"{name}_reference"])
+    assert np.array_equal(O.core_columns(aln), cons[f"{name}_core"])
+    for mc in (50, 80):
+        first, refs, no_al = O.get_reference_structures(aln, mc)
+        gfirst, grefs, gno = CC.reference_groups(cons, name, mc)
+        assert first == gfirst and list(refs.items()) == list(grefs.items()) and no_al == gno
+
+
+@pytest.mark.parametrize("name", CC.CASES)
+def test_consumers_superposition(cons, name):
+    ch = CC.chains_of(name, cons)
+    aln = cons[f"{name}_aln"]
+    coords = [ch.chain(p)[1] for p in range(ch.n)]
+    ref = int(cons[f"{name}_reference"])
+    tol = dict(rtol=0, atol=1e-9)                                        # downstream of the SVD (reference: LAPACK + BLAS)
+    if len(cons[f"{name}_core"]):
+        got, _, _ = O.superpose_core(aln, coords, ref)
+        np.testing.assert_allclose(np.concatenate(got), cons[f"{name}_sup_core"], **tol)
+        got, _, _ = O.superpose_core(aln, coords, (ref + 1) % ch.n)
+        np.testing.assert_allclose(np.concatenate(got), cons[f"{name}_sup_core_other"], **tol)
+    if len(cons[f"{name}_sup_reference"]):
+        got = O.superpose_reference(aln, coords, ref)[0]
+        np.testing.assert_allclose(np.concatenate(got), cons[f"{name}_sup_reference"], **tol)
+    else:
+        with pytest.raises(AssertionError):
+            O.superpose_reference(aln, coords, ref)
+    if len(cons[f"{name}_sup_auto"]):
+        np.testing.assert_allclose(np.concatenate(O.superpose(aln, coords)[2]), cons[f"{name}_sup_auto"], **tol)
+    for mc in (50, 80):
+        if len(cons[f"{name}_suprefs{mc}"]):
+            np.testing.assert_allclose(np.concatenate(O.superpose_references(aln, coords, mc)), cons[f"{name}_suprefs{mc}"], **tol)
+
+
+def test_consumers_text(cons):
+    for key in ("special", "random"):
+        M = cons[f"{key}_matrix"]
+        names = [f"n{i}" for i in range(M.shape[0])] if key == "special" else [f"id{i}/chain{'A' * (i % 4)}" for i in range(40)]
+        assert O.format_matrix(names, M) == cons[f"{key}_txt"].tobytes(), key
+    for name in CC.CASES:
+        names, seqs = [str(x) for x in cons[f"{name}_pnames"]], [str(x) for x in cons[f"{name}_seqs"]]
+        assert O.format_fasta(names, seqs, cons[f"{name}_aln"]) == cons[f"{name}_fasta"].tobytes(), name
+        assert O.format_matrix(names, cons[f"{name}_cg_distance"]) == cons[f"{name}_dist_txt"].tobytes(), name
