@@ -139,6 +139,11 @@ struct crt_ctx {
     DevBuf<unsigned char> nd_B;
     DevBuf<int> nd_a1, nd_a2, nd_len;
 
+    bool stage1_only = false;             // node contexts: the run stops after the traceback / Kabsch (no stage-2 fill)
+    DevBuf<DpProblem> lv_probs;           // crt_progressive_level: per-node problem records and packed level buffers
+    DevBuf<double> lv_mult, lv_xf2;
+    DevBuf<long long> lv_off;
+
     // text produced by crt_format_matrix / crt_format_fasta, fetched with crt_text_fetch
     DevBuf<char> text;
     long long text_len = 0;
@@ -553,6 +558,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         int r2;
         if ((r2 = launch_trace<10>(b.C, ta, nu, b.n_dense, st))) return r2;
         if (mid) CU(cudaEventRecord(mid, st));
+        if (c->stage1_only) return 0;
         k_rows2<<<nu, 256, 0, st>>>(ta, nu);
         CU(cudaGetLastError());
         return 0;
@@ -563,6 +569,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         FillOut fo{};
         fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
         fo.pair_score = c->score.p; fo.bnd = pipe ? ws.bnd2.p : ws.bnd.p;
+        if (c->stage1_only) return 0;
         if (f32) {
             Fill2Args a{reinterpret_cast<const float4 *>(ws.rows2.p) + ROW_PAD, c->cols2.p};
             return launch_fill2_f32(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
@@ -773,6 +780,7 @@ int crt_destroy(crt_ctx *c)
     if (c->node_ctx) { crt_destroy(c->node_ctx); c->node_ctx = nullptr; }
     c->nd_w.release(); c->nd_S.release(); c->nd_bnd.release(); c->nd_f.release(); c->nd_score.release(); c->nd_xf2.release();
     c->nd_t.release(); c->nd_c.release(); c->nd_wm.release(); c->nd_B.release(); c->nd_a1.release(); c->nd_a2.release(); c->nd_len.release(); c->text.release();
+    c->lv_probs.release(); c->lv_mult.release(); c->lv_xf2.release(); c->lv_off.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) {
         if (c->s_f1[k]) cudaStreamDestroy(c->s_f1[k]);
@@ -1346,6 +1354,7 @@ int crt_progressive_node(crt_ctx *c, const double *tensors1, const double *coord
     int rc;
     if (!c->node_ctx && (rc = crt_create(c->device, &c->node_ctx))) return rc;
     crt_ctx *nc = c->node_ctx;
+    nc->stage1_only = true;
     // ---- stage 1 of score_function on the two sequences: the fp64 pair kernels, pair (0, 1)
     std::vector<double> pc((size_t)(n + m) * 3), pt((size_t)(n + m) * d);
     std::memcpy(pc.data(), coords1, sizeof(double) * (size_t)n * 3);
@@ -1496,3 +1505,4 @@ int crt_fp32_peak(crt_ctx *c, double *ffma_per_s, double *elapsed_ms)
 }  // extern "C"
 
 #include "crt_consumers_api.inl"
+#include "crt_level_api.inl"

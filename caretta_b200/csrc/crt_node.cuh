@@ -8,6 +8,7 @@
 //   weights       = get_mean_weights(w1, w2, aln_1, aln_2)                (:217, :73-82)
 #pragma once
 #include "crt_kernels.cuh"
+#include "crt_dp_batch.cuh"
 
 namespace crt {
 
@@ -15,12 +16,10 @@ namespace crt {
 // paired_svd_superpose_with_subset (superposition_functions.py:38-60): c1' = c1 - mean(common_1),
 // c2' = (c2 - mean(common_2)) R; raw coordinates when the stage-1 alignment has <= 3 common positions (:337-342).
 // xf = k_trace's transform record of the pair: R[9], mean_1[3], mean_2[3], superpose flag.
-__global__ void __launch_bounds__(256) k_node_score(const double *c1, int n, const double *c2, int m, const double *xf,
-                                                    const double *w1, const double *w2, double mult1, double mult2,
-                                                    double neg_gamma_c, double neg_gamma_w, double *S)
+__device__ __forceinline__ void node_score_cell(long long q, const double *c1, int n, const double *c2, int m, const double *xf,
+                                                const double *w1, const double *w2, double mult1, double mult2,
+                                                double neg_gamma_c, double neg_gamma_w, double *S)
 {
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= (long long)n * m) return;
     const int a = (int)(q / m), b = (int)(q - (long long)a * m);
     double x0 = c1[a * 3], x1 = c1[a * 3 + 1], x2 = c1[a * 3 + 2];
     double y0 = c2[b * 3], y1 = c2[b * 3 + 1], y2 = c2[b * 3 + 2];
@@ -44,12 +43,33 @@ __global__ void __launch_bounds__(256) k_node_score(const double *c1, int n, con
     S[q] = __dadd_rn(sc, sw);
 }
 
+__global__ void __launch_bounds__(256) k_node_score(const double *c1, int n, const double *c2, int m, const double *xf,
+                                                    const double *w1, const double *w2, double mult1, double mult2,
+                                                    double neg_gamma_c, double neg_gamma_w, double *S)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)n * m) return;
+    node_score_cell(q, c1, n, c2, m, xf, w1, w2, mult1, mult2, neg_gamma_c, neg_gamma_w, S);
+}
+
+// A whole tree level at once (crt_progressive_level): node = blockIdx.y, its two children are consecutive chains of the packed
+// level arrays (child 1 at residue pr.aln_off, child 2 at pr.aln_off + n); xform / mult are indexed by node.
+__global__ void __launch_bounds__(256) k_level_score(const DpProblem *probs, const double *coords, const double *weights,
+                                                     const double *xform, const double *mult, double neg_gamma_c, double neg_gamma_w,
+                                                     double *S_all)
+{
+    const DpProblem pr = probs[blockIdx.y];
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)pr.n * pr.m) return;
+    node_score_cell(q, coords + pr.aln_off * 3, pr.n, coords + (pr.aln_off + pr.n) * 3, pr.m, xform + (long long)blockIdx.y * XF,
+                    weights + pr.aln_off, weights + pr.aln_off + pr.n, mult[2 * blockIdx.y], mult[2 * blockIdx.y + 1], neg_gamma_c,
+                    neg_gamma_w, S_all + pr.s_off);
+}
+
 // Superposition of mean_function (multiple_alignment.py:362-372) over the common positions of the DTW alignment.
 // One thread: the sums run in alignment order like helper.nb_mean_axis_0 (helper.py:45-53).  xf2: same record layout as xf.
-__global__ void k_node_kabsch(const double *c1, const double *c2, const int *aln1, const int *aln2, const int *len_p, double *xf2)
+__device__ inline void node_kabsch_one(const double *c1, const double *c2, const int *aln1, const int *aln2, int len, double *xf2)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int len = *len_p;
     int c = 0;
     double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
     for (int q = 0; q < len; ++q) {
@@ -77,13 +97,27 @@ __global__ void k_node_kabsch(const double *c1, const double *c2, const int *aln
     xf2[15] = superpose ? 1.0 : 0.0;
 }
 
-// Intermediate node: tensors_mean [len, d], coordinates_mean [len, 3], mean weights [len]; one thread per alignment column.
-__global__ void __launch_bounds__(128) k_node_mean(const double *t1, const double *c1, const double *w1, const double *t2,
-                                                   const double *c2, const double *w2, int d, const int *aln1, const int *aln2,
-                                                   const int *len_p, const double *xf2, double *t_out, double *c_out, double *w_out)
+__global__ void k_node_kabsch(const double *c1, const double *c2, const int *aln1, const int *aln2, const int *len_p, double *xf2)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *len_p) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    node_kabsch_one(c1, c2, aln1, aln2, *len_p, xf2);
+}
+
+__global__ void __launch_bounds__(32) k_level_kabsch(const DpProblem *probs, int n_nodes, const double *coords, const int *aln1,
+                                                     const int *aln2, const int *aln_len, double *xf2)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_nodes) return;
+    const DpProblem pr = probs[p];
+    node_kabsch_one(coords + pr.aln_off * 3, coords + (pr.aln_off + pr.n) * 3, aln1 + pr.aln_off, aln2 + pr.aln_off, aln_len[p],
+                    xf2 + (long long)p * XF);
+}
+
+// Intermediate node: tensors_mean [len, d], coordinates_mean [len, 3], mean weights [len]; one thread per alignment column.
+__device__ __forceinline__ void node_mean_col(int i, const double *t1, const double *c1, const double *w1, const double *t2,
+                                              const double *c2, const double *w2, int d, const int *aln1, const int *aln2,
+                                              const double *xf2, double *t_out, double *c_out, double *w_out)
+{
     const int x = aln1[i], y = aln2[i];
     for (int k = 0; k < d; ++k) {
         double v;
@@ -110,6 +144,28 @@ __global__ void __launch_bounds__(128) k_node_mean(const double *t1, const doubl
     if (x >= 0) w = __dadd_rn(w, w1[x]);
     if (y >= 0) w = __dadd_rn(w, w2[y]);
     w_out[i] = w;
+}
+
+__global__ void __launch_bounds__(128) k_node_mean(const double *t1, const double *c1, const double *w1, const double *t2,
+                                                   const double *c2, const double *w2, int d, const int *aln1, const int *aln2,
+                                                   const int *len_p, const double *xf2, double *t_out, double *c_out, double *w_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *len_p) return;
+    node_mean_col(i, t1, c1, w1, t2, c2, w2, d, aln1, aln2, xf2, t_out, c_out, w_out);
+}
+
+// outputs of node p go to rows pr.aln_off .. pr.aln_off + aln_len[p] of the packed output arrays (capacity n + m rows)
+__global__ void __launch_bounds__(128) k_level_mean(const DpProblem *probs, const double *tensors, const double *coords,
+                                                    const double *weights, int d, const int *aln1, const int *aln2, const int *aln_len,
+                                                    const double *xf2, double *t_out, double *c_out, double *w_out)
+{
+    const DpProblem pr = probs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= aln_len[blockIdx.y]) return;
+    const long long a = pr.aln_off, b = pr.aln_off + pr.n;
+    node_mean_col(i, tensors + a * d, coords + a * 3, weights + a, tensors + b * d, coords + b * 3, weights + b, d, aln1 + a, aln2 + a,
+                  xf2 + (long long)blockIdx.y * XF, t_out + a * d, c_out + a * 3, w_out + a);
 }
 
 }  // namespace crt

@@ -20,7 +20,7 @@ EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
-    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node",
+    "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node", "crt_progressive_level",
     "crt_coverage_gap_matrix", "crt_superpose", "crt_superpose_pairs", "crt_format_matrix", "crt_format_fasta", "crt_text_fetch",
 ]
 
@@ -79,6 +79,7 @@ def load_library():
     L.crt_neighbor_joining.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i64)]
     L.crt_progressive_node.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, dbl,
                                        vp, vp, C.POINTER(i32), vp, vp, vp, C.POINTER(dbl), C.POINTER(i32)]
+    L.crt_progressive_level.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp, vp, vp, vp, vp]
     L.crt_coverage_gap_matrix.argtypes = [vp, vp, i32, i64, vp, vp]
     L.crt_superpose.argtypes = [vp, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.crt_superpose_pairs.argtypes = [vp, vp, i64, vp, vp, i64, vp, i32, vp, vp, vp, vp]
@@ -383,6 +384,39 @@ class Engine:
         k = k.value
         return (a1[:k].astype(np.int64), a2[:k].astype(np.int64), tm[:k].copy(), cm[:k].copy(), wm[:k].reshape(-1, 1).copy(),
                 sc.value, st.value)
+
+    def progressive_level(self, children, mults, gamma_tensor=7.0, gamma_coords=0.03, gamma_weight=0.03, gap_open=1.0, gap_extend=0.01):
+        """All independent nodes of one guide-tree level in one device call (crt_progressive_level).  children: list of
+        ((t1, c1, w1), (t2, c2, w2)) per node, mults: list of (multiplier_n1, multiplier_n2).  Returns one tuple per node, like
+        progressive_node: (aln_1, aln_2, tensors_mean, coordinates_mean, weights_mean, dtw_score, status)."""
+        k = len(children)
+        if k == 0:
+            return []
+        seqs = [s for pair in children for s in pair]
+        d = int(np.asarray(seqs[0][0]).shape[1])
+        lens = np.array([np.asarray(s[0]).shape[0] for s in seqs], np.int64)
+        off = np.zeros(2 * k + 1, np.int64)
+        off[1:] = np.cumsum(lens)
+        total = int(off[-1])
+        T = np.concatenate([np.asarray(s[0], dtype=np.float64).reshape(-1, d) for s in seqs])
+        X = np.concatenate([np.asarray(s[1], dtype=np.float64).reshape(-1, 3) for s in seqs])
+        W = np.concatenate([np.asarray(s[2], dtype=np.float64).reshape(-1) for s in seqs])
+        if T.shape != (total, d) or X.shape != (total, 3) or W.shape != (total,):
+            raise ValueError("tensors [L,d], coordinates [L,3], weights [L] expected for every sequence")
+        M = np.ascontiguousarray(np.asarray(mults, dtype=np.float64).reshape(k, 2))
+        a1, a2 = np.empty(total, np.int32), np.empty(total, np.int32)
+        ln = np.empty(k, np.int32)
+        tm, cm, wm = np.empty((total, d)), np.empty((total, 3)), np.empty(total)
+        sc, st = np.empty(k), np.empty(k, np.int32)
+        self._check(self.lib.crt_progressive_level(self.h, k, d, _p(T), _p(X), _p(W), _p(off), _p(M), float(gamma_tensor), float(gamma_coords),
+                                                   float(gamma_weight), float(gap_open), float(gap_extend), _p(a1), _p(a2), _p(ln), _p(tm),
+                                                   _p(cm), _p(wm), _p(sc), _p(st)), "crt_progressive_level")
+        out = []
+        for q in range(k):
+            lo, hi = int(off[2 * q]), int(off[2 * q]) + int(ln[q])
+            out.append((a1[lo:hi].astype(np.int64), a2[lo:hi].astype(np.int64), tm[lo:hi].copy(), cm[lo:hi].copy(),
+                        wm[lo:hi].reshape(-1, 1).copy(), float(sc[q]), int(st[q])))
+        return out
 
     # ------------------------------------------------------------------------------------------------ alignment consumers
     def _aln(self, aln, need_chains=True):

@@ -141,47 +141,87 @@ class MultipleAlignment:
     # ------------------------------------------------------------------ guide tree + progressive alignment
     def progressive_align(self, tree, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight,
                           score_function_params=None, mean_function_params=None) -> typing.Dict[str, np.ndarray]:
-        """MultipleAlignment.progressive_align (multiple_alignment.py:172-253): same bookkeeping, every node's score matrix,
-        affine DTW and intermediate node computed on the device by crt_progressive_node."""
+        """MultipleAlignment.progressive_align (multiple_alignment.py:172-253): same bookkeeping and the same results; every node's
+        score matrix, affine DTW and intermediate node are computed on the device.  A node depends only on its two children, so all
+        nodes of one dependency level of the guide tree go to the device in ONE call (crt_progressive_level) instead of the
+        reference's one-node-at-a-time loop (CARETTA_B200_NODE_BATCH=0: one crt_progressive_node call per node, in tree order)."""
         p = dict(score_function_params or {})
         if p.get("flexible", False) or (mean_function_params or {}).get("flexible", False):
             raise NotImplementedError("flexible=True is not accelerated")
         gt, gc = p.get("gamma_tensor", 0.03), p.get("gamma_coords", 0.03)          # Protein.score_function defaults, :321-322
         eng = get_engine()
-        final_sequences = [s for s in self.sequences]
-        final_alignments = {s.name: {s.name: np.arange(len(s))} for s in final_sequences}
-        final_consensus_weights = [np.full((len(s), 1), consensus_weight, dtype=np.float64) for s in final_sequences]
-        statuses = []
-
-        def make_intermediate_node(n1, n2, n_int):
-            s1, s2 = final_sequences[n1], final_sequences[n2]
-            l1, l2 = len(final_alignments[s1.name]), len(final_alignments[s2.name])
-            multiplier_n1, multiplier_n2 = l2 / (2 * (l1 + l2)), l1 / (2 * (l1 + l2))
-            aln_1, aln_2, tm, cm, wm, _, st = eng.progressive_node(
-                s1.tensors, s1.coordinates, final_consensus_weights[n1], s2.tensors, s2.coordinates, final_consensus_weights[n2],
-                multiplier_n1, multiplier_n2, gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty)
-            statuses.append(st)
-            name_int = f"int-{n_int}"
-            final_alignments[s1.name] = {name: np.where(aln_1 != -1, seq[np.maximum(aln_1, 0)], -1)
-                                         for name, seq in final_alignments[s1.name].items()}
-            final_alignments[s2.name] = {name: np.where(aln_2 != -1, seq[np.maximum(aln_2, 0)], -1)
-                                         for name, seq in final_alignments[s2.name].items()}
-            final_alignments[name_int] = {**final_alignments[s1.name], **final_alignments[s2.name]}
-            final_sequences.append(Protein(name_int, tm, cm))
-            final_consensus_weights.append(wm)
-
+        n_leaves = len(self.sequences)
         tree = np.asarray(tree)
+        # (node_1, node_2, name) in the reference's creation order; the node made at step q gets index n_leaves + q (:236-247)
+        steps = []
         for x in range(0, tree.shape[0] - 1, 2):
             node_1, node_2, node_int = int(tree[x, 0]), int(tree[x + 1, 0]), int(tree[x, 1])
             assert int(tree[x + 1, 1]) == node_int
-            make_intermediate_node(node_1, node_2, node_int)
-        node_1, node_2 = int(tree[-1, 0]), int(tree[-1, 1])
-        make_intermediate_node(node_1, node_2, "final")
+            steps.append((node_1, node_2, f"int-{node_int}"))
+        steps.append((int(tree[-1, 0]), int(tree[-1, 1]), "int-final"))
+        n_total = n_leaves + len(steps)
+        final_sequences = [s for s in self.sequences] + [None] * len(steps)
+        final_consensus_weights = [np.full((len(s), 1), consensus_weight, dtype=np.float64) for s in self.sequences] + [None] * len(steps)
+        # members[i]: names under node i (children's order: first child's members, then the second's, like the dict merge of :229-232);
+        # rows[i]: int64 [len(members), len(node i)] = residue index of every member per column of node i, -1 = gap
+        members = [[s.name] for s in self.sequences] + [None] * len(steps)
+        rows = [np.arange(len(s), dtype=np.int64)[None, :] for s in self.sequences] + [None] * len(steps)
+        level = [0] * n_leaves + [0] * len(steps)
+        for q, (a, b, _) in enumerate(steps):
+            if not (0 <= a < n_leaves + q and 0 <= b < n_leaves + q):
+                raise IndexError("tree refers to a node that does not exist yet")
+            level[n_leaves + q] = 1 + max(level[a], level[b])
+        statuses = np.zeros(len(steps), np.int32)
+        in_parent_frame = {}                      # child index -> its members' rows re-indexed by the parent's alignment (:219-226)
+
+        def finish(q, res):
+            a, b, name_int = steps[q]
+            aln_1, aln_2, tm, cm, wm, _, st = res
+            statuses[q] = st
+            r1 = np.where(aln_1[None, :] != -1, rows[a][:, np.maximum(aln_1, 0)], -1)
+            r2 = np.where(aln_2[None, :] != -1, rows[b][:, np.maximum(aln_2, 0)], -1)
+            in_parent_frame[a], in_parent_frame[b] = r1, r2
+            i = n_leaves + q
+            members[i] = members[a] + members[b]
+            rows[i] = np.concatenate([r1, r2])
+            final_sequences[i] = Protein(name_int, tm, cm)
+            final_consensus_weights[i] = wm
+
+        def node_inputs(q):
+            a, b, _ = steps[q]
+            s1, s2 = final_sequences[a], final_sequences[b]
+            l1, l2 = len(members[a]), len(members[b])
+            return ((s1.tensors, s1.coordinates, final_consensus_weights[a]), (s2.tensors, s2.coordinates, final_consensus_weights[b])), \
+                (l2 / (2 * (l1 + l2)), l1 / (2 * (l1 + l2)))                # multiplier_n1, multiplier_n2 (:200-203)
+
+        if os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0":
+            for lv in range(1, max(level) + 1 if steps else 1):
+                qs = [q for q in range(len(steps)) if level[n_leaves + q] == lv]
+                inputs = [node_inputs(q) for q in qs]
+                results = eng.progressive_level([x[0] for x in inputs], [x[1] for x in inputs], gt, gc, gamma_weight,
+                                                gap_open_penalty, gap_extend_penalty)
+                for q, res in zip(qs, results):
+                    finish(q, res)
+        else:
+            for q in range(len(steps)):
+                (c1, c2), (m1, m2) = node_inputs(q)
+                finish(q, eng.progressive_node(*c1, *c2, m1, m2, gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty))
+
+        # the reference's dictionaries: every node's entry is re-written in its parent's frame when the parent is made (:219-226),
+        # the parent's own entry is the merge of the two (:227-232)
+        final_alignments = {}
+        for i in range(n_total):
+            name = final_sequences[i].name
+            r = in_parent_frame.get(i, rows[i])
+            final_alignments[name] = {mname: r[k] for k, mname in enumerate(members[i])}
+        last = n_total - 1
+        node_1, node_2 = steps[-1][0], steps[-1][1]
         alignment = {**final_alignments[final_sequences[node_1].name], **final_alignments[final_sequences[node_2].name]}
+        assert list(alignment) == members[last]
         self.final_consensus_weights = final_consensus_weights
         self.final_alignments = final_alignments
         self.final_sequences = final_sequences
-        self.last_status = np.array(statuses, np.int32)
+        self.last_status = statuses
         return alignment
 
     def multiple_align(self, pairwise_distance_matrix, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight,

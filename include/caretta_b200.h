@@ -150,6 +150,17 @@ int crt_progressive_node(crt_ctx *ctx, const double *tensors1, const double *coo
                          double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2, int32_t *aln_len,
                          double *tensors_mean, double *coords_mean, double *weights_mean, double *score, int32_t *status);
 
+/* All independent nodes of one level of the guide tree at once (nodes at the same depth are independent).
+ * Node k aligns child chains 2k and 2k+1 of the packed level arrays: tensors [sum,d], coords [sum,3], weights [sum],
+ * offsets [2 n_nodes + 1]; mult [n_nodes][2] = (multiplier_n1, multiplier_n2) of multiple_alignment.py:200-203.  Same computation
+ * per node as crt_progressive_node.  Outputs are packed like the inputs: node k owns rows offsets[2k] .. offsets[2k] + aln_len[k]
+ * (capacity n_k + m_k) of aln1 / aln2 (int32, -1 = gap), tensors_mean [sum,d], coords_mean [sum,3], weights_mean [sum];
+ * score / status [n_nodes] (may be NULL). */
+int crt_progressive_level(crt_ctx *ctx, int32_t n_nodes, int32_t d, const double *tensors, const double *coords, const double *weights,
+                          const int64_t *offsets, const double *mult, double gamma_tensor, double gamma_coords, double gamma_weight,
+                          double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2, int32_t *aln_len, double *tensors_mean,
+                          double *coords_mean, double *weights_mean, double *score, int32_t *status);
+
 /* Neighbor joining on the device: replaces caretta/neighbor_joining.py:17-99 (`neighbor_joining(distance_matrix)`, called
  * at multiple_alignment.py:277 on max(S) - S of the pairwise matrix).  distance_matrix: float64 [N,N] row-major (host),
  * N >= 3.  tree: uint64 [2N-3][2] rows (node_1, node_2), node ids >= N are intermediate nodes in creation order;

@@ -48,6 +48,14 @@ def main():
             out[f"{name}_final_tensors"] = fin.tensors
             out[f"{name}_final_coords"] = fin.coordinates
             out[f"{name}_final_weights"] = msa.final_consensus_weights[-1]
+            # the bookkeeping dictionaries (final_alignments: node name -> {member name -> indices}), flattened in dict order
+            keys, mem, lens, flat = [], [], [], []
+            for k, dct in msa.final_alignments.items():
+                for mname, arr in dct.items():
+                    keys.append(k); mem.append(mname); lens.append(len(arr)); flat.append(np.asarray(arr, dtype=np.int64))
+            out[f"{name}_fa_keys"], out[f"{name}_fa_members"] = np.array(keys), np.array(mem)
+            out[f"{name}_fa_lens"], out[f"{name}_fa_flat"] = np.array(lens), np.concatenate(flat)
+            out[f"{name}_fs_names"] = np.array([s.name for s in msa.final_sequences])
         print(f"[gen-msa] {name}: N={ch.n} alignment {A.shape}  {time.time() - t0:.1f}s")
     np.savez_compressed(os.path.join(GOLD, "msa.npz"), **out)
 

@@ -280,7 +280,7 @@ def mean_weights(w1, w2, aln_1, aln_2) -> np.ndarray:
 
 
 def progressive_align(seqs, tree, gap_open=1.0, gap_extend=0.01, consensus_weight=1.0, gamma_weight=0.03,
-                      gamma_t=7.0, gamma_c=0.03):
+                      gamma_t=7.0, gamma_c=0.03, want_final_alignments=False):
     """MultipleAlignment.progressive_align, multiple_alignment.py:172-253, on [(name, tensors, coords)] (small cases:
     Python loops).  Returns (alignment {name: int64[A]}, final_sequences [(name, tensors, coords)], final_weights)."""
     fs = [(n, _c(t), _c(c)) for n, t, c in seqs]
@@ -312,7 +312,21 @@ def progressive_align(seqs, tree, gap_open=1.0, gap_extend=0.01, consensus_weigh
     n1, n2 = int(tree[-1, 0]), int(tree[-1, 1])
     node(n1, n2, "final")
     alignment = {**fa[fs[n1][0]], **fa[fs[n2][0]]}
+    if want_final_alignments:
+        return alignment, fs, fw, fa
     return alignment, fs, fw
+
+
+def progressive_node(t1, c1, w1, t2, c2, w2, mult1, mult2, gamma_t=7.0, gamma_c=0.03, gamma_weight=0.03, gap_open=1.0, gap_extend=0.01):
+    """One make_intermediate_node (multiple_alignment.py:195-234) with the signature of Engine.progressive_node."""
+    t1, c1, t2, c2 = _c(t1), _c(c1), _c(t2), _c(c2)
+    w1, w2 = np.asarray(w1, dtype=np.float64).reshape(-1, 1), np.asarray(w2, dtype=np.float64).reshape(-1, 1)
+    S = score_matrix(t1, c1, t2, c2, gamma_t, gamma_c)
+    if not gamma_weight < 0:
+        S = S + rbf_matrix(w1 * mult1, w2 * mult2, gamma_weight)
+    a1, a2, sc = dtw_align(S, gap_open, gap_extend)
+    tmn, cmn = mean_function(t1, c1, t2, c2, a1, a2)
+    return a1, a2, tmn, cmn, mean_weights(w1, w2, a1, a2), sc, 0
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,69 @@
+"""Host logic of the progressive alignment mirror (caretta_b200.multiple_alignment.MultipleAlignment.progressive_align) on
+the CPU: the level batching and the final_alignments / final_sequences bookkeeping, with the oracle standing in for the device
+(a stand-in ENGINE for the test only -- the product never imports the oracle), against the reference's own output
+(tests/golden/msa.npz, made by oracle/gen_golden_msa.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from caretta_b200 import multiple_alignment as MA
+from caretta_b200 import synth
+from oracle import oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class OracleEngine:
+    """Implements the two engine calls progressive_align makes, node by node on the CPU restatement."""
+    calls = 0
+    batch_sizes = []
+
+    def progressive_node(self, t1, c1, w1, t2, c2, w2, m1, m2, gt, gc, gw, go, ge):
+        OracleEngine.calls += 1
+        return O.progressive_node(t1, c1, w1, t2, c2, w2, m1, m2, gt, gc, gw, go, ge)
+
+    def progressive_level(self, children, mults, gt, gc, gw, go, ge):
+        OracleEngine.calls += 1
+        OracleEngine.batch_sizes.append(len(children))
+        return [O.progressive_node(*a, *b, m[0], m[1], gt, gc, gw, go, ge) for (a, b), m in zip(children, mults)]
+
+
+@pytest.mark.parametrize("name", ["fam8", "ragged12"])
+@pytest.mark.parametrize("batch", ["1", "0"])
+def test_progressive_align_bookkeeping(monkeypatch, name, batch):
+    g = np.load(os.path.join(G, "msa.npz"))
+    L = g[f"{name}_lengths"]
+    ch = synth.make_chains(len(L), list(L), 10, seed=int(g[f"{name}_seed"]), family_size=int(g[f"{name}_family"]))
+    monkeypatch.setattr(MA, "get_engine", lambda: OracleEngine())
+    monkeypatch.setenv("CARETTA_B200_NODE_BATCH", batch)
+    OracleEngine.calls, OracleEngine.batch_sizes = 0, []
+    msa = MA.StructureMultiple.from_chains(ch)
+    aln = msa.progressive_align(g[f"{name}_tree"], 1.0, 0.01, 1.0, 0.03, dict(gamma_tensor=7.0, gamma_coords=0.03), None)
+    A = np.array([aln[f"s{p}"] for p in range(ch.n)])
+    assert np.array_equal(A, g[f"{name}_aln"])                                     # the reference's final alignment
+    assert list(aln) == [str(x) for x in g[f"{name}_fa_members"][g[f"{name}_fa_keys"] == "int-final"]]
+    if batch == "1":
+        assert OracleEngine.calls < ch.n - 1 and sum(OracleEngine.batch_sizes) == ch.n - 1       # fewer calls than nodes
+    else:
+        assert OracleEngine.calls == ch.n - 1
+    # final_sequences / final_alignments exactly like the reference's attributes (names, order, index arrays)
+    assert [s.name for s in msa.final_sequences] == [str(x) for x in g[f"{name}_fs_names"]]
+    keys, mem, lens, flat = g[f"{name}_fa_keys"], g[f"{name}_fa_members"], g[f"{name}_fa_lens"], g[f"{name}_fa_flat"]
+    got_keys = [(k, m) for k, dct in msa.final_alignments.items() for m in dct]
+    assert got_keys == [(str(k), str(m)) for k, m in zip(keys, mem)]
+    pos = 0
+    for k, m, ln in zip(keys, mem, lens):
+        assert np.array_equal(msa.final_alignments[str(k)][str(m)], flat[pos:pos + ln]), (k, m)
+        pos += ln
+    np.testing.assert_allclose(msa.final_sequences[-1].coordinates, g[f"{name}_final_coords"], rtol=0, atol=1e-9)
+    assert np.array_equal(msa.final_consensus_weights[-1], g[f"{name}_final_weights"])
+
+
+def test_tree_with_forward_reference_is_rejected(monkeypatch):
+    monkeypatch.setattr(MA, "get_engine", lambda: OracleEngine())
+    ch = synth.make_chains(3, [20, 22, 21], 10, seed=1, family_size=3)
+    msa = MA.StructureMultiple.from_chains(ch)
+    bad = np.array([[0, 3], [4, 3], [3, 2]], dtype=np.uint64)       # node 4 does not exist when node 3 is built
+    with pytest.raises(IndexError):
+        msa.progressive_align(bad, 1.0, 0.01, 1.0, 0.03, dict(gamma_tensor=7.0, gamma_coords=0.03), None)

@@ -1,0 +1,46 @@
+"""End-to-end timing of the guide tree + progressive alignment on one GPU: pair matrix, neighbor joining, nodes.
+python tools/msa_time.py [N] [L]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from caretta_b200 import multiple_alignment as MA, synth  # noqa: E402
+
+
+def tree_levels(tree, n):
+    """Dependency depth of every intermediate node of the reference's tree array (rows x, x+1 -> node tree[x, 1])."""
+    level = {i: 0 for i in range(n)}
+    for x in range(0, tree.shape[0] - 1, 2):
+        a, b, c = int(tree[x, 0]), int(tree[x + 1, 0]), int(tree[x, 1])
+        level[c] = 1 + max(level[a], level[b])
+    return level
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    L = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+    ch = synth.make_chains(n, L, 10, seed=3, family_size=20)
+    msa = MA.StructureMultiple.from_chains(ch)
+    prm = dict(MA.DEFAULT_SCORE_PARAMS)
+    t0 = time.perf_counter(); S = msa.make_pairwise_matrix(prm); t1 = time.perf_counter()
+    S = msa.make_pairwise_matrix(prm); t2 = time.perf_counter()
+    D = S.max() - S
+    from caretta_b200 import neighbor_joining as NJ
+    t3 = time.perf_counter(); tree, bl = NJ.neighbor_joining(D); t4 = time.perf_counter()
+    lv = tree_levels(tree, n)
+    depth = max(lv.values())
+    t5 = time.perf_counter()
+    aln = msa.progressive_align(tree, 1.0, 0.01, 1.0, 0.03, prm, dict(flexible=False))
+    t6 = time.perf_counter()
+    A = len(next(iter(aln.values())))
+    print(json.dumps({"N": n, "L": L, "pair_matrix_ms": (t2 - t1) * 1e3, "pair_matrix_first_ms": (t1 - t0) * 1e3, "nj_ms": (t4 - t3) * 1e3,
+                      "progressive_ms": (t6 - t5) * 1e3, "nodes": n - 1, "ms_per_node": (t6 - t5) * 1e3 / (n - 1), "tree_depth": depth,
+                      "alignment_length": A}))
+
+
+if __name__ == "__main__":
+    main()
