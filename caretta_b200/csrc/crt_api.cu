@@ -1323,9 +1323,11 @@ static int rmsd_cov_tm_impl(crt_ctx *c, const int64_t *aln, int64_t A, double *r
     cudaMemsetAsync(dBad.p, 0, sizeof(int), st);
     k_fill_diag<<<(unsigned)((NN + 255) / 256), 256, 0, st>>>(dR.p, dC.p, dT.p, N);
     const long long np = (long long)N * (N - 1) / 2;
+    cudaEventRecord(c->ev0, st);
     if (np > 0)
         k_rmsd_cov_tm<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(dAln.p, N, A, c->coords.p, c->d_offsets.p, c->centroid.p, dR.p, dC.p, dT.p, dBad.p, superpose);
     int bad = 0;
+    cudaEventRecord(c->ev1, st);
     cudaMemcpyAsync(rmsd, dR.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(cov, dC.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(tm, dT.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);
@@ -1333,6 +1335,8 @@ static int rmsd_cov_tm_impl(crt_ctx *c, const int64_t *aln, int64_t A, double *r
     cudaError_t e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess) return fail(CRT_E_CUDA, "crt_rmsd_cov_tm: %s", cudaGetErrorString(e));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->elapsed_ms = ms;
     if (n_bad) *n_bad = bad;
     return 0;
 }
@@ -1450,15 +1454,15 @@ int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, u
         ok(cudaMemcpyAsync(A, distance_matrix, NN * 8, cudaMemcpyHostToDevice, st));
         ok(cudaMemcpyAsync(t0, ident.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
         ok(cudaMemsetAsync(sel, 0, sizeof(NjSel), st));
+        ok(cudaFuncSetAttribute(k_nj_rebuild, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NJ_REBUILD_SMEM));
         CU(cudaEventRecord(c->ev0, st));
         k_nj_rowsums<<<(unsigned)(((size_t)N * 32 + 255) / 256), 256, 0, st>>>(A, N, S0);
         int n = N;
         while (n > 3 && e == cudaSuccess) {
-            const long long total = (long long)n * n;
-            const int n_part = (int)std::min<long long>(max_part, (total + NJ_ARGMIN_THREADS * 8 - 1) / (NJ_ARGMIN_THREADS * 8));
+            const int n_part = std::min(max_part, n);                    // one block per row, rows beyond max_part wrap around
             k_nj_argmin<<<n_part, NJ_ARGMIN_THREADS, 0, st>>>(A, S0, n, pq, plin);
             k_nj_select<<<1, NJ_ARGMIN_THREADS, 0, st>>>(A, S0, n, N, pq, plin, n_part, t0, sel, d_tree, d_bl);
-            k_nj_rebuild<<<(unsigned)(((size_t)(n - 1) * 32 + 255) / 256), 256, 0, st>>>(A, n, sel, N, t0, t1, B, S1);
+            k_nj_rebuild<<<(unsigned)((n - 1 + NJ_ROWS - 1) / NJ_ROWS), NJ_REBUILD_THREADS, NJ_REBUILD_SMEM, st>>>(A, n, sel, N, t0, t1, B, S1);
             std::swap(A, B); std::swap(S0, S1); std::swap(t0, t1);
             --n;
             if ((n & 255) == 0) ok(cudaGetLastError());

@@ -24,15 +24,29 @@ struct NjSel {
     long long n_inter;   // intermediate nodes created so far
 };
 
+// acc + v(lane 0) + v(lane 1) + ... in lane order.  Full chunks are unrolled so that the 32 shuffles issue back to back and only
+// the float64 adds form the dependent chain (the add order, hence the result, is the same as the rolled loop's).
+__device__ __forceinline__ double nj_chain32(double acc, double v, int lim)
+{
+    if (lim == 32) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, l));
+    } else {
+        for (int l = 0; l < lim; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, l));
+    }
+    return acc;
+}
+
 // sequential (index-order) sum of one row by a warp; returns the sum in every lane
 __device__ __forceinline__ double nj_row_sum(const double *row, int n, int lane)
 {
     double acc = 0.0;
+    double v = lane < n ? row[lane] : 0.0;
     for (int c0 = 0; c0 < n; c0 += 32) {
-        const int c = c0 + lane;
-        const double v = c < n ? row[c] : 0.0;
-        const int lim = min(32, n - c0);
-        for (int l = 0; l < lim; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, l));
+        const int c = c0 + 32 + lane;
+        const double vn = c < n ? row[c] : 0.0;
+        acc = nj_chain32(acc, v, min(32, n - c0));
+        v = vn;
     }
     return acc;
 }
@@ -52,17 +66,34 @@ __device__ __forceinline__ bool nj_better(double q, long long lin, double bq, lo
 
 constexpr int NJ_ARGMIN_THREADS = 256;
 
+// Block b scans rows b, b + gridDim.x, ...; its threads stride over the columns (coalesced, no index division).  The minimum is
+// taken over (q, linear index) pairs, so the traversal order does not matter: the winner is the first row-major minimum.
 __global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A, const double *S, int n, double *pq, long long *plin)
 {
-    const long long total = (long long)n * n;
     const double nm2 = (double)(n - 2);
     double bq = INFINITY;
     long long blin = 0;
-    for (long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x; lin < total; lin += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(lin / n), j = (int)(lin - (long long)i * n);
-        if (i == j) continue;
-        const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, A[lin]), S[i]), S[j]);
-        if (nj_better(q, lin, bq, blin)) { bq = q; blin = lin; }
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const double *row = A + (size_t)i * n;
+        const double si = S[i];
+        const long long base = (long long)i * n;
+        int j = threadIdx.x;
+        for (; j + 3 * NJ_ARGMIN_THREADS < n; j += 4 * NJ_ARGMIN_THREADS) {        // four independent loads in flight
+            double a[4], sj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = row[j + u * NJ_ARGMIN_THREADS]; sj[u] = S[j + u * NJ_ARGMIN_THREADS]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int jj = j + u * NJ_ARGMIN_THREADS;
+                const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, a[u]), si), sj[u]);
+                if (jj != i && nj_better(q, base + jj, bq, blin)) { bq = q; blin = base + jj; }
+            }
+        }
+        for (; j < n; j += NJ_ARGMIN_THREADS) {
+            if (i == j) continue;
+            const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, row[j]), si), S[j]);
+            if (nj_better(q, base + j, bq, blin)) { bq = q; blin = base + j; }
+        }
     }
     __shared__ double sq[NJ_ARGMIN_THREADS];
     __shared__ long long sl[NJ_ARGMIN_THREADS];
@@ -111,41 +142,83 @@ __global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_select(const double *A
     }
 }
 
-// new (n-1) x (n-1) matrix B from A and the row sums of B; one warp per row of B
-__global__ void __launch_bounds__(256) k_nj_rebuild(const double *A, int n, const NjSel *sel, int N, const long long *ti_old, long long *ti_new,
-                                                    double *B, double *S_new)
+// new (n-1) x (n-1) matrix B from A and the row sums of B.
+//
+// The row sums must be plain left-to-right float64 sums (numba's np.sum), i.e. one dependent add chain per row.  A CTA owns
+// NJ_ROWS consecutive rows of B and walks them in super-tiles of NJ_TCOLS columns: all 8 warps gather the tile (coalesced 256-byte
+// row segments of A -> B and into shared memory), then lane l of warp 0 adds the NJ_TCOLS values of row l in column order while
+// every warp already has the loads of the next tile in flight (two shared-memory buffers).  One add per element instead of a
+// 32-lane redundant chain with two shuffles per element: the kernel is bound by HBM (read n^2, write n^2), not by issue.
+constexpr int NJ_ROWS = 16, NJ_TCOLS = 256, NJ_TSTRIDE = NJ_TCOLS + 1, NJ_REBUILD_THREADS = 256;
+constexpr size_t NJ_REBUILD_SMEM = sizeof(double) * 2 * NJ_ROWS * NJ_TSTRIDE;
+
+__global__ void __launch_bounds__(NJ_REBUILD_THREADS) k_nj_rebuild(const double *A, int n, const NjSel *sel, int N, const long long *ti_old,
+                                                                   long long *ti_new, double *B, double *S_new)
 {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    extern __shared__ double nj_tile[];                 // [2][NJ_ROWS][NJ_TSTRIDE]
     const int nn = n - 1;
-    if (r >= nn) return;
+    const int r0 = blockIdx.x * NJ_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mi = sel->mi, mj = sel->mj;
     const int lo = min(mi, mj), hi = max(mi, mj);
     auto old_of = [&](int a) { int o = a; if (o >= lo) ++o; if (o >= hi) ++o; return o; };      // a-th remaining node -> old index
     const double dij = A[(size_t)mi * n + mj];
     const double *Ami = A + (size_t)mi * n, *Amj = A + (size_t)mj * n;
-    const int orow = r > 0 ? old_of(r - 1) : 0;
-    const double *Arow = A + (size_t)orow * n;
-    double *Brow = B + (size_t)r * nn;
-    double acc = 0.0;
-    for (int c0 = 0; c0 < nn; c0 += 32) {
-        const int c = c0 + lane;
-        double v = 0.0;
-        if (c < nn) {
-            if (r == 0) {
-                if (c > 0) { const int oc = old_of(c - 1); v = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ami[oc], Amj[oc]), dij)); }
-            } else if (c == 0) {
-                v = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ami[orow], Amj[orow]), dij));
-            } else {
-                v = Arow[old_of(c - 1)];
+    const int rows = min(NJ_ROWS, nn - r0);
+    // one super-tile: warp w takes the columns c0 + 32 w + lane of every row of the CTA.  fetch() only issues the loads (NJ_ROWS
+    // independent 8-byte loads per thread stay in flight while warp 0 runs the add chain of the previous tile), put() stores.
+    double v[NJ_ROWS];
+    auto fetch = [&](int c0) {
+        const int c = c0 + warp * 32 + lane;
+        const int oc = c > 0 ? old_of(c - 1) : 0;
+#pragma unroll
+        for (int rr = 0; rr < NJ_ROWS; ++rr) {
+            const int r = r0 + rr;
+            v[rr] = 0.0;
+            if (rr < rows && c < nn) {
+                if (r == 0) {
+                    if (c > 0) v[rr] = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ami[oc], Amj[oc]), dij));
+                } else {
+                    const int orow = old_of(r - 1);
+                    v[rr] = c == 0 ? __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ami[orow], Amj[orow]), dij)) : A[(size_t)orow * n + oc];
+                }
             }
-            Brow[c] = v;
         }
-        const int lim = min(32, nn - c0);
-        for (int l = 0; l < lim; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, l));
+    };
+    auto put = [&](int c0, double *buf) {
+        const int c = c0 + warp * 32 + lane;
+#pragma unroll
+        for (int rr = 0; rr < NJ_ROWS; ++rr) {
+            if (rr < rows && c < nn) B[(size_t)(r0 + rr) * nn + c] = v[rr];
+            buf[rr * NJ_TSTRIDE + warp * 32 + lane] = v[rr];
+        }
+    };
+    const int n_tiles = (nn + NJ_TCOLS - 1) / NJ_TCOLS;
+    double acc = 0.0;
+    fetch(0);
+    put(0, nj_tile);
+    __syncthreads();
+    for (int t = 0; t < n_tiles; ++t) {
+        const double *cur = nj_tile + (size_t)(t & 1) * NJ_ROWS * NJ_TSTRIDE;
+        const bool more = t + 1 < n_tiles;
+        if (more) fetch((t + 1) * NJ_TCOLS);
+        if (warp == 0 && lane < rows) {
+            const int lim = min(NJ_TCOLS, nn - t * NJ_TCOLS);
+            const double *rowv = cur + lane * NJ_TSTRIDE;
+            if (lim == NJ_TCOLS) {
+#pragma unroll 16
+                for (int k = 0; k < NJ_TCOLS; ++k) acc = __dadd_rn(acc, rowv[k]);
+            } else {
+                for (int k = 0; k < lim; ++k) acc = __dadd_rn(acc, rowv[k]);
+            }
+        }
+        if (more) put((t + 1) * NJ_TCOLS, nj_tile + (size_t)((t + 1) & 1) * NJ_ROWS * NJ_TSTRIDE);
+        __syncthreads();
     }
-    if (lane == 0) {
+    if (warp == 0 && lane < rows) {
+        const int r = r0 + lane;
         S_new[r] = acc;
-        ti_new[r] = r == 0 ? (sel->n_inter - 1 + N) : ti_old[orow];
+        ti_new[r] = r == 0 ? (sel->n_inter - 1 + N) : ti_old[old_of(r - 1)];
     }
 }
 

@@ -19,6 +19,7 @@ CASES = {
     "fam8": dict(n=8, lengths=60, seed=101, family_size=8),
     "ragged12": dict(n=12, lengths=[40, 55, 70, 61, 48, 90, 33, 120, 77, 64, 52, 85], seed=102, family_size=4),
     "two": dict(n=2, lengths=[50, 58], seed=103, family_size=2),
+    "mixed40": dict(n=40, lengths=[100 + (7 * k) % 41 for k in range(40)], seed=104, family_size=10),
 }
 PARAMS = dict(flexible=False, gamma_tensor=7.0, gamma_coords=0.03, verbose=False)
 

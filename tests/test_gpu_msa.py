@@ -20,7 +20,7 @@ def _case(g, name):
     return synth.make_chains(len(L), list(L), 10, seed=int(g[f"{name}_seed"]), family_size=int(g[f"{name}_family"]))
 
 
-@pytest.mark.parametrize("name", ["fam8", "ragged12"])
+@pytest.mark.parametrize("name", ["fam8", "ragged12", "mixed40"])
 def test_multiple_align_golden(name):
     g = np.load(os.path.join(G, "msa.npz"))
     ch = _case(g, name)

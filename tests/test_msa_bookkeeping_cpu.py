@@ -29,7 +29,7 @@ class OracleEngine:
         return [O.progressive_node(*a, *b, m[0], m[1], gt, gc, gw, go, ge) for (a, b), m in zip(children, mults)]
 
 
-@pytest.mark.parametrize("name", ["fam8", "ragged12"])
+@pytest.mark.parametrize("name", ["fam8", "ragged12", "mixed40"])
 @pytest.mark.parametrize("batch", ["1", "0"])
 def test_progressive_align_bookkeeping(monkeypatch, name, batch):
     g = np.load(os.path.join(G, "msa.npz"))

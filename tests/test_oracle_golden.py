@@ -212,7 +212,7 @@ def test_progressive_align_golden():
     """oracle.progressive_align (multiple_alignment.py:172-253 restated on the C primitives) against the reference's
     multiple_align output: identical final alignment, consensus node within 1e-11."""
     g = np.load(os.path.join(G, "msa.npz"))
-    for name in ("fam8", "ragged12"):
+    for name in ("fam8", "ragged12", "mixed40"):
         L = g[f"{name}_lengths"]
         ch = synth.make_chains(len(L), list(L), 10, seed=int(g[f"{name}_seed"]), family_size=int(g[f"{name}_family"]))
         S = O.pairwise_all(ch.coords, ch.tensors, ch.offsets)
