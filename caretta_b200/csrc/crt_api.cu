@@ -11,6 +11,7 @@
 #include "crt_consumers.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>

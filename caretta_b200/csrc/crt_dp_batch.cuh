@@ -48,9 +48,21 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
         double out1 = 0.0, out2 = 0.0;       // M[i][cend][1], [2] handed to lane + 1
         double dsave = 0.0;                  // M[i-1][c0-1][1]
         const bool last_strip = strip == n_strips - 1;
+        // the scores of step t + 1 are loaded while step t computes (they do not depend on the recurrence)
+        double sn[DPC];
+        auto load_scores = [&](int t) {
+            const int i = t - lane + 1;
+#pragma unroll
+            for (int c = 0; c < DPC; ++c) sn[c] = (i >= 1 && i <= n && c0 + c < m) ? S[(long long)(i - 1) * m + c0 + c] : 0.0;
+        };
+        load_scores(0);
         for (int t = 0; t < n + 31; ++t) {
             const int i = t - lane + 1;      // 1-based row
             const bool valid = i >= 1 && i <= n;
+            double sc[DPC];
+#pragma unroll
+            for (int c = 0; c < DPC; ++c) sc[c] = sn[c];
+            load_scores(t + 1);
             double L1 = shfl_up_d(out1), L2 = shfl_up_d(out2);
             if (lane == 0) {
                 if (strip == 0) { L1 = 0.0; L2 = MINF - open; }       // column 0: (0, 0, MIN - open)
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
 #pragma unroll
                 for (int c = 0; c < DPC; ++c) {
                     const int j = c0 + c;     // 0-based column
-                    const double s = j < m ? S[(long long)(i - 1) * m + j] : 0.0;
+                    const double s = sc[c];
                     const double l0 = P0[c] - ext, l1 = P1[c] - open;
                     const int ql = l1 > l0 ? 1 : 0;
                     const double lower = ql ? l1 : l0;

@@ -17,17 +17,22 @@ int crt_progressive_level(crt_ctx *c, int32_t n_nodes, int32_t d, const double *
     if (!c->node_ctx && (rc = crt_create(c->device, &c->node_ctx))) return rc;
     crt_ctx *nc = c->node_ctx;
     nc->stage1_only = true;
+    const bool timeline = getenv("CARETTA_B200_TIMELINE") && atoi(getenv("CARETTA_B200_TIMELINE")) != 0;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     // ---- stage 1 of score_function for every node: the fp64 pair kernels on the packed children, pairs (2k, 2k+1)
     if ((rc = crt_set_chains(nc, coords, tensors, offsets, 2 * n_nodes, d))) return rc;
     crt_params prm{};
     prm.gamma_tensor = gamma_tensor; prm.gamma_coords = gamma_coords; prm.sw_gap = 0.0; prm.precision = CRT_FP64;
     std::vector<int32_t> pi((size_t)n_nodes), pj((size_t)n_nodes), st1((size_t)n_nodes);
     for (int k = 0; k < n_nodes; ++k) { pi[(size_t)k] = 2 * k; pj[(size_t)k] = 2 * k + 1; }
+    const double t_chains = now();
     if ((rc = crt_pairwise_list(nc, &prm, pi.data(), pj.data(), n_nodes, nullptr, nullptr, nullptr, nullptr, st1.data(), nullptr, nullptr,
                                 nullptr, 0)))
         return rc;
     double pair_ms = nc->elapsed_ms;
     long long launches = nc->launches;
+    const double t_pairs = now();
     // ---- score matrices, affine DTW and the intermediate nodes, in chunks of nodes bounded by the workspace budget
     const long long total = offsets[2 * n_nodes];
     std::vector<DpProblem> probs((size_t)n_nodes);
@@ -96,6 +101,7 @@ int crt_progressive_level(crt_ctx *c, int32_t n_nodes, int32_t d, const double *
         k0 = k1;
     }
     CU(cudaEventRecord(c->ev1, st));
+    const double t_launched = now();
     CU(cudaMemcpyAsync(aln_len, c->nd_len.p, sizeof(int) * (size_t)n_nodes, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(aln1, c->nd_a1.p, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(aln2, c->nd_a2.p, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, st));
@@ -106,6 +112,9 @@ int crt_progressive_level(crt_ctx *c, int32_t n_nodes, int32_t d, const double *
     CU(cudaStreamSynchronize(st));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->elapsed_ms = pair_ms + ms;
+    if (timeline)
+        fprintf(stderr, "[level] nodes %5d residues %8lld: set_chains %7.3f  pair run %7.3f (device %7.3f)  enqueue %7.3f  kernels+D2H %7.3f (device %7.3f) ms\n",
+                n_nodes, total, t_chains - t_begin, t_pairs - t_chains, pair_ms, t_launched - t_pairs, now() - t_launched, (double)ms);
     c->launches = launches;
     for (int k = 0; k < n_nodes; ++k)
         if (aln_len[k] < 0 || aln_len[k] > probs[(size_t)k].n + probs[(size_t)k].m) return fail(CRT_E_STATE, "alignment length %d of node %d out of range", aln_len[k], k);
