@@ -476,6 +476,57 @@ def write_distance_matrix(names, distance_matrix, filename) -> None:
         f.write(text)
 
 
+@dataclass
+class OutputFiles:
+    """multiple_alignment.py:85-105 (the files this package can write; PDB / feature / class files stay the reference's)."""
+    output_folder: typing.Any = None
+    fasta_file: typing.Any = None
+    matrix_folder: typing.Any = None
+
+    @classmethod
+    def from_folder(cls, output_folder):
+        from pathlib import Path
+        output_folder = Path(output_folder)
+        return cls(output_folder, fasta_file=output_folder / "result.fasta", matrix_folder=output_folder / "result_matrix")
+
+
+def align_from_proteins(proteins, gap_open_penalty: float = 1.0, gap_extend_penalty: float = 0.01, consensus_weight: bool = True,
+                        output_folder=None, write_fasta: bool = False, write_matrix: bool = False, verbose: bool = False):
+    """align_from_structure_files (multiple_alignment.py:394-596) from the point where the features exist (:488-491): the list of
+    Protein(name, tensors, coordinates, sequence) that the reference builds from geometricus.  Same steps, same parameters and
+    the same output files as the reference with full=True (the caretta-cli default): all-vs-all matrix -> max - S (:498-501) ->
+    guide-tree distance text (:515-522) -> multiple_align (:524-533) -> result.fasta (:540-545) -> RMSD / coverage / TM matrices and
+    their text files (:571-591).  Returns (MultipleAlignment, OutputFiles)."""
+    from pathlib import Path
+    output_files = OutputFiles() if output_folder is None else OutputFiles.from_folder(output_folder)
+    if output_folder is not None:
+        Path(output_files.output_folder).mkdir(exist_ok=True)
+    msa_class = MultipleAlignment(list(proteins))
+    score_function_params = dict(DEFAULT_SCORE_PARAMS)
+    mean_function_params = dict(flexible=False)
+    pairwise_distance_matrix = np.array([[0, 1], [1, 0]])
+    if len(msa_class.sequences) > 2:
+        pairwise_distance_matrix = msa_class.make_pairwise_matrix(score_function_params=score_function_params)
+        pairwise_distance_matrix = pairwise_distance_matrix.max() - pairwise_distance_matrix
+    names = [s.name for s in msa_class.sequences]
+    if write_matrix:
+        Path(output_files.matrix_folder).mkdir(exist_ok=True)
+        write_distance_matrix(names, pairwise_distance_matrix, Path(output_files.matrix_folder) / "distance_matrix_guide_tree.txt")
+    msa_class.pairwise_distance_matrix = pairwise_distance_matrix
+    alignment = msa_class.multiple_align(pairwise_distance_matrix, gap_open_penalty=gap_open_penalty, gap_extend_penalty=gap_extend_penalty,
+                                         consensus_weight=float(consensus_weight), gamma_weight=1.0,
+                                         score_function_params=score_function_params, mean_function_params=mean_function_params)
+    if write_fasta:
+        msa_class.write_alignment(output_files.fasta_file)
+    if write_matrix:
+        rmsd, coverage, tm = make_rmsd_coverage_tm_matrix(alignment, msa_class.sequences, superpose_first=False)
+        for fname, M in (("rmsd.txt", rmsd), ("coverage.txt", coverage), ("tm.txt", tm)):
+            write_distance_matrix(names, M, Path(output_files.matrix_folder) / fname)
+    if verbose:
+        print(f"aligned {len(names)} structures, alignment length {len(next(iter(alignment.values())))}")
+    return msa_class, output_files
+
+
 def install(reference_multiple_alignment_module) -> None:
     """Monkey-patches the reference module in place: its MultipleAlignment.make_pairwise_matrix (the all-vs-all
     loop, :158-170) is replaced by the GPU path.  Everything else (neighbor joining, progressive alignment,
