@@ -441,4 +441,57 @@ __global__ void __launch_bounds__(256) k_fasta(const long long *aln, long long A
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast-mode guide matrix (align_from_structure_files with full=False, multiple_alignment.py:503-511):
+//   k_count_matrix   make_count_matrix (:128-134): out[i][r] += 1 for every shapemer index r of protein i
+//   k_braycurtis     braycurtis (:137-145): out[i][j] = sum_k |a_ik - b_jk| / sum_k |a_ik + b_jk|, float64, both sums taken
+//                    in k order with separate roundings like numba's sequential array.sum() (for count data every partial sum
+//                    is an exact integer anyway).
+// 32 x 32 pairs per block of 256 threads (2 x 2 pairs per thread), k in chunks of 32 staged in shared memory.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count_matrix(const long long *idx, const long long *off, int N, int K, double *out, int *bad)
+{
+    const int p = blockIdx.x;
+    for (long long q = off[p] + threadIdx.x; q < off[p + 1]; q += blockDim.x) {
+        const long long r = idx[q];
+        if (r < 0 || r >= K) { atomicOr(bad, 1); continue; }
+        atomicAdd(out + (long long)p * K + r, 1.0);          // counts stay far below 2^53: exact in any order
+    }
+}
+
+constexpr int BC_TILE = 32, BC_K = 32;
+
+__global__ void __launch_bounds__(256) k_braycurtis(const double *A, int n1, const double *Bm, int n2, int K, double *out)
+{
+    __shared__ double sa[BC_TILE][BC_K + 1], sb[BC_TILE][BC_K + 1];
+    const int i0 = blockIdx.y * BC_TILE, j0 = blockIdx.x * BC_TILE;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // thread -> pairs (ty, ty + 16) x (tx, tx + 16)
+    double num[2][2] = {{0, 0}, {0, 0}}, den[2][2] = {{0, 0}, {0, 0}};
+    for (int k0 = 0; k0 < K; k0 += BC_K) {
+        for (int e = threadIdx.x; e < BC_TILE * BC_K; e += 256) {
+            const int r = e / BC_K, k = e % BC_K;
+            sa[r][k] = (i0 + r < n1 && k0 + k < K) ? A[(long long)(i0 + r) * K + k0 + k] : 0.0;
+            sb[r][k] = (j0 + r < n2 && k0 + k < K) ? Bm[(long long)(j0 + r) * K + k0 + k] : 0.0;
+        }
+        __syncthreads();
+        const int kn = min(BC_K, K - k0);
+        for (int k = 0; k < kn; ++k) {
+            const double a0 = sa[ty][k], a1 = sa[ty + 16][k], b0 = sb[tx][k], b1 = sb[tx + 16][k];
+            num[0][0] = __dadd_rn(num[0][0], fabs(__dsub_rn(a0, b0))); den[0][0] = __dadd_rn(den[0][0], fabs(__dadd_rn(a0, b0)));
+            num[0][1] = __dadd_rn(num[0][1], fabs(__dsub_rn(a0, b1))); den[0][1] = __dadd_rn(den[0][1], fabs(__dadd_rn(a0, b1)));
+            num[1][0] = __dadd_rn(num[1][0], fabs(__dsub_rn(a1, b0))); den[1][0] = __dadd_rn(den[1][0], fabs(__dadd_rn(a1, b0)));
+            num[1][1] = __dadd_rn(num[1][1], fabs(__dsub_rn(a1, b1))); den[1][1] = __dadd_rn(den[1][1], fabs(__dadd_rn(a1, b1)));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int i = i0 + ty + 16 * u, j = j0 + tx + 16 * v;
+            if (i < n1 && j < n2) out[(long long)i * n2 + j] = num[u][v] / den[u][v];
+        }
+}
+
 }  // namespace crt

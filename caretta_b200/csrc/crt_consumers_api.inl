@@ -363,6 +363,68 @@ int crt_format_fasta(crt_ctx *c, const int64_t *aln, int32_t N, int64_t A, const
     return 0;
 }
 
+/* make_count_matrix, multiple_alignment.py:128-134 */
+int crt_count_matrix(crt_ctx *c, const int64_t *indices, const int64_t *offsets, int32_t N, int32_t alphabet_size, double *out)
+{
+    if (!c || !offsets || !out || (N > 0 && offsets[N] > 0 && !indices)) return fail(CRT_E_ARG, "null argument");
+    if (N <= 0 || alphabet_size <= 0) return fail(CRT_E_ARG, "empty count matrix (%d x %d)", N, alphabet_size);
+    if (offsets[0] != 0) return fail(CRT_E_ARG, "offsets[0] must be 0");
+    for (int p = 0; p < N; ++p)
+        if (offsets[p + 1] < offsets[p]) return fail(CRT_E_ARG, "offsets must be non-decreasing");
+    CU(cudaSetDevice(c->device));
+    Scratch sc;
+    long long *d_idx = nullptr, *d_off = nullptr;
+    double *d_out = nullptr;
+    int *d_bad = nullptr;
+    const size_t cells = (size_t)N * alphabet_size;
+    CU(sc.alloc(&d_idx, (size_t)offsets[N]));
+    CU(sc.alloc(&d_off, (size_t)N + 1));
+    CU(sc.alloc(&d_out, cells));
+    CU(sc.alloc(&d_bad, 1));
+    cudaStream_t st = c->stream;
+    if (offsets[N]) CU(cudaMemcpyAsync(d_idx, indices, sizeof(long long) * (size_t)offsets[N], cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_off, offsets, sizeof(long long) * ((size_t)N + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_out, 0, sizeof(double) * cells, st));
+    CU(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    CU(cudaEventRecord(c->ev0, st));
+    k_count_matrix<<<N, 256, 0, st>>>(d_idx, d_off, N, alphabet_size, d_out, d_bad);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev1, st));
+    c->launches = 1;
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out, d_out, sizeof(double) * cells, cudaMemcpyDeviceToHost, st));
+    int rc = finish_timed(c, "crt_count_matrix");
+    if (rc) return rc;
+    if (bad) return fail(CRT_E_ARG, "shapemer index outside [0, %d) (the reference indexes out of bounds)", alphabet_size);
+    return 0;
+}
+
+/* braycurtis, multiple_alignment.py:137-145 */
+int crt_braycurtis(crt_ctx *c, const double *counts_1, int32_t n1, const double *counts_2, int32_t n2, int32_t K, double *out)
+{
+    if (!c || !counts_1 || !counts_2 || !out) return fail(CRT_E_ARG, "null argument");
+    if (n1 <= 0 || n2 <= 0 || K <= 0) return fail(CRT_E_ARG, "empty input (%d, %d, %d)", n1, n2, K);
+    CU(cudaSetDevice(c->device));
+    Scratch sc;
+    double *d_a = nullptr, *d_b = nullptr, *d_out = nullptr;
+    CU(sc.alloc(&d_a, (size_t)n1 * K));
+    const bool same = counts_1 == counts_2 && n1 == n2;
+    if (!same) CU(sc.alloc(&d_b, (size_t)n2 * K));
+    CU(sc.alloc(&d_out, (size_t)n1 * n2));
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(d_a, counts_1, sizeof(double) * (size_t)n1 * K, cudaMemcpyHostToDevice, st));
+    if (!same) CU(cudaMemcpyAsync(d_b, counts_2, sizeof(double) * (size_t)n2 * K, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev0, st));
+    k_braycurtis<<<dim3((unsigned)((n2 + BC_TILE - 1) / BC_TILE), (unsigned)((n1 + BC_TILE - 1) / BC_TILE)), 256, 0, st>>>(d_a, n1, same ? d_a : d_b,
+                                                                                                                         n2, K, d_out);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev1, st));
+    c->launches = 1;
+    CU(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n1 * n2, cudaMemcpyDeviceToHost, st));
+    return finish_timed(c, "crt_braycurtis");
+}
+
 int crt_text_fetch(crt_ctx *c, char *out, int64_t cap)
 {
     if (!c || (!out && c->text_len > 0)) return fail(CRT_E_ARG, "null argument");

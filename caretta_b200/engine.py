@@ -21,7 +21,7 @@ EXPORTS = [
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node", "crt_progressive_level",
-    "crt_coverage_gap_matrix", "crt_superpose", "crt_superpose_pairs", "crt_format_matrix", "crt_format_fasta", "crt_text_fetch",
+    "crt_coverage_gap_matrix", "crt_superpose", "crt_superpose_pairs", "crt_format_matrix", "crt_format_fasta", "crt_text_fetch", "crt_count_matrix", "crt_braycurtis",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library():
     L.crt_format_matrix.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(i64)]
     L.crt_format_fasta.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, C.POINTER(i64)]
     L.crt_text_fetch.argtypes = [vp, vp, i64]
+    L.crt_count_matrix.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.crt_braycurtis.argtypes = [vp, vp, i32, vp, i32, i32, vp]
     L.crt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.crt_host_free.argtypes = [vp]
     for name in EXPORTS:
@@ -500,6 +502,27 @@ class Engine:
         self._check(self.lib.crt_format_fasta(self.h, _p(aln), aln.shape[0], aln.shape[1], _p(sb), _p(soff), _p(nb), _p(noff), C.byref(n)),
                     "crt_format_fasta")
         return self._fetch_text(n.value)
+
+    def count_matrix(self, residues_list, alphabet_size: int) -> np.ndarray:
+        """make_count_matrix (multiple_alignment.py:128-134): float64 [N, alphabet_size] shapemer counts."""
+        arrs = [np.asarray(r, dtype=np.int64).reshape(-1) for r in residues_list]
+        off = np.zeros(len(arrs) + 1, np.int64)
+        if arrs:
+            off[1:] = np.cumsum([len(a) for a in arrs])
+        idx = np.ascontiguousarray(np.concatenate(arrs)) if off[-1] else np.zeros(1, np.int64)
+        out = np.empty((len(arrs), int(alphabet_size)))
+        self._check(self.lib.crt_count_matrix(self.h, _p(idx), _p(off), len(arrs), int(alphabet_size), _p(out)), "crt_count_matrix")
+        return out
+
+    def braycurtis(self, counts_1, counts_2) -> np.ndarray:
+        """braycurtis (multiple_alignment.py:137-145): float64 [n1, n2]."""
+        a = np.ascontiguousarray(counts_1, dtype=np.float64)
+        b = a if counts_2 is counts_1 else np.ascontiguousarray(counts_2, dtype=np.float64)
+        if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
+            raise ValueError("count matrices [n1, K] and [n2, K] expected")
+        out = np.empty((a.shape[0], b.shape[0]))
+        self._check(self.lib.crt_braycurtis(self.h, _p(a), a.shape[0], _p(b), b.shape[0], a.shape[1], _p(out)), "crt_braycurtis")
+        return out
 
     def fp32_peak(self):
         v, ms = C.c_double(), C.c_double()

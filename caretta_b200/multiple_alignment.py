@@ -17,6 +17,7 @@ the C ABI (caretta_b200.engine).  Nothing here computes the path on the CPU.
       write_alignment
     helper.write_distance_matrix(names, matrix, file)    helper.py   write_distance_matrix, same bytes
                                                          :183-203
+    make_count_matrix / braycurtis (fast-mode guide)     :128-145    same signatures, bit-identical
     dtw.dtw_align / smith_waterman / smith_waterman_score            dtw_align / smith_waterman / smith_waterman_score
       (dynamic_time_warping.py:147-278)                              (batched: *_batch)
     StructureMultiple (name used by the CLI help and the legacy API) StructureMultiple facade
@@ -469,6 +470,16 @@ def superpose_references(alignment, proteins, minimum_coverage=50):
     return proteins
 
 
+def make_count_matrix(residues_list, alphabet_size: int) -> np.ndarray:
+    """multiple_alignment.py:128-134 (fast-mode guide matrix, :503-509): shapemer counts per protein."""
+    return get_engine().count_matrix(residues_list, alphabet_size)
+
+
+def braycurtis(counts_1, counts_2) -> np.ndarray:
+    """multiple_alignment.py:137-145: Bray-Curtis distance between every row of counts_1 and every row of counts_2."""
+    return get_engine().braycurtis(counts_1, counts_2)
+
+
 def write_distance_matrix(names, distance_matrix, filename) -> None:
     """helper.write_distance_matrix (helper.py:183-203): Clustal-style text, '%.4f' values formatted on the device, same bytes."""
     text = get_engine().format_matrix([str(n) for n in names], np.asarray(distance_matrix, dtype=np.float64))
@@ -558,7 +569,7 @@ def install(reference_multiple_alignment_module) -> None:
     if os.environ.get("CARETTA_B200_CONSUMERS", "1") != "0":
         # what consumes the alignment (CARETTA_B200_CONSUMERS=0 keeps the reference's)
         for fn in (make_coverage_gap_distance_matrix, get_reference_structures, superpose, superpose_core, superpose_reference,
-                   superpose_references, make_rmsd_coverage_tm_matrix):
+                   superpose_references, make_rmsd_coverage_tm_matrix, make_count_matrix, braycurtis):
             setattr(ref, fn.__name__, fn)
 
         def to_sequence_alignment(self, alignment=None):

@@ -215,6 +215,14 @@ int crt_format_fasta(crt_ctx *ctx, const int64_t *aln, int32_t N, int64_t A, con
                      const int64_t *name_off, int64_t *out_len);
 int crt_text_fetch(crt_ctx *ctx, char *out, int64_t cap);        /* the text of the last crt_format_* call */
 
+/* Fast-mode guide matrix (align_from_structure_files with full=False, multiple_alignment.py:503-511).
+ * crt_count_matrix = make_count_matrix (:128-134): indices = the shapemer indices of all proteins packed, offsets [N+1];
+ * out float64 [N, alphabet_size].  crt_braycurtis = braycurtis (:137-145): out[i][j] = sum_k |a_ik - b_jk| / sum_k |a_ik + b_jk|,
+ * float64 [n1, n2], sums in k order (bit-identical to the numba loop; two all-zero rows give nan where the reference raises
+ * ZeroDivisionError). */
+int crt_count_matrix(crt_ctx *ctx, const int64_t *indices, const int64_t *offsets, int32_t N, int32_t alphabet_size, double *out);
+int crt_braycurtis(crt_ctx *ctx, const double *counts_1, int32_t n1, const double *counts_2, int32_t n2, int32_t K, double *out);
+
 /* FP32 FFMA micro-benchmark used as the measured roofline denominator: returns lane-FFMA/s. */
 int crt_fp32_peak(crt_ctx *ctx, double *ffma_per_s, double *elapsed_ms);
 

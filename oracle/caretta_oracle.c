@@ -789,3 +789,30 @@ API int64_t crt_o_format_matrix(const double *M, int n_rows, int n_cols, const c
     }
     return pos;
 }
+
+/* make_count_matrix, multiple_alignment.py:128-134.  Returns -1 on an index outside [0, K). */
+API int crt_o_count_matrix(const int64_t *idx, const int64_t *off, int N, int K, double *out)
+{
+    memset(out, 0, sizeof(double) * (size_t)N * K);
+    for (int i = 0; i < N; ++i)
+        for (int64_t q = off[i]; q < off[i + 1]; ++q) {
+            if (idx[q] < 0 || idx[q] >= K) return -1;
+            out[(size_t)i * K + idx[q]] += 1.0;
+        }
+    return 0;
+}
+
+/* braycurtis, multiple_alignment.py:137-145: np.abs(a - b).sum() / np.abs(a + b).sum(), sums in index order. */
+API void crt_o_braycurtis(const double *A, int n1, const double *B, int n2, int K, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n1; ++i)
+        for (int j = 0; j < n2; ++j) {
+            double num = 0.0, den = 0.0;
+            for (int k = 0; k < K; ++k) {
+                num += fabs(A[(size_t)i * K + k] - B[(size_t)j * K + k]);
+                den += fabs(A[(size_t)i * K + k] + B[(size_t)j * K + k]);
+            }
+            out[(size_t)i * n2 + j] = num / den;
+        }
+}

@@ -146,6 +146,25 @@ def main():
         helper.write_distance_matrix(names, R, os.path.join(td, "r.txt"))
         out["random_matrix"] = R
         out["random_txt"] = np.frombuffer(open(os.path.join(td, "r.txt"), "rb").read(), dtype=np.uint8)
+    # fast-mode guide matrix: make_count_matrix + braycurtis (multiple_alignment.py:128-145) on synthetic shapemer indices
+    # (alphabet 2^10 like model.output_dimension = 10), and braycurtis on non-integer rows (summation order matters there)
+    import numba as nb
+    rng = np.random.default_rng(91)
+    K = 1024
+    hot = rng.choice(K, 60, replace=False)
+    res = nb.typed.List()
+    flat = []
+    for p in range(37):
+        L = int(rng.integers(40, 300))
+        r = np.where(rng.random(L) < 0.8, rng.choice(hot, L), rng.integers(0, K, L)).astype(np.int64)
+        res.append(r); flat.append(r)
+    counts = ma.make_count_matrix(res, K)
+    out["bc_indices"] = np.concatenate(flat)
+    out["bc_lengths"] = np.array([len(r) for r in flat])
+    out["bc_counts"] = counts
+    out["bc_dist"] = ma.braycurtis(counts, counts)
+    X, Y = rng.random((23, 77)) * 3, rng.random((19, 77)) * 3
+    out["bc_x"], out["bc_y"], out["bc_xy"] = X, Y, ma.braycurtis(X, Y)
     np.savez_compressed(os.path.join(GOLD, "consumers.npz"), **out)
     print("[gen-consumers] wrote", os.path.join(GOLD, "consumers.npz"), os.path.getsize(os.path.join(GOLD, "consumers.npz")), "bytes")
 

@@ -79,6 +79,10 @@ def lib():
         L.crt_o_coverage_gap_matrix.restype = C.c_int
         L.crt_o_format_matrix.argtypes = [_D, C.c_int, C.c_int, C.c_char_p, _I64, _P]
         L.crt_o_format_matrix.restype = C.c_int64
+        L.crt_o_count_matrix.argtypes = [_I64, _I64, C.c_int, C.c_int, _D]
+        L.crt_o_count_matrix.restype = C.c_int
+        L.crt_o_braycurtis.argtypes = [_D, C.c_int, _D, C.c_int, C.c_int, _D]
+        L.crt_o_braycurtis.restype = None
         _lib = L
     return _lib
 
@@ -478,6 +482,26 @@ def format_fasta(names, sequences, aln) -> bytes:
     for name, seq, row in zip(names, sequences, np.asarray(aln)):
         out.append(">" + name + "\n" + "".join(seq[int(i)] if i != -1 else "-" for i in row) + "\n")
     return "".join(out).encode("utf-8")
+
+
+def count_matrix(residues_list, alphabet_size: int) -> np.ndarray:
+    """make_count_matrix, multiple_alignment.py:128-134."""
+    arrs = [np.asarray(r, dtype=np.int64).reshape(-1) for r in residues_list]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    off[1:] = np.cumsum([len(a) for a in arrs])
+    idx = _c(np.concatenate(arrs), np.int64) if off[-1] else np.zeros(1, np.int64)
+    out = np.empty((len(arrs), alphabet_size))
+    if lib().crt_o_count_matrix(idx, off, len(arrs), alphabet_size, out) != 0:
+        raise IndexError("shapemer index out of range")
+    return out
+
+
+def braycurtis(counts_1, counts_2) -> np.ndarray:
+    """braycurtis, multiple_alignment.py:137-145."""
+    a, b = _c(counts_1), _c(counts_2)
+    out = np.empty((a.shape[0], b.shape[0]))
+    lib().crt_o_braycurtis(a, a.shape[0], b, b.shape[0], a.shape[1], out)
+    return out
 
 
 def num_threads() -> int:

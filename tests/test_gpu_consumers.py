@@ -207,3 +207,21 @@ def test_fasta_golden(cons, eng, tmp_path):
         assert seqaln == {lines[2 * q][1:]: lines[2 * q + 1] for q in range(ch.n)}
     with pytest.raises(engine.CrtError):
         eng.format_fasta(["a"], ["ACD"], np.array([[0, 1, 2, 3]]))
+
+
+def test_fast_mode_guide_matrix(cons, eng):
+    """make_count_matrix / braycurtis (multiple_alignment.py:128-145): bit-identical to the reference's numba output, and to the
+    oracle on a larger random case."""
+    off = np.concatenate([[0], np.cumsum(cons["bc_lengths"])])
+    res = [cons["bc_indices"][off[p]:off[p + 1]] for p in range(len(cons["bc_lengths"]))]
+    counts = MA.make_count_matrix(res, 1024)
+    assert counts.dtype == np.float64 and np.array_equal(counts, cons["bc_counts"])
+    assert np.array_equal(MA.braycurtis(counts, counts), cons["bc_dist"])
+    assert np.array_equal(MA.braycurtis(cons["bc_x"], cons["bc_y"]), cons["bc_xy"])
+    rng = np.random.default_rng(17)
+    big = [rng.integers(0, 1024, int(rng.integers(50, 400))) for _ in range(301)]
+    cb = eng.count_matrix(big, 1024)
+    assert np.array_equal(cb, O.count_matrix(big, 1024))
+    assert np.array_equal(eng.braycurtis(cb, cb[:77]), O.braycurtis(cb, cb[:77]))
+    with pytest.raises(engine.CrtError):
+        eng.count_matrix([np.array([5, 1024])], 1024)

@@ -285,3 +285,16 @@ def test_consumers_text(cons):
         names, seqs = [str(x) for x in cons[f"{name}_pnames"]], [str(x) for x in cons[f"{name}_seqs"]]
         assert O.format_fasta(names, seqs, cons[f"{name}_aln"]) == cons[f"{name}_fasta"].tobytes(), name
         assert O.format_matrix(names, cons[f"{name}_cg_distance"]) == cons[f"{name}_dist_txt"].tobytes(), name
+
+
+def test_consumers_fast_mode_guide_matrix(cons):
+    """make_count_matrix / braycurtis (multiple_alignment.py:128-145) against the reference's numba output: bit-exact, also on
+    non-integer rows where the summation order matters."""
+    off = np.concatenate([[0], np.cumsum(cons["bc_lengths"])])
+    res = [cons["bc_indices"][off[p]:off[p + 1]] for p in range(len(cons["bc_lengths"]))]
+    counts = O.count_matrix(res, 1024)
+    assert np.array_equal(counts, cons["bc_counts"])
+    assert np.array_equal(O.braycurtis(counts, counts), cons["bc_dist"])
+    assert np.array_equal(O.braycurtis(cons["bc_x"], cons["bc_y"]), cons["bc_xy"])
+    with pytest.raises(IndexError):
+        O.count_matrix([np.array([0, 1024])], 1024)

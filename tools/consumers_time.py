@@ -50,6 +50,14 @@ def main():
     seqs = ["".join(np.array(list("ACDEFGHIKLMNPQRSTVWY"))[rng.integers(0, 20, int(L))]) for L in lengths]
     ms, fa = wall(lambda: e.format_fasta(names, seqs, aln))
     res["format_fasta"] = {"wall_ms": ms, "device_ms": e.last_elapsed_ms(), "text_bytes": len(fa)}
+    shp = [rng.integers(0, 1024, int(L)) for L in lengths]
+    ms, cnt = wall(lambda: e.count_matrix(shp, 1024))
+    res["count_matrix"] = {"wall_ms": ms, "device_ms": e.last_elapsed_ms()}
+    ms, _ = wall(lambda: e.braycurtis(cnt, cnt))
+    res["braycurtis"] = {"wall_ms": ms, "device_ms": e.last_elapsed_ms(), "pair_dims": n * n * 1024}
+    kk = min(n, 400)
+    t0 = time.perf_counter(); O.braycurtis(cnt[:kk], cnt[:kk]); res["cpu_braycurtis_ms_scaled"] = (time.perf_counter() - t0) * 1e3 * (n / kk) ** 2
+    res["cpu_threads"] = O.num_threads()
     # CPU restatement beside it (bounded samples)
     k = min(n, 600)
     t0 = time.perf_counter(); O.coverage_gap_matrix(aln[:k]); res["cpu_coverage_gap_matrix_ms_scaled"] = (time.perf_counter() - t0) * 1e3 * (n / k) ** 2
