@@ -225,3 +225,45 @@ def test_fast_mode_guide_matrix(cons, eng):
     assert np.array_equal(eng.braycurtis(cb, cb[:77]), O.braycurtis(cb, cb[:77]))
     with pytest.raises(engine.CrtError):
         eng.count_matrix([np.array([5, 1024])], 1024)
+
+
+def test_consumer_edge_cases(eng, tmp_path):
+    # smallest alignments
+    d, a = eng.coverage_gap_matrix(np.array([[0]]))
+    assert d.tolist() == [[0.0]] and a.tolist() == [[1]]
+    d, a = eng.coverage_gap_matrix(np.array([[0, -1, 1], [-1, 0, 1]]))
+    assert d.tolist() == [[0.0, 0.5], [0.5, 0.0]] and a.tolist() == [[2, 1], [1, 2]]
+    with pytest.raises(engine.CrtError):                                   # a protein without any residue: the reference divides by zero
+        eng.coverage_gap_matrix(np.array([[0, 1], [-1, -1]]))
+    with pytest.raises(engine.CrtError):
+        eng.coverage_gap_matrix(np.array([[0, -2]]))
+    # two proteins, exactly 4 common columns (the reference's assert needs > 3), columns beyond one chain's end are errors
+    ch = synth.make_chains(2, [6, 5], 10, seed=9, family_size=2)
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    aln = np.array([[0, 1, 2, 3, 4, 5, -1], [0, 1, -1, 2, 3, -1, 4]])
+    res = eng.superpose(aln, engine.SUP_REFERENCE)
+    assert res["reference"] == 0 and res["ncommon"].tolist() == [6, 4] and res["n_core"] == 4
+    want = O.superpose_reference(aln, [ch.chain(0)[1], ch.chain(1)[1]], 0)[0]
+    np.testing.assert_allclose(res["coords"], np.concatenate(want), **TOL)
+    res = eng.superpose(aln, engine.SUP_AUTO)                              # 4 core columns of 7 >= 7 // 2 -> core branch
+    assert res["mode"] == engine.SUP_CORE
+    np.testing.assert_allclose(res["coords"], np.concatenate(O.superpose_core(aln, [ch.chain(0)[1], ch.chain(1)[1]], 0)[0]), **TOL)
+    with pytest.raises(engine.CrtError):
+        eng.superpose(np.array([[0, 1, 2, 3, 4, 6], [0, 1, 2, 3, 4, -1]]))
+    with pytest.raises(engine.CrtError):                                   # a supplied core column that holds a gap
+        eng.superpose(aln, engine.SUP_CORE, 0, core_columns=[0, 1, 2])
+    none = eng.superpose_pairs(aln, [], [], [0])                           # no pairs: coordinates pass through
+    assert np.array_equal(none["coords"], ch.coords)
+    few = eng.superpose_pairs(np.array([[0, 1, 2, -1, -1, -1, -1], [-1, 0, 1, 2, 3, 4, -1]]), [0], [1], [0, 1])
+    assert few["ncommon"].tolist() == [2] and np.array_equal(few["coords"], ch.coords)          # <= 3 common: skipped
+    # text: UTF-8 names, one row, gaps only
+    names = ["protéine/α", "b"]
+    M = np.array([[0.0, 1.23456], [1.23456, 0.0]])
+    f = tmp_path / "m.txt"
+    MA.write_distance_matrix(names, M, f)
+    assert f.read_bytes() == (f"2\n{names[0]} 0.0000 1.2346\n{names[1]} 1.2346 0.0000\n").encode("utf-8")
+    msa = MA.MultipleAlignment([MA.Protein("x", np.zeros((3, 10)), np.zeros((3, 3)), "ACD"), MA.Protein("y", np.zeros((2, 10)), np.zeros((2, 3)), "KL")],
+                               alignment={"x": np.array([0, -1, 1, 2]), "y": np.array([-1, -1, -1, -1])})
+    assert msa.to_sequence_alignment() == {"x": "A-CD", "y": "----"}
+    msa.write_alignment(tmp_path / "a.fasta")
+    assert (tmp_path / "a.fasta").read_bytes() == b">x\nA-CD\n>y\n----\n"
