@@ -416,8 +416,8 @@ class Engine:
         out = []
         for q in range(k):
             lo, hi = int(off[2 * q]), int(off[2 * q]) + int(ln[q])
-            out.append((a1[lo:hi].astype(np.int64), a2[lo:hi].astype(np.int64), tm[lo:hi].copy(), cm[lo:hi].copy(),
-                        wm[lo:hi].reshape(-1, 1).copy(), float(sc[q]), int(st[q])))
+            # views of this call's freshly allocated arrays (nothing else refers to them)
+            out.append((a1[lo:hi], a2[lo:hi], tm[lo:hi], cm[lo:hi], wm[lo:hi].reshape(-1, 1), float(sc[q]), int(st[q])))
         return out
 
     # ------------------------------------------------------------------------------------------------ alignment consumers

@@ -164,9 +164,15 @@ class MultipleAlignment:
         final_sequences = [s for s in self.sequences] + [None] * len(steps)
         final_consensus_weights = [np.full((len(s), 1), consensus_weight, dtype=np.float64) for s in self.sequences] + [None] * len(steps)
         # members[i]: names under node i (children's order: first child's members, then the second's, like the dict merge of :229-232);
-        # rows[i]: int64 [len(members), len(node i)] = residue index of every member per column of node i, -1 = gap
+        # rows[i]: int32 [len(members), len(node i) + 1] = residue index of every member per column of node i, -1 = gap; the extra
+        # last column is a -1 sentinel, so that re-indexing by an alignment with -1 gaps is ONE gather (index -1 picks the sentinel)
         members = [[s.name] for s in self.sequences] + [None] * len(steps)
-        rows = [np.arange(len(s), dtype=np.int64)[None, :] for s in self.sequences] + [None] * len(steps)
+        rows = [None] * n_total
+        for i, s in enumerate(self.sequences):
+            r = np.empty((1, len(s) + 1), np.int32)
+            r[0, :-1] = np.arange(len(s), dtype=np.int32)
+            r[0, -1] = -1
+            rows[i] = r
         level = [0] * n_leaves + [0] * len(steps)
         for q, (a, b, _) in enumerate(steps):
             if not (0 <= a < n_leaves + q and 0 <= b < n_leaves + q):
@@ -179,12 +185,15 @@ class MultipleAlignment:
             a, b, name_int = steps[q]
             aln_1, aln_2, tm, cm, wm, _, st = res
             statuses[q] = st
-            r1 = np.where(aln_1[None, :] != -1, rows[a][:, np.maximum(aln_1, 0)], -1)
-            r2 = np.where(aln_2[None, :] != -1, rows[b][:, np.maximum(aln_2, 0)], -1)
-            in_parent_frame[a], in_parent_frame[b] = r1, r2
             i = n_leaves + q
+            k1, k2, ln = len(members[a]), len(members[b]), len(aln_1)
+            r = np.empty((k1 + k2, ln + 1), np.int32)
+            np.take(rows[a], aln_1, axis=1, out=r[:k1, :ln])          # aln == -1 -> the sentinel column -> -1
+            np.take(rows[b], aln_2, axis=1, out=r[k1:, :ln])
+            r[:, ln] = -1
+            in_parent_frame[a], in_parent_frame[b] = r[:k1], r[k1:]
             members[i] = members[a] + members[b]
-            rows[i] = np.concatenate([r1, r2])
+            rows[i] = r
             final_sequences[i] = Protein(name_int, tm, cm)
             final_consensus_weights[i] = wm
 
@@ -209,11 +218,11 @@ class MultipleAlignment:
                 finish(q, eng.progressive_node(*c1, *c2, m1, m2, gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty))
 
         # the reference's dictionaries: every node's entry is re-written in its parent's frame when the parent is made (:219-226),
-        # the parent's own entry is the merge of the two (:227-232)
+        # the parent's own entry is the merge of the two (:227-232); index arrays are int64 like the reference's
         final_alignments = {}
         for i in range(n_total):
             name = final_sequences[i].name
-            r = in_parent_frame.get(i, rows[i])
+            r = in_parent_frame.get(i, rows[i])[:, :-1].astype(np.int64)
             final_alignments[name] = {mname: r[k] for k, mname in enumerate(members[i])}
         last = n_total - 1
         node_1, node_2 = steps[-1][0], steps[-1][1]

@@ -30,9 +30,12 @@ def main():
     S = msa.make_pairwise_matrix(prm); t2 = time.perf_counter()
     D = S.max() - S
     from caretta_b200 import neighbor_joining as NJ
+    NJ.neighbor_joining(D[:64, :64])                                   # first-use costs (kernel loading) stay out of the timing
     t3 = time.perf_counter(); tree, bl = NJ.neighbor_joining(D); t4 = time.perf_counter()
     lv = tree_levels(tree, n)
     depth = max(lv.values())
+    if os.environ.get("MSA_TIME_COLD", "0") == "0":
+        MA.StructureMultiple.from_chains(ch).progressive_align(tree, 1.0, 0.01, 1.0, 0.03, prm, dict(flexible=False))
     t5 = time.perf_counter()
     aln = msa.progressive_align(tree, 1.0, 0.01, 1.0, 0.03, prm, dict(flexible=False))
     t6 = time.perf_counter()
