@@ -27,6 +27,7 @@ the C ABI (caretta_b200.engine).  Nothing here computes the path on the CPU.
 """
 from __future__ import annotations
 
+import collections.abc
 import os
 import typing
 from dataclasses import dataclass, field
@@ -93,6 +94,31 @@ def get_engine() -> _engine.Engine:
         dev = int(os.environ.get("CARETTA_B200_DEVICE", os.environ.get("LOCAL_RANK", "-1")))
         _shared_engine = _engine.Engine(dev)
     return _shared_engine
+
+
+class _NodeAlignments(collections.abc.Mapping):
+    """MultipleAlignment.final_alignments of the reference (multiple_alignment.py:181-183, :219-232): node name -> {member name ->
+    int64 index array}.  A read-only mapping over the stacked int32 index matrices progressive_align keeps per node; a node's
+    dictionary is built on first access (at N = 5000 the eager dictionaries are 140 000 arrays nobody may ever read)."""
+
+    def __init__(self, names, members, matrices):
+        self._index = {n: i for i, n in enumerate(names)}
+        self._names, self._members, self._matrices = list(names), members, matrices
+        self._cache = {}
+
+    def __getitem__(self, name):
+        i = self._index[name]
+        d = self._cache.get(i)
+        if d is None:
+            r = self._matrices[i][:, :-1].astype(np.int64)
+            d = self._cache[i] = {m: r[k] for k, m in enumerate(self._members[i])}
+        return d
+
+    def __iter__(self):
+        return iter(self._names)
+
+    def __len__(self):
+        return len(self._names)
 
 
 @dataclass
@@ -218,15 +244,13 @@ class MultipleAlignment:
                 finish(q, eng.progressive_node(*c1, *c2, m1, m2, gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty))
 
         # the reference's dictionaries: every node's entry is re-written in its parent's frame when the parent is made (:219-226),
-        # the parent's own entry is the merge of the two (:227-232); index arrays are int64 like the reference's
-        final_alignments = {}
-        for i in range(n_total):
-            name = final_sequences[i].name
-            r = in_parent_frame.get(i, rows[i])[:, :-1].astype(np.int64)
-            final_alignments[name] = {mname: r[k] for k, mname in enumerate(members[i])}
+        # the parent's own entry is the merge of the two (:227-232).  Same keys, order and int64 arrays as the reference's
+        # final_alignments; the per-node dictionaries are materialised when they are read.
+        node_names = [fs.name for fs in final_sequences]
+        final_alignments = _NodeAlignments(node_names, members, [in_parent_frame.get(i, rows[i]) for i in range(n_total)])
         last = n_total - 1
         node_1, node_2 = steps[-1][0], steps[-1][1]
-        alignment = {**final_alignments[final_sequences[node_1].name], **final_alignments[final_sequences[node_2].name]}
+        alignment = {**final_alignments[node_names[node_1]], **final_alignments[node_names[node_2]]}
         assert list(alignment) == members[last]
         self.final_consensus_weights = final_consensus_weights
         self.final_alignments = final_alignments
