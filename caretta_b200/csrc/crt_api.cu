@@ -60,6 +60,24 @@ struct DevBuf {
         cap = want;
         return 0;
     }
+    // grow to n elements keeping the first `keep` (device-to-device copy on `st`, which is synchronised before the old block goes)
+    int grow_keep(size_t n, size_t keep, cudaStream_t st)
+    {
+        if (n <= cap) return 0;
+        T *old = p;
+        size_t want = n + n / 2 + 64;
+        T *np_ = nullptr;
+        cudaError_t e = cudaMalloc(&np_, want * sizeof(T));
+        if (e != cudaSuccess) return fail(CRT_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+        if (old && keep) {
+            e = cudaMemcpyAsync(np_, old, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(np_); return fail(CRT_E_CUDA, "pool copy failed: %s", cudaGetErrorString(e)); }
+        }
+        if (old) cudaFree(old);
+        p = np_; cap = want;
+        return 0;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
@@ -139,6 +157,17 @@ struct crt_ctx {
     DevBuf<double> nd_w, nd_S, nd_bnd, nd_f, nd_score, nd_xf2, nd_t, nd_c, nd_wm;
     DevBuf<unsigned char> nd_B;
     DevBuf<int> nd_a1, nd_a2, nd_len;
+
+    // crt_msa_*: device-resident sequence pool of the progressive alignment (leaves + every intermediate node)
+    struct MsaPool {
+        bool active = false;
+        int d = 0;
+        long long used = 0;                   // rows in use
+        DevBuf<double> t, c, w;               // tensors [rows, d], coordinates [rows, 3], consensus weights [rows]
+        std::vector<long long> off;           // first row of every sequence
+        std::vector<int> len;                 // its length
+    } pool;
+    DevBuf<long long> lv_tab, lv_out_off;
 
     bool stage1_only = false;             // node contexts: the run stops after the traceback / Kabsch (no stage-2 fill)
     DevBuf<DpProblem> lv_probs;           // crt_progressive_level: per-node problem records and packed level buffers
@@ -782,6 +811,7 @@ int crt_destroy(crt_ctx *c)
     c->nd_w.release(); c->nd_S.release(); c->nd_bnd.release(); c->nd_f.release(); c->nd_score.release(); c->nd_xf2.release();
     c->nd_t.release(); c->nd_c.release(); c->nd_wm.release(); c->nd_B.release(); c->nd_a1.release(); c->nd_a2.release(); c->nd_len.release(); c->text.release();
     c->lv_probs.release(); c->lv_mult.release(); c->lv_xf2.release(); c->lv_off.release();
+    c->pool.t.release(); c->pool.c.release(); c->pool.w.release(); c->lv_tab.release(); c->lv_out_off.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) {
         if (c->s_f1[k]) cudaStreamDestroy(c->s_f1[k]);
@@ -802,9 +832,15 @@ int crt_device_info(crt_ctx *c, int32_t *sm_count, int32_t *clock_khz, int64_t *
     return 0;
 }
 
-int crt_set_chains(crt_ctx *c, const double *coords, const double *tensors, const int64_t *offsets, int32_t n_chains, int32_t d)
+}  // extern "C"
+
+namespace {
+
+// crt_set_chains in two halves, so that a chain set can also be assembled on the device (crt_msa_level gathers the children of a
+// tree level from the sequence pool): chains_prepare validates the lengths and sizes every buffer, the caller fills
+// c->coords / c->tensors (host copy or device gather, on c->stream), chains_finish derives the tables and checks finiteness.
+int chains_prepare(crt_ctx *c, const int64_t *offsets, int32_t n_chains, int32_t d)
 {
-    if (!c || !coords || !tensors || !offsets) return fail(CRT_E_ARG, "null argument");
     if (n_chains <= 0) return fail(CRT_E_ARG, "n_chains must be > 0");
     const int D = pad_dim(d);
     if (d <= 0 || D < 0) return fail(CRT_E_ARG, "tensor width d=%d unsupported (1..16)", d);
@@ -835,10 +871,16 @@ int crt_set_chains(crt_ctx *c, const double *coords, const double *tensors, cons
     if ((rc = c->stats.ensure((size_t)(STATS_BLOCKS + 1) * 32))) return rc;
     if ((rc = c->flag.ensure(1))) return rc;
     c->offsets.assign(offsets, offsets + n_chains + 1);
+    c->max_len = max_len;
     CU(cudaMemsetAsync(c->flag.p, 0, sizeof(int), c->stream));
-    CU(cudaMemcpyAsync(c->coords.p, coords, sizeof(double) * (size_t)total * 3, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->tensors.p, tensors, sizeof(double) * (size_t)total * d, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_offsets.p, c->offsets.data(), sizeof(long long) * ((size_t)n_chains + 1), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int chains_finish(crt_ctx *c, int32_t n_chains, int32_t d)
+{
+    const int D = pad_dim(d);
+    const long long total = c->offsets[(size_t)n_chains];
     // chain index table, global tensor mean (the Gaussian is translation invariant; centring keeps the fp32 dot-product
     // form accurate) and the finiteness check run on the device; the only host wait is for the 4-byte flag
     {
@@ -857,13 +899,28 @@ int crt_set_chains(crt_ctx *c, const double *coords, const double *tensors, cons
     if (bad) return fail(CRT_E_ARG, "non-finite value in coords/tensors");
     {
         unsigned long long h = 1469598103934665603ull;
-        for (int p = 0; p <= n_chains; ++p) { h ^= (unsigned long long)offsets[p]; h *= 1099511628211ull; }
+        for (int p = 0; p <= n_chains; ++p) { h ^= (unsigned long long)c->offsets[(size_t)p]; h *= 1099511628211ull; }
         h ^= (unsigned long long)D; h *= 1099511628211ull;
         c->offsets_hash = h;
     }
-    c->N = n_chains; c->d = d; c->D = D; c->total = total; c->max_len = max_len;
+    c->N = n_chains; c->d = d; c->D = D; c->total = total;
     c->prep_gamma_t = c->prep_gamma_c = -1;
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crt_set_chains(crt_ctx *c, const double *coords, const double *tensors, const int64_t *offsets, int32_t n_chains, int32_t d)
+{
+    if (!c || !coords || !tensors || !offsets) return fail(CRT_E_ARG, "null argument");
+    int rc = chains_prepare(c, offsets, n_chains, d);
+    if (rc) return rc;
+    const long long total = offsets[n_chains];
+    CU(cudaMemcpyAsync(c->coords.p, coords, sizeof(double) * (size_t)total * 3, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->tensors.p, tensors, sizeof(double) * (size_t)total * d, cudaMemcpyHostToDevice, c->stream));
+    return chains_finish(c, n_chains, d);
 }
 
 }  // extern "C"

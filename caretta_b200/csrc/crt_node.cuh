@@ -156,16 +156,35 @@ __global__ void __launch_bounds__(128) k_node_mean(const double *t1, const doubl
 }
 
 // outputs of node p go to rows pr.aln_off .. pr.aln_off + aln_len[p] of the packed output arrays (capacity n + m rows)
+// out_off: row offset of every node's output (nullptr: the node's own rows pr.aln_off of the packed level arrays)
 __global__ void __launch_bounds__(128) k_level_mean(const DpProblem *probs, const double *tensors, const double *coords,
                                                     const double *weights, int d, const int *aln1, const int *aln2, const int *aln_len,
-                                                    const double *xf2, double *t_out, double *c_out, double *w_out)
+                                                    const double *xf2, const long long *out_off, double *t_out, double *c_out, double *w_out)
 {
     const DpProblem pr = probs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= aln_len[blockIdx.y]) return;
-    const long long a = pr.aln_off, b = pr.aln_off + pr.n;
+    const long long a = pr.aln_off, b = pr.aln_off + pr.n, o = out_off ? out_off[blockIdx.y] : a;
     node_mean_col(i, tensors + a * d, coords + a * 3, weights + a, tensors + b * d, coords + b * 3, weights + b, d, aln1 + a, aln2 + a,
-                  xf2 + (long long)blockIdx.y * XF, t_out + a * d, c_out + a * 3, w_out + a);
+                  xf2 + (long long)blockIdx.y * XF, t_out + o * d, c_out + o * 3, w_out + o);
+}
+
+// Sequence pool of the device-resident progressive alignment (crt_msa_*): copies the rows of each listed sequence from the pool
+// into the packed chain set of a level.  tab[q] = (pool row offset, packed row offset, length); grid (chunks, sequences).
+__global__ void __launch_bounds__(256) k_pool_gather(const long long *tab, const double *pt, const double *pc, const double *pw, int d,
+                                                     double *t_out, double *c_out, double *w_out)
+{
+    const long long src = tab[blockIdx.y * 3], dst = tab[blockIdx.y * 3 + 1], len = tab[blockIdx.y * 3 + 2];
+    const long long stride = (long long)gridDim.x * blockDim.x, first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long e = first; e < len * d; e += stride) t_out[dst * d + e] = pt[src * d + e];
+    for (long long e = first; e < len * 3; e += stride) c_out[dst * 3 + e] = pc[src * 3 + e];
+    for (long long e = first; e < len; e += stride) w_out[dst + e] = pw[src + e];
+}
+
+__global__ void __launch_bounds__(256) k_fill_value(double *p, long long n, double v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 }  // namespace crt

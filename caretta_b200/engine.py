@@ -21,6 +21,7 @@ EXPORTS = [
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node", "crt_progressive_level",
+    "crt_msa_begin", "crt_msa_level", "crt_msa_lengths", "crt_msa_fetch", "crt_msa_end",
     "crt_coverage_gap_matrix", "crt_superpose", "crt_superpose_pairs", "crt_format_matrix", "crt_format_fasta", "crt_text_fetch", "crt_count_matrix", "crt_braycurtis",
 ]
 
@@ -80,6 +81,11 @@ def load_library():
     L.crt_progressive_node.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, dbl,
                                        vp, vp, C.POINTER(i32), vp, vp, vp, C.POINTER(dbl), C.POINTER(i32)]
     L.crt_progressive_level.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.crt_msa_begin.argtypes = [vp, dbl, C.POINTER(i32)]
+    L.crt_msa_level.argtypes = [vp, i32, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, vp, vp, i64, vp, vp, vp, vp, C.POINTER(i32)]
+    L.crt_msa_lengths.argtypes = [vp, C.POINTER(i32), vp, i32]
+    L.crt_msa_fetch.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.crt_msa_end.argtypes = [vp]
     L.crt_coverage_gap_matrix.argtypes = [vp, vp, i32, i64, vp, vp]
     L.crt_superpose.argtypes = [vp, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.crt_superpose_pairs.argtypes = [vp, vp, i64, vp, vp, i64, vp, i32, vp, vp, vp, vp]
@@ -204,6 +210,7 @@ class Engine:
                     "crt_set_chains")
         self.n_chains = n
         self._offsets = offsets.copy()
+        self._tensor_width = int(tensors.shape[1])
 
     # ------------------------------------------------------------------------------------------------ all-vs-all
     def pairwise_all(self, prm: Params, want_rmsd_tm: bool = False, out=None):
@@ -419,6 +426,53 @@ class Engine:
             # views of this call's freshly allocated arrays (nothing else refers to them)
             out.append((a1[lo:hi], a2[lo:hi], tm[lo:hi], cm[lo:hi], wm[lo:hi].reshape(-1, 1), float(sc[q]), int(st[q])))
         return out
+
+    # ------------------------------------------------------------------------------------------------ device-resident MSA
+    def msa_begin(self, consensus_weight: float) -> int:
+        """Starts a progressive alignment on the chains of this engine: they become sequences 0..N-1 of the device pool."""
+        n = C.c_int32()
+        self._check(self.lib.crt_msa_begin(self.h, float(consensus_weight), C.byref(n)), "crt_msa_begin")
+        self._msa_generation = getattr(self, "_msa_generation", 0) + 1
+        self._msa_lengths = [int(x) for x in np.diff(self._offsets)]
+        self._msa_d = self._tensor_width
+        return n.value
+
+    def msa_level(self, child1, child2, mults, gamma_tensor=7.0, gamma_coords=0.03, gamma_weight=0.03, gap_open=1.0, gap_extend=0.01):
+        """All nodes (child1[k], child2[k]) of one tree level on the pool (crt_msa_level).  Returns (first_new_id,
+        [(aln_1 int32 view, aln_2 int32 view, dtw_score, status)])."""
+        c1 = np.ascontiguousarray(child1, dtype=np.int32)
+        c2 = np.ascontiguousarray(child2, dtype=np.int32)
+        k = len(c1)
+        M = np.ascontiguousarray(np.asarray(mults, dtype=np.float64).reshape(k, 2))
+        L = self._msa_lengths
+        cap = int(sum(L[a] + L[b] for a, b in zip(c1.tolist(), c2.tolist())))
+        a1, a2 = np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1), np.int32)
+        off, ln = np.zeros(k + 1, np.int64), np.empty(k, np.int32)
+        sc, st = np.empty(k), np.empty(k, np.int32)
+        first = C.c_int32()
+        self._check(self.lib.crt_msa_level(self.h, k, _p(c1), _p(c2), _p(M), float(gamma_tensor), float(gamma_coords), float(gamma_weight),
+                                           float(gap_open), float(gap_extend), _p(a1), _p(a2), cap, _p(off), _p(ln), _p(sc), _p(st),
+                                           C.byref(first)), "crt_msa_level")
+        self._msa_lengths.extend(int(x) for x in ln)
+        out = [(a1[int(off[q]):int(off[q]) + int(ln[q])], a2[int(off[q]):int(off[q]) + int(ln[q])], float(sc[q]), int(st[q])) for q in range(k)]
+        return first.value, out
+
+    def msa_fetch(self, ids):
+        """[(tensors [L,d], coordinates [L,3], weights [L,1])] of the listed pool sequences (views of three packed arrays)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        if len(ids) == 0:
+            return []
+        L = self._msa_lengths
+        lens = np.array([L[i] for i in ids.tolist()], np.int64)
+        off = np.concatenate([[0], np.cumsum(lens)])
+        rows = int(off[-1])
+        dd = self._msa_d
+        T, X, W = np.empty((rows, dd)), np.empty((rows, 3)), np.empty(rows)
+        self._check(self.lib.crt_msa_fetch(self.h, _p(ids), len(ids), _p(T), _p(X), _p(W)), "crt_msa_fetch")
+        return [(T[off[q]:off[q + 1]], X[off[q]:off[q + 1]], W[off[q]:off[q + 1]].reshape(-1, 1)) for q in range(len(ids))]
+
+    def msa_end(self):
+        self._check(self.lib.crt_msa_end(self.h), "crt_msa_end")
 
     # ------------------------------------------------------------------------------------------------ alignment consumers
     def _aln(self, aln, need_chains=True):

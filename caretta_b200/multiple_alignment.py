@@ -121,6 +121,49 @@ class _NodeAlignments(collections.abc.Mapping):
         return len(self._names)
 
 
+class _PoolNodes:
+    """The intermediate nodes of a progressive alignment that ran on the device pool (crt_msa_*): fetched from the device in one
+    call the first time any of them is read.  The pool is replaced by the next progressive alignment on the same engine; reading
+    after that raises (CARETTA_B200_FETCH_NODES=1 fetches eagerly)."""
+
+    def __init__(self, eng, ids, names):
+        self.eng, self.ids, self.names = eng, list(ids), list(names)
+        self.generation = eng._msa_generation
+        self.data = None
+
+    def fetch(self):
+        if self.data is None:
+            if self.eng._msa_generation != self.generation:
+                raise RuntimeError("the intermediate nodes of this alignment were not read before the next progressive alignment "
+                                   "replaced the device pool (set CARETTA_B200_FETCH_NODES=1 to fetch them eagerly)")
+            self.data = self.eng.msa_fetch(self.ids)
+        return self.data
+
+
+class _LazyNodeList(collections.abc.Sequence):
+    """final_sequences / final_consensus_weights (multiple_alignment.py:251-252): the leaves followed by the intermediate nodes."""
+
+    def __init__(self, head, nodes: _PoolNodes, make):
+        self._head, self._nodes, self._make, self._tail = list(head), nodes, make, None
+
+    def _materialise(self):
+        if self._tail is None:
+            self._tail = [self._make(q, rec) for q, rec in enumerate(self._nodes.fetch())]
+        return self._tail
+
+    def __len__(self):
+        return len(self._head) + len(self._nodes.ids)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return (self._head + self._materialise())[i]
+        if i < 0:
+            i += len(self)
+        if i < 0 or i >= len(self):
+            raise IndexError(i)
+        return self._head[i] if i < len(self._head) else self._materialise()[i - len(self._head)]
+
+
 @dataclass
 class MultipleAlignment:
     """The part of the reference's MultipleAlignment that sits on the hot path (multiple_alignment.py:148-170)."""
@@ -170,8 +213,11 @@ class MultipleAlignment:
                           score_function_params=None, mean_function_params=None) -> typing.Dict[str, np.ndarray]:
         """MultipleAlignment.progressive_align (multiple_alignment.py:172-253): same bookkeeping and the same results; every node's
         score matrix, affine DTW and intermediate node are computed on the device.  A node depends only on its two children, so all
-        nodes of one dependency level of the guide tree go to the device in ONE call (crt_progressive_level) instead of the
-        reference's one-node-at-a-time loop (CARETTA_B200_NODE_BATCH=0: one crt_progressive_node call per node, in tree order)."""
+        nodes of one dependency level of the guide tree go to the device in ONE call instead of the reference's one-node-at-a-time
+        loop, and the sequences (leaves and intermediate nodes) stay in a pool on the device (crt_msa_*): per level only the
+        alignments come back; final_sequences / final_consensus_weights are fetched when they are first read.
+        CARETTA_B200_MSA_POOL=0: crt_progressive_level with host arrays per level; CARETTA_B200_NODE_BATCH=0: one
+        crt_progressive_node call per node, in tree order."""
         p = dict(score_function_params or {})
         if p.get("flexible", False) or (mean_function_params or {}).get("flexible", False):
             raise NotImplementedError("flexible=True is not accelerated")
@@ -207,10 +253,14 @@ class MultipleAlignment:
         statuses = np.zeros(len(steps), np.int32)
         in_parent_frame = {}                      # child index -> its members' rows re-indexed by the parent's alignment (:219-226)
 
+        use_pool = os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0" and os.environ.get("CARETTA_B200_MSA_POOL", "1") != "0" \
+            and hasattr(eng, "msa_level")
+        node_len = [len(s) for s in self.sequences] + [0] * len(steps)
+
         def finish(q, res):
             a, b, name_int = steps[q]
-            aln_1, aln_2, tm, cm, wm, _, st = res
-            statuses[q] = st
+            aln_1, aln_2 = res[0], res[1]
+            statuses[q] = res[-1]
             i = n_leaves + q
             k1, k2, ln = len(members[a]), len(members[b]), len(aln_1)
             r = np.empty((k1 + k2, ln + 1), np.int32)
@@ -220,19 +270,41 @@ class MultipleAlignment:
             in_parent_frame[a], in_parent_frame[b] = r[:k1], r[k1:]
             members[i] = members[a] + members[b]
             rows[i] = r
-            final_sequences[i] = Protein(name_int, tm, cm)
-            final_consensus_weights[i] = wm
+            node_len[i] = ln
+            if len(res) > 4:                                        # host path: the node itself comes back with the alignment
+                final_sequences[i] = Protein(name_int, res[2], res[3])
+                final_consensus_weights[i] = res[4]
+
+        def multipliers(q):
+            a, b, _ = steps[q]
+            l1, l2 = len(members[a]), len(members[b])
+            return (l2 / (2 * (l1 + l2)), l1 / (2 * (l1 + l2)))         # multiplier_n1, multiplier_n2 (:200-203)
 
         def node_inputs(q):
             a, b, _ = steps[q]
             s1, s2 = final_sequences[a], final_sequences[b]
-            l1, l2 = len(members[a]), len(members[b])
             return ((s1.tensors, s1.coordinates, final_consensus_weights[a]), (s2.tensors, s2.coordinates, final_consensus_weights[b])), \
-                (l2 / (2 * (l1 + l2)), l1 / (2 * (l1 + l2)))                # multiplier_n1, multiplier_n2 (:200-203)
+                multipliers(q)
 
-        if os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0":
-            for lv in range(1, max(level) + 1 if steps else 1):
-                qs = [q for q in range(len(steps)) if level[n_leaves + q] == lv]
+        levels = [[q for q in range(len(steps)) if level[n_leaves + q] == lv] for lv in range(1, (max(level) if steps else 0) + 1)]
+        if use_pool:
+            # the sequences stay on the device: leaves = pool ids 0..N-1, every level appends its nodes; only alignments come back
+            eng.set_chains(*pack_sequences(self.sequences))
+            eng.msa_begin(consensus_weight)
+            pool_id = list(range(n_leaves)) + [None] * len(steps)
+            for qs in levels:
+                first, results = eng.msa_level([pool_id[steps[q][0]] for q in qs], [pool_id[steps[q][1]] for q in qs],
+                                               [multipliers(q) for q in qs], gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty)
+                for k, (q, res) in enumerate(zip(qs, results)):
+                    pool_id[n_leaves + q] = first + k
+                    finish(q, res)
+            nodes = _PoolNodes(eng, pool_id[n_leaves:], [st[2] for st in steps])
+            final_sequences = _LazyNodeList(final_sequences[:n_leaves], nodes, lambda q, rec: Protein(steps[q][2], rec[0], rec[1]))
+            final_consensus_weights = _LazyNodeList(final_consensus_weights[:n_leaves], nodes, lambda q, rec: rec[2])
+            if os.environ.get("CARETTA_B200_FETCH_NODES", "0") != "0":
+                nodes.fetch()
+        elif os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0":
+            for qs in levels:
                 inputs = [node_inputs(q) for q in qs]
                 results = eng.progressive_level([x[0] for x in inputs], [x[1] for x in inputs], gt, gc, gamma_weight,
                                                 gap_open_penalty, gap_extend_penalty)
@@ -246,7 +318,7 @@ class MultipleAlignment:
         # the reference's dictionaries: every node's entry is re-written in its parent's frame when the parent is made (:219-226),
         # the parent's own entry is the merge of the two (:227-232).  Same keys, order and int64 arrays as the reference's
         # final_alignments; the per-node dictionaries are materialised when they are read.
-        node_names = [fs.name for fs in final_sequences]
+        node_names = [s.name for s in self.sequences] + [st[2] for st in steps]
         final_alignments = _NodeAlignments(node_names, members, [in_parent_frame.get(i, rows[i]) for i in range(n_total)])
         last = n_total - 1
         node_1, node_2 = steps[-1][0], steps[-1][1]

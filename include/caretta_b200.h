@@ -161,6 +161,21 @@ int crt_progressive_level(crt_ctx *ctx, int32_t n_nodes, int32_t d, const double
                           double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2, int32_t *aln_len, double *tensors_mean,
                           double *coords_mean, double *weights_mean, double *score, int32_t *status);
 
+/* The whole progressive alignment with the sequences resident on the device (the loop of progressive_align,
+ * multiple_alignment.py:236-249, level by level).  crt_msa_begin puts the chains of the context (crt_set_chains) into a sequence
+ * pool as sequences 0..N-1 with consensus weight `consensus_weight` (:184-188).  crt_msa_level makes the n_nodes nodes
+ * (child1[k], child2[k]) -- pool ids, any earlier sequences -- exactly like crt_progressive_level and appends them to the pool as
+ * sequences *first_new_id + k; only the alignments come back: node k owns entries aln_off[k] .. aln_off[k] + aln_len[k] of
+ * aln1 / aln2 (capacity aln_cap >= sum of the children's lengths).  crt_msa_lengths: number and lengths of the pool's sequences;
+ * crt_msa_fetch: the listed sequences, packed (tensors [rows,d], coords [rows,3], weights [rows]); crt_msa_end frees the pool. */
+int crt_msa_begin(crt_ctx *ctx, double consensus_weight, int32_t *n_sequences);
+int crt_msa_level(crt_ctx *ctx, int32_t n_nodes, const int32_t *child1, const int32_t *child2, const double *mult, double gamma_tensor,
+                  double gamma_coords, double gamma_weight, double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2,
+                  int64_t aln_cap, int64_t *aln_off, int32_t *aln_len, double *score, int32_t *status, int32_t *first_new_id);
+int crt_msa_lengths(crt_ctx *ctx, int32_t *n_sequences, int32_t *lengths, int32_t cap);
+int crt_msa_fetch(crt_ctx *ctx, const int32_t *ids, int32_t count, double *tensors, double *coords, double *weights);
+int crt_msa_end(crt_ctx *ctx);
+
 /* Neighbor joining on the device: replaces caretta/neighbor_joining.py:17-99 (`neighbor_joining(distance_matrix)`, called
  * at multiple_alignment.py:277 on max(S) - S of the pairwise matrix).  distance_matrix: float64 [N,N] row-major (host),
  * N >= 3.  tree: uint64 [2N-3][2] rows (node_1, node_2), node ids >= N are intermediate nodes in creation order;

@@ -71,29 +71,50 @@ def test_node_vs_oracle():
 
 
 def test_level_batching_equals_node_by_node(monkeypatch):
-    """crt_progressive_level (all nodes of a tree level in one call) gives bit-identical nodes to crt_progressive_node."""
+    """The three ways to run the progressive alignment give bit-identical nodes: the device-resident pool (crt_msa_*, default),
+    one crt_progressive_level call per tree level with host arrays, one crt_progressive_node call per node."""
     ch = synth.make_chains(48, list(np.random.default_rng(8).integers(40, 140, 48)), 10, seed=21, family_size=6)
     monkeypatch.setenv("CARETTA_B200_PRECISION", "fp64")
     msa = MA.StructureMultiple.from_chains(ch)
     S = msa.make_pairwise_matrix(dict(PARAMS))
     out = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("CARETTA_B200_NODE_BATCH", mode)
+    for mode, (batch, pool) in dict(pool=("1", "1"), level=("1", "0"), node=("0", "0")).items():
+        monkeypatch.setenv("CARETTA_B200_NODE_BATCH", batch)
+        monkeypatch.setenv("CARETTA_B200_MSA_POOL", pool)
         m = MA.StructureMultiple.from_chains(ch)
         aln = m.multiple_align(np.max(S) - S, 1.0, 0.01, 1.0, 0.03, dict(PARAMS), None)
-        out[mode] = (aln, m)
-    a1, m1 = out["1"]
-    a0, m0 = out["0"]
-    assert list(a1) == list(a0) and all(np.array_equal(a1[k], a0[k]) for k in a1)
-    assert np.array_equal(m1.tree, m0.tree)
-    for s1, s0, w1, w0 in zip(m1.final_sequences, m0.final_sequences, m1.final_consensus_weights, m0.final_consensus_weights):
-        assert s1.name == s0.name and np.array_equal(s1.tensors, s0.tensors) and np.array_equal(s1.coordinates, s0.coordinates)
-        assert np.array_equal(w1, w0)
-    assert np.array_equal(m1.last_status, m0.last_status)
+        # read the nodes now: the pool belongs to the latest alignment on the engine
+        out[mode] = (aln, m, [(s.name, s.tensors.copy(), s.coordinates.copy()) for s in m.final_sequences],
+                     [np.array(w) for w in m.final_consensus_weights])
+    a0, m0, seq0, w0 = out["node"]
+    for mode in ("pool", "level"):
+        a1, m1, seq1, w1 = out[mode]
+        assert list(a1) == list(a0) and all(np.array_equal(a1[k], a0[k]) for k in a1), mode
+        assert np.array_equal(m1.tree, m0.tree)
+        assert len(seq1) == len(seq0) == 2 * ch.n - 1
+        for (n1, t1, c1), (n0, t0, c0), x1, x0 in zip(seq1, seq0, w1, w0):
+            assert n1 == n0 and np.array_equal(t1, t0) and np.array_equal(c1, c0) and np.array_equal(x1, x0), (mode, n1)
+        assert np.array_equal(m1.last_status, m0.last_status)
+        assert list(m1.final_alignments) == list(m0.final_alignments)
+        for k in m0.final_alignments:
+            assert list(m1.final_alignments[k]) == list(m0.final_alignments[k])
+            assert all(np.array_equal(m1.final_alignments[k][x], m0.final_alignments[k][x]) for x in m0.final_alignments[k])
     # and the alignment is the oracle's (the CPU restatement of the reference's progressive_align) on the same tree
     seqs = [(f"s{p}", *ch.chain(p)) for p in range(ch.n)]
-    want, _, _ = O.progressive_align(seqs, m1.tree, 1.0, 0.01, 1.0, 0.03, 7.0, 0.03)
-    assert all(np.array_equal(a1[k], want[k]) for k in want)
+    want, _, _ = O.progressive_align(seqs, m0.tree, 1.0, 0.01, 1.0, 0.03, 7.0, 0.03)
+    assert all(np.array_equal(a0[k], want[k]) for k in want)
+    # a pool that has been replaced refuses to hand out stale nodes
+    stale = out["pool"][1]
+    fresh = MA.StructureMultiple.from_chains(ch)
+    monkeypatch.setenv("CARETTA_B200_NODE_BATCH", "1")
+    monkeypatch.setenv("CARETTA_B200_MSA_POOL", "1")
+    m2 = MA.StructureMultiple.from_chains(ch)
+    m2.multiple_align(np.max(S) - S, 1.0, 0.01, 1.0, 0.03, dict(PARAMS), None)
+    m3 = MA.StructureMultiple.from_chains(ch)
+    m3.multiple_align(np.max(S) - S, 1.0, 0.01, 1.0, 0.03, dict(PARAMS), None)
+    with pytest.raises(RuntimeError):
+        m2.final_sequences[-1]
+    assert m3.final_sequences[-1].name == "int-final" and stale.final_sequences[0].name == "s0" and fresh is not None
 
 
 def test_level_call_with_mixed_shapes():
