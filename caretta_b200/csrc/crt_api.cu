@@ -169,6 +169,8 @@ struct crt_ctx {
     } pool;
     DevBuf<long long> lv_tab, lv_out_off;
 
+    DevBuf<char> arena;                   // scratch of the consumer / neighbor-joining calls (crt_consumers_api.inl: Scratch)
+    bool coords_only = false;             // chain set made by crt_set_coords: consumers only, no pair runs
     bool stage1_only = false;             // node contexts: the run stops after the traceback / Kabsch (no stage-2 fill)
     DevBuf<DpProblem> lv_probs;           // crt_progressive_level: per-node problem records and packed level buffers
     DevBuf<double> lv_mult, lv_xf2;
@@ -187,6 +189,37 @@ struct crt_ctx {
 };
 
 namespace {
+
+// Scratch memory of one call: bump allocation from an arena the context keeps (cudaMalloc / cudaFree of a few hundred MB per
+// call cost up to hundreds of milliseconds, erratically).  What does not fit is allocated for this call only and the arena
+// grows to the call's total when the call is over, so the next call of the same size allocates nothing.
+struct Scratch {
+    crt_ctx *c;
+    size_t used = 0, wanted = 0;
+    std::vector<void *> extra;
+    explicit Scratch(crt_ctx *ctx) : c(ctx) {}
+    ~Scratch()
+    {
+        for (void *p : extra) cudaFree(p);
+        if (wanted > c->arena.cap) { cudaStreamSynchronize(c->stream); c->arena.release(); c->arena.ensure(wanted + wanted / 8); }
+    }
+    template <typename T>
+    cudaError_t alloc(T **out, size_t n)
+    {
+        const size_t bytes = ((n ? n : 1) * sizeof(T) + 255) & ~(size_t)255;
+        wanted += bytes;
+        if (used + bytes <= c->arena.cap) {
+            *out = reinterpret_cast<T *>(c->arena.p + used);
+            used += bytes;
+            return cudaSuccess;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) extra.push_back(p);
+        *out = static_cast<T *>(p);
+        return e;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------- kernel dispatch
 struct Choice { int C; int n_strips; };
@@ -733,6 +766,7 @@ int check_params(const crt_ctx *c, const crt_params *prm)
     if (!c) return fail(CRT_E_ARG, "null context");
     if (!prm) return fail(CRT_E_ARG, "null params");
     if (c->N <= 0) return fail(CRT_E_STATE, "crt_set_chains has not been called");
+    if (c->coords_only) return fail(CRT_E_STATE, "the chain set was made by crt_set_coords (coordinates only): pair runs need crt_set_chains");
     if (prm->precision != CRT_FP64 && prm->precision != CRT_FP32) return fail(CRT_E_ARG, "precision must be CRT_FP64 or CRT_FP32");
     if (prm->sw_gap != 0.0) return fail(CRT_E_ARG, "sw_gap != 0 is not on the reference's pair path (multiple_alignment.py:335, :164)");
     if (!(prm->gamma_tensor >= 0) || !(prm->gamma_coords >= 0)) return fail(CRT_E_ARG, "gamma must be >= 0");
@@ -811,7 +845,7 @@ int crt_destroy(crt_ctx *c)
     c->nd_w.release(); c->nd_S.release(); c->nd_bnd.release(); c->nd_f.release(); c->nd_score.release(); c->nd_xf2.release();
     c->nd_t.release(); c->nd_c.release(); c->nd_wm.release(); c->nd_B.release(); c->nd_a1.release(); c->nd_a2.release(); c->nd_len.release(); c->text.release();
     c->lv_probs.release(); c->lv_mult.release(); c->lv_xf2.release(); c->lv_off.release();
-    c->pool.t.release(); c->pool.c.release(); c->pool.w.release(); c->lv_tab.release(); c->lv_out_off.release();
+    c->pool.t.release(); c->pool.c.release(); c->pool.w.release(); c->lv_tab.release(); c->lv_out_off.release(); c->arena.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (int k = 0; k < 2; ++k) {
         if (c->s_f1[k]) cudaStreamDestroy(c->s_f1[k]);
@@ -920,7 +954,22 @@ int crt_set_chains(crt_ctx *c, const double *coords, const double *tensors, cons
     const long long total = offsets[n_chains];
     CU(cudaMemcpyAsync(c->coords.p, coords, sizeof(double) * (size_t)total * 3, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->tensors.p, tensors, sizeof(double) * (size_t)total * d, cudaMemcpyHostToDevice, c->stream));
+    c->coords_only = false;
     return chains_finish(c, n_chains, d);
+}
+
+/* Coordinates only (the consumers of the alignment -- crt_superpose*, crt_rmsd_cov_tm* -- never read the shape tensors): the chain
+ * set gets a one-column zero tensor on the device instead of an upload of [sum L, d] doubles. */
+int crt_set_coords(crt_ctx *c, const double *coords, const int64_t *offsets, int32_t n_chains)
+{
+    if (!c || !coords || !offsets) return fail(CRT_E_ARG, "null argument");
+    int rc = chains_prepare(c, offsets, n_chains, 1);
+    if (rc) return rc;
+    const long long total = offsets[n_chains];
+    CU(cudaMemcpyAsync(c->coords.p, coords, sizeof(double) * (size_t)total * 3, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->tensors.p, 0, sizeof(double) * (size_t)total, c->stream));
+    c->coords_only = true;
+    return chains_finish(c, n_chains, 1);
 }
 
 }  // extern "C"
@@ -1370,12 +1419,17 @@ static int rmsd_cov_tm_impl(crt_ctx *c, const int64_t *aln, int64_t A, double *r
     crt_params prm{7.0, 0.03, 0.0, CRT_FP32, 0};
     int rc = ensure_prepared(c, c->prep_gamma_t >= 0 ? nullptr : &prm);
     if (rc) return rc;
-    DevBuf<long long> dAln;
-    DevBuf<double> dR, dC, dT;
-    DevBuf<int> dBad;
-    auto cleanup = [&]() { dAln.release(); dR.release(); dC.release(); dT.release(); dBad.release(); };
+    struct { long long *p = nullptr; } dAln;
+    struct { double *p = nullptr; } dR, dC, dT;
+    struct { int *p = nullptr; } dBad;
+    Scratch sc(c);
+    auto cleanup = [&]() {};
     const size_t NN = (size_t)N * N;
-    if ((rc = dAln.ensure((size_t)N * A)) || (rc = dR.ensure(NN)) || (rc = dC.ensure(NN)) || (rc = dT.ensure(NN)) || (rc = dBad.ensure(1))) { cleanup(); return rc; }
+    CU(sc.alloc(&dAln.p, (size_t)N * A));
+    CU(sc.alloc(&dR.p, NN));
+    CU(sc.alloc(&dC.p, NN));
+    CU(sc.alloc(&dT.p, NN));
+    CU(sc.alloc(&dBad.p, 1));
     cudaStream_t st = c->stream;
     cudaMemcpyAsync(dAln.p, aln, sizeof(long long) * (size_t)N * A, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(dBad.p, 0, sizeof(int), st);
@@ -1496,19 +1550,17 @@ int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, u
     long long *t0 = nullptr, *t1 = nullptr, *plin = nullptr;
     unsigned long long *d_tree = nullptr;
     NjSel *sel = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(A); cudaFree(B); cudaFree(S0); cudaFree(S1); cudaFree(pq); cudaFree(d_bl); cudaFree(t0); cudaFree(t1); cudaFree(plin);
-        cudaFree(d_tree); cudaFree(sel);
-    };
+    Scratch sc(c);                       // arena of the context: no cudaMalloc / cudaFree per call once it has grown
+    auto cleanup = [&]() {};
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return e == cudaSuccess; };
     std::vector<long long> ident((size_t)N);
     for (int q = 0; q < N; ++q) ident[(size_t)q] = q;
     cudaStream_t st = c->stream;
-    if (ok(cudaMalloc(&A, NN * 8)) && ok(cudaMalloc(&B, NN * 8)) && ok(cudaMalloc(&S0, (size_t)N * 8)) && ok(cudaMalloc(&S1, (size_t)N * 8)) &&
-        ok(cudaMalloc(&pq, max_part * 8)) && ok(cudaMalloc(&plin, max_part * 8)) && ok(cudaMalloc(&t0, (size_t)N * 8)) &&
-        ok(cudaMalloc(&t1, (size_t)N * 8)) && ok(cudaMalloc(&d_tree, rows_max * 16)) && ok(cudaMalloc(&d_bl, rows_max * 8)) &&
-        ok(cudaMalloc(&sel, sizeof(NjSel)))) {
+    if (ok(sc.alloc(&A, NN)) && ok(sc.alloc(&B, NN)) && ok(sc.alloc(&S0, (size_t)N)) && ok(sc.alloc(&S1, (size_t)N)) &&
+        ok(sc.alloc(&pq, (size_t)max_part)) && ok(sc.alloc(&plin, (size_t)max_part)) && ok(sc.alloc(&t0, (size_t)N)) &&
+        ok(sc.alloc(&t1, (size_t)N)) && ok(sc.alloc(&d_tree, rows_max * 2)) && ok(sc.alloc(&d_bl, rows_max)) &&
+        ok(sc.alloc(&sel, 1))) {
         ok(cudaMemcpyAsync(A, distance_matrix, NN * 8, cudaMemcpyHostToDevice, st));
         ok(cudaMemcpyAsync(t0, ident.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
         ok(cudaMemsetAsync(sel, 0, sizeof(NjSel), st));

@@ -3,21 +3,6 @@
 
 namespace {
 
-// RAII scratch (these calls are rare, once per run of the CLI; nothing is cached in the context except the text buffer)
-struct Scratch {
-    std::vector<void *> ptrs;
-    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
-    template <typename T>
-    cudaError_t alloc(T **out, size_t n)
-    {
-        void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
-        if (e == cudaSuccess) ptrs.push_back(p);
-        *out = static_cast<T *>(p);
-        return e;
-    }
-};
-
 struct AlnDev {
     long long *aln = nullptr;
     unsigned *bitsT = nullptr;
@@ -110,7 +95,7 @@ int crt_coverage_gap_matrix(crt_ctx *c, const int64_t *aln, int32_t N, int64_t A
     if (!c || !aln || !distance || !aligning) return fail(CRT_E_ARG, "null argument");
     if (N <= 0 || A <= 0) return fail(CRT_E_ARG, "empty alignment (%d x %lld)", N, (long long)A);
     CU(cudaSetDevice(c->device));
-    Scratch sc;
+    Scratch sc(c);
     AlnDev ad;
     std::vector<int> present;
     int rc = upload_alignment(c, sc, aln, N, A, nullptr, ad, present);
@@ -148,7 +133,7 @@ int crt_superpose(crt_ctx *c, const int64_t *aln, int64_t A, int32_t mode, int32
     const int N = c->N;
     if (reference >= N) return fail(CRT_E_ARG, "reference %d out of range", reference);
     CU(cudaSetDevice(c->device));
-    Scratch sc;
+    Scratch sc(c);
     AlnDev ad;
     std::vector<int> present;
     int rc = upload_alignment(c, sc, aln, N, A, c->d_offsets.p, ad, present);
@@ -240,7 +225,7 @@ int crt_superpose_pairs(crt_ctx *c, const int64_t *aln, int64_t A, const int32_t
         }
     }
     CU(cudaSetDevice(c->device));
-    Scratch sc;
+    Scratch sc(c);
     AlnDev ad;
     std::vector<int> present;
     int rc = upload_alignment(c, sc, aln, N, A, c->d_offsets.p, ad, present);
@@ -276,7 +261,7 @@ int crt_format_matrix(crt_ctx *c, const double *matrix, int32_t n_rows, int32_t 
         c->text_len = hl; *out_len = hl;
         return 0;
     }
-    Scratch sc;
+    Scratch sc(c);
     double *d_M = nullptr;
     char *d_names = nullptr;
     long long *d_noff = nullptr, *d_len = nullptr, *d_off = nullptr;
@@ -329,7 +314,7 @@ int crt_format_fasta(crt_ctx *c, const int64_t *aln, int32_t N, int64_t A, const
     const long long total = rec[(size_t)N];
     int rc = c->text.ensure((size_t)total + 16);
     if (rc) return rc;
-    Scratch sc;
+    Scratch sc(c);
     long long *d_aln = nullptr, *d_soff = nullptr, *d_noff = nullptr, *d_rec = nullptr;
     char *d_seqs = nullptr, *d_names = nullptr;
     int *d_bad = nullptr;
@@ -372,7 +357,7 @@ int crt_count_matrix(crt_ctx *c, const int64_t *indices, const int64_t *offsets,
     for (int p = 0; p < N; ++p)
         if (offsets[p + 1] < offsets[p]) return fail(CRT_E_ARG, "offsets must be non-decreasing");
     CU(cudaSetDevice(c->device));
-    Scratch sc;
+    Scratch sc(c);
     long long *d_idx = nullptr, *d_off = nullptr;
     double *d_out = nullptr;
     int *d_bad = nullptr;
@@ -406,7 +391,7 @@ int crt_braycurtis(crt_ctx *c, const double *counts_1, int32_t n1, const double 
     if (!c || !counts_1 || !counts_2 || !out) return fail(CRT_E_ARG, "null argument");
     if (n1 <= 0 || n2 <= 0 || K <= 0) return fail(CRT_E_ARG, "empty input (%d, %d, %d)", n1, n2, K);
     CU(cudaSetDevice(c->device));
-    Scratch sc;
+    Scratch sc(c);
     double *d_a = nullptr, *d_b = nullptr, *d_out = nullptr;
     CU(sc.alloc(&d_a, (size_t)n1 * K));
     const bool same = counts_1 == counts_2 && n1 == n2;

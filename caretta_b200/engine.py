@@ -17,7 +17,7 @@ SUP_AUTO, SUP_CORE, SUP_REFERENCE = 0, 1, 2
 ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE = 1, 2, 4
 
 EXPORTS = [
-    "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains",
+    "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains", "crt_set_coords",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node", "crt_progressive_level",
@@ -54,6 +54,7 @@ def load_library():
     L.crt_destroy.argtypes = [vp]
     L.crt_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.crt_set_chains.argtypes = [vp, vp, vp, vp, i32, i32]
+    L.crt_set_coords.argtypes = [vp, vp, vp, i32]
     L.crt_pairwise_shard.argtypes = [vp, C.POINTER(Params), i32, i32]
     L.crt_shard_size.argtypes = [vp, i32, i32]
     L.crt_shard_size.restype = i64
@@ -211,6 +212,17 @@ class Engine:
         self.n_chains = n
         self._offsets = offsets.copy()
         self._tensor_width = int(tensors.shape[1])
+
+    def set_coords(self, coords, offsets):
+        """Chain set with coordinates only (enough for superpose* / rmsd_cov_tm; pair runs need set_chains)."""
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        if coords.ndim != 2 or coords.shape[1] != 3 or offsets[-1] != coords.shape[0]:
+            raise ValueError("coords [sumL,3] and offsets [N+1] expected")
+        self._check(self.lib.crt_set_coords(self.h, _p(coords), _p(offsets), len(offsets) - 1), "crt_set_coords")
+        self.n_chains = len(offsets) - 1
+        self._offsets = offsets.copy()
+        self._tensor_width = 1
 
     # ------------------------------------------------------------------------------------------------ all-vs-all
     def pairwise_all(self, prm: Params, want_rmsd_tm: bool = False, out=None):

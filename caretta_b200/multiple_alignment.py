@@ -84,6 +84,21 @@ def pack_sequences(sequences) -> typing.Tuple[np.ndarray, np.ndarray, np.ndarray
     return coords, tensors, offsets
 
 
+def pack_coordinates(sequences) -> typing.Tuple[np.ndarray, np.ndarray]:
+    """Coordinates and offsets only (what the consumers of an alignment need)."""
+    if len(sequences) == 0:
+        raise ValueError("no sequences")
+    lens = []
+    for s in sequences:
+        c = np.asarray(s.coordinates)
+        if c.ndim != 2 or c.shape[1] != 3 or c.shape[0] == 0:
+            raise ValueError(f"{getattr(s, 'name', '?')}: coordinates must be [L,3]")
+        lens.append(c.shape[0])
+    offsets = np.zeros(len(sequences) + 1, np.int64)
+    offsets[1:] = np.cumsum(lens)
+    return np.concatenate([np.asarray(s.coordinates, dtype=np.float64) for s in sequences]), offsets
+
+
 _shared_engine: typing.Optional[_engine.Engine] = None
 
 
@@ -451,7 +466,7 @@ def make_rmsd_coverage_tm_matrix(alignment, proteins, superpose_first: bool = Tr
     names = [p.name for p in proteins]
     aln = np.array([np.asarray(alignment[n], dtype=np.int64) for n in names])
     eng = get_engine()
-    eng.set_chains(*pack_sequences(proteins))
+    eng.set_coords(*pack_coordinates(proteins))
     r, c, t, bad = eng.rmsd_cov_tm(aln, superpose=not superpose_first)
     assert bad == 0, "a pair has fewer than 3 common positions (the reference asserts here, :1034)"
     return r, c, t
@@ -516,7 +531,7 @@ def get_reference_structures(alignment, minimum_coverage=50, gap=-1):
 def _superpose_on_device(alignment, proteins, mode, reference_name=None, core_indices=None):
     names = [p.name for p in proteins]
     eng = get_engine()
-    eng.set_chains(*pack_sequences(proteins))
+    eng.set_coords(*pack_coordinates(proteins))
     ref = -1 if reference_name is None else names.index(reference_name)
     res = eng.superpose(_aln_array(alignment, names), mode, ref, core_indices)
     off = eng._offsets
@@ -566,7 +581,7 @@ def superpose_references(alignment, proteins, minimum_coverage=50):
                 mem += [index[n] for n in part]
                 batch_off.append(len(ref))
     eng = get_engine()
-    eng.set_chains(*pack_sequences(proteins))
+    eng.set_coords(*pack_coordinates(proteins))
     res = eng.superpose_pairs(_aln_array(alignment, names), ref, mem, batch_off)
     assert len(ref) == 0 or int(res["ncommon"].min()) > 3, "a structure has <= 3 positions in common with its reference (:941)"
     off = eng._offsets

@@ -78,6 +78,10 @@ int crt_device_info(crt_ctx *ctx, int32_t *sm_count, int32_t *clock_khz, int64_t
 int crt_set_chains(crt_ctx *ctx, const double *coords, const double *tensors, const int64_t *offsets,
                    int32_t n_chains, int32_t d);
 
+/* The same with coordinates only, for the consumers of an alignment (crt_superpose*, crt_rmsd_cov_tm*), which never read the
+ * shape tensors; pair runs on such a chain set fail with CRT_E_STATE. */
+int crt_set_coords(crt_ctx *ctx, const double *coords, const int64_t *offsets, int32_t n_chains);
+
 /* All-vs-all, the shard of `rank` out of `world` (world = 1 -> everything).  Pairs are grouped into units
  * (one column chain x a run of row chains), units are dealt to ranks by cost; the enumeration is deterministic
  * so every rank can reconstruct every other rank's pair list with crt_shard_pairs.

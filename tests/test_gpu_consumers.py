@@ -267,3 +267,21 @@ def test_consumer_edge_cases(eng, tmp_path):
     assert msa.to_sequence_alignment() == {"x": "A-CD", "y": "----"}
     msa.write_alignment(tmp_path / "a.fasta")
     assert (tmp_path / "a.fasta").read_bytes() == b">x\nA-CD\n>y\n----\n"
+
+
+def test_coordinates_only_chain_set(cons, eng):
+    """crt_set_coords: enough for the consumers, refused by the pair path."""
+    ch = CC.chains_of("fam8", cons)
+    aln = cons["fam8_aln"]
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    want = eng.superpose(aln, engine.SUP_CORE)
+    r0 = eng.rmsd_cov_tm(aln)
+    eng.set_coords(ch.coords, ch.offsets)
+    got = eng.superpose(aln, engine.SUP_CORE)
+    assert np.array_equal(got["coords"], want["coords"]) and np.array_equal(got["rot"], want["rot"])
+    r1 = eng.rmsd_cov_tm(aln)
+    assert all(np.array_equal(a, b) for a, b in zip(r0[:3], r1[:3]))
+    with pytest.raises(engine.CrtError):
+        eng.pairwise_all(eng.params())
+    eng.set_chains(ch.coords, ch.tensors, ch.offsets)
+    assert eng.pairwise_all(eng.params()).shape == (ch.n, ch.n)
