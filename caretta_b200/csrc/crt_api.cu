@@ -1425,6 +1425,11 @@ static int rmsd_cov_tm_impl(crt_ctx *c, const int64_t *aln, int64_t A, double *r
     Scratch sc(c);
     auto cleanup = [&]() {};
     const size_t NN = (size_t)N * N;
+    const int W = (int)((A + 31) / 32);
+    unsigned *dBits = nullptr;
+    int *dPresent = nullptr;
+    CU(sc.alloc(&dBits, (size_t)N * W));
+    CU(sc.alloc(&dPresent, (size_t)N));
     CU(sc.alloc(&dAln.p, (size_t)N * A));
     CU(sc.alloc(&dR.p, NN));
     CU(sc.alloc(&dC.p, NN));
@@ -1436,8 +1441,10 @@ static int rmsd_cov_tm_impl(crt_ctx *c, const int64_t *aln, int64_t A, double *r
     k_fill_diag<<<(unsigned)((NN + 255) / 256), 256, 0, st>>>(dR.p, dC.p, dT.p, N);
     const long long np = (long long)N * (N - 1) / 2;
     cudaEventRecord(c->ev0, st);
+    cudaMemsetAsync(dPresent, 0, sizeof(int) * (size_t)N, st);
+    k_aln_bits<<<(unsigned)(((long long)N * W * 32 + 255) / 256), 256, 0, st>>>(dAln.p, N, A, W, nullptr, dBits, dPresent, dBad.p);
     if (np > 0)
-        k_rmsd_cov_tm<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(dAln.p, N, A, c->coords.p, c->d_offsets.p, c->centroid.p, dR.p, dC.p, dT.p, dBad.p, superpose);
+        k_rmsd_cov_tm<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(dAln.p, N, A, dBits, W, c->coords.p, c->d_offsets.p, c->centroid.p, dR.p, dC.p, dT.p, dBad.p, superpose);
     int bad = 0;
     cudaEventRecord(c->ev1, st);
     cudaMemcpyAsync(rmsd, dR.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, st);

@@ -233,8 +233,11 @@ __global__ void k_sw_trace(const DpProblem *probs, int n_probs, const double *S_
 // ------------------------------------------------------------------------------------------------------------
 // make_rmsd_coverage_tm_matrix(superpose_first=False): one thread per pair i<j over the A alignment columns.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_rmsd_cov_tm(const long long *aln, int N, long long A, const double *coords, const long long *offsets,
-                              const double *centroid, double *rmsd, double *cov, double *tm, int *n_bad, int superpose)
+// bitsT[w * N + p] bit b <=> aln[p][32 w + b] != -1 (k_aln_bits): a pair only visits the columns where both have a residue
+// (mask_i & mask_j), in ascending column order like the reference's loop, instead of scanning all A columns twice.
+__global__ void k_rmsd_cov_tm(const long long *aln, int N, long long A, const unsigned *bitsT, int W, const double *coords,
+                              const long long *offsets, const double *centroid, double *rmsd, double *cov, double *tm, int *n_bad,
+                              int superpose)
 {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long np = (long long)N * (N - 1) / 2;
@@ -249,9 +252,10 @@ __global__ void k_rmsd_cov_tm(const long long *aln, int N, long long A, const do
     const double *ci = centroid + (long long)i * 3, *cj = centroid + (long long)j * 3;
     double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0}, Cr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int c = 0;
-    for (long long k = 0; k < A; ++k) {
+    for (int w = 0; w < W; ++w)
+    for (unsigned mbits = bitsT[(long long)w * N + i] & bitsT[(long long)w * N + j]; mbits; mbits &= mbits - 1) {
+        const long long k = (long long)w * 32 + (__ffs(mbits) - 1);
         const long long a = ai[k], b = aj[k];
-        if (a < 0 || b < 0) continue;
         ++c;
         double x1[3], x2[3];
         for (int d = 0; d < 3; ++d) { x1[d] = X[a * 3 + d] - ci[d]; x2[d] = Y[b * 3 + d] - cj[d]; s1[d] += x1[d]; s2[d] += x2[d]; }
@@ -274,9 +278,10 @@ __global__ void k_rmsd_cov_tm(const long long *aln, int N, long long A, const do
     const long long l1 = offsets[i + 1] - offsets[i], l2 = offsets[j + 1] - offsets[j];
     const double d1 = 1.24 * (double)(l1 - 15) / 3 - 1.8, d2 = 1.24 * (double)(l2 - 15) / 3 - 1.8;
     double ss = 0.0, t1 = 0.0, t2 = 0.0;
-    for (long long k = 0; k < A; ++k) {
+    for (int w = 0; w < W; ++w)
+    for (unsigned mbits = bitsT[(long long)w * N + i] & bitsT[(long long)w * N + j]; mbits; mbits &= mbits - 1) {
+        const long long k = (long long)w * 32 + (__ffs(mbits) - 1);
         const long long a = ai[k], b = aj[k];
-        if (a < 0 || b < 0) continue;
         const double y0 = Y[b * 3], y1 = Y[b * 3 + 1], y2 = Y[b * 3 + 2];
         double sm = 0.0;
         for (int d = 0; d < 3; ++d) {
