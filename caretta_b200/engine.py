@@ -541,13 +541,21 @@ class Engine:
         blob = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
         return blob, off
 
-    def _fetch_text(self, n: int) -> bytes:
-        buf = np.empty(max(n, 1), np.uint8)
+    def _fetch_text_view(self, n: int) -> memoryview:
+        """The text of the last crt_format_* call in a page-locked staging buffer the engine keeps (grow-only): valid until the
+        next call.  Large texts (a 5000 x 5000 matrix is 198 MB) go from here straight to the file, without another copy."""
+        buf = getattr(self, "_text_staging", None)
+        if buf is None or buf.size < n:
+            self._text_staging = buf = pinned_empty(max(n + n // 8, 1 << 16), np.uint8)
         self._check(self.lib.crt_text_fetch(self.h, _p(buf), n), "crt_text_fetch")
-        return buf[:n].tobytes()
+        return memoryview(buf)[:n]
 
-    def format_matrix(self, names, matrix) -> bytes:
-        """The bytes helper.write_distance_matrix (helper.py:183-203) writes: header, then 'name v v ...' rows with %.4f values."""
+    def _fetch_text(self, n: int) -> bytes:
+        return bytes(self._fetch_text_view(n))
+
+    def format_matrix(self, names, matrix, view: bool = False):
+        """The bytes helper.write_distance_matrix (helper.py:183-203) writes: header, then 'name v v ...' rows with %.4f values.
+        view=True: a memoryview of the engine's page-locked staging buffer (valid until the next format call) instead of bytes."""
         M = np.ascontiguousarray(matrix, dtype=np.float64)
         if M.ndim != 2 or M.shape[0] < len(names):
             raise IndexError("distance_matrix needs one row per name")
@@ -555,9 +563,9 @@ class Engine:
         blob, off = self._pack_text(names)
         n = C.c_int64()
         self._check(self.lib.crt_format_matrix(self.h, _p(M), M.shape[0], M.shape[1], _p(blob), _p(off), C.byref(n)), "crt_format_matrix")
-        return self._fetch_text(n.value)
+        return self._fetch_text_view(n.value) if view else self._fetch_text(n.value)
 
-    def format_fasta(self, names, sequences, aln) -> bytes:
+    def format_fasta(self, names, sequences, aln, view: bool = False):
         """The bytes MultipleAlignment.write_alignment (multiple_alignment.py:299-309) writes for aln int64 [N, A]."""
         aln = self._aln(aln, need_chains=False)
         if len(names) != aln.shape[0] or len(sequences) != aln.shape[0]:
@@ -567,7 +575,7 @@ class Engine:
         n = C.c_int64()
         self._check(self.lib.crt_format_fasta(self.h, _p(aln), aln.shape[0], aln.shape[1], _p(sb), _p(soff), _p(nb), _p(noff), C.byref(n)),
                     "crt_format_fasta")
-        return self._fetch_text(n.value)
+        return self._fetch_text_view(n.value) if view else self._fetch_text(n.value)
 
     def count_matrix(self, residues_list, alphabet_size: int) -> np.ndarray:
         """make_count_matrix (multiple_alignment.py:128-134): float64 [N, alphabet_size] shapemer counts."""

@@ -602,9 +602,9 @@ def braycurtis(counts_1, counts_2) -> np.ndarray:
 
 def write_distance_matrix(names, distance_matrix, filename) -> None:
     """helper.write_distance_matrix (helper.py:183-203): Clustal-style text, '%.4f' values formatted on the device, same bytes."""
-    text = get_engine().format_matrix([str(n) for n in names], np.asarray(distance_matrix, dtype=np.float64))
+    text = get_engine().format_matrix([str(n) for n in names], np.asarray(distance_matrix, dtype=np.float64), view=True)
     with open(filename, "wb") as f:
-        f.write(text)
+        f.write(text)                       # straight from the engine's page-locked staging buffer
 
 
 @dataclass
