@@ -1557,6 +1557,7 @@ int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, u
     long long *t0 = nullptr, *t1 = nullptr, *plin = nullptr;
     unsigned long long *d_tree = nullptr;
     NjSel *sel = nullptr;
+    unsigned *ticket = nullptr;
     Scratch sc(c);                       // arena of the context: no cudaMalloc / cudaFree per call once it has grown
     auto cleanup = [&]() {};
     cudaError_t e = cudaSuccess;
@@ -1567,7 +1568,8 @@ int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, u
     if (ok(sc.alloc(&A, NN)) && ok(sc.alloc(&B, NN)) && ok(sc.alloc(&S0, (size_t)N)) && ok(sc.alloc(&S1, (size_t)N)) &&
         ok(sc.alloc(&pq, (size_t)max_part)) && ok(sc.alloc(&plin, (size_t)max_part)) && ok(sc.alloc(&t0, (size_t)N)) &&
         ok(sc.alloc(&t1, (size_t)N)) && ok(sc.alloc(&d_tree, rows_max * 2)) && ok(sc.alloc(&d_bl, rows_max)) &&
-        ok(sc.alloc(&sel, 1))) {
+        ok(sc.alloc(&sel, 1)) && ok(sc.alloc(&ticket, 1))) {
+        ok(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
         ok(cudaMemcpyAsync(A, distance_matrix, NN * 8, cudaMemcpyHostToDevice, st));
         ok(cudaMemcpyAsync(t0, ident.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
         ok(cudaMemsetAsync(sel, 0, sizeof(NjSel), st));
@@ -1577,8 +1579,7 @@ int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, u
         int n = N;
         while (n > 3 && e == cudaSuccess) {
             const int n_part = std::min(max_part, n);                    // one block per row, rows beyond max_part wrap around
-            k_nj_argmin<<<n_part, NJ_ARGMIN_THREADS, 0, st>>>(A, S0, n, pq, plin);
-            k_nj_select<<<1, NJ_ARGMIN_THREADS, 0, st>>>(A, S0, n, N, pq, plin, n_part, t0, sel, d_tree, d_bl);
+            k_nj_argmin<<<n_part, NJ_ARGMIN_THREADS, 0, st>>>(A, S0, n, pq, plin, N, t0, sel, d_tree, d_bl, ticket);
             k_nj_rebuild<<<(unsigned)((n - 1 + NJ_ROWS - 1) / NJ_ROWS), NJ_REBUILD_THREADS, NJ_REBUILD_SMEM, st>>>(A, n, sel, N, t0, t1, B, S1);
             std::swap(A, B); std::swap(S0, S1); std::swap(t0, t1);
             --n;

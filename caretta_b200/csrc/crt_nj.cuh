@@ -68,7 +68,13 @@ constexpr int NJ_ARGMIN_THREADS = 256;
 
 // Block b scans rows b, b + gridDim.x, ...; its threads stride over the columns (coalesced, no index division).  The minimum is
 // taken over (q, linear index) pairs, so the traversal order does not matter: the winner is the first row-major minimum.
-__global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A, const double *S, int n, double *pq, long long *plin)
+__device__ void nj_select_block(const double *A, const double *S, int n, int N, const double *pq, const long long *plin, int n_part,
+                                const long long *true_idx, NjSel *sel, unsigned long long *tree, double *bl, double *sq, long long *sl);
+
+// The last block to finish (ticket counter) also runs the selection, so that one iteration is two launches, not three.
+__global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A, const double *S, int n, double *pq, long long *plin,
+                                                                 int N, const long long *true_idx, NjSel *sel, unsigned long long *tree,
+                                                                 double *bl, unsigned *ticket)
 {
     const double nm2 = (double)(n - 2);
     double bq = INFINITY;
@@ -105,20 +111,32 @@ __global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { pq[blockIdx.x] = sq[0]; plin[blockIdx.x] = sl[0]; }
+    __shared__ unsigned last;
+    if (threadIdx.x == 0) {
+        pq[blockIdx.x] = sq[0]; plin[blockIdx.x] = sl[0];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        nj_select_block(A, S, n, N, pq, plin, (int)gridDim.x, true_idx, sel, tree, bl, sq, sl);
+        if (threadIdx.x == 0) *ticket = 0;
+    }
 }
 
 // one block: reduce the partials, write the two tree rows and branch lengths of the joined pair
-__global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_select(const double *A, const double *S, int n, int N, const double *pq,
-                                                                 const long long *plin, int n_part, const long long *true_idx,
-                                                                 NjSel *sel, unsigned long long *tree, double *bl)
+__device__ void nj_select_block(const double *A, const double *S, int n, int N, const double *pq, const long long *plin, int n_part,
+                                const long long *true_idx, NjSel *sel, unsigned long long *tree, double *bl, double *sq, long long *sl)
 {
-    __shared__ double sq[NJ_ARGMIN_THREADS];
-    __shared__ long long sl[NJ_ARGMIN_THREADS];
     double bq = INFINITY;
     long long blin = 0;
-    for (int k = threadIdx.x; k < n_part; k += blockDim.x)
-        if (nj_better(pq[k], plin[k], bq, blin)) { bq = pq[k]; blin = plin[k]; }
+    for (int k = threadIdx.x; k < n_part; k += blockDim.x) {
+        const double q = __ldcg(pq + k);
+        const long long l = __ldcg(plin + k);
+        if (nj_better(q, l, bq, blin)) { bq = q; blin = l; }
+    }
+    __syncthreads();
     sq[threadIdx.x] = bq; sl[threadIdx.x] = blin;
     __syncthreads();
     for (int w = NJ_ARGMIN_THREADS / 2; w > 0; w >>= 1) {
