@@ -64,7 +64,7 @@ __device__ __forceinline__ bool nj_better(double q, long long lin, double bq, lo
     return q < bq || (q == bq && lin < blin);
 }
 
-constexpr int NJ_ARGMIN_THREADS = 256;
+constexpr int NJ_ARGMIN_THREADS = 256, NJ_UNROLL = 4;
 
 // Block b scans rows b, b + gridDim.x, ...; its threads stride over the columns (coalesced, no index division).  The minimum is
 // taken over (q, linear index) pairs, so the traversal order does not matter: the winner is the first row-major minimum.
@@ -84,12 +84,12 @@ __global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A
         const double si = S[i];
         const long long base = (long long)i * n;
         int j = threadIdx.x;
-        for (; j + 3 * NJ_ARGMIN_THREADS < n; j += 4 * NJ_ARGMIN_THREADS) {        // four independent loads in flight
-            double a[4], sj[4];
+        for (; j + (NJ_UNROLL - 1) * NJ_ARGMIN_THREADS < n; j += NJ_UNROLL * NJ_ARGMIN_THREADS) {   // independent loads in flight
+            double a[NJ_UNROLL], sj[NJ_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { a[u] = row[j + u * NJ_ARGMIN_THREADS]; sj[u] = S[j + u * NJ_ARGMIN_THREADS]; }
+            for (int u = 0; u < NJ_UNROLL; ++u) { a[u] = __ldcs(row + j + u * NJ_ARGMIN_THREADS); sj[u] = S[j + u * NJ_ARGMIN_THREADS]; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < NJ_UNROLL; ++u) {
                 const int jj = j + u * NJ_ARGMIN_THREADS;
                 const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, a[u]), si), sj[u]);
                 if (jj != i && nj_better(q, base + jj, bq, blin)) { bq = q; blin = base + jj; }
