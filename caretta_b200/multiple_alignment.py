@@ -113,20 +113,19 @@ def get_engine() -> _engine.Engine:
 
 class _NodeAlignments(collections.abc.Mapping):
     """MultipleAlignment.final_alignments of the reference (multiple_alignment.py:181-183, :219-232): node name -> {member name ->
-    int64 index array}.  A read-only mapping over the stacked int32 index matrices progressive_align keeps per node; a node's
-    dictionary is built on first access (at N = 5000 the eager dictionaries are 140 000 arrays nobody may ever read)."""
+    int64 index array}, same keys and order.  A read-only mapping; a node's dictionary is composed from the stored pairwise
+    alignments when it is first read (at N = 5000 the eager dictionaries are 140 000 arrays nobody may ever read)."""
 
-    def __init__(self, names, members, matrices):
+    def __init__(self, names, build):
         self._index = {n: i for i, n in enumerate(names)}
-        self._names, self._members, self._matrices = list(names), members, matrices
+        self._names, self._build = list(names), build
         self._cache = {}
 
     def __getitem__(self, name):
         i = self._index[name]
         d = self._cache.get(i)
         if d is None:
-            r = self._matrices[i][:, :-1].astype(np.int64)
-            d = self._cache[i] = {m: r[k] for k, m in enumerate(self._members[i])}
+            d = self._cache[i] = self._build(i)
         return d
 
     def __iter__(self):
@@ -250,49 +249,45 @@ class MultipleAlignment:
         n_total = n_leaves + len(steps)
         final_sequences = [s for s in self.sequences] + [None] * len(steps)
         final_consensus_weights = [np.full((len(s), 1), consensus_weight, dtype=np.float64) for s in self.sequences] + [None] * len(steps)
-        # members[i]: names under node i (children's order: first child's members, then the second's, like the dict merge of :229-232);
-        # rows[i]: int32 [len(members), len(node i) + 1] = residue index of every member per column of node i, -1 = gap; the extra
-        # last column is a -1 sentinel, so that re-indexing by an alignment with -1 gaps is ONE gather (index -1 picks the sentinel)
-        members = [[s.name] for s in self.sequences] + [None] * len(steps)
-        rows = [None] * n_total
-        for i, s in enumerate(self.sequences):
-            r = np.empty((1, len(s) + 1), np.int32)
-            r[0, :-1] = np.arange(len(s), dtype=np.int32)
-            r[0, -1] = -1
-            rows[i] = r
+        # Bookkeeping.  The reference re-indexes the index arrays of EVERY member of both children at every node (:219-226), which
+        # is O(N x depth x length) in total.  Here a node only keeps its two alignments; index arrays are composed top-down when
+        # they are needed: the map (columns of a frame -> columns of node j) goes down the tree with one gather per edge, and at
+        # a leaf the map IS the index array.  The final alignment costs O(nodes x length); any node's final_alignments entry
+        # costs O(its subtree) when it is read.
         level = [0] * n_leaves + [0] * len(steps)
+        count = [1] * n_leaves + [0] * len(steps)                     # sequences under a node = len(final_alignments[name]) (:200-203)
         for q, (a, b, _) in enumerate(steps):
             if not (0 <= a < n_leaves + q and 0 <= b < n_leaves + q):
                 raise IndexError("tree refers to a node that does not exist yet")
             level[n_leaves + q] = 1 + max(level[a], level[b])
+            count[n_leaves + q] = count[a] + count[b]
         statuses = np.zeros(len(steps), np.int32)
-        in_parent_frame = {}                      # child index -> its members' rows re-indexed by the parent's alignment (:219-226)
-
+        node_len = [len(s) for s in self.sequences] + [0] * len(steps)
+        down = [None] * n_total                   # node -> (aln_1, aln_2) with a -1 sentinel appended: index -1 (gap) picks -1
+        parent_side = [None] * n_total            # child -> its side of the parent's alignment (columns of the parent -> columns of the child)
         use_pool = os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0" and os.environ.get("CARETTA_B200_MSA_POOL", "1") != "0" \
             and hasattr(eng, "msa_level")
-        node_len = [len(s) for s in self.sequences] + [0] * len(steps)
 
         def finish(q, res):
             a, b, name_int = steps[q]
-            aln_1, aln_2 = res[0], res[1]
-            statuses[q] = res[-1]
             i = n_leaves + q
-            k1, k2, ln = len(members[a]), len(members[b]), len(aln_1)
-            r = np.empty((k1 + k2, ln + 1), np.int32)
-            np.take(rows[a], aln_1, axis=1, out=r[:k1, :ln])          # aln == -1 -> the sentinel column -> -1
-            np.take(rows[b], aln_2, axis=1, out=r[k1:, :ln])
-            r[:, ln] = -1
-            in_parent_frame[a], in_parent_frame[b] = r[:k1], r[k1:]
-            members[i] = members[a] + members[b]
-            rows[i] = r
-            node_len[i] = ln
+            statuses[q] = res[-1]
+            ext = []
+            for al in (res[0], res[1]):
+                e = np.empty(len(al) + 1, np.int32)
+                e[:-1] = al
+                e[-1] = -1
+                ext.append(e)
+            down[i] = (ext[0], ext[1])
+            parent_side[a], parent_side[b] = ext[0][:-1], ext[1][:-1]
+            node_len[i] = len(res[0])
             if len(res) > 4:                                        # host path: the node itself comes back with the alignment
                 final_sequences[i] = Protein(name_int, res[2], res[3])
                 final_consensus_weights[i] = res[4]
 
         def multipliers(q):
             a, b, _ = steps[q]
-            l1, l2 = len(members[a]), len(members[b])
+            l1, l2 = count[a], count[b]
             return (l2 / (2 * (l1 + l2)), l1 / (2 * (l1 + l2)))         # multiplier_n1, multiplier_n2 (:200-203)
 
         def node_inputs(q):
@@ -330,15 +325,30 @@ class MultipleAlignment:
                 (c1, c2), (m1, m2) = node_inputs(q)
                 finish(q, eng.progressive_node(*c1, *c2, m1, m2, gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty))
 
-        # the reference's dictionaries: every node's entry is re-written in its parent's frame when the parent is made (:219-226),
-        # the parent's own entry is the merge of the two (:227-232).  Same keys, order and int64 arrays as the reference's
-        # final_alignments; the per-node dictionaries are materialised when they are read.
         node_names = [s.name for s in self.sequences] + [st[2] for st in steps]
-        final_alignments = _NodeAlignments(node_names, members, [in_parent_frame.get(i, rows[i]) for i in range(n_total)])
+
+        def leaf_maps(i, frame_map):
+            """[(leaf, int64 index array)] of the sequences under node i, first child's first (the dict merge order of :229-232);
+            frame_map: columns of the frame -> columns of node i (-1 = gap)."""
+            out, stack = [], [(i, frame_map)]
+            while stack:
+                j, mp = stack.pop()
+                if j < n_leaves:
+                    out.append((j, mp.astype(np.int64)))            # a leaf's columns are its residue indices
+                    continue
+                a, b = steps[j - n_leaves][0], steps[j - n_leaves][1]
+                stack.append((b, np.take(down[j][1], mp)))
+                stack.append((a, np.take(down[j][0], mp)))
+            return out
+
+        def node_alignments(i):
+            # every node's entry is re-written in its parent's frame when the parent is made (:219-226); the last node keeps its own
+            frame = parent_side[i] if parent_side[i] is not None else np.arange(node_len[i], dtype=np.int32)
+            return {node_names[leaf]: arr for leaf, arr in leaf_maps(i, frame)}
+
+        final_alignments = _NodeAlignments(node_names, node_alignments)
         last = n_total - 1
-        node_1, node_2 = steps[-1][0], steps[-1][1]
-        alignment = {**final_alignments[node_names[node_1]], **final_alignments[node_names[node_2]]}
-        assert list(alignment) == members[last]
+        alignment = {node_names[leaf]: arr for leaf, arr in leaf_maps(last, np.arange(node_len[last], dtype=np.int32))}
         self.final_consensus_weights = final_consensus_weights
         self.final_alignments = final_alignments
         self.final_sequences = final_sequences
