@@ -138,3 +138,19 @@ def test_level_call_with_mixed_shapes():
     o = O.progressive_node(*children[3][0], *children[3][1], *mults[3], 7.0, 0.03, 0.03, 1.0, 0.01)
     assert np.array_equal(got[3][0], o[0]) and np.array_equal(got[3][1], o[1])
     np.testing.assert_allclose(got[3][3], o[3], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("d", [3, 13, 16])
+def test_progressive_alignment_other_tensor_widths(d, monkeypatch):
+    """Tensor widths other than 10 through the whole progressive alignment (pool mode) against the oracle's restatement."""
+    ch = synth.make_chains(9, [44, 61, 38, 72, 55, 49, 66, 41, 58], d, seed=400 + d, family_size=3)
+    monkeypatch.setenv("CARETTA_B200_PRECISION", "fp64")
+    msa = MA.StructureMultiple.from_chains(ch)
+    S = msa.make_pairwise_matrix(dict(PARAMS))
+    aln = msa.multiple_align(np.max(S) - S, 1.0, 0.01, 1.0, 0.03, dict(PARAMS), None)
+    seqs = [(f"s{p}", *ch.chain(p)) for p in range(ch.n)]
+    want, fs, fw = O.progressive_align(seqs, msa.tree, 1.0, 0.01, 1.0, 0.03, 7.0, 0.03)
+    assert list(aln) == list(want) and all(np.array_equal(aln[k], want[k]) for k in want)
+    np.testing.assert_allclose(msa.final_sequences[-1].tensors, fs[-1][1], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(msa.final_sequences[-1].coordinates, fs[-1][2], rtol=0, atol=1e-9)
+    assert np.array_equal(msa.final_consensus_weights[-1], fw[-1])
