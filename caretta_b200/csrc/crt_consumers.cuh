@@ -227,8 +227,13 @@ __device__ __forceinline__ Fmt4 fmt4_decode(double x)
 
 __device__ __forceinline__ int u64_digits(unsigned long long v)
 {
-    int n = 1;
-    while (v >= 10ull) { v /= 10ull; ++n; }
+    if (v < 100000ull) {                                   // the usual case (a distance, a score): comparisons only
+        const unsigned u = (unsigned)v;
+        return 1 + (u >= 10u) + (u >= 100u) + (u >= 1000u) + (u >= 10000u);
+    }
+    int n = 5;
+    v /= 100000ull;
+    while (v) { v /= 10ull; ++n; }
     return n;
 }
 
@@ -290,8 +295,13 @@ __device__ __forceinline__ int fmt4_write(const Fmt4 &f, char *o)
     if (f.neg) o[k++] = '-';
     if (f.kind == 2) { o[k] = 'i'; o[k + 1] = 'n'; o[k + 2] = 'f'; return k + 3; }
     const int nd = u64_digits(f.ip);
-    unsigned long long v = f.ip;
-    for (int z = nd - 1; z >= 0; --z) { o[k + z] = (char)('0' + (int)(v % 10ull)); v /= 10ull; }
+    if (f.ip < 4294967296ull) {                              // 32-bit digit loop (division by a constant = multiply + shift)
+        unsigned v = (unsigned)f.ip;
+        for (int z = nd - 1; z >= 0; --z) { o[k + z] = (char)('0' + v % 10u); v /= 10u; }
+    } else {
+        unsigned long long v = f.ip;
+        for (int z = nd - 1; z >= 0; --z) { o[k + z] = (char)('0' + (int)(v % 10ull)); v /= 10ull; }
+    }
     k += nd;
     unsigned q = f.frac;
     o[k] = '.';
@@ -386,12 +396,10 @@ __global__ void __launch_bounds__(FMT_THREADS) k_fmt_write(const double *M, int 
         const char sep = (j == C - 1) ? '\n' : ' ';
         const int shift = (int)((unsigned long long)(dst + base) & 15ull);
         if (!big && shift + total <= FMT_STAGE) {
-            if (j < C) {
-                char buf[28];
-                const int n = fmt4_write(f, buf);
-                buf[n] = sep;
+            if (j < C) {                                                // digits go straight into the staging tile (no local buffer)
                 char *s = stage + shift + off;
-                for (int k = 0; k <= n; ++k) s[k] = buf[k];
+                const int n = fmt4_write(f, s);
+                s[n] = sep;
             }
             __syncthreads();
             char *g = dst + base - shift;                               // 16-byte aligned
