@@ -47,7 +47,10 @@ int level_core(crt_ctx *c, crt_ctx *nc, int32_t n_nodes, int32_t d, const int64_
         p.aln_off = offsets[2 * k];
         max_cells = std::max(max_cells, (long long)p.n * p.m);
     }
-    const long long cell_budget = std::max<long long>(max_cells, (long long)std::min<size_t>(c->mem_total / 4, (size_t)24 << 30) / 9);
+    // score matrix + backtrack bytes: 9 B per cell, bounded by min(memory / 4, 24 GB); CARETTA_B200_LEVEL_CELLS overrides (tests)
+    long long cell_budget = (long long)std::min<size_t>(c->mem_total / 4, (size_t)24 << 30) / 9;
+    if (const char *e = getenv("CARETTA_B200_LEVEL_CELLS")) { const long long v = atoll(e); if (v > 0) cell_budget = v; }
+    cell_budget = std::max<long long>(max_cells, cell_budget);
     if ((rc = c->lv_probs.ensure((size_t)n_nodes))) return rc;
     if ((rc = c->lv_mult.ensure((size_t)n_nodes * 2))) return rc;
     if ((rc = c->lv_xf2.ensure((size_t)n_nodes * XF))) return rc;

@@ -154,3 +154,23 @@ def test_progressive_alignment_other_tensor_widths(d, monkeypatch):
     np.testing.assert_allclose(msa.final_sequences[-1].tensors, fs[-1][1], rtol=0, atol=1e-12)
     np.testing.assert_allclose(msa.final_sequences[-1].coordinates, fs[-1][2], rtol=0, atol=1e-9)
     assert np.array_equal(msa.final_consensus_weights[-1], fw[-1])
+
+
+def test_level_is_cut_into_chunks_under_a_small_workspace(monkeypatch):
+    """A level whose score matrices exceed the workspace budget runs in several chunks of nodes: same results."""
+    rng = np.random.default_rng(6)
+    eng = MA.get_engine()
+    children, mults = [], []
+    for q in range(11):
+        n, m = int(rng.integers(20, 90)), int(rng.integers(20, 90))
+        ch = synth.make_chains(2, [n, m], 10, seed=500 + q, family_size=2)
+        (t1, c1), (t2, c2) = ch.chain(0), ch.chain(1)
+        children.append(((t1, c1, np.full((n, 1), 1.0 + q % 3)), (t2, c2, np.full((m, 1), 2.0))))
+        mults.append((0.2 + 0.01 * q, 0.3))
+    monkeypatch.delenv("CARETTA_B200_LEVEL_CELLS", raising=False)
+    want = eng.progressive_level(children, mults, 7.0, 0.03, 0.03, 1.0, 0.01)
+    monkeypatch.setenv("CARETTA_B200_LEVEL_CELLS", "9000")                 # 2-3 nodes per chunk
+    got = eng.progressive_level(children, mults, 7.0, 0.03, 0.03, 1.0, 0.01)
+    for g_, w_ in zip(got, want):
+        for x, y in zip(g_, w_):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
