@@ -618,6 +618,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         ta.rec64 = c->rec64.p; ta.d64 = c->D; ta.neg_gamma_t = -prm->gamma_tensor;
         ta.scale2 = (float)std::sqrt(prm->gamma_coords * 1.4426950408889634);
         ta.precision = prec;
+        ta.skip_byproducts = c->stage1_only ? 1 : 0;
         int r2;
         if ((r2 = launch_trace<10>(b.C, ta, nu, b.n_dense, st))) return r2;
         if (mid) CU(cudaEventRecord(mid, st));

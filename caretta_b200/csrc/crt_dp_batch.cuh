@@ -14,6 +14,7 @@ namespace crt {
 
 constexpr int DPC = 4;                // columns per lane
 constexpr int DPSTRIP = 32 * DPC;
+constexpr int DTW_PF = 4;             // wavefront steps of prefetch distance in k_dtw_fill
 
 struct DpProblem {
     long long s_off;      // offset of S (doubles)
@@ -48,25 +49,37 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
         double out1 = 0.0, out2 = 0.0;       // M[i][cend][1], [2] handed to lane + 1
         double dsave = 0.0;                  // M[i-1][c0-1][1]
         const bool last_strip = strip == n_strips - 1;
-        // the scores of step t + 1 are loaded while step t computes (they do not depend on the recurrence)
-        double sn[DPC];
-        auto load_scores = [&](int t) {
+        // Scores and (strips > 0) the boundary column do not depend on the recurrence: they are loaded DTW_PF wavefront steps
+        // ahead into a register ring (an L2 round trip is several steps long), the loop is unrolled by the ring size so that
+        // every slot index is a compile-time constant.
+        double sn[DTW_PF][DPC], bq1[DTW_PF], bq2[DTW_PF];
+        auto prefetch = [&](int t, double (&dst)[DPC], double &q1, double &q2) {
             const int i = t - lane + 1;
+            const bool ok = i >= 1 && i <= n;
 #pragma unroll
-            for (int c = 0; c < DPC; ++c) sn[c] = (i >= 1 && i <= n && c0 + c < m) ? S[(long long)(i - 1) * m + c0 + c] : 0.0;
+            for (int c = 0; c < DPC; ++c) dst[c] = (ok && c0 + c < m) ? S[(long long)(i - 1) * m + c0 + c] : 0.0;
+            q1 = 0.0; q2 = 0.0;
+            if (lane == 0 && strip > 0 && ok) { q1 = bnd1[i - 1]; q2 = bnd2[i - 1]; }
         };
-        load_scores(0);
-        for (int t = 0; t < n + 31; ++t) {
+#pragma unroll
+        for (int u = 0; u < DTW_PF; ++u) prefetch(u, sn[u], bq1[u], bq2[u]);
+        const int T = n + 31;
+        for (int t0 = 0; t0 < T; t0 += DTW_PF) {
+#pragma unroll
+          for (int u = 0; u < DTW_PF; ++u) {
+            const int t = t0 + u;
+            if (t >= T) break;
             const int i = t - lane + 1;      // 1-based row
             const bool valid = i >= 1 && i <= n;
             double sc[DPC];
 #pragma unroll
-            for (int c = 0; c < DPC; ++c) sc[c] = sn[c];
-            load_scores(t + 1);
+            for (int c = 0; c < DPC; ++c) sc[c] = sn[u][c];
+            const double b1 = bq1[u], b2 = bq2[u];
+            prefetch(t + DTW_PF, sn[u], bq1[u], bq2[u]);
             double L1 = shfl_up_d(out1), L2 = shfl_up_d(out2);
             if (lane == 0) {
                 if (strip == 0) { L1 = 0.0; L2 = MINF - open; }       // column 0: (0, 0, MIN - open)
-                else if (valid) { L1 = bnd1[i - 1]; L2 = bnd2[i - 1]; }
+                else if (valid) { L1 = b1; L2 = b2; }
             }
             if (i == 1) dsave = 0.0;          // M[0][j][1] = 0
             const double in1 = L1;
@@ -96,6 +109,7 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
                 dsave = in1;
                 if (!last_strip && lane == 31) { bnd1[i - 1] = out1; bnd2[i - 1] = out2; }
             }
+          }
         }
         __syncwarp();
     }

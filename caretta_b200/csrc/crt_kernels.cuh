@@ -376,6 +376,7 @@ struct TraceArgs {
     const double *rec64; int d64; double neg_gamma_t;
     float scale2;                 // sqrt(gamma_c * log2 e) (fp32 only)
     int precision;                // 0 fp64, 1 fp32
+    int skip_byproducts;          // 1: no RMSD / TM pass over the path (node contexts only use the transform)
 };
 
 __device__ inline bool s1_is_zero(const TraceArgs &a, long long ri, long long ci)
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
     xf[15] = superpose ? 1.0 : 0.0;
     // ---- pass 3: by-products over the matched residues, ascending residue order like the reference's sums
     double rmsd = 0.0, tm = 0.0;
-    if (c >= 1) {
+    if (c >= 1 && !a.skip_byproducts) {
         const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
         double ss = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll 2
