@@ -695,7 +695,16 @@ __global__ void k_centroid(PrepArgs a)
     if (ch >= a.n_chains) return;
     double s[3] = {0, 0, 0};
     const long long b = a.offsets[ch], e = a.offsets[ch + 1];
-    for (long long r = b; r < e; ++r)
+    // same left-to-right sums; eight residues of loads are issued before their adds (one thread walks a whole chain)
+    long long r = b;
+    for (; r + 8 <= e; r += 8) {
+        double v[24];
+#pragma unroll
+        for (int q = 0; q < 24; ++q) v[q] = a.coords[r * 3 + q];
+#pragma unroll
+        for (int q = 0; q < 24; ++q) s[q % 3] += v[q];
+    }
+    for (; r < e; ++r)
         for (int k = 0; k < 3; ++k) s[k] += a.coords[r * 3 + k];
     const double inv = e > b ? 1.0 / (double)(e - b) : 0.0;
     for (int k = 0; k < 3; ++k) a.centroid[(long long)ch * 3 + k] = s[k] * inv;

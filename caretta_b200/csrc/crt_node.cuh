@@ -70,25 +70,51 @@ __global__ void __launch_bounds__(256) k_level_score(const DpProblem *probs, con
 // One thread: the sums run in alignment order like helper.nb_mean_axis_0 (helper.py:45-53).  xf2: same record layout as xf.
 __device__ inline void node_kabsch_one(const double *c1, const double *c2, const int *aln1, const int *aln2, int len, double *xf2)
 {
+    // The sums run in alignment order (one thread); the loads of four columns are issued together before their adds, so that
+    // the walk is not one memory round trip per column.
     int c = 0;
     double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
-    for (int q = 0; q < len; ++q) {
-        const int x = aln1[q], y = aln2[q];
-        if (x < 0 || y < 0) continue;
-        ++c;
-        for (int k = 0; k < 3; ++k) { s1[k] += c1[x * 3 + k]; s2[k] += c2[y * 3 + k]; }
+    for (int q0 = 0; q0 < len; q0 += 4) {
+        int xs[4], ys[4];
+        double v1[4][3], v2[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xs[u] = q0 + u < len ? aln1[q0 + u] : -1; ys[u] = q0 + u < len ? aln2[q0 + u] : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool ok = xs[u] >= 0 && ys[u] >= 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { v1[u][k] = ok ? c1[xs[u] * 3 + k] : 0.0; v2[u][k] = ok ? c2[ys[u] * 3 + k] : 0.0; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (xs[u] < 0 || ys[u] < 0) continue;
+            ++c;
+            for (int k = 0; k < 3; ++k) { s1[k] += v1[u][k]; s2[k] += v2[u][k]; }
+        }
     }
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
     const bool superpose = c > 3;
     if (superpose) {
         for (int k = 0; k < 3; ++k) { m1[k] = s1[k] / (double)c; m2[k] = s2[k] / (double)c; }
         double Cm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int q = 0; q < len; ++q) {
-            const int x = aln1[q], y = aln2[q];
-            if (x < 0 || y < 0) continue;
-            for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < 3; ++b)
-                    Cm[a * 3 + b] = __dadd_rn(Cm[a * 3 + b], __dmul_rn(__dsub_rn(c2[y * 3 + a], m2[a]), __dsub_rn(c1[x * 3 + b], m1[b])));
+        for (int q0 = 0; q0 < len; q0 += 4) {
+            int xs[4], ys[4];
+            double v1[4][3], v2[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { xs[u] = q0 + u < len ? aln1[q0 + u] : -1; ys[u] = q0 + u < len ? aln2[q0 + u] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = xs[u] >= 0 && ys[u] >= 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { v1[u][k] = ok ? c1[xs[u] * 3 + k] : 0.0; v2[u][k] = ok ? c2[ys[u] * 3 + k] : 0.0; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (xs[u] < 0 || ys[u] < 0) continue;
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        Cm[a * 3 + b] = __dadd_rn(Cm[a * 3 + b], __dmul_rn(__dsub_rn(v2[u][a], m2[a]), __dsub_rn(v1[u][b], m1[b])));
+            }
         }
         kabsch_rotation(Cm, R);
     }
