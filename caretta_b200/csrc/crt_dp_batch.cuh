@@ -149,6 +149,74 @@ __global__ void k_dtw_trace(const DpProblem *probs, int n_probs, const unsigned 
     aln_len[p] = k;
 }
 
+// The same traceback with one warp per problem: the backtrack bytes the walk can reach next -- a tile of DTT_ROWS rows x DTT_COLS
+// columns ending at the current cell -- are fetched by the whole warp (one row per lane, aligned 32-bit loads) into shared
+// memory, lane 0 walks inside the tile, and the warp reloads when the walk leaves it.  One memory round trip per tile instead
+// of one per step; identical output.
+constexpr int DTT_ROWS = 32, DTT_COLS = 64, DTT_WORDS = DTT_COLS / 4 + 1;
+
+__global__ void __launch_bounds__(32) k_dtw_trace_w(const DpProblem *probs, int n_probs, const unsigned char *B_all, const double *final3,
+                                                    int *aln1, int *aln2, int *aln_len, double *score)
+{
+    __shared__ unsigned tile[DTT_ROWS][DTT_WORDS + 1];
+    __shared__ int tshift[DTT_ROWS];
+    const int p = blockIdx.x, lane = threadIdx.x;
+    if (p >= n_probs) return;
+    const DpProblem pr = probs[p];
+    const unsigned char *B = B_all + pr.b_off;
+    const double f0 = final3[p * 3], f1 = final3[p * 3 + 1], f2 = final3[p * 3 + 2];
+    int dir = 0; double best = f0;
+    if (f1 > best) { best = f1; dir = 1; }
+    if (f2 > best) { best = f2; dir = 2; }
+    if (lane == 0) score[p] = best;
+    int *a1 = aln1 + pr.aln_off, *a2 = aln2 + pr.aln_off;
+    int n = pr.n, m = pr.m, k = 0;
+    const int mm = pr.m;
+    while (!(n == 0 && m == 0)) {
+        // tile = rows r_lo..n-1, columns c_lo..m-1 of B (empty when the walk is on a border: no byte is needed there)
+        const int r_hi = n - 1, c_hi = m - 1;
+        const int r_lo = max(0, r_hi - DTT_ROWS + 1), c_lo = max(0, c_hi - DTT_COLS + 1);
+        if (n > 0 && m > 0) {
+            const int r = r_lo + lane;
+            if (r <= r_hi) {
+                const unsigned long long addr = (unsigned long long)(B + (long long)r * mm + c_lo);
+                const unsigned *src = reinterpret_cast<const unsigned *>(addr & ~3ull);
+                const int sh = (int)(addr & 3ull);
+                const int words = (sh + (c_hi - c_lo + 1) + 3) >> 2;
+                for (int w = 0; w < words; ++w) tile[lane][w] = src[w];
+                tshift[lane] = sh;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            while (!(n == 0 && m == 0)) {
+                if (m == 0) { --n; a1[k] = n; a2[k] = -1; ++k; }
+                else if (n == 0) { --m; a1[k] = -1; a2[k] = m; ++k; }
+                else {
+                    if (n - 1 < r_lo || m - 1 < c_lo) break;                 // left the tile
+                    const int rr = n - 1 - r_lo, bo = tshift[rr] + (m - 1 - c_lo);
+                    const unsigned b = (tile[rr][bo >> 2] >> ((bo & 3) * 8)) & 0xffu;
+                    if (dir == 0) { dir = b & 1; --n; a1[k] = n; a2[k] = -1; ++k; }
+                    else if (dir == 1) {
+                        dir = (b >> 1) & 3;
+                        if (dir == 1) { --n; --m; a1[k] = n; a2[k] = m; ++k; }
+                    } else { dir = ((b >> 3) & 1) + 1; --m; a1[k] = -1; a2[k] = m; ++k; }
+                }
+            }
+        }
+        n = __shfl_sync(FULL, n, 0); m = __shfl_sync(FULL, m, 0); dir = __shfl_sync(FULL, dir, 0); k = __shfl_sync(FULL, k, 0);
+        __syncwarp();
+    }
+    __syncwarp();
+    for (int x = lane; x < k / 2; x += 32) {                                 // the walk wrote the path backwards
+        const int y = k - 1 - x;
+        const int t1 = a1[x], t2 = a2[x];
+        a1[x] = a1[y]; a2[x] = a2[y];
+        a1[y] = t1; a2[y] = t2;
+    }
+    if (lane == 0) aln_len[p] = k;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Smith-Waterman with a linear gap (any value), H stored in fp64; first row-major maximum; literal traceback.
 // ------------------------------------------------------------------------------------------------------------

@@ -95,7 +95,7 @@ int level_core(crt_ctx *c, crt_ctx *nc, int32_t n_nodes, int32_t d, const int64_
                                                                                        c->lv_mult.p + (size_t)k0 * 2, -lp.gamma_coords,
                                                                                        -lp.gamma_weight, c->nd_S.p);
         k_dtw_fill<<<nk, 32, 0, st>>>(dp, nk, c->nd_S.p, c->nd_B.p, c->nd_bnd.p, c->nd_f.p + (size_t)k0 * 3, lp.gap_open, lp.gap_extend);
-        k_dtw_trace<<<(nk + 31) / 32, 32, 0, st>>>(dp, nk, c->nd_B.p, c->nd_f.p + (size_t)k0 * 3, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0,
+        k_dtw_trace_w<<<nk, 32, 0, st>>>(dp, nk, c->nd_B.p, c->nd_f.p + (size_t)k0 * 3, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0,
                                                    c->nd_score.p + k0);
         k_level_kabsch<<<(nk + 31) / 32, 32, 0, st>>>(dp, nk, nc->coords.p, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0, c->lv_xf2.p + (size_t)k0 * XF);
         k_level_mean<<<dim3((unsigned)((ml + 127) / 128), (unsigned)nk), 128, 0, st>>>(dp, nc->tensors.p, nc->coords.p, c->nd_w.p, d, c->nd_a1.p,
