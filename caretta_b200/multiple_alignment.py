@@ -500,42 +500,47 @@ def make_coverage_gap_distance_matrix(alignment_array):
 
 
 def get_reference_structures(alignment, minimum_coverage=50, gap=-1):
-    """multiple_alignment.py:740-784 with the O(N^2 A) matrix computed on the device; the greedy selection over that matrix is
-    the reference's.  Returns (first reference name, {reference name: [member names]}, [names that align to nobody])."""
+    """multiple_alignment.py:740-784: a set of reference structures such that every structure shares at least
+    minimum_coverage % of its residues with the reference it is assigned to.  The O(N^2 A) counting runs on the device
+    (crt_coverage_gap_matrix); the greedy choice over the two N x N matrices is host logic with the reference's rules:
+    the first reference minimises the median gap fraction, every further one is the already assigned structure with the
+    smallest median gap fraction towards the structures still waiting (plain minimum when only one waits).
+    Returns (first reference name, {reference name: [member names]}, [names that align to nobody])."""
     _check_gap(gap)
-    names = list(alignment.keys())
-    alignment_array = _aln_array(alignment, names)
-    distance_matrix, matrix_aligning = make_coverage_gap_distance_matrix(alignment_array)
-    minimum_coverage = np.array([minimum_coverage * int((alignment_array[i] != gap).sum()) / 100 for i in range(len(names))])
-    reference_structures = {}
-    first_reference_structure = int(np.argmin(np.median(distance_matrix, axis=0)))
-    not_covered = np.where(matrix_aligning[:, first_reference_structure] < minimum_coverage[:])[0]
-    covered = list(np.where(matrix_aligning[:, first_reference_structure] >= minimum_coverage[:])[0])
-    reference_structures[first_reference_structure] = [names[c] for c in covered]
-    problematic = []
-    while len(not_covered) > 0:
-        if len(not_covered) > 1:
-            reference_structure = covered[int(np.argmin(np.median(distance_matrix[not_covered, :][:, covered], axis=0)))]
-        else:
-            reference_structure = covered[int(np.argmin(distance_matrix[not_covered, :][:, covered]))]
-        covered_i = not_covered[np.where(matrix_aligning[not_covered, reference_structure] >= minimum_coverage[not_covered])[0]]
-        if len(covered_i) == 0:
-            problematic += list(not_covered)
+    names = list(alignment)
+    aln = _aln_array(alignment, names)
+    gap_fraction, shared = make_coverage_gap_distance_matrix(aln)
+    need = minimum_coverage * (aln != gap).sum(axis=1) / 100            # residues a structure must share with its reference
+
+    def split(ref, who):
+        ok = shared[who, ref] >= need[who]
+        return who[ok], who[~ok]
+
+    groups = {}                                                         # reference index -> member indices, insertion order
+    first = int(np.argmin(np.median(gap_fraction, axis=0)))
+    taken, waiting = split(first, np.arange(len(names)))
+    groups[first] = [int(i) for i in taken]
+    assigned = list(groups[first])
+    stranded = []
+    while waiting.size:
+        towards = gap_fraction[np.ix_(waiting, assigned)]
+        pick = np.argmin(np.median(towards, axis=0)) if waiting.size > 1 else np.argmin(towards)
+        ref = assigned[int(pick)]
+        taken, rest = split(ref, waiting)
+        if taken.size == 0:                                             # nobody can take the rest: try them one by one below
+            stranded = [int(i) for i in waiting]
             break
-        not_covered = not_covered[np.where(matrix_aligning[not_covered, reference_structure] < minimum_coverage[not_covered])[0]]
-        reference_structures[reference_structure] = [names[c] for c in covered_i]
-        covered += list(covered_i)
-    no_aligning = []
-    for i in problematic:
-        found = False
-        for j in covered:
-            if matrix_aligning[i, j] >= minimum_coverage[i]:
-                reference_structures[j].append(names[i])
-                found = True
-                break
-        if not found:
-            no_aligning.append(names[i])
-    return names[first_reference_structure], {names[k]: v for k, v in reference_structures.items()}, no_aligning
+        groups[ref] = [int(i) for i in taken]
+        assigned += groups[ref]
+        waiting = rest
+    alone = []
+    for i in stranded:
+        home = next((j for j in assigned if shared[i, j] >= need[i]), None)
+        if home is None:
+            alone.append(names[i])
+        else:
+            groups[home].append(i)
+    return names[first], {names[r]: [names[i] for i in members] for r, members in groups.items()}, alone
 
 
 def _superpose_on_device(alignment, proteins, mode, reference_name=None, core_indices=None):

@@ -97,3 +97,20 @@ def test_tree_with_forward_reference_is_rejected(monkeypatch):
     bad = np.array([[0, 3], [4, 3], [3, 2]], dtype=np.uint64)       # node 4 does not exist when node 3 is built
     with pytest.raises(IndexError):
         msa.progressive_align(bad, 1.0, 0.01, 1.0, 0.03, dict(gamma_tensor=7.0, gamma_coords=0.03), None)
+
+
+@pytest.mark.parametrize("name", ["fam8", "ragged12", "blocks", "sparse"])
+def test_reference_structure_selection(monkeypatch, name):
+    """get_reference_structures (host logic over the device-made coverage matrices) against the reference's own output; the
+    oracle's coverage matrix stands in for the device call."""
+    from tests import consumer_cases as CC
+    cons = CC.load()
+    monkeypatch.setattr(MA, "make_coverage_gap_distance_matrix", lambda a: O.coverage_gap_matrix(a))
+    names = [str(x) for x in cons[f"{name}_pnames"]]
+    alignment = {n: cons[f"{name}_aln"][p] for p, n in enumerate(names)}
+    for mc in (50, 80):
+        first, refs, alone = MA.get_reference_structures(alignment, mc)
+        gfirst, grefs, gno = CC.reference_groups(cons, name, mc)
+        assert first == names[gfirst]
+        assert list(refs.items()) == [(names[k], [names[x] for x in v]) for k, v in grefs.items()]
+        assert alone == [names[x] for x in gno]
