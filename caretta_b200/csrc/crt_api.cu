@@ -501,8 +501,11 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     const size_t row2sz = f32 ? 16 : 32;
     const int rs32 = ((c->D + 2 + 3) / 4) * 4;
     const bool want_paths = sink && sink->want;
+    // Protein.score_function(flexible=True) (multiple_alignment.py:323-326): the score matrix is the tensor Gaussian alone, so the
+    // pair score is the stage-1 Smith-Waterman score; no traceback, no superposition, no stage 2
+    const bool flexible = (prm->flags & CRT_FLEXIBLE) != 0;
     const int NS = want_paths ? 1 : env_streams();
-    const bool pipe = !want_paths && NS > 1 && env_pipe();
+    const bool pipe = !want_paths && NS > 1 && env_pipe() && !flexible;
     const int NW = pipe ? 4 : NS;                 // workspace sets in flight
     int rc;
     if ((rc = c->score.ensure((size_t)n_pairs + 1))) return rc;
@@ -515,6 +518,13 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     if ((rc = c->pair_zflag.ensure((size_t)n_pairs + 1))) return rc;
     if ((rc = c->path_len.ensure((size_t)n_pairs + 1))) return rc;
     if ((rc = c->xform.ensure(((size_t)n_pairs + 1) * XF))) return rc;
+    if (flexible) {
+        if (want_paths) return fail(CRT_E_ARG, "flexible scoring has no alignment paths (the reference only takes the score)");
+        CU(cudaMemsetAsync(c->rmsd.p, 0, sizeof(double) * (size_t)n_pairs, c->stream));
+        CU(cudaMemsetAsync(c->tm.p, 0, sizeof(double) * (size_t)n_pairs, c->stream));
+        CU(cudaMemsetAsync(c->ncommon.p, 0, sizeof(int) * (size_t)n_pairs, c->stream));
+        CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)n_pairs, c->stream));
+    }
     if (want_paths) { sink->a1.assign((size_t)n_pairs, {}); sink->a2.assign((size_t)n_pairs, {}); }
 
     std::vector<Batch> batches;
@@ -594,7 +604,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         const int nu = (int)b.count;
         FillOut fo{};
         fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
-        fo.pair_score = c->score1.p; fo.bnd = ws.bnd.p;
+        fo.pair_score = flexible ? c->score.p : c->score1.p; fo.bnd = ws.bnd.p;
         if (f32) {
             Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
             if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
@@ -608,6 +618,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     auto stage_trace = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st, cudaEvent_t mid) -> int {
         const Unit *du = c->d_units.p + b.first;
         const int nu = (int)b.count;
+        if (flexible) { if (mid) CU(cudaEventRecord(mid, st)); return 0; }
         TraceArgs ta{};
         ta.units = du; ta.tb = ws.tb.p; ta.pair_istar = c->pair_istar.p; ta.pair_zflag = c->pair_zflag.p;
         ta.offsets = c->d_offsets.p; ta.coords = c->coords.p; ta.centroid = c->centroid.p;
@@ -633,7 +644,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         FillOut fo{};
         fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
         fo.pair_score = c->score.p; fo.bnd = pipe ? ws.bnd2.p : ws.bnd.p;
-        if (c->stage1_only) return 0;
+        if (c->stage1_only || flexible) return 0;
         if (f32) {
             Fill2Args a{reinterpret_cast<const float4 *>(ws.rows2.p) + ROW_PAD, c->cols2.p};
             return launch_fill2_f32(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
@@ -718,7 +729,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         if ((rc = stage_trace(b, ws, st, timed ? ws.ev[2] : nullptr))) return rc;
         if ((rc = stage2(b, ws, st))) return rc;
         if (timed) CU(cudaEventRecord(ws.ev[3], st));
-        c->launches += 4;
+        c->launches += flexible ? 1 : 4;
 
         if (timed) {
             // one stream: phase timing (and, for the tests, the paths) per batch
@@ -771,6 +782,7 @@ int check_params(const crt_ctx *c, const crt_params *prm)
     if (prm->precision != CRT_FP64 && prm->precision != CRT_FP32) return fail(CRT_E_ARG, "precision must be CRT_FP64 or CRT_FP32");
     if (prm->sw_gap != 0.0) return fail(CRT_E_ARG, "sw_gap != 0 is not on the reference's pair path (multiple_alignment.py:335, :164)");
     if (!(prm->gamma_tensor >= 0) || !(prm->gamma_coords >= 0)) return fail(CRT_E_ARG, "gamma must be >= 0");
+    if (prm->flags & ~CRT_FLEXIBLE) return fail(CRT_E_ARG, "unknown flags 0x%x", (unsigned)prm->flags);
     return 0;
 }
 
@@ -1474,6 +1486,19 @@ int crt_progressive_node(crt_ctx *c, const double *tensors1, const double *coord
         !tensors_mean || !coords_mean || !weights_mean)
         return fail(CRT_E_ARG, "null argument");
     if (n <= 0 || m <= 0) return fail(CRT_E_ARG, "empty sequence (%d x %d)", n, m);
+    if (gamma_coords < 0.0) {            // flexible=True: the level path with one node (same kernels, same outputs)
+        std::vector<double> pt((size_t)(n + m) * d), pc((size_t)(n + m) * 3), pw((size_t)n + m);
+        std::memcpy(pt.data(), tensors1, sizeof(double) * (size_t)n * d);
+        std::memcpy(pt.data() + (size_t)n * d, tensors2, sizeof(double) * (size_t)m * d);
+        std::memcpy(pc.data(), coords1, sizeof(double) * (size_t)n * 3);
+        std::memcpy(pc.data() + (size_t)n * 3, coords2, sizeof(double) * (size_t)m * 3);
+        std::memcpy(pw.data(), weights1, sizeof(double) * (size_t)n);
+        std::memcpy(pw.data() + n, weights2, sizeof(double) * (size_t)m);
+        const int64_t off[3] = {0, n, (int64_t)n + m};
+        const double mult[2] = {mult1, mult2};
+        return crt_progressive_level(c, 1, d, pt.data(), pc.data(), pw.data(), off, mult, gamma_tensor, gamma_coords, gamma_weight, gap_open,
+                                     gap_extend, aln1, aln2, aln_len, tensors_mean, coords_mean, weights_mean, score, status);
+    }
     CU(cudaSetDevice(c->device));
     int rc;
     if (!c->node_ctx && (rc = crt_create(c->device, &c->node_ctx))) return rc;

@@ -16,6 +16,10 @@ double now_ms()
 
 struct LevelParams {
     double gamma_tensor, gamma_coords, gamma_weight, gap_open, gap_extend;
+    // the C ABI's sentinels in gamma_coords: CRT_GAMMA_COORDS_FLEXIBLE (-1) = score_function and mean_function flexible=True,
+    // CRT_GAMMA_COORDS_FLEXIBLE_SCORE (-2) = score_function flexible=True only (the node still superposes its coordinates)
+    bool flexible() const { return gamma_coords < 0.0; }
+    bool flexible_mean() const { return gamma_coords < 0.0 && gamma_coords > -1.5; }
 };
 
 // The level on a chain set that is already in the node context `nc` (children 2k, 2k+1 = node k, packed offsets `offsets`) with
@@ -31,11 +35,19 @@ int level_core(crt_ctx *c, crt_ctx *nc, int32_t n_nodes, int32_t d, const int64_
     std::vector<int32_t> pi((size_t)n_nodes), pj((size_t)n_nodes), st1((size_t)n_nodes);
     for (int k = 0; k < n_nodes; ++k) { pi[(size_t)k] = 2 * k; pj[(size_t)k] = 2 * k + 1; }
     // ---- stage 1 of score_function for every node: the fp64 pair kernels on the packed children, pairs (2k, 2k+1)
-    if ((rc = crt_pairwise_list(nc, &prm, pi.data(), pj.data(), n_nodes, nullptr, nullptr, nullptr, nullptr, st1.data(), nullptr, nullptr,
-                                nullptr, 0)))
-        return rc;
-    const double pair_ms = nc->elapsed_ms;
-    long long launches = nc->launches;
+    //      (flexible nodes score on the tensors alone: no stage-1 alignment, no superposition)
+    const bool flexible = lp.flexible();
+    double pair_ms = 0.0;
+    long long launches = 0;
+    if (!flexible) {
+        if ((rc = crt_pairwise_list(nc, &prm, pi.data(), pj.data(), n_nodes, nullptr, nullptr, nullptr, nullptr, st1.data(), nullptr, nullptr,
+                                    nullptr, 0)))
+            return rc;
+        pair_ms = nc->elapsed_ms;
+        launches = nc->launches;
+    } else {
+        std::fill(st1.begin(), st1.end(), 0);
+    }
     // ---- score matrices, affine DTW and the intermediate nodes, in chunks of nodes bounded by the workspace budget
     const long long total = offsets[2 * n_nodes];
     std::vector<DpProblem> probs((size_t)n_nodes);
@@ -91,13 +103,21 @@ int level_core(crt_ctx *c, crt_ctx *nc, int32_t n_nodes, int32_t d, const int64_
             mc = std::max(mc, (long long)probs[(size_t)k].n * probs[(size_t)k].m);
             ml = std::max(ml, probs[(size_t)k].n + probs[(size_t)k].m);
         }
-        k_level_score<<<dim3((unsigned)((mc + 255) / 256), (unsigned)nk), 256, 0, st>>>(dp, nc->coords.p, c->nd_w.p, nc->xform.p + (size_t)k0 * XF,
-                                                                                       c->lv_mult.p + (size_t)k0 * 2, -lp.gamma_coords,
-                                                                                       -lp.gamma_weight, c->nd_S.p);
+        if (flexible)
+            k_level_score_flex<<<dim3((unsigned)((mc + 255) / 256), (unsigned)nk), 256, 0, st>>>(dp, nc->tensors.p, d, c->nd_w.p,
+                                                                                                c->lv_mult.p + (size_t)k0 * 2,
+                                                                                                -lp.gamma_tensor, -lp.gamma_weight, c->nd_S.p);
+        else
+            k_level_score<<<dim3((unsigned)((mc + 255) / 256), (unsigned)nk), 256, 0, st>>>(dp, nc->coords.p, c->nd_w.p, nc->xform.p + (size_t)k0 * XF,
+                                                                                           c->lv_mult.p + (size_t)k0 * 2, -lp.gamma_coords,
+                                                                                           -lp.gamma_weight, c->nd_S.p);
         k_dtw_fill<<<nk, 32, 0, st>>>(dp, nk, c->nd_S.p, c->nd_B.p, c->nd_bnd.p, c->nd_f.p + (size_t)k0 * 3, lp.gap_open, lp.gap_extend);
         k_dtw_trace_w<<<nk, 32, 0, st>>>(dp, nk, c->nd_B.p, c->nd_f.p + (size_t)k0 * 3, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0,
                                                    c->nd_score.p + k0);
-        k_level_kabsch<<<(nk + 31) / 32, 32, 0, st>>>(dp, nk, nc->coords.p, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0, c->lv_xf2.p + (size_t)k0 * XF);
+        if (lp.flexible_mean())   // mean_function(flexible=True) makes no coordinates (:359-360): flag 0 = no superposition, raw means (unused)
+            CU(cudaMemsetAsync(c->lv_xf2.p + (size_t)k0 * XF, 0, sizeof(double) * (size_t)nk * XF, st));
+        else
+            k_level_kabsch<<<(nk + 31) / 32, 32, 0, st>>>(dp, nk, nc->coords.p, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0, c->lv_xf2.p + (size_t)k0 * XF);
         k_level_mean<<<dim3((unsigned)((ml + 127) / 128), (unsigned)nk), 128, 0, st>>>(dp, nc->tensors.p, nc->coords.p, c->nd_w.p, d, c->nd_a1.p,
                                                                                       c->nd_a2.p, c->nd_len.p + k0, c->lv_xf2.p + (size_t)k0 * XF,
                                                                                       d_out_off ? d_out_off + k0 : nullptr, t_out, c_out, w_out);

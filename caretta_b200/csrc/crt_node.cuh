@@ -66,6 +66,32 @@ __global__ void __launch_bounds__(256) k_level_score(const DpProblem *probs, con
                     neg_gamma_w, S_all + pr.s_off);
 }
 
+// flexible=True (multiple_alignment.py:323-326): the score matrix is the Gaussian of the shape tensors alone (no stage-1
+// alignment, no superposition), plus the consensus-weight term.  Sequential sum with separate roundings like
+// score_functions.py:11.
+__global__ void __launch_bounds__(256) k_level_score_flex(const DpProblem *probs, const double *tensors, int d, const double *weights,
+                                                          const double *mult, double neg_gamma_t, double neg_gamma_w, double *S_all)
+{
+    const DpProblem pr = probs[blockIdx.y];
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)pr.n * pr.m) return;
+    const int a = (int)(q / pr.m), b = (int)(q - (long long)a * pr.m);
+    const double *x = tensors + (pr.aln_off + a) * d, *y = tensors + (pr.aln_off + pr.n + b) * d;
+    double acc = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double t = __dsub_rn(x[k], y[k]);
+        acc = __dadd_rn(acc, __dmul_rn(t, t));
+    }
+    const double sc = exp(__dmul_rn(neg_gamma_t, acc));
+    double sw = 0.0;
+    if (!(neg_gamma_w > 0.0)) {
+        const double dw = __dsub_rn(__dmul_rn(weights[pr.aln_off + a], mult[2 * blockIdx.y]),
+                                    __dmul_rn(weights[pr.aln_off + pr.n + b], mult[2 * blockIdx.y + 1]));
+        sw = exp(__dmul_rn(neg_gamma_w, __dmul_rn(dw, dw)));
+    }
+    S_all[pr.s_off + q] = __dadd_rn(sc, sw);
+}
+
 // Superposition of mean_function (multiple_alignment.py:362-372) over the common positions of the DTW alignment.
 // One thread: the sums run in alignment order like helper.nb_mean_axis_0 (helper.py:45-53).  xf2: same record layout as xf.
 __device__ inline void node_kabsch_one(const double *c1, const double *c2, const int *aln1, const int *aln2, int len, double *xf2)

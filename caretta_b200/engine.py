@@ -15,6 +15,9 @@ LIB_PATH = os.environ.get("CARETTA_B200_LIB") or os.path.join(_HERE, "libcaretta
 FP64, FP32 = 0, 1
 SUP_AUTO, SUP_CORE, SUP_REFERENCE = 0, 1, 2
 ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE = 1, 2, 4
+FLAG_FLEXIBLE = 1                                  # crt_params.flags: Protein.score_function(flexible=True)
+# gamma_coords sentinels of progressive_node / progressive_level / msa_level (include/caretta_b200.h)
+GC_FLEXIBLE, GC_FLEXIBLE_SCORE = -1.0, -2.0
 
 EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains", "crt_set_coords",
@@ -32,7 +35,7 @@ class CrtError(RuntimeError):
 
 class Params(C.Structure):
     _fields_ = [("gamma_tensor", C.c_double), ("gamma_coords", C.c_double), ("sw_gap", C.c_double),
-                ("precision", C.c_int32), ("reserved", C.c_int32)]
+                ("precision", C.c_int32), ("flags", C.c_int32)]
 
 
 _lib = None
@@ -196,8 +199,8 @@ class Engine:
         return dict(sm_count=sm.value, clock_khz=clk.value, mem_bytes=mem.value)
 
     @staticmethod
-    def params(gamma_tensor=7.0, gamma_coords=0.03, precision=FP32, sw_gap=0.0) -> Params:
-        return Params(float(gamma_tensor), float(gamma_coords), float(sw_gap), int(precision), 0)
+    def params(gamma_tensor=7.0, gamma_coords=0.03, precision=FP32, sw_gap=0.0, flexible=False) -> Params:
+        return Params(float(gamma_tensor), float(gamma_coords), float(sw_gap), int(precision), FLAG_FLEXIBLE if flexible else 0)
 
     def set_chains(self, coords, tensors, offsets):
         coords = np.ascontiguousarray(coords, dtype=np.float64)

@@ -63,23 +63,29 @@ class Protein:
         return self.sequence
 
 
-def pack_sequences(sequences) -> typing.Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """List of Protein-like objects (anything with .tensors [L,d] and .coordinates [L,3]) -> packed chain set."""
+def pack_sequences(sequences, need_coordinates: bool = True) -> typing.Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """List of Protein-like objects (anything with .tensors [L,d] and .coordinates [L,3]) -> packed chain set.
+    need_coordinates=False (flexible=True runs, where the reference never reads them, multiple_alignment.py:323-326): a sequence
+    whose coordinates are None gets zeros."""
     if len(sequences) == 0:
         raise ValueError("no sequences")
     d = int(np.asarray(sequences[0].tensors).shape[1])
-    lens = []
+    lens, cs = [], []
     for s in sequences:
         t = np.asarray(s.tensors)
-        c = np.asarray(s.coordinates)
         if t.ndim != 2 or t.shape[1] != d:
             raise ValueError(f"{getattr(s, 'name', '?')}: tensors must be [L,{d}]")
+        if getattr(s, "coordinates", None) is None and not need_coordinates:
+            c = np.zeros((t.shape[0], 3))
+        else:
+            c = np.asarray(s.coordinates)
         if c.ndim != 2 or c.shape[1] != 3 or c.shape[0] != t.shape[0]:
             raise ValueError(f"{getattr(s, 'name', '?')}: coordinates must be [L,3] with the same L as tensors")
         lens.append(t.shape[0])
+        cs.append(np.asarray(c, dtype=np.float64))
     offsets = np.zeros(len(sequences) + 1, np.int64)
     offsets[1:] = np.cumsum(lens)
-    coords = np.concatenate([np.asarray(s.coordinates, dtype=np.float64) for s in sequences])
+    coords = np.concatenate(cs)
     tensors = np.concatenate([np.asarray(s.tensors, dtype=np.float64) for s in sequences])
     return coords, tensors, offsets
 
@@ -206,17 +212,15 @@ class MultipleAlignment:
             if "gamma_coords" not in score_function_params:
                 p["gamma_coords"] = 0.03
             p.update(score_function_params)
-        if p.get("flexible", False):
-            raise NotImplementedError("flexible=True (tensor-only scoring, multiple_alignment.py:323-326) is not on the "
-                                      "all-vs-all path and is not accelerated")
         prec = self.precision if self.precision is not None else _precision_from_env()
-        return _engine.Engine.params(p["gamma_tensor"], p["gamma_coords"], prec)
+        # flexible=True (:323-326): the score matrix is the tensor Gaussian alone -> smith_waterman_score of it, gamma_coords unused
+        return _engine.Engine.params(p["gamma_tensor"], p["gamma_coords"], prec, flexible=bool(p.get("flexible", False)))
 
     def make_pairwise_matrix(self, score_function_params=None) -> np.ndarray:
         """float64 [N,N] similarity, symmetric, zero diagonal (the caller turns it into max - S, :501)."""
         eng = get_engine()
-        eng.set_chains(*pack_sequences(self.sequences))
         prm = self._params(score_function_params)
+        eng.set_chains(*pack_sequences(self.sequences, need_coordinates=not prm.flags & _engine.FLAG_FLEXIBLE))
         n = len(self.sequences)
         if n < 2:
             return np.zeros((n, n))
@@ -233,9 +237,18 @@ class MultipleAlignment:
         CARETTA_B200_MSA_POOL=0: crt_progressive_level with host arrays per level; CARETTA_B200_NODE_BATCH=0: one
         crt_progressive_node call per node, in tree order."""
         p = dict(score_function_params or {})
-        if p.get("flexible", False) or (mean_function_params or {}).get("flexible", False):
-            raise NotImplementedError("flexible=True is not accelerated")
+        flex_score, flex_mean = bool(p.get("flexible", False)), bool((mean_function_params or {}).get("flexible", False))
         gt, gc = p.get("gamma_tensor", 0.03), p.get("gamma_coords", 0.03)          # Protein.score_function defaults, :321-322
+        if flex_mean and not flex_score and len(self.sequences) > 2:
+            # the reference makes coordinate-less nodes (:359-360) and then fails scoring them with flexible=False (:337-349)
+            raise ValueError("mean_function_params flexible=True needs score_function_params flexible=True: a flexible node has no "
+                             "coordinates to score on")
+        if flex_score:                             # tensor-only score matrices; the C ABI's sentinels for gamma_coords
+            gc = _engine.GC_FLEXIBLE if flex_mean else _engine.GC_FLEXIBLE_SCORE
+        need_xyz = not (flex_score and flex_mean)
+
+        def make_node(name, tensors, coordinates):
+            return Protein(name, tensors) if flex_mean else Protein(name, tensors, coordinates)
         eng = get_engine()
         n_leaves = len(self.sequences)
         tree = np.asarray(tree)
@@ -282,7 +295,7 @@ class MultipleAlignment:
             parent_side[a], parent_side[b] = ext[0][:-1], ext[1][:-1]
             node_len[i] = len(res[0])
             if len(res) > 4:                                        # host path: the node itself comes back with the alignment
-                final_sequences[i] = Protein(name_int, res[2], res[3])
+                final_sequences[i] = make_node(name_int, res[2], res[3])
                 final_consensus_weights[i] = res[4]
 
         def multipliers(q):
@@ -293,13 +306,14 @@ class MultipleAlignment:
         def node_inputs(q):
             a, b, _ = steps[q]
             s1, s2 = final_sequences[a], final_sequences[b]
-            return ((s1.tensors, s1.coordinates, final_consensus_weights[a]), (s2.tensors, s2.coordinates, final_consensus_weights[b])), \
+            xyz = [s.coordinates if need_xyz or getattr(s, "coordinates", None) is not None else np.zeros((len(s), 3)) for s in (s1, s2)]
+            return ((s1.tensors, xyz[0], final_consensus_weights[a]), (s2.tensors, xyz[1], final_consensus_weights[b])), \
                 multipliers(q)
 
         levels = [[q for q in range(len(steps)) if level[n_leaves + q] == lv] for lv in range(1, (max(level) if steps else 0) + 1)]
         if use_pool:
             # the sequences stay on the device: leaves = pool ids 0..N-1, every level appends its nodes; only alignments come back
-            eng.set_chains(*pack_sequences(self.sequences))
+            eng.set_chains(*pack_sequences(self.sequences, need_coordinates=need_xyz))
             eng.msa_begin(consensus_weight)
             pool_id = list(range(n_leaves)) + [None] * len(steps)
             for qs in levels:
@@ -309,7 +323,7 @@ class MultipleAlignment:
                     pool_id[n_leaves + q] = first + k
                     finish(q, res)
             nodes = _PoolNodes(eng, pool_id[n_leaves:], [st[2] for st in steps])
-            final_sequences = _LazyNodeList(final_sequences[:n_leaves], nodes, lambda q, rec: Protein(steps[q][2], rec[0], rec[1]))
+            final_sequences = _LazyNodeList(final_sequences[:n_leaves], nodes, lambda q, rec: make_node(steps[q][2], rec[0], rec[1]))
             final_consensus_weights = _LazyNodeList(final_consensus_weights[:n_leaves], nodes, lambda q, rec: rec[2])
             if os.environ.get("CARETTA_B200_FETCH_NODES", "0") != "0":
                 nodes.fetch()
@@ -363,9 +377,12 @@ class MultipleAlignment:
             p = dict(score_function_params or {})
             s1, s2 = self.sequences
             # two structures: dtw_align on the plain score matrix (:263-275); gamma_weight < 0 switches the weight term off
+            flex = bool(p.get("flexible", False))                  # tensor-only score matrix (:323-326); coordinates are not read
+            xyz = [np.zeros((len(s), 3)) if flex and getattr(s, "coordinates", None) is None else s.coordinates for s in (s1, s2)]
             aln_1, aln_2, *_ = get_engine().progressive_node(
-                s1.tensors, s1.coordinates, np.zeros(len(s1)), s2.tensors, s2.coordinates, np.zeros(len(s2)), 0.0, 0.0,
-                p.get("gamma_tensor", 0.03), p.get("gamma_coords", 0.03), -1.0, gap_open_penalty, gap_extend_penalty)
+                s1.tensors, xyz[0], np.zeros(len(s1)), s2.tensors, xyz[1], np.zeros(len(s2)), 0.0, 0.0,
+                p.get("gamma_tensor", 0.03), _engine.GC_FLEXIBLE if flex else p.get("gamma_coords", 0.03), -1.0,
+                gap_open_penalty, gap_extend_penalty)
             self.alignment = {s1.name: aln_1, s2.name: aln_2}
             return self.alignment
         self.tree, self.branch_lengths = _nj.neighbor_joining(pairwise_distance_matrix)

@@ -63,8 +63,14 @@ typedef struct crt_params {
     double gamma_coords;   /* 0.03 */
     double sw_gap;         /* 0.0 -- the only value the reference uses on this path; others -> CRT_E_ARG */
     int32_t precision;     /* CRT_FP64 | CRT_FP32 */
-    int32_t reserved;
+    int32_t flags;         /* 0, or CRT_FLEXIBLE: Protein.score_function(flexible=True) (multiple_alignment.py:323-326): the score
+                              matrix is the tensor Gaussian alone -> pair score = smith_waterman_score of it; rmsd / tm / ncommon 0 */
 } crt_params;
+
+enum { CRT_FLEXIBLE = 1 };
+/* gamma_coords sentinels of the progressive-alignment calls (crt_progressive_node / _level, crt_msa_level) */
+#define CRT_GAMMA_COORDS_FLEXIBLE (-1.0)        /* score_function(flexible=True) and mean_function(flexible=True) */
+#define CRT_GAMMA_COORDS_FLEXIBLE_SCORE (-2.0)  /* score_function(flexible=True), mean_function(flexible=False) */
 
 const char *crt_last_error(void);
 int crt_version(void);
@@ -147,7 +153,11 @@ int crt_rmsd_cov_tm_superposed(crt_ctx *ctx, const int64_t *aln, int64_t A, doub
  * get_mean_weights (:73-82).  All float64.  tensors: [n,d] / [m,d], coords: [n,3] / [m,3], weights: [n] / [m] (host).
  * Outputs: aln1/aln2 int32 with -1 = gap (capacity n + m), *aln_len, the intermediate node tensors_mean [len,d],
  * coords_mean [len,3], weights_mean [len]; *score = the DTW score; *status = status bits of the stage-1 pair run.
- * gamma_weight < 0 leaves the weight term out (multiple_align with two structures, :263-275). */
+ * gamma_weight < 0 leaves the weight term out (multiple_align with two structures, :263-275).
+ * gamma_coords < 0 selects flexible=True for this and the level / pool calls below (score_function :323-326): the score matrix is
+ * the tensor Gaussian plus the weight term, no stage-1 alignment.  CRT_GAMMA_COORDS_FLEXIBLE: mean_function(flexible=True) too
+ * (:359-360) -- no superposition, coords_mean is meaningless (the reference's flexible node has no coordinates);
+ * CRT_GAMMA_COORDS_FLEXIBLE_SCORE: the node still superposes its children on the DTW alignment and averages coordinates. */
 int crt_progressive_node(crt_ctx *ctx, const double *tensors1, const double *coords1, const double *weights1, int32_t n,
                          const double *tensors2, const double *coords2, const double *weights2, int32_t m, int32_t d,
                          double mult1, double mult2, double gamma_tensor, double gamma_coords, double gamma_weight,

@@ -223,6 +223,19 @@ def pairwise_all(coords, tensors, offsets, gamma_t=7.0, gamma_c=0.03, nthreads=0
     return out
 
 
+def pairwise_all_flexible(tensors, offsets, gamma_t=7.0) -> np.ndarray:
+    """make_pairwise_matrix (multiple_alignment.py:158-170) with score_function_params flexible=True (:323-326):
+    smith_waterman_score of the tensor Gaussian of every pair (small cases: a Python loop over the pairs)."""
+    tensors, offsets = _c(tensors), _c(offsets, np.int64)
+    N = len(offsets) - 1
+    out = np.zeros((N, N))
+    for i in range(N - 1):
+        for j in range(i + 1, N):
+            out[i, j] = out[j, i] = smith_waterman_score(
+                rbf_matrix(tensors[offsets[i]:offsets[i + 1]], tensors[offsets[j]:offsets[j + 1]], gamma_t), 0.0)
+    return out
+
+
 def rmsd_cov_tm(aln, coords, offsets):
     aln = _c(aln, np.int64)
     coords = _c(coords)
@@ -247,20 +260,26 @@ def neighbor_joining(distance_matrix) -> Tuple[np.ndarray, np.ndarray]:
     return tree[:k], bl[:k].reshape(-1, 1)
 
 
-def score_matrix(t1, c1, t2, c2, gamma_t=7.0, gamma_c=0.03) -> np.ndarray:
-    """Protein.score_function(flexible=False), multiple_alignment.py:321-349: the full n x m matrix."""
+def score_matrix(t1, c1, t2, c2, gamma_t=7.0, gamma_c=0.03, flexible=False) -> np.ndarray:
+    """Protein.score_function, multiple_alignment.py:321-349: the full n x m matrix (flexible=True, :323-326: the tensor
+    Gaussian alone)."""
+    if flexible:
+        return rbf_matrix(t1, t2, gamma_t)
     t1, c1, t2, c2 = _c(t1), _c(c1), _c(t2), _c(c2)
     S = np.empty((t1.shape[0], t2.shape[0]))
     lib().crt_o_score_matrix(t1, c1, t1.shape[0], t2, c2, t2.shape[0], t1.shape[1], gamma_t, gamma_c, S)
     return S
 
 
-def mean_function(t1, c1, t2, c2, aln_1, aln_2):
-    """Protein.mean_function(flexible=False), multiple_alignment.py:351-383 -> (tensors_mean, coordinates_mean)."""
+def mean_function(t1, c1, t2, c2, aln_1, aln_2, flexible=False):
+    """Protein.mean_function, multiple_alignment.py:351-383 -> (tensors_mean, coordinates_mean); flexible=True (:359-360): the
+    node has no coordinates (None)."""
     k = len(aln_1)
     tm = np.zeros((k, t1.shape[1]))
     for i, (x, y) in enumerate(zip(aln_1, aln_2)):
         tm[i] = t2[y] if x == -1 else (t1[x] if y == -1 else (t1[x] + t2[y]) / 2)
+    if flexible:
+        return tm, None
     p1, p2 = common_positions(aln_1, aln_2)
     if len(p1) <= 3:
         k1, k2 = np.array(c1), np.array(c2)
@@ -284,10 +303,11 @@ def mean_weights(w1, w2, aln_1, aln_2) -> np.ndarray:
 
 
 def progressive_align(seqs, tree, gap_open=1.0, gap_extend=0.01, consensus_weight=1.0, gamma_weight=0.03,
-                      gamma_t=7.0, gamma_c=0.03, want_final_alignments=False):
+                      gamma_t=7.0, gamma_c=0.03, want_final_alignments=False, flexible_score=False, flexible_mean=False):
     """MultipleAlignment.progressive_align, multiple_alignment.py:172-253, on [(name, tensors, coords)] (small cases:
-    Python loops).  Returns (alignment {name: int64[A]}, final_sequences [(name, tensors, coords)], final_weights)."""
-    fs = [(n, _c(t), _c(c)) for n, t, c in seqs]
+    Python loops).  Returns (alignment {name: int64[A]}, final_sequences [(name, tensors, coords)], final_weights).
+    flexible_score / flexible_mean: the flexible flags of score_function_params / mean_function_params."""
+    fs = [(n, _c(t), None if c is None else _c(c)) for n, t, c in seqs]
     fa = {n: {n: np.arange(len(t))} for n, t, _ in fs}
     fw = [np.full((len(t), 1), consensus_weight, dtype=np.float64) for _, t, _ in fs]
 
@@ -297,10 +317,10 @@ def progressive_align(seqs, tree, gap_open=1.0, gap_extend=0.01, consensus_weigh
         l1, l2 = len(fa[name_1]), len(fa[name_2])
         mult1, mult2 = l2 / (2 * (l1 + l2)), l1 / (2 * (l1 + l2))
         name_int = f"int-{n_int}"
-        S = score_matrix(t1, c1, t2, c2, gamma_t, gamma_c)
+        S = score_matrix(t1, c1, t2, c2, gamma_t, gamma_c, flexible_score)
         S += rbf_matrix(w1 * mult1, w2 * mult2, gamma_weight)
         a1, a2, _ = dtw_align(S, gap_open, gap_extend)
-        tmn, cmn = mean_function(t1, c1, t2, c2, a1, a2)
+        tmn, cmn = mean_function(t1, c1, t2, c2, a1, a2, flexible_mean)
         wmn = mean_weights(w1, w2, a1, a2)
         fa[name_1] = {k: np.array([v[i] if i != -1 else -1 for i in a1]) for k, v in fa[name_1].items()}
         fa[name_2] = {k: np.array([v[i] if i != -1 else -1 for i in a2]) for k, v in fa[name_2].items()}
@@ -321,15 +341,16 @@ def progressive_align(seqs, tree, gap_open=1.0, gap_extend=0.01, consensus_weigh
     return alignment, fs, fw
 
 
-def progressive_node(t1, c1, w1, t2, c2, w2, mult1, mult2, gamma_t=7.0, gamma_c=0.03, gamma_weight=0.03, gap_open=1.0, gap_extend=0.01):
+def progressive_node(t1, c1, w1, t2, c2, w2, mult1, mult2, gamma_t=7.0, gamma_c=0.03, gamma_weight=0.03, gap_open=1.0, gap_extend=0.01,
+                     flexible_score=False, flexible_mean=False):
     """One make_intermediate_node (multiple_alignment.py:195-234) with the signature of Engine.progressive_node."""
     t1, c1, t2, c2 = _c(t1), _c(c1), _c(t2), _c(c2)
     w1, w2 = np.asarray(w1, dtype=np.float64).reshape(-1, 1), np.asarray(w2, dtype=np.float64).reshape(-1, 1)
-    S = score_matrix(t1, c1, t2, c2, gamma_t, gamma_c)
+    S = score_matrix(t1, c1, t2, c2, gamma_t, gamma_c, flexible_score)
     if not gamma_weight < 0:
         S = S + rbf_matrix(w1 * mult1, w2 * mult2, gamma_weight)
     a1, a2, sc = dtw_align(S, gap_open, gap_extend)
-    tmn, cmn = mean_function(t1, c1, t2, c2, a1, a2)
+    tmn, cmn = mean_function(t1, c1, t2, c2, a1, a2, flexible_mean)
     return a1, a2, tmn, cmn, mean_weights(w1, w2, a1, a2), sc, 0
 
 

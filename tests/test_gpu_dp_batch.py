@@ -97,5 +97,6 @@ def test_mirror_make_pairwise_matrix(eng):
     np.testing.assert_allclose(S64, g["score_matrix"], rtol=1e-11)
     S32 = MA.StructureMultiple(prots).make_pairwise_matrix(params)
     np.testing.assert_allclose(S32, g["score_matrix"], rtol=1e-4)
-    with pytest.raises(NotImplementedError):
-        MA.MultipleAlignment(prots).make_pairwise_matrix(dict(flexible=True))
+    # flexible=True is the tensor-only matrix (tests/test_gpu_flexible.py has the golden cases)
+    F = MA.MultipleAlignment(prots, precision=engine.FP64).make_pairwise_matrix(dict(flexible=True, gamma_tensor=7.0))
+    assert F.shape == S64.shape and np.array_equal(F, F.T) and not np.allclose(F, S64)

@@ -226,6 +226,35 @@ def test_progressive_align_golden():
         assert np.array_equal(fw[-1], g[f"{name}_final_weights"])
 
 
+def test_flexible_golden():
+    """flexible=True (tensor-only score matrices, multiple_alignment.py:323-326; coordinate-less nodes, :359-360): the oracle's
+    restatement against the reference's outputs (oracle/gen_golden_flexible.py) -- score matrix bit-exact, identical alignments
+    for mean_function flexible=True ("tt") and False ("tf")."""
+    g = np.load(os.path.join(G, "flexible.npz"))
+    for name in ("fam8", "ragged12", "short5"):
+        L = g[f"{name}_lengths"]
+        ch = synth.make_chains(len(L), list(L), 10, seed=int(g[f"{name}_seed"]), family_size=int(g[f"{name}_family"]))
+        S = O.pairwise_all_flexible(ch.tensors, ch.offsets, 7.0)
+        assert np.array_equal(S, g[f"{name}_score"]), name
+        tree, _ = O.neighbor_joining(np.max(S) - S)
+        assert np.array_equal(tree, g[f"{name}_tree"])
+        for tag, mean_flex in (("tt", True), ("tf", False)):
+            aln, fs, fw = O.progressive_align([(f"s{p}",) + ch.chain(p) for p in range(ch.n)], tree, flexible_score=True,
+                                              flexible_mean=mean_flex)
+            A = np.array([aln[f"s{p}"] for p in range(ch.n)])
+            assert np.array_equal(A, g[f"{name}_{tag}_aln"]), (name, tag)
+            assert np.array_equal(fs[-1][1], g[f"{name}_{tag}_final_tensors"])
+            assert np.array_equal(fw[-1], g[f"{name}_{tag}_final_weights"])
+            if mean_flex:
+                assert fs[-1][2] is None
+            else:
+                np.testing.assert_allclose(fs[-1][2], g[f"{name}_{tag}_final_coords"], rtol=0, atol=1e-10)
+    L = g["two_lengths"]
+    ch = synth.make_chains(2, list(L), 10, seed=int(g["two_seed"]), family_size=int(g["two_family"]))
+    a1, a2, _ = O.dtw_align(O.score_matrix(*ch.chain(0), *ch.chain(1), 7.0, 0.03, flexible=True), 1.0, 0.01)
+    assert np.array_equal(np.array([a1, a2]), g["two_tt_aln"]) and np.array_equal(g["two_tt_aln"], g["two_tf_aln"])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Consumers of the multiple alignment (SURVEY 8f ranks 3-4): the oracle restatement against the reference's outputs
 # ------------------------------------------------------------------------------------------------------------------
