@@ -1570,6 +1570,150 @@ int crt_progressive_node(crt_ctx *c, const double *tensors1, const double *coord
     return 0;
 }
 
+/* Protein.score_function (multiple_alignment.py:321-349): the n x m float64 score matrix of one pair, as the reference returns it. */
+int crt_score_matrix(crt_ctx *c, const double *tensors1, const double *coords1, int32_t n, const double *tensors2, const double *coords2,
+                     int32_t m, int32_t d, double gamma_tensor, double gamma_coords, int32_t flexible, double *score_matrix, int32_t *status)
+{
+    if (!c || !tensors1 || !tensors2 || !score_matrix) return fail(CRT_E_ARG, "null argument");
+    if (!flexible && (!coords1 || !coords2)) return fail(CRT_E_ARG, "coordinates are needed unless flexible is set");
+    if (n <= 0 || m <= 0 || d <= 0) return fail(CRT_E_ARG, "empty sequence (%d x %d, d = %d)", n, m, d);
+    if (!(gamma_tensor >= 0) || (!flexible && !(gamma_coords >= 0))) return fail(CRT_E_ARG, "gamma must be >= 0");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if (!c->node_ctx && (rc = crt_create(c->device, &c->node_ctx))) return rc;
+    crt_ctx *nc = c->node_ctx;
+    nc->stage1_only = true;
+    std::vector<double> pc((size_t)(n + m) * 3, 0.0), pt((size_t)(n + m) * d);
+    if (coords1) std::memcpy(pc.data(), coords1, sizeof(double) * (size_t)n * 3);
+    if (coords2) std::memcpy(pc.data() + (size_t)n * 3, coords2, sizeof(double) * (size_t)m * 3);
+    std::memcpy(pt.data(), tensors1, sizeof(double) * (size_t)n * d);
+    std::memcpy(pt.data() + (size_t)n * d, tensors2, sizeof(double) * (size_t)m * d);
+    const int64_t off[3] = {0, n, (int64_t)n + m};
+    if ((rc = crt_set_chains(nc, pc.data(), pt.data(), off, 2, d))) return rc;
+    int32_t st1 = 0;
+    if (!flexible) {                       // stage 1 of score_function: the fp64 pair kernels leave the superposition in nc->xform
+        crt_params prm{};
+        prm.gamma_tensor = gamma_tensor; prm.gamma_coords = gamma_coords; prm.sw_gap = 0.0; prm.precision = CRT_FP64;
+        const int32_t pi = 0, pj = 1;
+        if ((rc = crt_pairwise_list(nc, &prm, &pi, &pj, 1, nullptr, nullptr, nullptr, nullptr, &st1, nullptr, nullptr, nullptr, 0))) return rc;
+    }
+    const size_t cells = (size_t)n * m;
+    if ((rc = c->nd_S.ensure(cells))) return rc;
+    if ((rc = c->nd_w.ensure((size_t)n + m))) return rc;
+    if ((rc = c->d_units.ensure(1))) return rc;
+    cudaStream_t st = c->stream;
+    DpProblem pr{};
+    pr.n = n; pr.m = m;
+    DpProblem *d_pr = reinterpret_cast<DpProblem *>(c->d_units.p);
+    CU(cudaMemcpyAsync(d_pr, &pr, sizeof(pr), cudaMemcpyHostToDevice, st));
+    // the weight term is switched off (neg_gamma_w > 0): the weights / multipliers are not read
+    if (flexible)
+        k_level_score_flex<<<dim3((unsigned)((cells + 255) / 256), 1), 256, 0, st>>>(d_pr, nc->tensors.p, d, c->nd_w.p, c->nd_w.p, -gamma_tensor, 1.0,
+                                                                                   c->nd_S.p);
+    else
+        k_node_score<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(nc->coords.p, n, nc->coords.p + (size_t)n * 3, m, nc->xform.p, c->nd_w.p,
+                                                                     c->nd_w.p + n, 0.0, 0.0, -gamma_coords, 1.0, c->nd_S.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(score_matrix, c->nd_S.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (status) *status = st1;
+    return 0;
+}
+
+namespace {
+// alignment columns of mean_function / get_mean_weights: int64 with -1 = gap -> int32; a column must have a residue on one side
+int check_columns(const int64_t *aln1, const int64_t *aln2, int64_t len, int n, int m, std::vector<int> &a1, std::vector<int> &a2, int *n_common)
+{
+    a1.resize((size_t)len); a2.resize((size_t)len);
+    int common = 0;
+    for (int64_t q = 0; q < len; ++q) {
+        const int64_t x = aln1[q], y = aln2[q];
+        if (x < -1 || x >= n || y < -1 || y >= m) return fail(CRT_E_ARG, "alignment column %lld: index (%lld, %lld) out of range", (long long)q, (long long)x, (long long)y);
+        if (x < 0 && y < 0) return fail(CRT_E_ARG, "alignment column %lld has a gap on both sides", (long long)q);
+        a1[(size_t)q] = (int)x; a2[(size_t)q] = (int)y;
+        common += x >= 0 && y >= 0;
+    }
+    if (n_common) *n_common = common;
+    return 0;
+}
+}  // namespace
+
+/* Protein.mean_function (multiple_alignment.py:351-383) for a given alignment. */
+int crt_mean_function(crt_ctx *c, const double *tensors1, const double *coords1, int32_t n, const double *tensors2, const double *coords2,
+                      int32_t m, int32_t d, const int64_t *aln1, const int64_t *aln2, int64_t len, int32_t flexible, double *tensors_mean,
+                      double *coords_mean, int32_t *status)
+{
+    if (!c || !tensors1 || !tensors2 || !tensors_mean || (len > 0 && (!aln1 || !aln2))) return fail(CRT_E_ARG, "null argument");
+    if (!flexible && (!coords1 || !coords2 || !coords_mean)) return fail(CRT_E_ARG, "coordinates are needed unless flexible is set");
+    if (n <= 0 || m <= 0 || d <= 0) return fail(CRT_E_ARG, "empty sequence (%d x %d, d = %d)", n, m, d);
+    if (len < 0 || len > (int64_t)n + m) return fail(CRT_E_ARG, "alignment length %lld out of range (<= n + m)", (long long)len);
+    std::vector<int> a1, a2;
+    int common = 0, rc;
+    if ((rc = check_columns(aln1, aln2, len, n, m, a1, a2, &common))) return rc;
+    if (status) *status = (!flexible && common <= 3) ? CRT_ST_FEW_COMMON : 0;
+    if (len == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    const size_t rows = (size_t)n + m, alen = (size_t)len;
+    // the two sequences go to the score-matrix workspace (free here): tensors [n + m, d], then coordinates [n + m, 3]
+    if ((rc = c->nd_S.ensure(rows * ((size_t)d + 3))) || (rc = c->nd_w.ensure(rows)) || (rc = c->nd_xf2.ensure(XF)) ||
+        (rc = c->nd_a1.ensure(alen + 1)) || (rc = c->nd_a2.ensure(alen + 1)) || (rc = c->nd_len.ensure(1)) || (rc = c->nd_t.ensure(alen * (size_t)d)) ||
+        (rc = c->nd_c.ensure(alen * 3)) || (rc = c->nd_wm.ensure(alen)))
+        return rc;
+    cudaStream_t st = c->stream;
+    double *dt1 = c->nd_S.p, *dt2 = dt1 + (size_t)n * d, *dc1 = c->nd_S.p + rows * (size_t)d, *dc2 = dc1 + (size_t)n * 3;
+    const int ilen = (int)len;
+    CU(cudaMemcpyAsync(dt1, tensors1, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dt2, tensors2, sizeof(double) * (size_t)m * d, cudaMemcpyHostToDevice, st));
+    if (flexible) {
+        CU(cudaMemsetAsync(dc1, 0, sizeof(double) * rows * 3, st));
+    } else {
+        CU(cudaMemcpyAsync(dc1, coords1, sizeof(double) * (size_t)n * 3, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dc2, coords2, sizeof(double) * (size_t)m * 3, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemsetAsync(c->nd_w.p, 0, sizeof(double) * rows, st));
+    CU(cudaMemcpyAsync(c->nd_a1.p, a1.data(), sizeof(int) * alen, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->nd_a2.p, a2.data(), sizeof(int) * alen, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->nd_len.p, &ilen, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (flexible)
+        CU(cudaMemsetAsync(c->nd_xf2.p, 0, sizeof(double) * XF, st));             // flag 0: no superposition
+    else
+        k_node_kabsch<<<1, 32, 0, st>>>(dc1, dc2, c->nd_a1.p, c->nd_a2.p, c->nd_len.p, c->nd_xf2.p);
+    k_node_mean<<<(unsigned)((alen + 127) / 128), 128, 0, st>>>(dt1, dc1, c->nd_w.p, dt2, dc2, c->nd_w.p + n, d, c->nd_a1.p, c->nd_a2.p, c->nd_len.p,
+                                                                c->nd_xf2.p, c->nd_t.p, c->nd_c.p, c->nd_wm.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(tensors_mean, c->nd_t.p, sizeof(double) * alen * d, cudaMemcpyDeviceToHost, st));
+    if (!flexible) CU(cudaMemcpyAsync(coords_mean, c->nd_c.p, sizeof(double) * alen * 3, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+/* get_mean_weights (multiple_alignment.py:73-82). */
+int crt_mean_weights(crt_ctx *c, const double *weights1, int32_t n, const double *weights2, int32_t m, const int64_t *aln1, const int64_t *aln2,
+                     int64_t len, double *weights_mean)
+{
+    if (!c || !weights1 || !weights2 || (len > 0 && (!aln1 || !aln2 || !weights_mean))) return fail(CRT_E_ARG, "null argument");
+    if (n <= 0 || m <= 0) return fail(CRT_E_ARG, "empty sequence (%d x %d)", n, m);
+    if (len < 0) return fail(CRT_E_ARG, "negative alignment length");
+    std::vector<int> a1, a2;
+    int rc;
+    if ((rc = check_columns(aln1, aln2, len, n, m, a1, a2, nullptr))) return rc;
+    if (len == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    const size_t alen = (size_t)len;
+    if ((rc = c->nd_w.ensure((size_t)n + m)) || (rc = c->nd_a1.ensure(alen + 1)) || (rc = c->nd_a2.ensure(alen + 1)) || (rc = c->nd_wm.ensure(alen)))
+        return rc;
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->nd_w.p, weights1, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->nd_w.p + n, weights2, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->nd_a1.p, a1.data(), sizeof(int) * alen, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->nd_a2.p, a2.data(), sizeof(int) * alen, cudaMemcpyHostToDevice, st));
+    k_mean_weights<<<(unsigned)((alen + 255) / 256), 256, 0, st>>>(c->nd_w.p, c->nd_w.p + n, c->nd_a1.p, c->nd_a2.p, (long long)len, c->nd_wm.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(weights_mean, c->nd_wm.p, sizeof(double) * alen, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 /* neighbor_joining.py:17-99 on the device: guide tree (node_1, node_2) rows + branch lengths, bit-identical to the
  * reference for any float64 input (symmetric or not).  tree: [2N-3][2] uint64, branch_lengths: [2N-3] float64. */
 int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, uint64_t *tree, double *branch_lengths, int64_t *n_rows)

@@ -207,6 +207,19 @@ __global__ void __launch_bounds__(128) k_node_mean(const double *t1, const doubl
     node_mean_col(i, t1, c1, w1, t2, c2, w2, d, aln1, aln2, xf2, t_out, c_out, w_out);
 }
 
+// get_mean_weights (multiple_alignment.py:73-82) for a given alignment: one thread per column.
+__global__ void __launch_bounds__(256) k_mean_weights(const double *w1, const double *w2, const int *aln1, const int *aln2, long long len,
+                                                      double *w_out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    const int x = aln1[i], y = aln2[i];
+    double w = 0.0;
+    if (x >= 0) w = __dadd_rn(w, w1[x]);
+    if (y >= 0) w = __dadd_rn(w, w2[y]);
+    w_out[i] = w;
+}
+
 // outputs of node p go to rows pr.aln_off .. pr.aln_off + aln_len[p] of the packed output arrays (capacity n + m rows)
 // out_off: row offset of every node's output (nullptr: the node's own rows pr.aln_off of the packed level arrays)
 __global__ void __launch_bounds__(128) k_level_mean(const DpProblem *probs, const double *tensors, const double *coords,

@@ -24,6 +24,7 @@ EXPORTS = [
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node", "crt_progressive_level",
+    "crt_score_matrix", "crt_mean_function", "crt_mean_weights",
     "crt_msa_begin", "crt_msa_level", "crt_msa_lengths", "crt_msa_fetch", "crt_msa_end",
     "crt_coverage_gap_matrix", "crt_superpose", "crt_superpose_pairs", "crt_format_matrix", "crt_format_fasta", "crt_text_fetch", "crt_count_matrix", "crt_braycurtis",
 ]
@@ -84,6 +85,9 @@ def load_library():
     L.crt_neighbor_joining.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i64)]
     L.crt_progressive_node.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, dbl,
                                        vp, vp, C.POINTER(i32), vp, vp, vp, C.POINTER(dbl), C.POINTER(i32)]
+    L.crt_score_matrix.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, dbl, dbl, i32, vp, C.POINTER(i32)]
+    L.crt_mean_function.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, i64, i32, vp, vp, C.POINTER(i32)]
+    L.crt_mean_weights.argtypes = [vp, vp, i32, vp, i32, vp, vp, i64, vp]
     L.crt_progressive_level.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp, vp, vp, vp, vp]
     L.crt_msa_begin.argtypes = [vp, dbl, C.POINTER(i32)]
     L.crt_msa_level.argtypes = [vp, i32, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, vp, vp, i64, vp, vp, vp, vp, C.POINTER(i32)]
@@ -408,6 +412,58 @@ class Engine:
         k = k.value
         return (a1[:k].astype(np.int64), a2[:k].astype(np.int64), tm[:k].copy(), cm[:k].copy(), wm[:k].reshape(-1, 1).copy(),
                 sc.value, st.value)
+
+    def score_matrix(self, t1, c1, t2, c2, gamma_tensor=0.03, gamma_coords=0.03, flexible=False):
+        """Protein.score_function (multiple_alignment.py:321-349): (float64 [n,m] score matrix, status).  flexible=True: the tensor
+        Gaussian alone, c1 / c2 may be None."""
+        t1, t2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (t1, t2))
+        if t1.ndim != 2 or t2.ndim != 2 or t1.shape[1] != t2.shape[1]:
+            raise ValueError("tensors [n,d] and [m,d] expected")
+        n, m, d = t1.shape[0], t2.shape[0], t1.shape[1]
+        c1, c2 = (None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (c1, c2))
+        if not flexible and (c1 is None or c2 is None or c1.shape != (n, 3) or c2.shape != (m, 3)):
+            raise ValueError("coordinates [n,3] and [m,3] expected")
+        if flexible and ((c1 is not None and c1.shape != (n, 3)) or (c2 is not None and c2.shape != (m, 3))):
+            c1 = c2 = None
+        S = np.empty((n, m))
+        st = C.c_int32()
+        self._check(self.lib.crt_score_matrix(self.h, _p(t1), _p(c1), n, _p(t2), _p(c2), m, d, float(gamma_tensor), float(gamma_coords),
+                                              1 if flexible else 0, _p(S), C.byref(st)), "crt_score_matrix")
+        return S, st.value
+
+    def mean_function(self, t1, c1, t2, c2, aln_1, aln_2, flexible=False):
+        """Protein.mean_function (multiple_alignment.py:351-383): (tensors_mean [k,d], coordinates_mean [k,3] or None, status)."""
+        t1, t2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (t1, t2))
+        if t1.ndim != 2 or t2.ndim != 2 or t1.shape[1] != t2.shape[1]:
+            raise ValueError("tensors [n,d] and [m,d] expected")
+        n, m, d = t1.shape[0], t2.shape[0], t1.shape[1]
+        a1, a2 = (np.ascontiguousarray(a, dtype=np.int64).reshape(-1) for a in (aln_1, aln_2))
+        if len(a1) != len(a2):
+            raise ValueError("aln_1 and aln_2 must have the same length")
+        if not flexible:
+            c1, c2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (c1, c2))
+            if c1.shape != (n, 3) or c2.shape != (m, 3):
+                raise ValueError("coordinates [n,3] and [m,3] expected")
+        else:
+            c1 = c2 = None
+        k = len(a1)
+        tm = np.zeros((k, d))
+        cm = None if flexible else np.zeros((k, 3))
+        st = C.c_int32()
+        self._check(self.lib.crt_mean_function(self.h, _p(t1), _p(c1), n, _p(t2), _p(c2), m, d, _p(a1), _p(a2), k, 1 if flexible else 0,
+                                               _p(tm), _p(cm), C.byref(st)), "crt_mean_function")
+        return tm, cm, st.value
+
+    def mean_weights(self, w1, w2, aln_1, aln_2) -> np.ndarray:
+        """get_mean_weights (multiple_alignment.py:73-82): float64 [k,1]."""
+        w1 = np.ascontiguousarray(np.asarray(w1, dtype=np.float64).reshape(-1))
+        w2 = np.ascontiguousarray(np.asarray(w2, dtype=np.float64).reshape(-1))
+        a1, a2 = (np.ascontiguousarray(a, dtype=np.int64).reshape(-1) for a in (aln_1, aln_2))
+        if len(a1) != len(a2):
+            raise ValueError("aln_1 and aln_2 must have the same length")
+        out = np.zeros((len(a1), 1))
+        self._check(self.lib.crt_mean_weights(self.h, _p(w1), len(w1), _p(w2), len(w2), _p(a1), _p(a2), len(a1), _p(out)), "crt_mean_weights")
+        return out
 
     def progressive_level(self, children, mults, gamma_tensor=7.0, gamma_coords=0.03, gamma_weight=0.03, gap_open=1.0, gap_extend=0.01):
         """All independent nodes of one guide-tree level in one device call (crt_progressive_level).  children: list of

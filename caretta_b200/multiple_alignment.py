@@ -27,6 +27,7 @@ the C ABI (caretta_b200.engine).  Nothing here computes the path on the CPU.
 """
 from __future__ import annotations
 
+import abc
 import collections.abc
 import os
 import typing
@@ -48,19 +49,72 @@ def _precision_from_env() -> int:
     raise ValueError(f"CARETTA_B200_PRECISION={v!r}: expected fp32 or fp64")
 
 
+class SequenceBase(abc.ABC):
+    """The type the reference's driver is generic over (multiple_alignment.py:109-127): anything with a score_function, a
+    mean_function, a length and a string form.  Sequences that carry .tensors (and .coordinates) take the fused device path;
+    any other SequenceBase goes through its own score_function / mean_function with the DPs on the device."""
+    name: str
+
+    @abc.abstractmethod
+    def score_function(self, other: "SequenceBase", **kwargs) -> np.ndarray:
+        pass
+
+    def mean_function(self, other: "SequenceBase", aln_1: np.ndarray, aln_2: np.ndarray, name_int: str, **kwargs) -> "SequenceBase":
+        pass
+
+    @abc.abstractmethod
+    def __len__(self) -> int:
+        pass
+
+    @abc.abstractmethod
+    def __str__(self) -> str:
+        pass
+
+
+def _echo_few_positions(name_1, name_2) -> None:
+    print(f"Too few aligning positions for {name_1} and {name_2}, continuing without superposition")
+
+
 @dataclass
-class Protein:
-    """Same fields as the reference's Protein (multiple_alignment.py:312-319)."""
+class Protein(SequenceBase):
+    """Same fields and methods as the reference's Protein (multiple_alignment.py:312-389); the methods run on the device."""
     name: str
     tensors: np.ndarray
     coordinates: np.ndarray = None
     sequence: str = ""
+
+    def score_function(self, other: "Protein", flexible=False, gamma_tensor=0.03, gamma_coords=0.03, verbose=True) -> np.ndarray:
+        """multiple_alignment.py:321-349: the float64 [len(self), len(other)] score matrix (crt_score_matrix)."""
+        S, status = get_engine().score_matrix(self.tensors, None if flexible else self.coordinates, other.tensors,
+                                              None if flexible else other.coordinates, gamma_tensor, gamma_coords, flexible)
+        if verbose and status & _engine.ST_FEW_COMMON:
+            _echo_few_positions(self.name, other.name)
+        return S
+
+    def mean_function(self, other: "Protein", aln_1: np.ndarray, aln_2: np.ndarray, name_int: str, flexible=False,
+                      verbose=True) -> "Protein":
+        """multiple_alignment.py:351-383: the intermediate node of an alignment of self and other (crt_mean_function)."""
+        tm, cm, status = get_engine().mean_function(self.tensors, None if flexible else self.coordinates, other.tensors,
+                                                    None if flexible else other.coordinates, aln_1, aln_2, flexible)
+        if verbose and status & _engine.ST_FEW_COMMON:
+            _echo_few_positions(self.name, other.name)
+        return Protein(name_int, tm) if flexible else Protein(name_int, tm, cm)
 
     def __len__(self) -> int:
         return self.tensors.shape[0]
 
     def __str__(self) -> str:
         return self.sequence
+
+
+def get_mean_weights(weights_1: np.ndarray, weights_2: np.ndarray, aln_1: np.ndarray, aln_2: np.ndarray) -> np.ndarray:
+    """multiple_alignment.py:73-82: float64 [len(aln_1), 1] (crt_mean_weights)."""
+    return get_engine().mean_weights(weights_1, weights_2, aln_1, aln_2)
+
+
+def _on_fused_path(sequences) -> bool:
+    """True when every sequence carries shape tensors: the whole pair recipe then runs inside the device kernels."""
+    return all(getattr(s, "tensors", None) is not None for s in sequences)
 
 
 def pack_sequences(sequences, need_coordinates: bool = True) -> typing.Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -219,12 +273,75 @@ class MultipleAlignment:
     def make_pairwise_matrix(self, score_function_params=None) -> np.ndarray:
         """float64 [N,N] similarity, symmetric, zero diagonal (the caller turns it into max - S, :501)."""
         eng = get_engine()
+        if not _on_fused_path(self.sequences):
+            return self._pairwise_matrix_generic(score_function_params or {})
         prm = self._params(score_function_params)
         eng.set_chains(*pack_sequences(self.sequences, need_coordinates=not prm.flags & _engine.FLAG_FLEXIBLE))
         n = len(self.sequences)
         if n < 2:
             return np.zeros((n, n))
         return eng.pairwise_all(prm)
+
+    def _pairwise_matrix_generic(self, params, batch_bytes: int = 256 << 20) -> np.ndarray:
+        """Sequences of any other SequenceBase type (:109-127): their own score_function makes each matrix on the host, the
+        Smith-Waterman scores (dynamic_time_warping.py:204-222) are computed on the device in batches of matrices."""
+        eng = get_engine()
+        n = len(self.sequences)
+        out = np.zeros((n, n))
+        todo, mats, size = [], [], 0
+
+        def flush():
+            nonlocal todo, mats, size
+            for (i, j), res in zip(todo, eng.sw_align_batch(mats, 0.0, want_paths=False)):
+                out[i, j] = out[j, i] = res[2]
+            todo, mats, size = [], [], 0
+
+        for i in range(n - 1):
+            for j in range(i + 1, n):
+                m = np.ascontiguousarray(self.sequences[i].score_function(self.sequences[j], **params), dtype=np.float64)
+                if m.shape != (len(self.sequences[i]), len(self.sequences[j])):
+                    raise ValueError(f"score_function of {self.sequences[i].name} returned shape {m.shape}")
+                todo.append((i, j)); mats.append(m); size += m.nbytes
+                if size >= batch_bytes:
+                    flush()
+        if todo:
+            flush()
+        return out
+
+    def _progressive_align_generic(self, tree, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight, sparams, mparams):
+        """progressive_align (:172-253) for sequences without shape tensors: score_function / mean_function are the sequences'
+        own; the weight Gaussian (:206-210), the affine DTW (:211-214) and get_mean_weights (:217) run on the device."""
+        eng = get_engine()
+        nodes = list(self.sequences)
+        weights = [np.full((len(s), 1), consensus_weight, dtype=np.float64) for s in nodes]
+        members = {s.name: {s.name: np.arange(len(s))} for s in nodes}
+
+        def join(a, b, label):
+            sa, sb = nodes[a], nodes[b]
+            ka, kb = len(members[sa.name]), len(members[sb.name])
+            S = np.array(sa.score_function(sb, **sparams), dtype=np.float64)
+            S += eng.score_matrix(weights[a] * (kb / (2 * (ka + kb))), None, weights[b] * (ka / (2 * (ka + kb))), None,
+                                  gamma_weight, 0.0, flexible=True)[0]
+            al_a, al_b, _ = eng.dtw_align_batch([S], gap_open_penalty, gap_extend_penalty)[0]
+            al_a, al_b = al_a.astype(np.int64), al_b.astype(np.int64)
+            merged = {}
+            for side, al in ((sa.name, al_a), (sb.name, al_b)):
+                ext = {k: np.where(al >= 0, np.asarray(v)[np.maximum(al, 0)], -1) for k, v in members[side].items()}
+                members[side] = ext
+                merged.update(ext)
+            name = f"int-{label}"
+            members[name] = merged
+            nodes.append(sa.mean_function(sb, al_a, al_b, name, **mparams))
+            weights.append(eng.mean_weights(weights[a], weights[b], al_a, al_b))
+
+        tree = np.asarray(tree)
+        for x in range(0, tree.shape[0] - 1, 2):
+            assert int(tree[x + 1, 1]) == int(tree[x, 1])
+            join(int(tree[x, 0]), int(tree[x + 1, 0]), int(tree[x, 1]))
+        a, b = int(tree[-1, 0]), int(tree[-1, 1])
+        join(a, b, "final")
+        self.final_consensus_weights, self.final_alignments, self.final_sequences = weights, members, nodes
+        return {**members[nodes[a].name], **members[nodes[b].name]}
 
     # ------------------------------------------------------------------ guide tree + progressive alignment (SURVEY 8f)
     def progressive_align(self, tree, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight,
@@ -237,6 +354,9 @@ class MultipleAlignment:
         CARETTA_B200_MSA_POOL=0: crt_progressive_level with host arrays per level; CARETTA_B200_NODE_BATCH=0: one
         crt_progressive_node call per node, in tree order."""
         p = dict(score_function_params or {})
+        if not _on_fused_path(self.sequences):
+            return self._progressive_align_generic(tree, gap_open_penalty, gap_extend_penalty, consensus_weight, gamma_weight, p,
+                                                   dict(mean_function_params or {}))
         flex_score, flex_mean = bool(p.get("flexible", False)), bool((mean_function_params or {}).get("flexible", False))
         gt, gc = p.get("gamma_tensor", 0.03), p.get("gamma_coords", 0.03)          # Protein.score_function defaults, :321-322
         if flex_mean and not flex_score and len(self.sequences) > 2:
@@ -373,6 +493,12 @@ class MultipleAlignment:
                        score_function_params=None, mean_function_params=None) -> typing.Dict[str, np.ndarray]:
         """MultipleAlignment.multiple_align (multiple_alignment.py:255-285): neighbor joining + progressive alignment."""
         from . import neighbor_joining as _nj
+        if len(self.sequences) == 2 and not _on_fused_path(self.sequences):
+            s1, s2 = self.sequences
+            S = np.ascontiguousarray(s1.score_function(s2, **(score_function_params or {})), dtype=np.float64)
+            aln_1, aln_2, _ = get_engine().dtw_align_batch([S], gap_open_penalty, gap_extend_penalty)[0]
+            self.alignment = {s1.name: aln_1.astype(np.int64), s2.name: aln_2.astype(np.int64)}
+            return self.alignment
         if len(self.sequences) == 2:
             p = dict(score_function_params or {})
             s1, s2 = self.sequences

@@ -164,6 +164,27 @@ int crt_progressive_node(crt_ctx *ctx, const double *tensors1, const double *coo
                          double gap_open, double gap_extend, int32_t *aln1, int32_t *aln2, int32_t *aln_len,
                          double *tensors_mean, double *coords_mean, double *weights_mean, double *score, int32_t *status);
 
+/* Protein.score_function (multiple_alignment.py:321-349) as the reference returns it: the full float64 [n,m] score matrix of
+ * one pair (row-major, host).  flexible = 0: tensor Gaussian -> smith_waterman (gap 0) -> common positions -> Kabsch (skipped
+ * when <= 3, *status = CRT_ST_FEW_COMMON) -> Gaussian of the superposed coordinates; flexible != 0 (:323-326): the tensor
+ * Gaussian itself, coords1 / coords2 may be NULL.  Same kernels as the node path (crt_progressive_node without weight term). */
+int crt_score_matrix(crt_ctx *ctx, const double *tensors1, const double *coords1, int32_t n, const double *tensors2,
+                     const double *coords2, int32_t m, int32_t d, double gamma_tensor, double gamma_coords, int32_t flexible,
+                     double *score_matrix, int32_t *status);
+
+/* Protein.mean_function (multiple_alignment.py:351-383) for a given alignment (aln1 / aln2 int64 [len], -1 = gap, a column
+ * with two gaps is CRT_E_ARG): tensors_mean [len,d] and -- flexible = 0 -- coords_mean [len,3] after superposing both chains on
+ * the common positions of the alignment (no superposition when <= 3, *status = CRT_ST_FEW_COMMON).  flexible != 0 (:359-360):
+ * tensors only, coords1 / coords2 / coords_mean may be NULL. */
+int crt_mean_function(crt_ctx *ctx, const double *tensors1, const double *coords1, int32_t n, const double *tensors2,
+                      const double *coords2, int32_t m, int32_t d, const int64_t *aln1, const int64_t *aln2, int64_t len,
+                      int32_t flexible, double *tensors_mean, double *coords_mean, int32_t *status);
+
+/* get_mean_weights (multiple_alignment.py:73-82): weights_mean[i] = (aln1[i] != -1 ? weights1[aln1[i]] : 0) +
+ * (aln2[i] != -1 ? weights2[aln2[i]] : 0), float64 [len]. */
+int crt_mean_weights(crt_ctx *ctx, const double *weights1, int32_t n, const double *weights2, int32_t m, const int64_t *aln1,
+                     const int64_t *aln2, int64_t len, double *weights_mean);
+
 /* All independent nodes of one level of the guide tree at once (nodes at the same depth are independent).
  * Node k aligns child chains 2k and 2k+1 of the packed level arrays: tensors [sum,d], coords [sum,3], weights [sum],
  * offsets [2 n_nodes + 1]; mult [n_nodes][2] = (multiplier_n1, multiplier_n2) of multiple_alignment.py:200-203.  Same computation

@@ -50,6 +50,23 @@ def main():
                     out[f"{name}_{tag}_final_coords"] = fin.coordinates
                 out[f"{name}_{tag}_final_weights"] = msa.final_consensus_weights[-1]
         print(f"[gen-flexible] {name}: N={ch.n} alignment {out[f'{name}_tt_aln'].shape}  {time.time() - t0:.1f}s")
+    # Protein.score_function / mean_function / get_mean_weights called directly (:321-383, :73-82), both flexible settings
+    for name, (lens, seed) in dict(fn_a=([73, 91], 211), fn_short=([3, 2], 212), fn_b=([140, 37], 213)).items():
+        ch = synth.make_chains(2, lens, 10, seed=seed, family_size=2)
+        out[f"{name}_lengths"], out[f"{name}_seed"] = np.array(lens), seed
+        p1, p2 = ref_harness.proteins_from_chains(ma, ch)
+        rng = np.random.default_rng(seed)
+        w1, w2 = rng.integers(1, 5, (lens[0], 1)).astype(np.float64), rng.integers(1, 4, (lens[1], 1)).astype(np.float64)
+        for tag, flex in (("rigid", False), ("flex", True)):
+            S = p1.score_function(p2, flexible=flex, gamma_tensor=7.0, gamma_coords=0.03, verbose=False)
+            a1, a2, _ = dtw.dtw_align(np.arange(lens[0]), np.arange(lens[1]), S, gap_open_penalty=1.0, gap_extend_penalty=0.01)
+            node = p1.mean_function(p2, a1, a2, "int-x", flexible=flex, verbose=False)
+            out[f"{name}_{tag}_S"], out[f"{name}_{tag}_aln"] = S, np.array([a1, a2])
+            out[f"{name}_{tag}_tensors"] = node.tensors
+            if not flex:
+                out[f"{name}_{tag}_coords"] = node.coordinates
+            out[f"{name}_{tag}_weights"] = ma.get_mean_weights(w1, w2, a1, a2)
+        print(f"[gen-flexible] {name}: {lens}")
     np.savez_compressed(os.path.join(GOLD, "flexible.npz"), **out)
 
 

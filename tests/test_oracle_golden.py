@@ -255,6 +255,31 @@ def test_flexible_golden():
     assert np.array_equal(np.array([a1, a2]), g["two_tt_aln"]) and np.array_equal(g["two_tt_aln"], g["two_tf_aln"])
 
 
+def test_protein_methods_golden():
+    """Protein.score_function / mean_function / get_mean_weights (multiple_alignment.py:321-383, :73-82) called directly on the
+    reference: the oracle's score_matrix / mean_function / mean_weights against its outputs, both flexible settings."""
+    g = np.load(os.path.join(G, "flexible.npz"))
+    for name in ("fn_a", "fn_short", "fn_b"):
+        lens, seed = [int(x) for x in g[f"{name}_lengths"]], int(g[f"{name}_seed"])
+        ch = synth.make_chains(2, lens, 10, seed=seed, family_size=2)
+        (t1, c1), (t2, c2) = ch.chain(0), ch.chain(1)
+        rng = np.random.default_rng(seed)
+        w1, w2 = rng.integers(1, 5, (lens[0], 1)).astype(np.float64), rng.integers(1, 4, (lens[1], 1)).astype(np.float64)
+        for tag, flex in (("rigid", False), ("flex", True)):
+            S = O.score_matrix(t1, c1, t2, c2, 7.0, 0.03, flexible=flex)
+            if flex:
+                assert np.array_equal(S, g[f"{name}_{tag}_S"])
+            else:
+                np.testing.assert_allclose(S, g[f"{name}_{tag}_S"], rtol=1e-10, atol=1e-300)
+            a1, a2, _ = O.dtw_align(g[f"{name}_{tag}_S"], 1.0, 0.01)
+            assert np.array_equal(np.array([a1, a2]), g[f"{name}_{tag}_aln"])
+            tm, cm = O.mean_function(t1, c1, t2, c2, a1, a2, flexible=flex)
+            assert np.array_equal(tm, g[f"{name}_{tag}_tensors"])
+            if not flex:
+                np.testing.assert_allclose(cm, g[f"{name}_{tag}_coords"], rtol=0, atol=1e-10)
+            assert np.array_equal(O.mean_weights(w1, w2, a1, a2), g[f"{name}_{tag}_weights"])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Consumers of the multiple alignment (SURVEY 8f ranks 3-4): the oracle restatement against the reference's outputs
 # ------------------------------------------------------------------------------------------------------------------
