@@ -765,6 +765,46 @@ def write_distance_matrix(names, distance_matrix, filename) -> None:
         f.write(text)                       # straight from the engine's page-locked staging buffer
 
 
+def read_distance_matrix(filename):
+    """helper.read_distance_matrix (helper.py:205-229): the inverse of write_distance_matrix -- (names, float64 [N,N]).  File
+    parsing (host I/O, not part of the compute path): first line N, then 'name v v ...' rows; a name is cut at its first '/'."""
+    with open(filename, "rb") as f:
+        lines = f.read().split(b"\n")
+    n = int(lines[0].strip())
+    rows = [ln.split() for ln in lines[1:] if ln.strip()]
+    names = [r[0].decode("utf-8").strip().split("/")[0].strip() for r in rows]
+    assert len(names) == n
+    matrix = np.array([[float(x) for x in r[1:n + 1]] for r in rows], dtype=np.float64)
+    return names, matrix
+
+
+def alignment_to_numpy(alignment) -> typing.Dict[str, np.ndarray]:
+    """multiple_alignment.py:30-42: {name: aligned string with '-'} -> {name: residue index per column, -1 = gap}."""
+    out = {}
+    for name, text in alignment.items():
+        residue = np.frombuffer(text.encode("utf-8") if isinstance(text, str) else bytes(text), dtype=np.uint8) != ord("-")
+        out[name] = np.where(residue, np.cumsum(residue) - 1, -1).astype(np.int64)
+    return out
+
+
+def get_gaussian_score(coord_1, coord_2, gamma=0.03):
+    """score_functions.get_gaussian_score (score_functions.py:6-11) for two points; as the score_function argument of
+    make_score_matrix it selects the device kernel."""
+    return make_score_matrix(np.asarray(coord_1, dtype=np.float64).reshape(1, -1), np.asarray(coord_2, dtype=np.float64).reshape(1, -1),
+                             get_gaussian_score, gamma)[0, 0]
+
+
+def make_score_matrix(coords_1, coords_2, score_function=get_gaussian_score, gamma=0.03, normalized=False) -> np.ndarray:
+    """score_functions.make_score_matrix (score_functions.py:22-51): float64 [n,m] of exp(-gamma sum_k (x[a,k] - y[b,k])^2), in the
+    reference's operation order, on the device (crt_score_matrix, flexible form).  Only the Gaussian score the reference uses is a
+    device kernel; normalized=True (never used by the reference's callers) is not provided."""
+    if score_function is not get_gaussian_score and getattr(score_function, "__name__", "") != "get_gaussian_score":
+        raise NotImplementedError("make_score_matrix: only get_gaussian_score runs on the device")
+    if normalized:
+        raise NotImplementedError("make_score_matrix(normalized=True) is not used on caretta's path and is not provided")
+    return get_engine().score_matrix(coords_1, None, coords_2, None, gamma, 0.0, flexible=True)[0]
+
+
 @dataclass
 class OutputFiles:
     """multiple_alignment.py:85-105 (the files this package can write; PDB / feature / class files stay the reference's)."""

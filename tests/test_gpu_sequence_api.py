@@ -117,3 +117,17 @@ def test_generic_two_sequences_and_batches():
     one = MA.MultipleAlignment(seqs)._pairwise_matrix_generic(dict(gamma=7.0))
     many = MA.MultipleAlignment(seqs)._pairwise_matrix_generic(dict(gamma=7.0), batch_bytes=40000)
     assert np.array_equal(one, many) and np.array_equal(one, O.pairwise_all_flexible(ch.tensors, ch.offsets, 7.0))
+
+
+def test_make_score_matrix_is_the_reference_gaussian():
+    """score_functions.make_score_matrix with get_gaussian_score on the device against the oracle's RBF (pinned bit-exact on the
+    reference's): any feature width, both gammas of the path; agreement to the last ulp of CUDA's exp (<= 1e-14 relative)."""
+    rng = np.random.default_rng(12)
+    for (n, m, k, gamma) in ((37, 51, 10, 7.0), (64, 20, 3, 0.03), (5, 9, 1, 1.0), (1, 1, 16, 0.5)):
+        x, y = rng.normal(0, 0.4, (n, k)), rng.normal(0, 0.4, (m, k))
+        S = MA.make_score_matrix(x, y, MA.get_gaussian_score, gamma)
+        assert S.shape == (n, m)
+        np.testing.assert_allclose(S, O.rbf_matrix(x, y, gamma), rtol=1e-14, atol=0)
+    assert MA.get_gaussian_score(np.array([1.0, 2.0, 3.0]), np.array([1.5, 2.0, 2.0]), 0.03) == pytest.approx(np.exp(-0.03 * 1.25), rel=1e-15)
+    with pytest.raises(NotImplementedError):
+        MA.make_score_matrix(x, y, lambda a, b, g: 0.0, 1.0)

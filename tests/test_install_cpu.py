@@ -44,3 +44,35 @@ def test_install_replaces_existing_reference_attributes(monkeypatch):
             setattr(ma.MultipleAlignment, n, f)
         helper.write_distance_matrix = before_h
         nj.neighbor_joining = before_nj
+
+
+def test_mirror_signatures_of_the_sequence_interface():
+    """Protein / SequenceBase methods, get_mean_weights, make_score_matrix: the reference's parameter names."""
+    ma, dtw, sf, sup, helper, nj = ref_harness.load()
+    from caretta_b200 import multiple_alignment as MA
+    for cls, meths in ((ma.Protein, ["score_function", "mean_function"]), (ma.SequenceBase, ["score_function", "mean_function"])):
+        for m in meths:
+            ref_params = list(inspect.signature(getattr(cls, m)).parameters)
+            got_params = list(inspect.signature(getattr(getattr(MA, cls.__name__), m)).parameters)
+            assert got_params == ref_params, (cls.__name__, m, ref_params, got_params)
+    assert [f.name for f in __import__("dataclasses").fields(MA.Protein)] == [f.name for f in __import__("dataclasses").fields(ma.Protein)]
+    for fn, ref_fn in (("get_mean_weights", ma.get_mean_weights), ("make_score_matrix", sf.make_score_matrix.py_func),
+                       ("get_gaussian_score", sf.get_gaussian_score.py_func), ("read_distance_matrix", helper.read_distance_matrix),
+                       ("alignment_to_numpy", ma.alignment_to_numpy)):
+        assert list(inspect.signature(getattr(MA, fn)).parameters) == list(inspect.signature(ref_fn).parameters), fn
+
+
+def test_host_side_format_helpers_match_the_reference(tmp_path):
+    """read_distance_matrix / alignment_to_numpy are file and string parsing on the host: same results as the reference's."""
+    import numpy as np
+    ma, dtw, sf, sup, helper, nj = ref_harness.load()
+    from caretta_b200 import multiple_alignment as MA
+    aln = {"a": "AC--GT-", "b/x": "-CCC--T", "c": "-------", "d": "ACDEFGH"}
+    r, m = ma.alignment_to_numpy(aln), MA.alignment_to_numpy(aln)
+    assert list(r) == list(m) and all(np.array_equal(r[k], m[k]) for k in r)
+    names = ["p1/A", "q_2", "r3", "s/t/u"]
+    M = np.random.default_rng(0).random((4, 4)) * 100
+    fn = tmp_path / "m.txt"
+    helper.write_distance_matrix(names, M, fn)
+    a, b = helper.read_distance_matrix(fn), MA.read_distance_matrix(fn)
+    assert a[0] == b[0] == ["p1", "q_2", "r3", "s"] and np.array_equal(a[1], b[1]) and b[1].dtype == np.float64
