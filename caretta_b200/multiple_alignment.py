@@ -194,6 +194,11 @@ class _NodeAlignments(collections.abc.Mapping):
     def __len__(self):
         return len(self._names)
 
+    def __reduce__(self):
+        # pickled (the reference's --write-class dumps the whole MultipleAlignment, :557-559) and deep-copied as the plain
+        # dictionary of dictionaries the reference holds
+        return dict, ({name: dict(self[name]) for name in self._names},)
+
 
 class _PoolNodes:
     """The intermediate nodes of a progressive alignment that ran on the device pool (crt_msa_*): fetched from the device in one
@@ -227,6 +232,9 @@ class _LazyNodeList(collections.abc.Sequence):
 
     def __len__(self):
         return len(self._head) + len(self._nodes.ids)
+
+    def __reduce__(self):
+        return list, (self._head + self._materialise(),)              # pickles as the reference's plain list (nodes fetched now)
 
     def __getitem__(self, i):
         if isinstance(i, slice):

@@ -90,6 +90,32 @@ def test_progressive_align_bookkeeping(monkeypatch, name, batch):
     assert np.array_equal(msa.final_consensus_weights[-1], g[f"{name}_final_weights"])
 
 
+@pytest.mark.parametrize("batch", ["pool", "1"])
+def test_alignment_object_pickles_like_the_reference(monkeypatch, batch):
+    """--write-class pickles the whole MultipleAlignment (multiple_alignment.py:557-559): the lazily built final_alignments /
+    final_sequences / final_consensus_weights travel as the plain dict / lists the reference holds."""
+    import copy
+    import pickle
+    g = np.load(os.path.join(G, "msa.npz"))
+    L = g["ragged12_lengths"]
+    ch = synth.make_chains(len(L), list(L), 10, seed=int(g["ragged12_seed"]), family_size=int(g["ragged12_family"]))
+    the_engine = OraclePoolEngine() if batch == "pool" else OracleEngine()
+    monkeypatch.setattr(MA, "get_engine", lambda: the_engine)
+    monkeypatch.setenv("CARETTA_B200_NODE_BATCH", "1")
+    msa = MA.StructureMultiple.from_chains(ch)
+    msa.alignment = msa.progressive_align(g["ragged12_tree"], 1.0, 0.01, 1.0, 0.03, dict(gamma_tensor=7.0, gamma_coords=0.03), None)
+    for clone in (pickle.loads(pickle.dumps(msa)), copy.deepcopy(msa)):
+        assert type(clone.final_alignments) is dict and type(clone.final_sequences) is list and type(clone.final_consensus_weights) is list
+        assert list(clone.final_alignments) == list(msa.final_alignments)
+        for k in msa.final_alignments:
+            assert list(clone.final_alignments[k]) == list(msa.final_alignments[k])
+            assert all(np.array_equal(clone.final_alignments[k][m], msa.final_alignments[k][m]) for m in msa.final_alignments[k])
+        assert [s.name for s in clone.final_sequences] == [str(x) for x in g["ragged12_fs_names"]]
+        assert np.array_equal(clone.final_sequences[-1].tensors, msa.final_sequences[-1].tensors)
+        assert np.array_equal(clone.final_consensus_weights[-1], g["ragged12_final_weights"])
+        assert all(np.array_equal(clone.alignment[k], msa.alignment[k]) for k in msa.alignment)
+
+
 def test_tree_with_forward_reference_is_rejected(monkeypatch):
     monkeypatch.setattr(MA, "get_engine", lambda: OracleEngine())
     ch = synth.make_chains(3, [20, 22, 21], 10, seed=1, family_size=3)
