@@ -1325,7 +1325,8 @@ int dp_batch(crt_ctx *c, bool affine, const double *S, const int64_t *shape_off,
         if (n[p] <= 0 || m[p] <= 0) return fail(CRT_E_ARG, "problem %d has an empty dimension (%d x %d)", p, n[p], m[p]);
         probs[p].s_off = shape_off[p]; probs[p].b_off = cells; probs[p].bnd_off = rows; probs[p].aln_off = alen;
         probs[p].n = n[p]; probs[p].m = m[p];
-        cells += (long long)n[p] * m[p]; rows += n[p]; alen += (long long)n[p] + m[p] + 1;
+        // workspace per problem: backtrack bytes [n][dtw_pitch(m)] (affine) or the H matrix [n][m] (Smith-Waterman)
+        cells += (long long)n[p] * (affine ? dtw_pitch(m[p]) : m[p]); rows += n[p]; alen += (long long)n[p] + m[p] + 1;
         s_end = std::max<long long>(s_end, shape_off[p] + (long long)n[p] * m[p]);
     }
     DevBuf<double> dS, dW, dBnd, dF, dScore;
@@ -1522,7 +1523,7 @@ int crt_progressive_node(crt_ctx *c, const double *tensors1, const double *coord
     const size_t cells = (size_t)n * m, alen = (size_t)n + m + 1;
     if ((rc = c->nd_w.ensure((size_t)n + m))) return rc;
     if ((rc = c->nd_S.ensure(cells))) return rc;
-    if ((rc = c->nd_B.ensure(cells))) return rc;
+    if ((rc = c->nd_B.ensure((size_t)n * dtw_pitch(m)))) return rc;
     if ((rc = c->nd_bnd.ensure((size_t)n * 2 + 2))) return rc;
     if ((rc = c->nd_f.ensure(3))) return rc;
     if ((rc = c->nd_score.ensure(1))) return rc;

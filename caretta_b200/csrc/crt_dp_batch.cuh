@@ -14,7 +14,7 @@ namespace crt {
 
 constexpr int DPC = 4;                // columns per lane
 constexpr int DPSTRIP = 32 * DPC;
-constexpr int DTW_PF = 4;             // wavefront steps of prefetch distance in k_dtw_fill
+constexpr int DTW_PF = 8;             // wavefront steps of prefetch distance in k_dtw_fill (power of two)
 
 struct DpProblem {
     long long s_off;      // offset of S (doubles)
@@ -26,21 +26,41 @@ struct DpProblem {
 
 __device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(FULL, v, 1); }
 
+// Row pitch of the affine DP's backtrack bytes: rows start on a 4-byte boundary so that a lane stores its DPC = 4 codes of a row as
+// one 32-bit word (the fill is bound by the number of memory transactions per wavefront step: every lane is on a different row).
+__host__ __device__ __forceinline__ int dtw_pitch(int m) { return (m + 3) & ~3; }
+static_assert(DPC == 4, "k_dtw_fill packs the DPC backtrack codes of a lane into one 32-bit store");
+
 // ------------------------------------------------------------------------------------------------------------
 // Affine three-state DP.  States: 0 = lower (consumes i), 1 = match, 2 = upper (consumes j); ties -> lowest index
 // (np.argmax).  One byte per cell: bit0 = B[.,.,0], bits1-2 = B[.,.,1], bit3 = B[.,.,2] - 1.
 // ------------------------------------------------------------------------------------------------------------
+// Scores and (strips > 0) the boundary column do not depend on the recurrence: they are fetched DTW_PF wavefront steps ahead
+// with cp.async into a ring in shared memory (one 8-byte slot per lane and column), so that the loop body stays ONE step long.
+// (A register ring needs the loop unrolled by the ring size; at four steps the body was 22 KB of code and the kernel ran at the
+// instruction-fetch rate -- measured: half the unroll, 20 % faster; three warps of one CTA on different steps, 3.7x slower each.)
+__device__ __forceinline__ void dtw_cp_async8(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void dtw_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void dtw_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_probs, const double *S_all, unsigned char *B_all,
                                                  double *bnd_all, double *final3, double open, double ext)
 {
+    __shared__ double ring[DTW_PF][DPC + 2][32];                      // [step slot][column 0..3, boundary 1, boundary 2][lane]
     if ((int)blockIdx.x >= n_probs) return;
     const DpProblem pr = probs[blockIdx.x];
     const int lane = threadIdx.x, n = pr.n, m = pr.m;
     const double *S = S_all + pr.s_off;
-    unsigned char *B = B_all + pr.b_off;
+    unsigned char *B = B_all + pr.b_off;                              // [n][dtw_pitch(m)]
+    const int mp = dtw_pitch(m);
     double *bnd1 = bnd_all + pr.bnd_off * 2, *bnd2 = bnd1 + n;        // M[i][cend][1], M[i][cend][2] per row i (1-based -> i-1)
     const double MINF = -DBL_MAX;
     const int n_strips = (m + DPSTRIP - 1) / DPSTRIP;
+    for (int q = 0; q < DTW_PF * (DPC + 2); ++q) (&ring[0][0][0])[q * 32 + lane] = 0.0;     // columns past m are never fetched
+    __syncwarp();
     for (int strip = 0; strip < n_strips; ++strip) {
         const int c0 = strip * DPSTRIP + lane * DPC;                 // 0-based first owned column
         double P0[DPC], P1[DPC];
@@ -49,33 +69,30 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
         double out1 = 0.0, out2 = 0.0;       // M[i][cend][1], [2] handed to lane + 1
         double dsave = 0.0;                  // M[i-1][c0-1][1]
         const bool last_strip = strip == n_strips - 1;
-        // Scores and (strips > 0) the boundary column do not depend on the recurrence: they are loaded DTW_PF wavefront steps
-        // ahead into a register ring (an L2 round trip is several steps long), the loop is unrolled by the ring size so that
-        // every slot index is a compile-time constant.
-        double sn[DTW_PF][DPC], bq1[DTW_PF], bq2[DTW_PF];
-        auto prefetch = [&](int t, double (&dst)[DPC], double &q1, double &q2) {
+        auto prefetch = [&](int t) {         // one (possibly empty) cp.async group per wavefront step
             const int i = t - lane + 1;
-            const bool ok = i >= 1 && i <= n;
+            if (i >= 1 && i <= n) {
+                double (*slot)[32] = ring[t & (DTW_PF - 1)];
+                const double *src = S + (long long)(i - 1) * m + c0;
 #pragma unroll
-            for (int c = 0; c < DPC; ++c) dst[c] = (ok && c0 + c < m) ? S[(long long)(i - 1) * m + c0 + c] : 0.0;
-            q1 = 0.0; q2 = 0.0;
-            if (lane == 0 && strip > 0 && ok) { q1 = bnd1[i - 1]; q2 = bnd2[i - 1]; }
+                for (int c = 0; c < DPC; ++c)
+                    if (c0 + c < m) dtw_cp_async8(&slot[c][lane], src + c);
+                if (lane == 0 && strip > 0) { dtw_cp_async8(&slot[DPC][0], bnd1 + i - 1); dtw_cp_async8(&slot[DPC + 1][0], bnd2 + i - 1); }
+            }
+            dtw_cp_commit();
         };
-#pragma unroll
-        for (int u = 0; u < DTW_PF; ++u) prefetch(u, sn[u], bq1[u], bq2[u]);
+        for (int u = 0; u < DTW_PF; ++u) prefetch(u);
         const int T = n + 31;
-        for (int t0 = 0; t0 < T; t0 += DTW_PF) {
-#pragma unroll
-          for (int u = 0; u < DTW_PF; ++u) {
-            const int t = t0 + u;
-            if (t >= T) break;
+        for (int t = 0; t < T; ++t) {
             const int i = t - lane + 1;      // 1-based row
             const bool valid = i >= 1 && i <= n;
+            dtw_cp_wait<DTW_PF - 1>();     // the group of step t has landed (DTW_PF - 1 younger groups may be in flight)
+            double (*slot)[32] = ring[t & (DTW_PF - 1)];
             double sc[DPC];
 #pragma unroll
-            for (int c = 0; c < DPC; ++c) sc[c] = sn[u][c];
-            const double b1 = bq1[u], b2 = bq2[u];
-            prefetch(t + DTW_PF, sn[u], bq1[u], bq2[u]);
+            for (int c = 0; c < DPC; ++c) sc[c] = slot[c][lane];
+            const double b1 = slot[DPC][0], b2 = slot[DPC + 1][0];
+            prefetch(t + DTW_PF);            // refills this slot; every lane has read its entries above
             double L1 = shfl_up_d(out1), L2 = shfl_up_d(out2);
             if (lane == 0) {
                 if (strip == 0) { L1 = 0.0; L2 = MINF - open; }       // column 0: (0, 0, MIN - open)
@@ -85,6 +102,7 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
             const double in1 = L1;
             double D1 = dsave;
             if (valid) {
+                unsigned codes = 0;
 #pragma unroll
                 for (int c = 0; c < DPC; ++c) {
                     const int j = c0 + c;     // 0-based column
@@ -99,18 +117,19 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
                     double v = lower; int q = 0;
                     if (dg > v) { v = dg; q = 1; }
                     if (upper > v) { v = upper; q = 2; }
-                    if (j < m) B[(long long)(i - 1) * m + j] = (unsigned char)(ql | (q << 1) | (qu << 3));
+                    codes |= (unsigned)(ql | (q << 1) | (qu << 3)) << (8 * c);
                     if (i == n && j == m - 1) { final3[blockIdx.x * 3] = lower; final3[blockIdx.x * 3 + 1] = v; final3[blockIdx.x * 3 + 2] = upper; }
                     D1 = P1[c];
                     P0[c] = lower; P1[c] = v;
                     L1 = v; L2 = upper;
                 }
+                if (c0 < m) *reinterpret_cast<unsigned *>(B + (long long)(i - 1) * mp + c0) = codes;     // bytes past column m - 1: padding
                 out1 = L1; out2 = L2;
                 dsave = in1;
                 if (!last_strip && lane == 31) { bnd1[i - 1] = out1; bnd2[i - 1] = out2; }
             }
-          }
         }
+        dtw_cp_wait<0>();
         __syncwarp();
     }
 }
@@ -129,7 +148,7 @@ __global__ void k_dtw_trace(const DpProblem *probs, int n_probs, const unsigned 
     score[p] = best;
     int *a1 = aln1 + pr.aln_off, *a2 = aln2 + pr.aln_off;
     int n = pr.n, m = pr.m, k = 0;
-    const int mm = pr.m;
+    const int mm = dtw_pitch(pr.m);
     while (!(n == 0 && m == 0)) {
         if (m == 0) { --n; a1[k] = n; a2[k] = -1; ++k; }
         else if (n == 0) { --m; a1[k] = -1; a2[k] = m; ++k; }
@@ -171,7 +190,7 @@ __global__ void __launch_bounds__(32) k_dtw_trace_w(const DpProblem *probs, int 
     if (lane == 0) score[p] = best;
     int *a1 = aln1 + pr.aln_off, *a2 = aln2 + pr.aln_off;
     int n = pr.n, m = pr.m, k = 0;
-    const int mm = pr.m;
+    const int mm = dtw_pitch(pr.m);
     while (!(n == 0 && m == 0)) {
         // tile = rows r_lo..n-1, columns c_lo..m-1 of B (empty when the walk is on a border: no byte is needed there)
         const int r_hi = n - 1, c_hi = m - 1;

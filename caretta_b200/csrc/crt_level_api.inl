@@ -82,18 +82,19 @@ int level_core(crt_ctx *c, crt_ctx *nc, int32_t n_nodes, int32_t d, const int64_
     CU(cudaEventRecord(c->ev0, st));
     int k0 = 0;
     while (k0 < n_nodes) {
-        long long cells = 0, rows = 0;
+        long long cells = 0, bytes = 0, rows = 0;
         int k1 = k0;
         while (k1 < n_nodes && k1 - k0 < 65535 && (k1 == k0 || cells + (long long)probs[(size_t)k1].n * probs[(size_t)k1].m <= cell_budget)) {
             DpProblem &p = probs[(size_t)k1];
-            p.s_off = cells; p.b_off = cells; p.bnd_off = rows;
+            p.s_off = cells; p.b_off = bytes; p.bnd_off = rows;
             cells += (long long)p.n * p.m;
+            bytes += (long long)p.n * dtw_pitch(p.m);
             rows += p.n;
             ++k1;
         }
         const int nk = k1 - k0;
         if ((rc = c->nd_S.ensure((size_t)cells))) return rc;
-        if ((rc = c->nd_B.ensure((size_t)cells))) return rc;
+        if ((rc = c->nd_B.ensure((size_t)bytes))) return rc;
         if ((rc = c->nd_bnd.ensure((size_t)rows * 2 + 2))) return rc;
         DpProblem *dp = c->lv_probs.p + k0;
         CU(cudaMemcpyAsync(dp, probs.data() + k0, sizeof(DpProblem) * (size_t)nk, cudaMemcpyHostToDevice, st));

@@ -819,21 +819,25 @@ class OutputFiles:
     output_folder: typing.Any = None
     fasta_file: typing.Any = None
     matrix_folder: typing.Any = None
+    class_file: typing.Any = None
 
     @classmethod
     def from_folder(cls, output_folder):
         from pathlib import Path
         output_folder = Path(output_folder)
-        return cls(output_folder, fasta_file=output_folder / "result.fasta", matrix_folder=output_folder / "result_matrix")
+        return cls(output_folder, fasta_file=output_folder / "result.fasta", matrix_folder=output_folder / "result_matrix",
+                   class_file=output_folder / "result_class.pkl")
 
 
 def align_from_proteins(proteins, gap_open_penalty: float = 1.0, gap_extend_penalty: float = 0.01, consensus_weight: bool = True,
-                        output_folder=None, write_fasta: bool = False, write_matrix: bool = False, verbose: bool = False):
+                        output_folder=None, write_fasta: bool = False, write_matrix: bool = False, verbose: bool = False,
+                        full: bool = True, shapemer_indices=None, alphabet_size: typing.Optional[int] = None, write_class: bool = False):
     """align_from_structure_files (multiple_alignment.py:394-596) from the point where the features exist (:488-491): the list of
     Protein(name, tensors, coordinates, sequence) that the reference builds from geometricus.  Same steps, same parameters and
     the same output files as the reference with full=True (the caretta-cli default): all-vs-all matrix -> max - S (:498-501) ->
     guide-tree distance text (:515-522) -> multiple_align (:524-533) -> result.fasta (:540-545) -> RMSD / coverage / TM matrices and
-    their text files (:571-591).  Returns (MultipleAlignment, OutputFiles)."""
+    their text files (:571-591).  full=False is --fast (:503-511) from given shapemer indices; write_class pickles the
+    MultipleAlignment (:557-559).  Returns (MultipleAlignment, OutputFiles)."""
     from pathlib import Path
     output_files = OutputFiles() if output_folder is None else OutputFiles.from_folder(output_folder)
     if output_folder is not None:
@@ -843,8 +847,16 @@ def align_from_proteins(proteins, gap_open_penalty: float = 1.0, gap_extend_pena
     mean_function_params = dict(flexible=False)
     pairwise_distance_matrix = np.array([[0, 1], [1, 0]])
     if len(msa_class.sequences) > 2:
-        pairwise_distance_matrix = msa_class.make_pairwise_matrix(score_function_params=score_function_params)
-        pairwise_distance_matrix = pairwise_distance_matrix.max() - pairwise_distance_matrix
+        if full:
+            pairwise_distance_matrix = msa_class.make_pairwise_matrix(score_function_params=score_function_params)
+            pairwise_distance_matrix = pairwise_distance_matrix.max() - pairwise_distance_matrix
+        else:
+            # --fast (:503-511): Bray-Curtis distances of the shapemer counts; the shapemer indices per protein (geometricus'
+            # map_protein_to_shapemer_indices) and the number of shapemer keys are inputs here
+            if shapemer_indices is None or alphabet_size is None:
+                raise ValueError("full=False needs shapemer_indices (one index array per protein) and alphabet_size")
+            count_matrix = make_count_matrix(list(shapemer_indices), int(alphabet_size))
+            pairwise_distance_matrix = braycurtis(count_matrix, count_matrix)
     names = [s.name for s in msa_class.sequences]
     if write_matrix:
         Path(output_files.matrix_folder).mkdir(exist_ok=True)
@@ -855,6 +867,10 @@ def align_from_proteins(proteins, gap_open_penalty: float = 1.0, gap_extend_pena
                                          score_function_params=score_function_params, mean_function_params=mean_function_params)
     if write_fasta:
         msa_class.write_alignment(output_files.fasta_file)
+    if write_class:                                                         # :557-559
+        import pickle
+        with open(output_files.class_file, "wb") as f:
+            pickle.dump(msa_class, f)
     if write_matrix:
         rmsd, coverage, tm = make_rmsd_coverage_tm_matrix(alignment, msa_class.sequences, superpose_first=False)
         for fname, M in (("rmsd.txt", rmsd), ("coverage.txt", coverage), ("tm.txt", tm)):

@@ -62,3 +62,40 @@ def test_align_from_proteins_fp32_same_alignment(tmp_path, monkeypatch):
     msa, out = MA.align_from_proteins(proteins, output_folder=tmp_path / "r", write_fasta=True)
     assert np.array_equal(np.array([msa.alignment[n] for n in names]), g["aln"])
     assert out.fasta_file.read_bytes() == g["file_result.fasta"].tobytes()
+
+
+@pytest.mark.gpu
+def test_align_from_proteins_fast_mode_and_class_file(tmp_path, monkeypatch):
+    """--fast (multiple_alignment.py:503-511): the guide matrix is the Bray-Curtis distance of shapemer counts (here: given index
+    arrays), everything after it as in the full run, checked against the oracle's composition; --class (:557-559): the pickled
+    object carries the plain dictionaries / lists of the reference."""
+    import pickle
+    from caretta_b200 import multiple_alignment as MA
+    from oracle import oracle as O
+    g, ch, names, seqs = _inputs()
+    monkeypatch.setenv("CARETTA_B200_PRECISION", "fp64")
+    rng = np.random.default_rng(31)
+    K = 64
+    # family members share most of their shapemers, so the guide tree is not degenerate
+    base = [rng.integers(0, K, 40) for _ in range(1 + ch.n // int(g["family"]))]
+    idx = [np.concatenate([base[p // int(g["family"])], rng.integers(0, K, 6)]) for p in range(ch.n)]
+    proteins = [MA.Protein(names[p], ch.chain(p)[0].copy(), ch.chain(p)[1].copy(), seqs[p]) for p in range(ch.n)]
+    msa, out = MA.align_from_proteins(proteins, output_folder=tmp_path / "fast", write_fasta=True, write_matrix=True, full=False,
+                                      shapemer_indices=idx, alphabet_size=K, write_class=True)
+    counts = O.count_matrix(idx, K)
+    D = O.braycurtis(counts, counts)
+    assert np.array_equal(msa.pairwise_distance_matrix, D)
+    assert (out.matrix_folder / "distance_matrix_guide_tree.txt").read_bytes() == O.format_matrix(names, D)
+    tree, bl = O.neighbor_joining(D)
+    assert np.array_equal(msa.tree, tree) and np.array_equal(msa.branch_lengths, bl)
+    want, _, _ = O.progressive_align([(names[p],) + ch.chain(p) for p in range(ch.n)], tree, 1.0, 0.01, 1.0, 1.0, 7.0, 0.03)
+    A = np.array([want[n] for n in names])
+    assert np.array_equal(np.array([msa.alignment[n] for n in names]), A)
+    assert out.fasta_file.read_bytes() == O.format_fasta(names, seqs, A)
+    clone = pickle.loads(out.class_file.read_bytes())
+    assert type(clone.final_alignments) is dict and type(clone.final_sequences) is list
+    assert [s.name for s in clone.final_sequences][-1] == "int-final" and len(clone.final_sequences) == 2 * ch.n - 1
+    assert all(np.array_equal(clone.alignment[n], msa.alignment[n]) for n in names)
+    assert np.array_equal(clone.tree, tree)
+    with pytest.raises(ValueError):
+        MA.align_from_proteins(proteins, full=False)
