@@ -140,3 +140,118 @@ def test_reference_structure_selection(monkeypatch, name):
         assert first == names[gfirst]
         assert list(refs.items()) == [(names[k], [names[x] for x in v]) for k, v in grefs.items()]
         assert alone == [names[x] for x in gno]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# flexible=True and the generic SequenceBase driver: host logic against the reference's flexible golden run
+# (tests/golden/flexible.npz, oracle/gen_golden_flexible.py), the oracle standing in for the device calls
+# ------------------------------------------------------------------------------------------------------------------
+from caretta_b200 import engine as _E  # noqa: E402
+
+
+def _flex(gc):
+    """(flexible_score, flexible_mean) encoded in the gamma_coords sentinels of the node / level / pool calls."""
+    return (gc < 0, gc == _E.GC_FLEXIBLE)
+
+
+class FlexOracleEngine(OraclePoolEngine):
+    def progressive_node(self, t1, c1, w1, t2, c2, w2, m1, m2, gt, gc, gw, go, ge):
+        fs, fm = _flex(gc)
+        a1, a2, tm, cm, wm, sc, st = O.progressive_node(t1, c1, w1, t2, c2, w2, m1, m2, gt, 0.03 if fs else gc, gw, go, ge,
+                                                        flexible_score=fs, flexible_mean=fm)
+        return a1, a2, tm, (np.zeros((len(a1), 3)) if cm is None else cm), wm, sc, st
+
+    def progressive_level(self, children, mults, gt, gc, gw, go, ge):
+        return [self.progressive_node(*a, *b, m[0], m[1], gt, gc, gw, go, ge) for (a, b), m in zip(children, mults)]
+
+    def msa_level(self, child1, child2, mults, gt, gc, gw, go, ge):
+        first, out = len(self.pool), []
+        for a, b, m in zip(child1, child2, mults):
+            a1, a2, tm, cm, wm, sc, st = self.progressive_node(*self.pool[a], *self.pool[b], m[0], m[1], gt, gc, gw, go, ge)
+            out.append((a1.astype(np.int32), a2.astype(np.int32), sc, st))
+            self.pool.append((tm, cm, wm))
+        return first, out
+
+    # the calls of the generic SequenceBase driver
+    def sw_align_batch(self, mats, gap=0.0, want_paths=True):
+        return [(None, None, O.smith_waterman_score(m, gap), 0) for m in mats]
+
+    def score_matrix(self, t1, c1, t2, c2, gamma_tensor=0.03, gamma_coords=0.03, flexible=False):
+        return O.score_matrix(np.asarray(t1, float), c1, np.asarray(t2, float), c2, gamma_tensor, gamma_coords, flexible=flexible), 0
+
+    def dtw_align_batch(self, mats, go, ge):
+        return [O.dtw_align(m, go, ge) for m in mats]
+
+    def mean_weights(self, w1, w2, a1, a2):
+        return O.mean_weights(w1, w2, a1, a2)
+
+
+@pytest.mark.parametrize("name", ["fam8", "ragged12", "short5"])
+@pytest.mark.parametrize("tag", ["tt", "tf"])
+@pytest.mark.parametrize("batch", ["pool", "1", "0"])
+def test_flexible_progressive_align_host_logic(monkeypatch, name, tag, batch):
+    g = np.load(os.path.join(G, "flexible.npz"))
+    L = g[f"{name}_lengths"]
+    ch = synth.make_chains(len(L), list(L), 10, seed=int(g[f"{name}_seed"]), family_size=int(g[f"{name}_family"]))
+    the_engine = FlexOracleEngine()
+    monkeypatch.setattr(MA, "get_engine", lambda: the_engine)
+    monkeypatch.setenv("CARETTA_B200_NODE_BATCH", "0" if batch == "0" else "1")
+    monkeypatch.setenv("CARETTA_B200_MSA_POOL", "1" if batch == "pool" else "0")
+    mean_flex = tag == "tt"
+    prots = [MA.Protein(f"s{p}", ch.chain(p)[0], None if mean_flex else ch.chain(p)[1], "A" * ch.length(p)) for p in range(ch.n)]
+    msa = MA.MultipleAlignment(prots)
+    aln = msa.progressive_align(g[f"{name}_tree"], 1.0, 0.01, 1.0, 0.03, dict(flexible=True, gamma_tensor=7.0, gamma_coords=0.03),
+                                dict(flexible=mean_flex))
+    assert np.array_equal(np.array([aln[f"s{p}"] for p in range(ch.n)]), g[f"{name}_{tag}_aln"])
+    fin = msa.final_sequences[-1]
+    assert np.array_equal(fin.tensors, g[f"{name}_{tag}_final_tensors"])
+    assert (fin.coordinates is None) == mean_flex
+    if not mean_flex:
+        np.testing.assert_allclose(fin.coordinates, g[f"{name}_{tag}_final_coords"], rtol=0, atol=1e-10)
+    assert np.array_equal(msa.final_consensus_weights[-1], g[f"{name}_{tag}_final_weights"])
+    with pytest.raises(ValueError):                                   # coordinate-less nodes cannot be scored rigidly
+        MA.MultipleAlignment(prots).progressive_align(g[f"{name}_tree"], 1.0, 0.01, 1.0, 0.03, dict(gamma_tensor=7.0), dict(flexible=True))
+
+
+class _Feature(MA.SequenceBase):
+    """A SequenceBase without shape tensors: the driver calls ITS score / mean functions (host code by definition)."""
+
+    def __init__(self, name, feat):
+        self.name, self.feat = name, feat
+
+    def score_function(self, other, gamma=1.0):
+        return O.rbf_matrix(self.feat, other.feat, gamma)
+
+    def mean_function(self, other, aln_1, aln_2, name_int):
+        out = np.zeros((len(aln_1), self.feat.shape[1]))
+        for i, (x, y) in enumerate(zip(aln_1, aln_2)):
+            out[i] = other.feat[y] if x == -1 else (self.feat[x] if y == -1 else (self.feat[x] + other.feat[y]) / 2)
+        return _Feature(name_int, out)
+
+    def __len__(self):
+        return self.feat.shape[0]
+
+    def __str__(self):
+        return "X" * len(self)
+
+
+@pytest.mark.parametrize("name", ["fam8", "ragged12", "short5"])
+def test_generic_sequence_base_driver_host_logic(monkeypatch, name):
+    """A user-defined tensor-Gaussian SequenceBase is the reference's flexible=True run: same matrix, alignment, consensus, and the
+    reference's final_alignments bookkeeping (dictionary order = tree order)."""
+    g = np.load(os.path.join(G, "flexible.npz"))
+    L = g[f"{name}_lengths"]
+    ch = synth.make_chains(len(L), list(L), 10, seed=int(g[f"{name}_seed"]), family_size=int(g[f"{name}_family"]))
+    the_engine = FlexOracleEngine()
+    monkeypatch.setattr(MA, "get_engine", lambda: the_engine)
+    seqs = [_Feature(f"s{p}", ch.chain(p)[0]) for p in range(ch.n)]
+    msa = MA.MultipleAlignment(seqs)
+    S = msa.make_pairwise_matrix(dict(gamma=7.0))
+    assert np.array_equal(S, g[f"{name}_score"]) and np.array_equal(S, S.T) and not np.diag(S).any()
+    assert np.array_equal(MA.MultipleAlignment(seqs)._pairwise_matrix_generic(dict(gamma=7.0), batch_bytes=20000), S)   # several device batches
+    aln = msa.progressive_align(g[f"{name}_tree"], 1.0, 0.01, 1.0, 0.03, dict(gamma=7.0), None)
+    assert np.array_equal(np.array([aln[f"s{p}"] for p in range(ch.n)]), g[f"{name}_tt_aln"])
+    assert np.array_equal(msa.final_sequences[-1].feat, g[f"{name}_tt_final_tensors"])
+    assert np.array_equal(msa.final_consensus_weights[-1], g[f"{name}_tt_final_weights"])
+    assert list(msa.final_alignments)[:ch.n] == [f"s{p}" for p in range(ch.n)] and list(msa.final_alignments)[-1] == "int-final"
+    assert list(msa.final_alignments["int-final"]) == list(aln)
