@@ -528,6 +528,36 @@ class Engine:
         out = [(a1[int(off[q]):int(off[q]) + int(ln[q])], a2[int(off[q]):int(off[q]) + int(ln[q])], float(sc[q]), int(st[q])) for q in range(k)]
         return first.value, out
 
+    def msa_level_ext(self, child1, child2, mults, gamma_tensor=7.0, gamma_coords=0.03, gamma_weight=0.03, gap_open=1.0, gap_extend=0.01):
+        """msa_level whose alignments are views that end in a -1 sentinel (entry [len] = -1: a gap index -1 then gathers -1):
+        [(aln_1 int32 [len + 1], aln_2 int32 [len + 1], dtw_score, status)], no per-node copies."""
+        c1 = np.ascontiguousarray(child1, dtype=np.int32)
+        c2 = np.ascontiguousarray(child2, dtype=np.int32)
+        k = len(c1)
+        M = np.ascontiguousarray(np.asarray(mults, dtype=np.float64).reshape(k, 2))
+        L = np.asarray(self._msa_lengths, dtype=np.int64)
+        caps = L[c1] + L[c2]
+        cap = int(caps.sum())
+        # one spare slot at the end: the sentinel of a last node that fills its whole capacity (all-gap alignments only)
+        a1, a2 = np.empty(cap + 1, np.int32), np.empty(cap + 1, np.int32)
+        off, ln = np.zeros(k + 1, np.int64), np.empty(k, np.int32)
+        sc, st = np.empty(k), np.empty(k, np.int32)
+        first = C.c_int32()
+        self._check(self.lib.crt_msa_level(self.h, k, _p(c1), _p(c2), _p(M), float(gamma_tensor), float(gamma_coords), float(gamma_weight),
+                                           float(gap_open), float(gap_extend), _p(a1), _p(a2), cap, _p(off), _p(ln), _p(sc), _p(st),
+                                           C.byref(first)), "crt_msa_level")
+        self._msa_lengths.extend(ln.tolist())
+        ends = off[:-1] + ln
+        room = ln < caps                         # the sentinel fits into the node's own slots ...
+        room[k - 1] = True                       # ... or into the spare slot behind the last node
+        a1[ends[room]] = -1
+        a2[ends[room]] = -1
+        lo, hi, scl, stl = off[:-1].tolist(), (ends + 1).tolist(), sc.tolist(), st.tolist()
+        out = [(a1[lo[q]:hi[q]], a2[lo[q]:hi[q]], scl[q], stl[q]) for q in range(k)]
+        for q in np.nonzero(~room)[0].tolist():  # a node that fills its whole capacity (no column pairs two residues): copies
+            out[q] = (np.append(a1[lo[q]:hi[q] - 1], np.int32(-1)), np.append(a2[lo[q]:hi[q] - 1], np.int32(-1)), scl[q], stl[q])
+        return first.value, out
+
     def msa_fetch(self, ids):
         """[(tensors [L,d], coordinates [L,3], weights [L,1])] of the listed pool sequences (views of three packed arrays)."""
         ids = np.ascontiguousarray(ids, dtype=np.int32)

@@ -123,24 +123,25 @@ def pack_sequences(sequences, need_coordinates: bool = True) -> typing.Tuple[np.
     whose coordinates are None gets zeros."""
     if len(sequences) == 0:
         raise ValueError("no sequences")
-    d = int(np.asarray(sequences[0].tensors).shape[1])
-    lens, cs = [], []
-    for s in sequences:
-        t = np.asarray(s.tensors)
+    asarray = np.asarray
+    ts = [asarray(s.tensors) for s in sequences]
+    d = int(ts[0].shape[1]) if ts[0].ndim == 2 else -1
+    cs = []
+    for s, t in zip(sequences, ts):
         if t.ndim != 2 or t.shape[1] != d:
             raise ValueError(f"{getattr(s, 'name', '?')}: tensors must be [L,{d}]")
-        if getattr(s, "coordinates", None) is None and not need_coordinates:
+        c = getattr(s, "coordinates", None)
+        if c is None and not need_coordinates:
             c = np.zeros((t.shape[0], 3))
         else:
-            c = np.asarray(s.coordinates)
+            c = asarray(c)
         if c.ndim != 2 or c.shape[1] != 3 or c.shape[0] != t.shape[0]:
             raise ValueError(f"{getattr(s, 'name', '?')}: coordinates must be [L,3] with the same L as tensors")
-        lens.append(t.shape[0])
-        cs.append(np.asarray(c, dtype=np.float64))
+        cs.append(c)
     offsets = np.zeros(len(sequences) + 1, np.int64)
-    offsets[1:] = np.cumsum(lens)
-    coords = np.concatenate(cs)
-    tensors = np.concatenate([np.asarray(s.tensors, dtype=np.float64) for s in sequences])
+    np.cumsum([t.shape[0] for t in ts], out=offsets[1:])
+    coords = np.concatenate(cs, dtype=np.float64)
+    tensors = np.concatenate(ts, dtype=np.float64)
     return coords, tensors, offsets
 
 
@@ -409,19 +410,24 @@ class MultipleAlignment:
         use_pool = os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0" and os.environ.get("CARETTA_B200_MSA_POOL", "1") != "0" \
             and hasattr(eng, "msa_level")
 
+        with_sentinel = False
+
         def finish(q, res):
             a, b, name_int = steps[q]
             i = n_leaves + q
             statuses[q] = res[-1]
-            ext = []
-            for al in (res[0], res[1]):
-                e = np.empty(len(al) + 1, np.int32)
-                e[:-1] = al
-                e[-1] = -1
-                ext.append(e)
+            if with_sentinel:                                       # msa_level_ext: views that already end in the -1 sentinel
+                ext = (res[0], res[1])
+            else:
+                ext = []
+                for al in (res[0], res[1]):
+                    e = np.empty(len(al) + 1, np.int32)
+                    e[:-1] = al
+                    e[-1] = -1
+                    ext.append(e)
             down[i] = (ext[0], ext[1])
             parent_side[a], parent_side[b] = ext[0][:-1], ext[1][:-1]
-            node_len[i] = len(res[0])
+            node_len[i] = len(ext[0]) - 1
             if len(res) > 4:                                        # host path: the node itself comes back with the alignment
                 final_sequences[i] = make_node(name_int, res[2], res[3])
                 final_consensus_weights[i] = res[4]
@@ -444,9 +450,13 @@ class MultipleAlignment:
             eng.set_chains(*pack_sequences(self.sequences, need_coordinates=need_xyz))
             eng.msa_begin(consensus_weight)
             pool_id = list(range(n_leaves)) + [None] * len(steps)
+            level_call = getattr(eng, "msa_level_ext", None)          # alignments come back with the sentinel in place: no copies
+            with_sentinel = level_call is not None
+            if level_call is None:
+                level_call = eng.msa_level
             for qs in levels:
-                first, results = eng.msa_level([pool_id[steps[q][0]] for q in qs], [pool_id[steps[q][1]] for q in qs],
-                                               [multipliers(q) for q in qs], gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty)
+                first, results = level_call([pool_id[steps[q][0]] for q in qs], [pool_id[steps[q][1]] for q in qs],
+                                            [multipliers(q) for q in qs], gt, gc, gamma_weight, gap_open_penalty, gap_extend_penalty)
                 for k, (q, res) in enumerate(zip(qs, results)):
                     pool_id[n_leaves + q] = first + k
                     finish(q, res)

@@ -58,13 +58,21 @@ class OraclePoolEngine(OracleEngine):
         return [self.pool[i] for i in ids]
 
 
+class OraclePoolEngineExt(OraclePoolEngine):
+    """The product engine's msa_level_ext: alignments come back as arrays that already end in the -1 sentinel."""
+
+    def msa_level_ext(self, child1, child2, mults, gt, gc, gw, go, ge):
+        first, out = self.msa_level(child1, child2, mults, gt, gc, gw, go, ge)
+        return first, [(np.append(a1, np.int32(-1)), np.append(a2, np.int32(-1)), sc, st) for a1, a2, sc, st in out]
+
+
 @pytest.mark.parametrize("name", ["fam8", "ragged12", "mixed40"])
-@pytest.mark.parametrize("batch", ["pool", "1", "0"])
+@pytest.mark.parametrize("batch", ["pool", "poolx", "1", "0"])
 def test_progressive_align_bookkeeping(monkeypatch, name, batch):
     g = np.load(os.path.join(G, "msa.npz"))
     L = g[f"{name}_lengths"]
     ch = synth.make_chains(len(L), list(L), 10, seed=int(g[f"{name}_seed"]), family_size=int(g[f"{name}_family"]))
-    the_engine = OraclePoolEngine() if batch == "pool" else OracleEngine()
+    the_engine = OraclePoolEngineExt() if batch == "poolx" else OraclePoolEngine() if batch == "pool" else OracleEngine()
     monkeypatch.setattr(MA, "get_engine", lambda: the_engine)
     monkeypatch.setenv("CARETTA_B200_NODE_BATCH", "0" if batch == "0" else "1")
     OracleEngine.calls, OracleEngine.batch_sizes = 0, []
