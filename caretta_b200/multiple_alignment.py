@@ -220,11 +220,26 @@ class _PoolNodes:
         return self.data
 
 
+class _LeafWeights(collections.abc.Sequence):
+    """The consensus weights of the leaves (multiple_alignment.py:184-188): np.full((len, 1), consensus_weight), made when read."""
+
+    def __init__(self, lengths, consensus_weight):
+        self._lengths, self._w = list(lengths), float(consensus_weight)
+
+    def __len__(self):
+        return len(self._lengths)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        return np.full((self._lengths[i], 1), self._w, dtype=np.float64)
+
+
 class _LazyNodeList(collections.abc.Sequence):
     """final_sequences / final_consensus_weights (multiple_alignment.py:251-252): the leaves followed by the intermediate nodes."""
 
     def __init__(self, head, nodes: _PoolNodes, make):
-        self._head, self._nodes, self._make, self._tail = list(head), nodes, make, None
+        self._head, self._nodes, self._make, self._tail = head if isinstance(head, _LeafWeights) else list(head), nodes, make, None
 
     def _materialise(self):
         if self._tail is None:
@@ -235,11 +250,11 @@ class _LazyNodeList(collections.abc.Sequence):
         return len(self._head) + len(self._nodes.ids)
 
     def __reduce__(self):
-        return list, (self._head + self._materialise(),)              # pickles as the reference's plain list (nodes fetched now)
+        return list, (list(self._head) + self._materialise(),)        # pickles as the reference's plain list (nodes fetched now)
 
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return (self._head + self._materialise())[i]
+            return (list(self._head) + self._materialise())[i]
         if i < 0:
             i += len(self)
         if i < 0 or i >= len(self):
@@ -390,7 +405,12 @@ class MultipleAlignment:
         steps.append((int(tree[-1, 0]), int(tree[-1, 1]), "int-final"))
         n_total = n_leaves + len(steps)
         final_sequences = [s for s in self.sequences] + [None] * len(steps)
-        final_consensus_weights = [np.full((len(s), 1), consensus_weight, dtype=np.float64) for s in self.sequences] + [None] * len(steps)
+        leaf_lengths = [len(s) for s in self.sequences]
+        use_pool = os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0" and os.environ.get("CARETTA_B200_MSA_POOL", "1") != "0" \
+            and hasattr(eng, "msa_level")
+        # (:184-188) with the sequences in the device pool the leaves' weights are only made when somebody reads them
+        final_consensus_weights = None if use_pool else \
+            [np.full((n, 1), consensus_weight, dtype=np.float64) for n in leaf_lengths] + [None] * len(steps)
         # Bookkeeping.  The reference re-indexes the index arrays of EVERY member of both children at every node (:219-226), which
         # is O(N x depth x length) in total.  Here a node only keeps its two alignments; index arrays are composed top-down when
         # they are needed: the map (columns of a frame -> columns of node j) goes down the tree with one gather per edge, and at
@@ -404,12 +424,9 @@ class MultipleAlignment:
             level[n_leaves + q] = 1 + max(level[a], level[b])
             count[n_leaves + q] = count[a] + count[b]
         statuses = np.zeros(len(steps), np.int32)
-        node_len = [len(s) for s in self.sequences] + [0] * len(steps)
+        node_len = leaf_lengths + [0] * len(steps)
         down = [None] * n_total                   # node -> (aln_1, aln_2) with a -1 sentinel appended: index -1 (gap) picks -1
         parent_side = [None] * n_total            # child -> its side of the parent's alignment (columns of the parent -> columns of the child)
-        use_pool = os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0" and os.environ.get("CARETTA_B200_MSA_POOL", "1") != "0" \
-            and hasattr(eng, "msa_level")
-
         with_sentinel = False
 
         def finish(q, res):
@@ -444,7 +461,9 @@ class MultipleAlignment:
             return ((s1.tensors, xyz[0], final_consensus_weights[a]), (s2.tensors, xyz[1], final_consensus_weights[b])), \
                 multipliers(q)
 
-        levels = [[q for q in range(len(steps)) if level[n_leaves + q] == lv] for lv in range(1, (max(level) if steps else 0) + 1)]
+        levels = [[] for _ in range(max(level) if steps else 0)]
+        for q in range(len(steps)):
+            levels[level[n_leaves + q] - 1].append(q)
         if use_pool:
             # the sequences stay on the device: leaves = pool ids 0..N-1, every level appends its nodes; only alignments come back
             eng.set_chains(*pack_sequences(self.sequences, need_coordinates=need_xyz))
@@ -462,7 +481,7 @@ class MultipleAlignment:
                     finish(q, res)
             nodes = _PoolNodes(eng, pool_id[n_leaves:], [st[2] for st in steps])
             final_sequences = _LazyNodeList(final_sequences[:n_leaves], nodes, lambda q, rec: make_node(steps[q][2], rec[0], rec[1]))
-            final_consensus_weights = _LazyNodeList(final_consensus_weights[:n_leaves], nodes, lambda q, rec: rec[2])
+            final_consensus_weights = _LazyNodeList(_LeafWeights(leaf_lengths, consensus_weight), nodes, lambda q, rec: rec[2])
             if os.environ.get("CARETTA_B200_FETCH_NODES", "0") != "0":
                 nodes.fetch()
         elif os.environ.get("CARETTA_B200_NODE_BATCH", "1") != "0":
