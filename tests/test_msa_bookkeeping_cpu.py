@@ -263,3 +263,43 @@ def test_generic_sequence_base_driver_host_logic(monkeypatch, name):
     assert np.array_equal(msa.final_consensus_weights[-1], g[f"{name}_tt_final_weights"])
     assert list(msa.final_alignments)[:ch.n] == [f"s{p}" for p in range(ch.n)] and list(msa.final_alignments)[-1] == "int-final"
     assert list(msa.final_alignments["int-final"]) == list(aln)
+
+
+def test_msa_level_ext_sentinels_without_a_device():
+    """Engine.msa_level_ext hands out views of the packed alignment arrays that end in the -1 sentinel.  A node that fills its whole
+    capacity (no column pairs two residues) has no room for it inside its own slots: it must get a copy, and its neighbour's first
+    entry must stay intact.  The C call is replaced by a stand-in that writes through the pointers like crt_msa_level does."""
+    import ctypes as C
+    eng = object.__new__(_E.Engine)
+    eng.h = None
+    eng._msa_lengths = [2, 3, 1, 1, 4, 2]                      # pool: six sequences
+    plan = {0: ([0, 1, -1], [0, 1, 2]),                        # children (0, 1): 3 of 5 slots used
+            1: ([0, -1], [-1, 0]),                             # children (2, 3): 2 of 2 slots used -> no room for the sentinel
+            2: ([0, 1, 2, 3, -1, -1], [-1, -1, -1, -1, 0, 1])}  # children (4, 5), last node: 6 of 6 slots, spare slot behind it
+
+    class Lib:
+        @staticmethod
+        def crt_msa_level(h, k, c1, c2, M, gt, gc, gw, go, ge, a1, a2, cap, off, ln, sc, st, first):
+            A1, A2 = (C.c_int32 * (cap + 1)).from_address(a1.value), (C.c_int32 * (cap + 1)).from_address(a2.value)
+            OFF, LN = (C.c_int64 * (k + 1)).from_address(off.value), (C.c_int32 * k).from_address(ln.value)
+            SC, ST = (C.c_double * k).from_address(sc.value), (C.c_int32 * k).from_address(st.value)
+            caps, pos = [5, 2, 6], 0
+            for q in range(k):
+                x, y = plan[q]
+                OFF[q] = pos
+                for i, (u, v) in enumerate(zip(x, y)):
+                    A1[pos + i], A2[pos + i] = u, v
+                for i in range(len(x), caps[q]):
+                    A1[pos + i], A2[pos + i] = 77, 77       # unused capacity
+                LN[q], SC[q], ST[q] = len(x), 1.5 + q, 0
+                pos += caps[q]
+            OFF[k] = pos
+            first._obj.value = 6
+            return 0
+
+    eng.lib = Lib()
+    first, out = eng.msa_level_ext([0, 2, 4], [1, 3, 5], [(0.25, 0.25)] * 3)
+    assert first == 6 and eng._msa_lengths[6:] == [3, 2, 6]
+    for q, (x, y) in plan.items():
+        assert out[q][0].tolist() == x + [-1] and out[q][1].tolist() == y + [-1] and out[q][0].dtype == np.int32
+        assert out[q][2] == 1.5 + q and out[q][3] == 0
