@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcaretta_b200.so")
-SOURCES = ["crt_api.cu", "crt_kernels.cuh", "crt_fill_f32.cuh", "crt_fill1_v2.cuh", "crt_fill2_v3.cuh", "crt_dp_batch.cuh", "crt_nj.cuh", "crt_node.cuh", "crt_consumers.cuh", "crt_consumers_api.inl", "crt_level_api.inl", os.path.join("..", "..", "include", "caretta_b200.h"), "Makefile"]
+SOURCES = ["crt_api.cu", "crt_kernels.cuh", "crt_fill_f32.cuh", "crt_fill1_v2.cuh", "crt_fill1_v4.cuh", "crt_multi.inl", "crt_fill2_v3.cuh", "crt_dp_batch.cuh", "crt_nj.cuh", "crt_node.cuh", "crt_consumers.cuh", "crt_consumers_api.inl", "crt_level_api.inl", os.path.join("..", "..", "include", "caretta_b200.h"), "Makefile"]
 
 
 def needs_build() -> bool:

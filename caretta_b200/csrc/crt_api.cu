@@ -4,6 +4,7 @@
 #include "crt_kernels.cuh"
 #include "crt_fill_f32.cuh"
 #include "crt_fill1_v2.cuh"
+#include "crt_fill1_v4.cuh"
 #include "crt_fill2_v3.cuh"
 #include "crt_dp_batch.cuh"
 #include "crt_nj.cuh"
@@ -81,6 +82,18 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// result slots whose status carries ST_TIE: list[atomicAdd(count)] = slot (the host sorts the list)
+__global__ void k_collect_tie(const int *status, long long n, int *list, int *count)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n && (status[q] & ST_TIE)) list[atomicAdd(count, 1)] = (int)q;
+}
+__global__ void k_mark_status(int *status, const int *list, int n, int bit)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) status[list[q]] |= bit;
+}
+
 struct HostUnit {
     Unit u;
     int C;          // columns per lane
@@ -95,7 +108,7 @@ struct Batch { size_t first, count; int C, multi; size_t tb_n, rows2_n, bnd_n, p
 struct crt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     int sm_count = 0, clock_khz = 0;
     size_t mem_total = 0;
 
@@ -130,10 +143,20 @@ struct crt_ctx {
     static constexpr int MAX_WS = 4;
     Workspace ws[MAX_WS];
     int n_streams = 3;
-    DevBuf<Unit> d_units;
+    DevBuf<Unit> d_units, d_units2;      // d_units2: the float64 re-run of the tie pairs
+    DevBuf<int> tie_list;                // [0] = count, [1..] = result slots marked ST_TIE
+    long long rerun_pairs = 0;
+    double rerun_ms = 0;
+    double tb_bytes = 0;                 // traceback words the stage-1 fills of the last run wrote (all batches)
     DevBuf<int> path_len, pair_istar, pair_zflag, ncommon, status;
     DevBuf<int> d_pi, d_pj;              // pair ids of the cached all-vs-all plan, result order (device copy for the dense scatter)
     DevBuf<double> dense;                // [1 or 3][N][N] dense matrices of crt_pairwise_all
+    // crt_scatter_gathered: the pairs of every rank's shard (rank-major, shard order), cached per chain set and world
+    DevBuf<int> lay_pi, lay_pj;
+    DevBuf<long long> lay_off;
+    unsigned long long lay_hash = 0;
+    int lay_world = 0;
+    long long lay_total = 0;
     DevBuf<double> score, score1, rmsd, tm, xform;
     DevBuf<float> f32tmp;
     double phase_ms[4] = {0, 0, 0, 0};      // fill1, trace, rows2, fill2 (only meaningful with one stream)
@@ -268,15 +291,16 @@ int launch_fill_c(int C, bool multi, const Unit *units, int n, typename P::Args 
     return 0;
 }
 
-// stage-1 fp32 kernel: k_fill1_v3 (two columns per packed FMA, fast/checked row groups)
+// stage-1 fp32 kernel: k_fill1_v4 (two columns per packed FMA, fast/checked row groups, tie flags: 3 bits per cell)
 template <int D>
-int launch_fill1_f32(int C, bool multi, const Unit *units, int n, Fill1Args args, FillOut out, const long long *offsets, cudaStream_t st)
+int launch_fill1_f32(int C, bool multi, const Unit *units, int n, Fill1Args args, FillOut out, const long long *offsets, TieArgs tie,
+                     cudaStream_t st)
 {
 #define CRT_CASE(CC)                                                                                  \
     case CC:                                                                                          \
         if constexpr (CC * D <= 100) {                                                                \
-            if (multi) k_fill1_v3<D, CC, true><<<n, 32, 0, st>>>(units, n, args, out, offsets);        \
-            else k_fill1_v3<D, CC, false><<<n, 32, 0, st>>>(units, n, args, out, offsets);            \
+            if (multi) k_fill1_v4<D, CC, true><<<n, 32, 0, st>>>(units, n, args, out, offsets, tie);   \
+            else k_fill1_v4<D, CC, false><<<n, 32, 0, st>>>(units, n, args, out, offsets, tie);       \
             break;                                                                                    \
         } else return fail(CRT_E_ARG, "no fp32 stage-1 kernel for C=%d D=%d", C, D);
     switch (C) {
@@ -475,21 +499,37 @@ int env_batches()
     return std::min(std::max(n, 1), 256);
 }
 
-template <int CMAXT>
-int launch_trace(int C, const TraceArgs &ta, int nu, int n_dense, cudaStream_t st)
+// tie3: the codes come from k_fill1_v4 (3 bits per cell); otherwise from the float64 k_fill (2 bits per cell)
+int launch_trace(int C, const TraceArgs &ta, int nu, int n_dense, cudaStream_t st, bool tie3)
 {
     const int grid = (n_dense + TRACE_THREADS - 1) / TRACE_THREADS;
+#define CRT_CASE(CC)                                                                          \
+    case CC:                                                                                  \
+        if (tie3) k_trace<CC, true><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense);          \
+        else k_trace<CC, false><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense);             \
+        break;
     switch (C) {
-    case 2: k_trace<2><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
-    case 3: k_trace<3><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
-    case 4: k_trace<4><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
-    case 6: k_trace<6><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
-    case 8: k_trace<8><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
-    case 10: k_trace<10><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense); break;
+        CRT_CASE(2) CRT_CASE(3) CRT_CASE(4) CRT_CASE(6) CRT_CASE(8) CRT_CASE(10)
     default: return fail(CRT_E_ARG, "no trace kernel for C=%d", C);
     }
+#undef CRT_CASE
     CU(cudaGetLastError());
     return 0;
+}
+
+// Tie detection of the fp32 production mode (crt_fill1_v4.cuh).  CARETTA_B200_TIE_C: candidates closer than C * 2^-53 * H tie in
+// the reference's float64 matrix (default 8; 2 catches every such pair of config C3, 1 misses 5 of 814); CARETTA_B200_TIE_EPS: relative closeness fp32 cannot order (default 1e-4);
+// CARETTA_B200_TIE_RERUN=0 leaves the marked pairs as fp32 computed them (study runs).
+TieArgs env_tie()
+{
+    const char *ec = getenv("CARETTA_B200_TIE_C"), *ee = getenv("CARETTA_B200_TIE_EPS");
+    const double cc = ec ? atof(ec) : 8.0, ep = ee ? atof(ee) : 1e-4;
+    return TieArgs{(float)(cc * 1.1102230246251565e-16), (float)ep};
+}
+bool env_tie_rerun()
+{
+    const char *e = getenv("CARETTA_B200_TIE_RERUN");
+    return e ? atoi(e) != 0 : true;
 }
 
 int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, long long n_pairs, PathSink *sink,
@@ -527,52 +567,57 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     }
     if (want_paths) { sink->a1.assign((size_t)n_pairs, {}); sink->a2.assign((size_t)n_pairs, {}); }
 
+    // group by kernel variant so that each launch is homogeneous (inside a group the order is kept), then carve batches:
+    // same (C, multi), bounded workspace; pipeline mode aims at env_batches() batches, the stream-per-batch mode at two per stream
+    auto carve = [&](std::vector<HostUnit> &uv, int uprec, bool main_run, std::vector<Batch> &bout, std::vector<Unit> &hout) {
+        const size_t tsz_u = uprec == CRT_FP32 ? 4 : 8, row2sz_u = uprec == CRT_FP32 ? 16 : 32;
+        std::stable_sort(uv.begin(), uv.end(), [](const HostUnit &a, const HostUnit &b) {
+            if (a.multi != b.multi) return a.multi < b.multi;
+            return a.C < b.C;
+        });
+        size_t total_bytes = 0;
+        auto unit_bytes = [&](const HostUnit &h) {
+            return (size_t)h.u.n_strips * h.u.tchunks * 32 * 16 + (size_t)h.u.G * row2sz_u + (size_t)h.u.n_pairs * h.u.path_stride * 4 +
+                   (h.multi ? ((size_t)h.u.tchunks * 4 + 8) * tsz_u : 0);
+        };
+        for (auto &h : uv) total_bytes += unit_bytes(h);
+        size_t budget = env_budget();
+        budget = std::min(budget, std::max<size_t>(c->mem_total / 20, (size_t)64 << 20));
+        if (main_run) {
+            if (pipe) budget = std::min(budget, std::max<size_t>(total_bytes / env_batches() + 1, (size_t)64 << 20));
+            else if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
+        }
+        hout.resize(uv.size());
+        bout.clear();
+        size_t pos = 0;
+        while (pos < uv.size()) {
+            Batch b{pos, 0, uv[pos].C, uv[pos].multi, 0, 0, 0, 0, 0};
+            size_t end = pos;
+            while (end < uv.size() && uv[end].C == b.C && uv[end].multi == b.multi) {
+                HostUnit &h = uv[end];
+                const size_t tb_u = (size_t)h.u.n_strips * h.u.tchunks * 32, rows_u = (size_t)h.u.G;
+                const size_t path_u = (size_t)h.u.n_pairs * h.u.path_stride, bnd_u = b.multi ? (size_t)h.u.tchunks * 4 + 8 : 0;
+                const size_t bytes = (b.tb_n + tb_u) * 16 + (b.rows2_n + rows_u) * row2sz_u + (b.path_n + path_u) * 4 + (b.bnd_n + bnd_u) * tsz_u;
+                if (end > pos && bytes > budget) break;
+                h.u.tb_base = (long long)b.tb_n; h.u.rows2_base = (long long)b.rows2_n;
+                h.u.path_base = (long long)b.path_n; h.u.bnd_base = (long long)b.bnd_n;
+                h.u.dense_base = b.n_dense; b.n_dense += h.u.n_pairs;
+                b.tb_n += tb_u; b.rows2_n += rows_u; b.path_n += path_u; b.bnd_n += bnd_u;
+                hout[end] = h.u;
+                ++end;
+            }
+            b.count = end - pos;
+            bout.push_back(b);
+            pos = end;
+        }
+    };
     std::vector<Batch> batches;
     std::vector<Unit> hu;
     if (use_cached_plan) {
         batches = c->plan.batches;
         hu = c->plan.hu;
     } else {
-    // group by kernel variant so that each launch is homogeneous; inside a group keep the (j, i0) order
-    std::stable_sort(units.begin(), units.end(), [](const HostUnit &a, const HostUnit &b) {
-        if (a.multi != b.multi) return a.multi < b.multi;
-        return a.C < b.C;
-    });
-
-    // ---- carve batches: same (C, multi), bounded workspace; pipeline mode aims at env_batches() batches, the
-    //      stream-per-batch mode at two batches per stream
-    size_t total_bytes = 0;
-    auto unit_bytes = [&](const HostUnit &h) {
-        return (size_t)h.u.n_strips * h.u.tchunks * 32 * 16 + (size_t)h.u.G * row2sz + (size_t)h.u.n_pairs * h.u.path_stride * 4 +
-               (h.multi ? ((size_t)h.u.tchunks * 4 + 8) * tsz : 0);
-    };
-    for (auto &h : units) total_bytes += unit_bytes(h);
-    size_t budget = env_budget();
-    budget = std::min(budget, std::max<size_t>(c->mem_total / 20, (size_t)64 << 20));
-    if (pipe) budget = std::min(budget, std::max<size_t>(total_bytes / env_batches() + 1, (size_t)64 << 20));
-    else if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
-    hu.resize(units.size());
-    size_t pos = 0;
-    while (pos < units.size()) {
-        Batch b{pos, 0, units[pos].C, units[pos].multi, 0, 0, 0, 0, 0};
-        size_t end = pos;
-        while (end < units.size() && units[end].C == b.C && units[end].multi == b.multi) {
-            HostUnit &h = units[end];
-            const size_t tb_u = (size_t)h.u.n_strips * h.u.tchunks * 32, rows_u = (size_t)h.u.G;
-            const size_t path_u = (size_t)h.u.n_pairs * h.u.path_stride, bnd_u = b.multi ? (size_t)h.u.tchunks * 4 + 8 : 0;
-            const size_t bytes = (b.tb_n + tb_u) * 16 + (b.rows2_n + rows_u) * row2sz + (b.path_n + path_u) * 4 + (b.bnd_n + bnd_u) * tsz;
-            if (end > pos && bytes > budget) break;
-            h.u.tb_base = (long long)b.tb_n; h.u.rows2_base = (long long)b.rows2_n;
-            h.u.path_base = (long long)b.path_n; h.u.bnd_base = (long long)b.bnd_n;
-            h.u.dense_base = b.n_dense; b.n_dense += h.u.n_pairs;
-            b.tb_n += tb_u; b.rows2_n += rows_u; b.path_n += path_u; b.bnd_n += bnd_u;
-            hu[end] = h.u;
-            ++end;
-        }
-        b.count = end - pos;
-        batches.push_back(b);
-        pos = end;
-    }
+    carve(units, prec, true, batches, hu);
     if (store_plan) { c->plan.batches = batches; c->plan.hu = hu; }
     }
     // ---- size the workspaces once (no allocation inside the timed region after the first run of a shape)
@@ -591,6 +636,8 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     }
     if ((rc = c->d_units.ensure(hu.size()))) return rc;
 
+    c->tb_bytes = 0;
+    for (auto &b : batches) c->tb_bytes += (double)b.tb_n * 16.0;
     c->launches = 0;
     c->last_streams = NS;
     for (int k = 0; k < 4; ++k) c->phase_ms[k] = 0;
@@ -598,60 +645,88 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     if (!use_cached_plan) CU(cudaMemcpyAsync(c->d_units.p, hu.data(), sizeof(Unit) * hu.size(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
 
-    // ---- the three stages of one batch
-    auto stage1 = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st) -> int {
-        const Unit *du = c->d_units.p + b.first;
+    // ---- the three stages of one batch (dunits / f32x: the main run's units in the run's precision, or the float64 re-run
+    //      of the pairs the fp32 traceback marked)
+    const TieArgs tie = env_tie();
+    auto stage1 = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st, const Unit *dunits, bool f32x) -> int {
+        const Unit *du = dunits + b.first;
         const int nu = (int)b.count;
         FillOut fo{};
         fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
         fo.pair_score = flexible ? c->score.p : c->score1.p; fo.bnd = ws.bnd.p;
-        if (f32) {
+        if (f32x) {
             Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
-            if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
-            return launch_fill1_f32<16>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
+            if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, tie, st);
+            return launch_fill1_f32<16>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, tie, st);
         }
         if (c->D == 10) { P1F64<10>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; return launch_fill_c<P1F64<10>, false, true, 4>(b.C, b.multi, du, nu, a, fo, st); }
         P1F64<16>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor};
         return launch_fill_c<P1F64<16>, false, true, 3>(b.C, b.multi, du, nu, a, fo, st);
     };
     // traceback + Kabsch, then the stage-2 row records
-    auto stage_trace = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st, cudaEvent_t mid) -> int {
-        const Unit *du = c->d_units.p + b.first;
+    // f32x: code layout and zero test of the stage-1 fill that ran; rows_f32: format of the stage-2 row records
+    auto stage_trace = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st, cudaEvent_t mid, const Unit *dunits, bool f32x,
+                           bool do_trace = true, bool do_rows2 = true, bool rows_f32 = false) -> int {
+        const Unit *du = dunits + b.first;
         const int nu = (int)b.count;
         if (flexible) { if (mid) CU(cudaEventRecord(mid, st)); return 0; }
+        const bool r32 = f32x || rows_f32;
+        const size_t r2sz = r32 ? 16 : 32;
         TraceArgs ta{};
         ta.units = du; ta.tb = ws.tb.p; ta.pair_istar = c->pair_istar.p; ta.pair_zflag = c->pair_zflag.p;
         ta.offsets = c->d_offsets.p; ta.coords = c->coords.p; ta.centroid = c->centroid.p;
         ta.path = ws.path.p; ta.path_len = c->path_len.p; ta.rmsd = c->rmsd.p; ta.tm = c->tm.p;
         ta.ncommon = c->ncommon.p; ta.status = c->status.p; ta.xform = c->xform.p; ta.meta = c->meta.p + ROW_PAD;
-        ta.rows2 = ws.rows2.p + (size_t)ROW_PAD * row2sz;
+        ta.rows2 = ws.rows2.p + (size_t)ROW_PAD * r2sz;
         ta.rec32 = c->rec32.p + (size_t)ROW_PAD * rs32; ta.rs32 = rs32; ta.d32 = c->D;
         ta.rec64 = c->rec64.p; ta.d64 = c->D; ta.neg_gamma_t = -prm->gamma_tensor;
         ta.scale2 = (float)std::sqrt(prm->gamma_coords * 1.4426950408889634);
-        ta.precision = prec;
+        ta.precision = f32x ? CRT_FP32 : CRT_FP64;
+        ta.rows2_f32 = r32 ? 1 : 0;
         ta.skip_byproducts = c->stage1_only ? 1 : 0;
         int r2;
-        if ((r2 = launch_trace<10>(b.C, ta, nu, b.n_dense, st))) return r2;
+        if (do_trace && (r2 = launch_trace(b.C, ta, nu, b.n_dense, st, f32x))) return r2;
         if (mid) CU(cudaEventRecord(mid, st));
-        if (c->stage1_only) return 0;
+        if (c->stage1_only || !do_rows2) return 0;
         k_rows2<<<nu, 256, 0, st>>>(ta, nu);
         CU(cudaGetLastError());
         return 0;
     };
-    auto stage2 = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st) -> int {
-        const Unit *du = c->d_units.p + b.first;
+    auto stage2 = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st, const Unit *dunits, bool f32x) -> int {
+        const Unit *du = dunits + b.first;
         const int nu = (int)b.count;
         FillOut fo{};
         fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
         fo.pair_score = c->score.p; fo.bnd = pipe ? ws.bnd2.p : ws.bnd.p;
         if (c->stage1_only || flexible) return 0;
-        if (f32) {
+        if (f32x) {
             Fill2Args a{reinterpret_cast<const float4 *>(ws.rows2.p) + ROW_PAD, c->cols2.p};
             return launch_fill2_f32(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, st);
         }
         P2F64::Args a{reinterpret_cast<const double *>(ws.rows2.p) + (size_t)ROW_PAD * 4, c->coords.p, -prm->gamma_coords};
         return launch_fill_c<P2F64, false, false, 4>(b.C, b.multi, du, nu, a, fo, st);
     };
+    // the paths of one finished batch, copied back for the caller (tests, progressive-alignment nodes)
+    auto fetch_paths = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st, const std::vector<Unit> &hunits) -> int {
+        std::vector<short2> hp(b.path_n + 1);
+        std::vector<int> hl((size_t)n_pairs);
+        CU(cudaMemcpyAsync(hp.data(), ws.path.p, b.path_n * sizeof(short2), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hl.data(), c->path_len.p, (size_t)n_pairs * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (size_t k = b.first; k < b.first + b.count; ++k) {
+            const Unit &u = hunits[k];
+            for (int q = 0; q < u.n_pairs; ++q) {
+                const int pidx = u.pair_base + q, len = hl[pidx];
+                const short2 *pp = hp.data() + u.path_base + (size_t)q * u.path_stride;
+                auto &v1 = sink->a1[pidx];
+                auto &v2 = sink->a2[pidx];
+                v1.resize(len); v2.resize(len);
+                for (int k2 = 0; k2 < len; ++k2) { v1[k2] = pp[len - 1 - k2].x; v2[k2] = pp[len - 1 - k2].y; }
+            }
+        }
+        return 0;
+    };
+    const Unit *DU = c->d_units.p;
 
     if (pipe) {
         // ---- stage pipeline: s_f1[] run the stage-1 fills (alternating, so consecutive launches overlap at their
@@ -682,18 +757,18 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             cudaStream_t sf1 = c->s_f1[bi & 1], sf2 = c->s_f2[bi & 1];
             if (bi >= (size_t)NW) CU(cudaStreamWaitEvent(sf1, ws.e_t, 0));
             mark0("fill1", bi, sf1);
-            if ((rc = stage1(b, ws, sf1))) return rc;
+            if ((rc = stage1(b, ws, sf1, DU, f32))) return rc;
             mark1(sf1);
             CU(cudaEventRecord(ws.e_f1, sf1));
             CU(cudaStreamWaitEvent(c->s_tr, ws.e_f1, 0));
             if (bi >= (size_t)NW) CU(cudaStreamWaitEvent(c->s_tr, ws.e_f2, 0));
             mark0("trace", bi, c->s_tr);
-            if ((rc = stage_trace(b, ws, c->s_tr, nullptr))) return rc;
+            if ((rc = stage_trace(b, ws, c->s_tr, nullptr, DU, f32))) return rc;
             mark1(c->s_tr);
             CU(cudaEventRecord(ws.e_t, c->s_tr));
             CU(cudaStreamWaitEvent(sf2, ws.e_t, 0));
             mark0("fill2", bi, sf2);
-            if ((rc = stage2(b, ws, sf2))) return rc;
+            if ((rc = stage2(b, ws, sf2, DU, f32))) return rc;
             mark1(sf2);
             CU(cudaEventRecord(ws.e_f2, sf2));
             c->launches += 4;
@@ -724,10 +799,10 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         cudaStream_t st = ws.stream;
         const bool timed = NS == 1;
         if (timed) CU(cudaEventRecord(ws.ev[0], st));
-        if ((rc = stage1(b, ws, st))) return rc;
+        if ((rc = stage1(b, ws, st, DU, f32))) return rc;
         if (timed) CU(cudaEventRecord(ws.ev[1], st));
-        if ((rc = stage_trace(b, ws, st, timed ? ws.ev[2] : nullptr))) return rc;
-        if ((rc = stage2(b, ws, st))) return rc;
+        if ((rc = stage_trace(b, ws, st, timed ? ws.ev[2] : nullptr, DU, f32))) return rc;
+        if ((rc = stage2(b, ws, st, DU, f32))) return rc;
         if (timed) CU(cudaEventRecord(ws.ev[3], st));
         c->launches += flexible ? 1 : 4;
 
@@ -740,29 +815,87 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             CU(cudaEventElapsedTime(&m23, ws.ev[2], ws.ev[3]));
             c->phase_ms[0] += m01; c->phase_ms[1] += m12; c->phase_ms[3] += m23;
         }
-        if (want_paths) {
-            std::vector<short2> hp(b.path_n + 1);
-            std::vector<int> hl((size_t)n_pairs);
-            CU(cudaMemcpyAsync(hp.data(), ws.path.p, b.path_n * sizeof(short2), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(hl.data(), c->path_len.p, (size_t)n_pairs * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            for (size_t k = b.first; k < b.first + b.count; ++k) {
-                const Unit &u = hu[k];
-                for (int q = 0; q < u.n_pairs; ++q) {
-                    const int pidx = u.pair_base + q, len = hl[pidx];
-                    const short2 *pp = hp.data() + u.path_base + (size_t)q * u.path_stride;
-                    auto &v1 = sink->a1[pidx];
-                    auto &v2 = sink->a2[pidx];
-                    v1.resize(len); v2.resize(len);
-                    for (int k2 = 0; k2 < len; ++k2) { v1[k2] = pp[len - 1 - k2].x; v2[k2] = pp[len - 1 - k2].y; }
-                }
-            }
-        }
+        if (want_paths && (rc = fetch_paths(b, ws, st, hu))) return rc;
     }
     for (int w = 0; w < NS; ++w) {
         CU(cudaEventRecord(c->ws[w].done, c->ws[w].stream));
         CU(cudaStreamWaitEvent(c->stream, c->ws[w].done, 0));
     }
+    }
+    // ---- fp32 production mode: the pairs whose traceback met a decision the reference's float64 DP may take differently
+    //      (ST_TIE, crt_fill1_v4.cuh) are computed again by the float64 parity kernels, one pair per unit, into the same slots
+    c->rerun_pairs = 0; c->rerun_ms = 0;
+    if (f32 && !flexible && env_tie_rerun()) {
+        if ((rc = c->tie_list.ensure((size_t)n_pairs + 1))) return rc;
+        CU(cudaMemsetAsync(c->tie_list.p, 0, sizeof(int), c->stream));
+        k_collect_tie<<<(unsigned)((n_pairs + 255) / 256), 256, 0, c->stream>>>(c->status.p, n_pairs, c->tie_list.p + 1, c->tie_list.p);
+        CU(cudaGetLastError());
+        int n_tie = 0;
+        CU(cudaMemcpyAsync(&n_tie, c->tie_list.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (n_tie > 0) {
+            CU(cudaEventRecord(c->ev2, c->stream));
+            std::vector<int> slots((size_t)n_tie);
+            CU(cudaMemcpyAsync(slots.data(), c->tie_list.p + 1, sizeof(int) * (size_t)n_tie, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            std::sort(slots.begin(), slots.end());
+            std::vector<std::pair<int, int>> by_base(hu.size());          // (pair_base, unit) -> the (i, j) of a result slot
+            for (size_t k = 0; k < hu.size(); ++k) by_base[k] = {hu[k].pair_base, (int)k};
+            std::sort(by_base.begin(), by_base.end());
+            std::vector<HostUnit> ru((size_t)n_tie);
+            for (int q = 0; q < n_tie; ++q) {
+                auto it = std::upper_bound(by_base.begin(), by_base.end(), std::make_pair(slots[q], 0x7fffffff));
+                const Unit &src = hu[(size_t)(it - 1)->second];
+                const int i = src.row_chain0 + (slots[q] - src.pair_base), j = src.col_chain;
+                HostUnit h{};
+                h.u.row_chain0 = i; h.u.row_base = c->offsets[i];
+                h.u.col_chain = j; h.u.col_base = (int)c->offsets[j]; h.u.m = (int)(c->offsets[j + 1] - c->offsets[j]);
+                h.u.G = (int)(c->offsets[i + 1] - c->offsets[i]); h.u.n_pairs = 1; h.u.pair_base = slots[q];
+                h.u.path_stride = h.u.G + h.u.m;
+                finish_unit(c, h, CRT_FP64);
+                ru[(size_t)q] = h;
+            }
+            // stage 1 + traceback in float64 (the reference's decisions), stage 2 by the fp32 kernel on the float64 alignment:
+            // two unit lists over the same pairs, each with the columns-per-lane / strips of its precision
+            std::vector<HostUnit> ru32 = ru;
+            for (auto &h : ru32) finish_unit(c, h, CRT_FP32);
+            std::vector<Batch> rb, rb32;
+            std::vector<Unit> rhu, rhu32;
+            carve(ru, CRT_FP64, false, rb, rhu);
+            carve(ru32, CRT_FP32, false, rb32, rhu32);
+            crt_ctx::Workspace &ws = c->ws[0];
+            size_t tb_n = 0, rows2_n = 0, bnd_n = 0, bnd32_n = 0, path_n = 0;
+            for (auto &b : rb) { tb_n = std::max(tb_n, b.tb_n); bnd_n = std::max(bnd_n, b.bnd_n); path_n = std::max(path_n, b.path_n); }
+            for (auto &b : rb32) { rows2_n = std::max(rows2_n, b.rows2_n); bnd32_n = std::max(bnd32_n, b.bnd_n); }
+            if ((rc = ws.tb.ensure(tb_n + 1))) return rc;
+            if ((rc = ws.rows2.ensure((rows2_n + 2 * ROW_PAD) * 16))) return rc;
+            if ((rc = ws.path.ensure(path_n + 1))) return rc;
+            if ((rc = ws.bnd.ensure(std::max(bnd_n * 8, bnd32_n * 4) + 16))) return rc;
+            if ((rc = ws.bnd2.ensure(std::max(bnd_n * 8, bnd32_n * 4) + 16))) return rc;
+            if ((rc = c->d_units2.ensure(rhu.size() + rhu32.size()))) return rc;
+            CU(cudaMemcpyAsync(c->d_units2.p, rhu.data(), sizeof(Unit) * rhu.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->d_units2.p + rhu.size(), rhu32.data(), sizeof(Unit) * rhu32.size(), cudaMemcpyHostToDevice, c->stream));
+            for (auto &b : rb) {
+                if ((rc = stage1(b, ws, c->stream, c->d_units2.p, false))) return rc;
+                if ((rc = stage_trace(b, ws, c->stream, nullptr, c->d_units2.p, false, true, false))) return rc;
+                c->launches += 2;
+                if (want_paths && (rc = fetch_paths(b, ws, c->stream, rhu))) return rc;
+            }
+            for (auto &b : rb32) {
+                if ((rc = stage_trace(b, ws, c->stream, nullptr, c->d_units2.p + rhu.size(), false, false, true, true))) return rc;
+                if ((rc = stage2(b, ws, c->stream, c->d_units2.p + rhu.size(), true))) return rc;
+                c->launches += 2;
+            }
+            k_mark_status<<<(unsigned)((n_tie + 255) / 256), 256, 0, c->stream>>>(c->status.p, c->tie_list.p + 1, n_tie, CRT_ST_FP64);
+            CU(cudaGetLastError());
+            c->launches += 2;
+            CU(cudaEventRecord(c->ev3, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            float rms = 0;
+            CU(cudaEventElapsedTime(&rms, c->ev2, c->ev3));
+            c->rerun_ms = rms;
+            c->rerun_pairs = n_tie;
+        }
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -815,6 +948,8 @@ int crt_create(int device, crt_ctx **out)
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreate(&c->ev2));
+    CU(cudaEventCreate(&c->ev3));
     for (int w = 0; w < crt_ctx::MAX_WS; ++w) {
         CU(cudaStreamCreateWithFlags(&c->ws[w].stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ws[w].done, cudaEventDisableTiming));
@@ -859,7 +994,8 @@ int crt_destroy(crt_ctx *c)
     c->nd_t.release(); c->nd_c.release(); c->nd_wm.release(); c->nd_B.release(); c->nd_a1.release(); c->nd_a2.release(); c->nd_len.release(); c->text.release();
     c->lv_probs.release(); c->lv_mult.release(); c->lv_xf2.release(); c->lv_off.release();
     c->pool.t.release(); c->pool.c.release(); c->pool.w.release(); c->lv_tab.release(); c->lv_out_off.release(); c->arena.release();
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
+    c->d_units2.release(); c->tie_list.release(); c->lay_pi.release(); c->lay_pj.release(); c->lay_off.release();
     for (int k = 0; k < 2; ++k) {
         if (c->s_f1[k]) cudaStreamDestroy(c->s_f1[k]);
         if (c->s_f2[k]) cudaStreamDestroy(c->s_f2[k]);
@@ -1179,7 +1315,15 @@ int crt_last_phase_ms(crt_ctx *c, double *out4)
     return 0;
 }
 int64_t crt_last_launches(crt_ctx *c) { return c ? c->launches : -1; }
+int crt_last_rerun(crt_ctx *c, int64_t *pairs, double *ms)
+{
+    if (!c) return fail(CRT_E_ARG, "null context");
+    if (pairs) *pairs = c->rerun_pairs;
+    if (ms) *ms = c->rerun_ms;
+    return 0;
+}
 double crt_last_cell_updates(crt_ctx *c) { return c ? c->cell_updates : -1.0; }
+double crt_last_traceback_bytes(crt_ctx *c) { return c ? c->tb_bytes : -1.0; }
 
 int crt_pairwise_all(crt_ctx *c, const crt_params *prm, double *out_score, double *out_rmsd, double *out_tm)
 {
@@ -1799,3 +1943,5 @@ int crt_fp32_peak(crt_ctx *c, double *ffma_per_s, double *elapsed_ms)
 
 #include "crt_consumers_api.inl"
 #include "crt_level_api.inl"
+
+#include "crt_multi.inl"

@@ -23,6 +23,8 @@ namespace crt {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS_PER_CTA = 4;
+constexpr int ISTAR_TIE = 1 << 30;   // pair_istar flag: rows after the start row grew by less than the float64 resolution of H
+constexpr int ST_TIE = 8;            // = CRT_ST_TIE: the fp32 walk met a decision the reference's float64 DP may take differently
 
 struct Unit {
     long long row_base;    // packed residue index of the first row of the stream
@@ -375,7 +377,8 @@ struct TraceArgs {
     const float *rec32; int rs32; int d32;
     const double *rec64; int d64; double neg_gamma_t;
     float scale2;                 // sqrt(gamma_c * log2 e) (fp32 only)
-    int precision;                // 0 fp64, 1 fp32
+    int precision;                // 0 fp64, 1 fp32: the stage-1 fill that ran (records of the exact zero test)
+    int rows2_f32;                // format of the stage-2 row records: 1 = float4 (fp32 stage 2), 0 = double[4]
     int skip_byproducts;          // 1: no RMSD / TM pass over the path (node contexts only use the transform)
 };
 
@@ -409,7 +412,10 @@ __device__ __forceinline__ void prefetch_tb(const void *p) { asm volatile("prefe
 //      is entered, so most dependent loads hit L1/L2 instead of HBM;
 //   2. Kabsch moments over the matched residues, read back from the path (independent loads, unrolled);
 //   3. the by-products (RMSD, TM) with the rotation applied.
-template <int C>
+// TIE3 = false: 2 bits per cell, (H != diag + S) << 1 | (H != left), written by the float64 k_fill.
+// TIE3 = true : 3 bits per cell, (S attains the maximum) << 2 | (left attains it) << 1 | suspect, written by k_fill1_v4; a walk
+//               that meets a suspect cell sets ST_TIE in the pair's status (the host re-runs those pairs in float64).
+template <int C, bool TIE3>
 __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceArgs a, int n_units, int n_dense)
 {
     const int gid = blockIdx.x * TRACE_THREADS + threadIdx.x;
@@ -449,6 +455,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
     };
     int cidx = -1;
     uint4 cw = make_uint4(0, 0, 0, 0);
+    unsigned tie = 0;
     auto code = [&]() -> unsigned {                       // (nA << 1) | nB of the current cell
         const int t = w_trow + w_l;
         const int idx = (w_strip * u.tchunks + (t >> 2)) * 32 + w_l;
@@ -461,6 +468,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
         }
         const int q = t & 3;
         const unsigned w = q == 0 ? cw.x : (q == 1 ? cw.y : (q == 2 ? cw.z : cw.w));
+        if (TIE3) {
+            const unsigned raw = (w >> (3 * (C - 1 - w_k))) & 7u;
+            // suspect cell, or S and the left value attain the maximum together (an exact fp32 tie the reference may not share)
+            tie |= (raw & 1u) | (raw >= 6u ? 1u : 0u);
+            return ((raw ^ 6u) >> 1) & 3u;
+        }
         return (w >> (2 * (C - 1 - w_k))) & 3u;
     };
 
@@ -478,6 +491,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
     // ---- pass 1: the walk
     int i = a.pair_istar[pair], j = m;
     int st = 0, len = 0, c = 0;
+    if (i & ISTAR_TIE) { tie = 1; i &= ~ISTAR_TIE; }
     if (i <= 0) {
         st |= 2;                      // CRT_ST_NO_POSITIVE
     } else {
@@ -506,6 +520,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
     }
     a.path_len[pair] = len;
     a.ncommon[pair] = c;
+    if (tie) st |= ST_TIE;
 
     // ---- pass 2: moments of the matched residues, relative to the chains' own centroids (translation does not change
     // the covariance; it keeps the raw-moment form well conditioned).  Same summation order as the walk (descending).
@@ -602,7 +617,7 @@ __global__ void __launch_bounds__(256) k_rows2(TraceArgs a, int n_units)
             y2 = (x0 * xf[6] + x1 * xf[7] + x2 * xf[8]) + xf[14];
         }
         const long long idx = u.rows2_base + g;
-        if (a.precision == 1) {
+        if (a.rows2_f32) {
             float4 v;
             v.x = (float)((y0 - c0) * (double)a.scale2);
             v.y = (float)((y1 - c1) * (double)a.scale2);

@@ -1,7 +1,13 @@
-"""Multi-GPU all-vs-all: one process per GPU (torchrun), pairs sharded by cost with no data-path collective, then ONE
-all-gather of the packed score / RMSD / TM vectors (NCCL over NVLink in production; the same code runs over gloo
-with CPU tensors in the tests).  The shard enumeration is deterministic (crt_plan_shard_pairs), so every rank can
-scatter every other rank's packed vector into the dense [N,N] matrices the reference's consumers expect."""
+"""Multi-GPU all-vs-all, one process per GPU (torchrun): pairs sharded by cost with no data-path collective, then ONE
+all-gather of the packed score | rmsd | tm vectors (NCCL over NVLink in production; the same code runs over gloo with CPU
+tensors in the tests).  The shard enumeration is deterministic (crt_plan_shard_pairs), so the gathered block can be scattered
+into the dense [N,N] matrices the reference's consumers expect; that scatter and the one device-to-host copy happen on the
+ranks that ask for the result (rank 0 by default), on the device, through the C ABI (crt_scatter_gathered).
+
+The packed vectors are float32 in the production mode and float64 in the parity mode (CRT_FP64), so that a multi-rank float64
+run is bitwise the single-rank one.  The single-process layout (all GPUs behind one call, NCCL inside the library) is
+engine.MultiEngine / crt_multi_*.
+"""
 from __future__ import annotations
 
 from typing import Dict, Optional, Sequence
@@ -32,76 +38,54 @@ def gather_packed(local: torch.Tensor, world: int, group=None) -> torch.Tensor:
     return out.view(world, local.numel())
 
 
-_LAYOUT_CACHE: dict = {}
-
-
-def _device_layout(shards, pad: int, device: torch.device):
-    """Index tensors of the scatter on ``device`` (cached per shard layout): positions of every rank's valid entries in
-    the flattened [world, pad] field, and the (i, j) they belong to."""
-    key = (id(shards), pad, str(device))
-    hit = _LAYOUT_CACHE.get(key)
-    if hit is not None and hit[0] is shards:
-        return hit[1]
-    src = np.concatenate([r * pad + np.arange(len(pi), dtype=np.int64) for r, (pi, _) in enumerate(shards)])
-    ii = np.concatenate([np.asarray(pi, dtype=np.int64) for pi, _ in shards])
-    jj = np.concatenate([np.asarray(pj, dtype=np.int64) for _, pj in shards])
-    lay = tuple(torch.from_numpy(a).to(device) for a in (src, ii, jj))
-    _LAYOUT_CACHE.clear()                       # one layout at a time: it can be hundreds of MB at N = 5000
-    _LAYOUT_CACHE[key] = (shards, lay)
-    return lay
-
-
-def scatter_to_device_matrices(gathered: torch.Tensor, shards, pad: int, n: int) -> torch.Tensor:
-    """gathered [world, 3*pad] (any float dtype) -> [3, n, n] float64 on the same device: score, rmsd, tm, symmetric, with
-    the reference's diagonals (score 0: multiple_alignment.py:161-170; rmsd 0, tm 1: :1019-1024)."""
-    world = gathered.shape[0]
-    src, ii, jj = _device_layout(shards, pad, gathered.device)
-    g = gathered.view(world, len(FIELDS), pad)
-    out = torch.zeros(len(FIELDS), n, n, dtype=torch.float64, device=gathered.device)
+def scatter_to_matrices(gathered: torch.Tensor, shards, pad: int, n: int) -> Dict[str, np.ndarray]:
+    """Host-side restatement of crt_scatter_gathered for CPU tensors (the gloo tests of the exchange logic): gathered
+    [world, 3 * pad] -> dense symmetric float64 matrices with the reference's diagonals (score 0: multiple_alignment.py:161-170;
+    rmsd 0, tm 1: :1019-1024)."""
+    g = gathered.detach().cpu().numpy().reshape(len(shards), len(FIELDS), pad)
+    out = {}
     for f, name in enumerate(FIELDS):
-        v = g[:, f, :].reshape(-1).index_select(0, src).to(torch.float64)
-        out[f].index_put_((ii, jj), v)
-        out[f].index_put_((jj, ii), v)
+        M = np.zeros((n, n))
+        for r, (pi, pj) in enumerate(shards):
+            v = g[r, f, :len(pi)].astype(np.float64)
+            M[pi, pj] = v
+            M[pj, pi] = v
         if name == "tm":
-            out[f].diagonal().fill_(1.0)
+            np.fill_diagonal(M, 1.0)
+        out[name] = M
     return out
-
-
-def scatter_to_matrices(gathered: torch.Tensor, shards, pad: int, n: int, out: Optional[torch.Tensor] = None) -> Dict[str, np.ndarray]:
-    """Dense symmetric float64 matrices on the host.  The scatter runs where ``gathered`` lives (the GPU in production);
-    ``out``: optional pinned [3, n, n] float64 host tensor that receives the copy."""
-    dense = scatter_to_device_matrices(gathered.detach(), shards, pad, n)
-    if out is None:
-        host = dense.cpu()
-    else:
-        out.copy_(dense)
-        host = out
-    h = host.numpy()
-    return {name: h[f] for f, name in enumerate(FIELDS)}
 
 
 _SHARD_CACHE: dict = {}
 
 
-def _shard_layout_cached(offsets, world: int):
+def _pad_cached(offsets, world: int) -> int:
     key = (np.asarray(offsets).tobytes(), world)
     hit = _SHARD_CACHE.get(key)
     if hit is None:
         _SHARD_CACHE.clear()
-        hit = _SHARD_CACHE[key] = shard_layout(offsets, world)
+        lib = _engine.load_library()
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        hit = _SHARD_CACHE[key] = max(1, max(int(lib.crt_plan_shard_size(_engine._p(off), len(off) - 1, r, world)) for r in range(world)))
     return hit
 
 
-def all_vs_all(eng: "_engine.Engine", prm, rank: int, world: int, group=None, out: Optional[torch.Tensor] = None) -> Dict[str, np.ndarray]:
-    """Full pipeline on one rank: compute the shard on the GPU, all-gather the packed vectors, scatter them into the dense
-    matrices on the GPU, copy to the host.  Returns score/rmsd/tm [N,N] float64 (views of ``out`` when given)."""
+def all_vs_all(eng: "_engine.Engine", prm, rank: int, world: int, group=None, out=None,
+               result_ranks: Optional[Sequence[int]] = (0,)) -> Optional[Dict[str, np.ndarray]]:
+    """One rank's part of the multi-GPU make_pairwise_matrix: compute the shard, pack it on the device, all-gather, and -- on
+    the ranks listed in ``result_ranks`` (None = every rank) -- scatter into the dense matrices on the device and copy them to
+    the host.  ``out``: optional (score, rmsd, tm) C-contiguous float64 [N,N] arrays (e.g. pinned) that receive the result.
+    Returns {"score", "rmsd", "tm"} on the result ranks, None elsewhere."""
     offsets = eng._offsets
-    n = len(offsets) - 1
-    shards, pad = _shard_layout_cached(offsets, world)
+    pad = _pad_cached(offsets, world)
+    f64 = int(prm.precision) == _engine.FP64
     eng.pairwise_shard(prm, rank, world)
     dev = torch.device("cuda", torch.cuda.current_device())
-    local = torch.zeros(len(FIELDS) * pad, dtype=torch.float32, device=dev)
-    p = local.data_ptr()
-    eng.fetch_device(p, p + 4 * pad, p + 8 * pad, pad)
+    local = torch.empty(len(FIELDS) * pad, dtype=torch.float64 if f64 else torch.float32, device=dev)
+    eng.pack_results(local.data_ptr(), pad, f64)
     gathered = gather_packed(local, world, group)
-    return scatter_to_matrices(gathered, shards, pad, n, out=out)
+    if result_ranks is not None and rank not in result_ranks:
+        return None
+    torch.cuda.current_stream().synchronize()            # the all-gather ran on torch's stream, the scatter runs on the engine's
+    S, R, T = eng.scatter_gathered(gathered.data_ptr(), world, pad, f64, want_rmsd_tm=True, out=out)
+    return {"score": S, "rmsd": R, "tm": T}

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("CARETTA_B200_LIB") or os.path.join(_HERE, "libcaretta
 
 FP64, FP32 = 0, 1
 SUP_AUTO, SUP_CORE, SUP_REFERENCE = 0, 1, 2
-ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE = 1, 2, 4
+ST_FEW_COMMON, ST_NO_POSITIVE, ST_NONFINITE, ST_TIE, ST_FP64 = 1, 2, 4, 8, 16
 FLAG_FLEXIBLE = 1                                  # crt_params.flags: Protein.score_function(flexible=True)
 # gamma_coords sentinels of progressive_node / progressive_level / msa_level (include/caretta_b200.h)
 GC_FLEXIBLE, GC_FLEXIBLE_SCORE = -1.0, -2.0
@@ -22,10 +22,12 @@ GC_FLEXIBLE, GC_FLEXIBLE_SCORE = -1.0, -2.0
 EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains", "crt_set_coords",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
-    "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_cell_updates", "crt_pairwise_all", "crt_pairwise_list",
+    "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_rerun", "crt_last_cell_updates", "crt_last_traceback_bytes", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node", "crt_progressive_level",
     "crt_score_matrix", "crt_mean_function", "crt_mean_weights",
     "crt_msa_begin", "crt_msa_level", "crt_msa_lengths", "crt_msa_fetch", "crt_msa_end",
+    "crt_pack_results", "crt_scatter_gathered", "crt_multi_create", "crt_multi_destroy", "crt_multi_devices", "crt_multi_ctx",
+    "crt_multi_set_chains", "crt_multi_pairwise_all", "crt_multi_last_timing",
     "crt_coverage_gap_matrix", "crt_superpose", "crt_superpose_pairs", "crt_format_matrix", "crt_format_fasta", "crt_text_fetch", "crt_count_matrix", "crt_braycurtis",
 ]
 
@@ -73,8 +75,12 @@ def load_library():
     L.crt_last_phase_ms.argtypes = [vp, vp]
     L.crt_last_launches.argtypes = [vp]
     L.crt_last_launches.restype = i64
+    L.crt_last_rerun.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.crt_last_rerun.restype = C.c_int
     L.crt_last_cell_updates.argtypes = [vp]
     L.crt_last_cell_updates.restype = dbl
+    L.crt_last_traceback_bytes.argtypes = [vp]
+    L.crt_last_traceback_bytes.restype = dbl
     L.crt_pairwise_all.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
     L.crt_pairwise_list.argtypes = [vp, C.POINTER(Params), vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64]
     L.crt_sw_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, dbl, vp, vp, vp, i64, vp, vp]
@@ -102,6 +108,17 @@ def load_library():
     L.crt_text_fetch.argtypes = [vp, vp, i64]
     L.crt_count_matrix.argtypes = [vp, vp, vp, i32, i32, vp]
     L.crt_braycurtis.argtypes = [vp, vp, i32, vp, i32, i32, vp]
+    L.crt_pack_results.argtypes = [vp, vp, i64, i32]
+    L.crt_scatter_gathered.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
+    L.crt_multi_create.argtypes = [i32, vp, C.POINTER(vp)]
+    L.crt_multi_destroy.argtypes = [vp]
+    L.crt_multi_devices.argtypes = [vp]
+    L.crt_multi_devices.restype = i32
+    L.crt_multi_ctx.argtypes = [vp, i32]
+    L.crt_multi_ctx.restype = vp
+    L.crt_multi_set_chains.argtypes = [vp, vp, vp, vp, i32, i32]
+    L.crt_multi_pairwise_all.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
+    L.crt_multi_last_timing.argtypes = [vp, vp, C.POINTER(i64)]
     L.crt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.crt_host_free.argtypes = [vp]
     for name in EXPORTS:
@@ -166,6 +183,78 @@ def plan_shard(offsets, rank: int, world: int):
     if rc != 0:
         raise CrtError(f"crt_plan_shard_pairs failed: {L.crt_last_error().decode()}")
     return pi[:np_], pj[:np_]
+
+
+class MultiEngine:
+    """Every GPU of the box behind one call (crt_multi_*): one context per device, cost-sharded pairs, one NCCL all-gather inside
+    the library, dense float64 matrices out.  devices: None = all visible devices."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if devices is None:
+            rc = self.lib.crt_multi_create(0, None, C.byref(h))
+        else:
+            ids = np.ascontiguousarray(list(devices), dtype=np.int32)
+            rc = self.lib.crt_multi_create(len(ids), _p(ids), C.byref(h))
+        if rc != 0:
+            raise CrtError(f"crt_multi_create failed ({rc}): {self.lib.crt_last_error().decode()}")
+        self.h = h
+        self.n_devices = int(self.lib.crt_multi_devices(h))
+        self.n_chains = 0
+        self._offsets = None
+
+    params = staticmethod(lambda *a, **k: Engine.params(*a, **k))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.crt_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise CrtError(f"{what} failed ({rc}): {self.lib.crt_last_error().decode()}")
+
+    def set_chains(self, coords, tensors, offsets):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        tensors = np.ascontiguousarray(tensors, dtype=np.float64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        if coords.ndim != 2 or coords.shape[1] != 3 or tensors.ndim != 2 or coords.shape[0] != tensors.shape[0] \
+                or offsets[-1] != coords.shape[0]:
+            raise ValueError("coords [sumL,3], tensors [sumL,d], offsets [N+1] expected")
+        self._check(self.lib.crt_multi_set_chains(self.h, _p(coords), _p(tensors), _p(offsets), n, tensors.shape[1]),
+                    "crt_multi_set_chains")
+        self.n_chains = n
+        self._offsets = offsets.copy()
+
+    def pairwise_all(self, prm: Params, want_rmsd_tm: bool = False, out=None):
+        n = self.n_chains
+        if out is not None:
+            out = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+            for a in out:
+                if a.dtype != np.float64 or a.shape != (n, n) or not a.flags.c_contiguous:
+                    raise ValueError("out arrays must be C-contiguous float64 [N,N]")
+            score = out[0]
+            rm, tm = (out[1], out[2]) if want_rmsd_tm else (None, None)
+        else:
+            score = np.empty((n, n))
+            rm = np.empty((n, n)) if want_rmsd_tm else None
+            tm = np.empty((n, n)) if want_rmsd_tm else None
+        self._check(self.lib.crt_multi_pairwise_all(self.h, C.byref(prm), _p(score), _p(rm), _p(tm)), "crt_multi_pairwise_all")
+        return (score, rm, tm) if want_rmsd_tm else score
+
+    def last_timing(self):
+        out = np.zeros(3)
+        n = C.c_int64(0)
+        self._check(self.lib.crt_multi_last_timing(self.h, _p(out), C.byref(n)), "crt_multi_last_timing")
+        return dict(shard_ms=float(out[0]), gather_ms=float(out[1]), wall_ms=float(out[2]), rerun_pairs=int(n.value))
 
 
 class Engine:
@@ -278,6 +367,29 @@ class Engine:
             out.update(rmsd=rm[:n], tm=tm[:n], ncommon=nc[:n], status=st[:n])
         return out
 
+    def pack_results(self, d_dst: int, pad: int, f64: bool = False):
+        """score | rmsd | tm of the last shard packed into the DEVICE buffer d_dst [3 * pad] (float32, or float64 when f64)."""
+        self._check(self.lib.crt_pack_results(self.h, C.c_void_p(d_dst), int(pad), 1 if f64 else 0), "crt_pack_results")
+
+    def scatter_gathered(self, d_gathered: int, world: int, pad: int, f64: bool = False, want_rmsd_tm: bool = True, out=None):
+        """[world][3][pad] all-gathered block (DEVICE address) -> dense symmetric float64 [N,N] score (, rmsd, tm) on the host.
+        ``out``: optional preallocated C-contiguous float64 [N,N] arrays (score,) or (score, rmsd, tm)."""
+        n = self.n_chains
+        if out is not None:
+            out = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+            for a in out:
+                if a.dtype != np.float64 or a.shape != (n, n) or not a.flags.c_contiguous:
+                    raise ValueError("out arrays must be C-contiguous float64 [N,N]")
+            score = out[0]
+            rm, tm = (out[1], out[2]) if want_rmsd_tm else (None, None)
+        else:
+            score = np.empty((n, n))
+            rm = np.empty((n, n)) if want_rmsd_tm else None
+            tm = np.empty((n, n)) if want_rmsd_tm else None
+        self._check(self.lib.crt_scatter_gathered(self.h, C.c_void_p(d_gathered), int(world), int(pad), 1 if f64 else 0,
+                                                  _p(score), _p(rm), _p(tm)), "crt_scatter_gathered")
+        return (score, rm, tm) if want_rmsd_tm else score
+
     def fetch_device(self, d_score: int, d_rmsd: int, d_tm: int, n: int):
         self._check(self.lib.crt_fetch_device(self.h, C.c_void_p(d_score), C.c_void_p(d_rmsd), C.c_void_p(d_tm), n),
                     "crt_fetch_device")
@@ -290,8 +402,17 @@ class Engine:
         self._check(self.lib.crt_last_phase_ms(self.h, _p(out)), "crt_last_phase_ms")
         return dict(fill1=out[0], trace=out[1], fill2=out[3])
 
+    def last_traceback_bytes(self) -> float:
+        return float(self.lib.crt_last_traceback_bytes(self.h))
+
     def last_launches(self) -> int:
         return int(self.lib.crt_last_launches(self.h))
+
+    def last_rerun(self):
+        """(pairs, device ms) the fp32 mode's tie detection sent through the float64 kernels in the last run."""
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        self._check(self.lib.crt_last_rerun(self.h, C.byref(n), C.byref(ms)), "crt_last_rerun")
+        return int(n.value), float(ms.value)
 
     def last_cell_updates(self) -> float:
         return float(self.lib.crt_last_cell_updates(self.h))

@@ -172,6 +172,35 @@ def get_engine() -> _engine.Engine:
     return _shared_engine
 
 
+_shared_multi: typing.Optional[_engine.MultiEngine] = None
+# below this many residue pairs a second GPU costs more (upload + all-gather) than it saves
+MULTI_GPU_MIN_CELLS = 2.0e9
+
+
+def get_multi_engine() -> typing.Optional[_engine.MultiEngine]:
+    """Every visible GPU behind the one call the reference makes (multiple_alignment.py:498-500): crt_multi_* (one context per
+    device, NCCL all-gather inside the library).  CARETTA_B200_DEVICES = "all" (default), "1" / "0,2,3" (a list of device ids);
+    a single id, a torchrun launch (LOCAL_RANK set: one process per GPU, caretta_b200.distributed) or a one-GPU box -> None."""
+    global _shared_multi
+    if _shared_multi is not None:
+        return _shared_multi
+    spec = os.environ.get("CARETTA_B200_DEVICES", "all").strip().lower()
+    if "LOCAL_RANK" in os.environ or "CARETTA_B200_DEVICE" in os.environ:
+        return None
+    devices = None if spec in ("all", "") else [int(x) for x in spec.split(",") if x.strip() != ""]
+    if devices is not None and len(devices) < 2:
+        return None
+    try:
+        m = _engine.MultiEngine(devices)
+    except _engine.CrtError:
+        return None
+    if m.n_devices < 2:
+        m.close()
+        return None
+    _shared_multi = m
+    return m
+
+
 class _NodeAlignments(collections.abc.Mapping):
     """MultipleAlignment.final_alignments of the reference (multiple_alignment.py:181-183, :219-232): node name -> {member name ->
     int64 index array}, same keys and order.  A read-only mapping; a node's dictionary is composed from the stored pairwise
@@ -300,8 +329,16 @@ class MultipleAlignment:
         if not _on_fused_path(self.sequences):
             return self._pairwise_matrix_generic(score_function_params or {})
         prm = self._params(score_function_params)
-        eng.set_chains(*pack_sequences(self.sequences, need_coordinates=not prm.flags & _engine.FLAG_FLEXIBLE))
+        packed = pack_sequences(self.sequences, need_coordinates=not prm.flags & _engine.FLAG_FLEXIBLE)
         n = len(self.sequences)
+        lens = np.diff(packed[2]).astype(np.float64)
+        cells = 0.5 * (lens.sum() ** 2 - (lens ** 2).sum())
+        multi = get_multi_engine() if cells >= MULTI_GPU_MIN_CELLS else None
+        if multi is not None:
+            # all GPUs of the box: shards by cost, one all-gather, bitwise the one-GPU matrix (tests/test_gpu_multi.py)
+            multi.set_chains(*packed)
+            return multi.pairwise_all(prm)
+        eng.set_chains(*packed)
         if n < 2:
             return np.zeros((n, n))
         return eng.pairwise_all(prm)

@@ -27,6 +27,9 @@
  *       CRT_ST_FEW_COMMON  <= 3 matched residues, superposition skipped exactly like multiple_alignment.py:337-342
  *       CRT_ST_NO_POSITIVE stage-1 score matrix had no cell > 0 (the reference raises from
  *                          dynamic_time_warping.py:250); the pair is scored without superposition
+ *       CRT_ST_TIE         (CRT_FP32) the fp32 traceback met a decision the reference's float64 H matrix may take differently
+ *                          (dynamic_time_warping.py:241-247, :260-277: increments below ulp(H) tie exactly there)
+ *       CRT_ST_FP64        (CRT_FP32) such a pair was recomputed by the float64 kernels: its results are the CRT_FP64 ones
  *   - chain layout: coords[(offsets[p] + r) * 3 + axis], tensors[(offsets[p] + r) * d + k], float64, offsets[N+1].
  *   - precision: CRT_FP64 reproduces the reference's arithmetic (sequential non-fused RBF sum, equality
  *     traceback, row-major first maximum): stage-1 paths are identical to the reference's.  CRT_FP32 is the
@@ -55,7 +58,7 @@ enum {
     CRT_E_NOMEM = -4       /* device or host allocation failed */
 };
 
-enum { CRT_ST_FEW_COMMON = 1, CRT_ST_NO_POSITIVE = 2, CRT_ST_NONFINITE = 4 };
+enum { CRT_ST_FEW_COMMON = 1, CRT_ST_NO_POSITIVE = 2, CRT_ST_NONFINITE = 4, CRT_ST_TIE = 8, CRT_ST_FP64 = 16 };
 
 /* Parameters of the pair recipe; defaults are the reference's (multiple_alignment.py:490-492, :335). */
 typedef struct crt_params {
@@ -112,7 +115,37 @@ double crt_last_elapsed_ms(crt_ctx *ctx);        /* device time of the last run 
  * otherwise the phases of different batches overlap and every entry is -1. */
 int crt_last_phase_ms(crt_ctx *ctx, double *out4);
 int64_t crt_last_launches(crt_ctx *ctx);         /* kernels launched by the last run */
+/* CRT_FP32 runs: how many pairs the tie detection sent through the float64 kernels, and the device time that took */
+int crt_last_rerun(crt_ctx *ctx, int64_t *pairs, double *ms);
 double crt_last_cell_updates(crt_ctx *ctx);      /* sum over pairs of 2 * L1 * L2 */
+/* bytes of traceback words the stage-1 fills of the last run wrote (from the allocation: strips x chunks x 32 lanes x 16 B per
+ * unit) -- the HBM traffic of the dominant kernel */
+double crt_last_traceback_bytes(crt_ctx *ctx);
+
+/* ---- multi-GPU (the reference's seam is one process calling one method, multiple_alignment.py:498-500) ----
+ * Packed exchange format of a shard: score | rmsd | tm, each `pad` elements (pad >= the largest shard), float32 in the
+ * production mode or float64 (is_f64 = 1, exact) in the parity mode.  crt_pack_results fills that vector on the device
+ * (d_dst is a DEVICE address, e.g. the input of an all-gather); crt_scatter_gathered takes the all-gathered
+ * [world][3][pad] block (DEVICE address on the context's device), scatters it into the dense symmetric matrices on the
+ * device and copies them to the caller's float64 [N,N] host arrays (out_rmsd / out_tm may be NULL). */
+int crt_pack_results(crt_ctx *ctx, void *d_dst, int64_t pad, int32_t is_f64);
+int crt_scatter_gathered(crt_ctx *ctx, const void *d_gathered, int32_t world, int64_t pad, int32_t is_f64,
+                         double *out_score, double *out_rmsd, double *out_tm);
+/* One process, several devices: a context per device and a NCCL communicator over them (ncclCommInitAll; NCCL is resolved with
+ * dlopen, environment CARETTA_B200_NCCL overrides the library name).  n_dev <= 0: every visible device.
+ * crt_multi_set_chains uploads the chains to every device (one host thread per device); crt_multi_pairwise_all =
+ * make_pairwise_matrix over all of them: cost-sharded units, ONE grouped ncclAllGather of the packed vectors, dense scatter on
+ * the first device, one copy to the host arrays.  Bitwise the one-GPU matrices. */
+typedef struct crt_multi crt_multi;
+int crt_multi_create(int32_t n_dev, const int32_t *dev_ids, crt_multi **out);
+int crt_multi_destroy(crt_multi *m);
+int32_t crt_multi_devices(crt_multi *m);
+crt_ctx *crt_multi_ctx(crt_multi *m, int32_t index);
+int crt_multi_set_chains(crt_multi *m, const double *coords, const double *tensors, const int64_t *offsets,
+                         int32_t n_chains, int32_t d);
+int crt_multi_pairwise_all(crt_multi *m, const crt_params *prm, double *out_score, double *out_rmsd, double *out_tm);
+/* out3 = {max over devices of the shard's device ms, device ms of the all-gather, host wall ms of the call} */
+int crt_multi_last_timing(crt_multi *m, double *out3, int64_t *rerun_pairs);
 
 /* make_pairwise_matrix: dense symmetric float64 [N,N], diagonal 0 (rmsd/tm by-products: diagonal 0 / 1).
  * Convenience wrapper = crt_pairwise_shard(world=1) + crt_fetch + scatter. out_rmsd/out_tm may be NULL. */

@@ -1,15 +1,18 @@
 """TEST INFRASTRUCTURE ONLY.  Imports the *unmodified* reference (TurtleTools/caretta at /root/reference)
 in the build container so that golden vectors can be generated and the C restatement can be pinned.
 
-/root/reference does not exist on the GPU box: nothing under tests/ -m gpu, smoke() or bench.py may
-import this module.  Recipe: SURVEY.md Appendix C (I/O-only third-party modules are replaced by mocks;
+/root/reference does not exist on the GPU box; there the unmodified copy under oracle/_ref (build output of
+oracle/build_ref.py, git-ignored) is imported instead -- only by bench.py's CPU legs and parity gate.  Recipe: SURVEY.md Appendix C (I/O-only third-party modules are replaced by mocks;
 no arithmetic lives in them on the hot path).
 """
 import os
 import sys
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("CARETTA_REFERENCE", "/root/reference")
+from . import build_ref as _build_ref
+
+# /root/reference in the build container; on the GPU box the unmodified copy build() left under oracle/_ref (build_ref.py)
+REFERENCE_ROOT = _build_ref.root() or os.environ.get("CARETTA_REFERENCE", "/root/reference")
 
 
 def available() -> bool:

@@ -41,7 +41,10 @@ def _check_fp64(res, gold_a1, gold_a2, gold_off, gold, n):
     np.testing.assert_allclose(res["tm"], gold["tm"], rtol=1e-8, atol=1e-12)
 
 
-def _check_fp32(res, gold_a1, gold_a2, gold_off, gold, n, min_cols=0.999, min_same=0.8):
+def _check_fp32(res, gold_a1, gold_a2, gold_off, gold, n, min_cols=0.999, min_same=0.999):
+    """north_star: score / RMSD / TM within 1e-4 relative on EVERY pair, >= 99.9 % identical aligned columns.  The fp32 fill
+    marks the decisions the reference's float64 H matrix may take differently (crt_fill1_v4.cuh) and the marked pairs are
+    recomputed by the float64 kernels, so no pair is exempt."""
     tot = same = 0
     same_path = np.zeros(n, bool)
     for q in range(n):
@@ -52,16 +55,12 @@ def _check_fp32(res, gold_a1, gold_a2, gold_off, gold, n, min_cols=0.999, min_sa
         same += len(cr & cg)
         same_path[q] = cr == cg
     assert same / max(tot, 1) >= min_cols, f"identical aligned columns {same}/{tot}"
-    # the 1e-4 bound is a statement about arithmetic, so it is checked where the stage-1 alignment is the same one
-    # (the fp32 difference-form DP keeps increments the fp64 reference absorbs below 2^-53 * H, so a few low-similarity
-    # pairs legitimately extend their paths by columns whose score is < 1e-16)
-    sp = same_path
-    assert sp.mean() >= min_same
+    assert same_path.mean() >= min_same, (same_path.mean(), np.nonzero(~same_path)[0][:10])
     # fp32 flushes scores below ~1e-38 to zero (pairs of 1-2 residue chains that do not match at all)
-    np.testing.assert_allclose(res["score"][sp], gold["score"][sp], rtol=1e-4, atol=1e-30)
-    np.testing.assert_allclose(res["rmsd"][sp], gold["rmsd"][sp], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(res["tm"][sp], gold["tm"][sp], rtol=1e-4, atol=1e-6)
-    return same / max(tot, 1), sp.mean()
+    np.testing.assert_allclose(res["score"], gold["score"], rtol=1e-4, atol=1e-30)
+    np.testing.assert_allclose(res["rmsd"], gold["rmsd"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(res["tm"], gold["tm"], rtol=1e-4, atol=1e-6)
+    return same / max(tot, 1), same_path.mean()
 
 
 @pytest.fixture(scope="module")
@@ -120,8 +119,9 @@ def test_c2_all_19900_pairs(eng):
     res = eng.pairwise_list(eng.params(precision=engine.FP64), pi, pj, want_paths=True)
     _check_fp64(res, g["aln1"], g["aln2"], g["aln_off"], g, len(pi))
     res = eng.pairwise_list(eng.params(precision=engine.FP32), pi, pj, want_paths=True)
-    frac, same = _check_fp32(res, g["aln1"], g["aln2"], g["aln_off"], g, len(pi), min_same=0.999)
-    assert frac >= 0.9999
+    frac, same = _check_fp32(res, g["aln1"], g["aln2"], g["aln_off"], g, len(pi), min_same=1.0)
+    assert frac == 1.0                                  # all 19 900 pairs take the reference's alignment
+    assert (res["status"] & engine.ST_FP64).sum() >= 5  # among them the 5 pairs the plain fp32 DP resolves differently
 
 
 def _oracle_compare(eng, ch, pi, pj, prec):
@@ -288,9 +288,8 @@ def test_c3_full_size_properties(eng):
     EVERY pair, the fp64 mode against the oracle on a random sample, symmetry, zero diagonal, and invariance of a pair's result
     under the composition of the run (a 200-chain subset gives the same numbers).
 
-    Measured on B200 (tools/c3_fp32_vs_fp64.py): 498 686 of 499 500 pairs agree to <= 9e-7 relative; the other 814 (0.16 %, all
-    between unrelated families, none inside a family) are exactly the pairs whose fp32 stage-1 path differs from the fp64 one in
-    a few columns (alternatives that tie below fp32 resolution); identical aligned columns overall 99.98 %."""
+    Without the tie detection 814 of the 499 500 pairs (0.16 %, all between unrelated families) took another one of several
+    alignments that tie in the reference's float64 H matrix and missed the 1e-4 bound (round 1); with it every pair holds it."""
     ch = synth.config("C3")
     eng.set_chains(ch.coords, ch.tensors, ch.offsets)
     S32, R32, T32 = eng.pairwise_all(eng.params(precision=engine.FP32), want_rmsd_tm=True)
@@ -302,15 +301,13 @@ def test_c3_full_size_properties(eng):
     assert np.all(s64 > 1e-30)
     rel = np.abs(s32 - s64) / s64
     within = rel <= 1e-4
-    same_family = (pi // 20) == (pj // 20)                      # synth.config: families of 20 consecutive chains
-    assert within.mean() >= 0.998, within.mean()
-    assert within[same_family].all()
+    assert within.all(), (int((~within).sum()), float(rel.max()), list(zip(pi[~within][:8], pj[~within][:8])))
     close = np.isclose(R32[pi, pj], R64[pi, pj], rtol=1e-4, atol=1e-6) & np.isclose(T32[pi, pj], T64[pi, pj], rtol=1e-4, atol=1e-9)
-    assert close.mean() >= 0.998, close.mean()
-    # paths on a sample (2000 random pairs + up to 200 of the pairs outside the tolerance): >= 99.9 % identical aligned columns,
-    # and the 1e-4 bound holds wherever the stage-1 alignment is the same one
+    assert close.all(), int((~close).sum())
+    n_rerun, _ = eng.last_rerun()
+    # paths on a random sample of 3000 pairs: identical alignments
     rng = np.random.default_rng(33)
-    samp = np.unique(np.concatenate([rng.choice(len(pi), 2000, replace=False), np.nonzero(~within)[0][:200]]))
+    samp = np.sort(rng.choice(len(pi), 3000, replace=False))
     r32 = eng.pairwise_list(eng.params(precision=engine.FP32), pi[samp], pj[samp], want_paths=True)
     r64 = eng.pairwise_list(eng.params(precision=engine.FP64), pi[samp], pj[samp], want_paths=True)
     tot = same = 0
@@ -318,11 +315,10 @@ def test_c3_full_size_properties(eng):
     for q in range(len(samp)):
         c32, c64 = _cols(*_paths(r32, q)), _cols(*_paths(r64, q))
         tot += len(c64); same += len(c64 & c32); same_path[q] = c32 == c64
-    random_part = within[samp]
-    assert same_path[random_part].all() and same / tot >= 0.999, (same / tot, same_path.mean())
-    np.testing.assert_allclose(r32["score"][same_path], r64["score"][same_path], rtol=1e-4)
-    np.testing.assert_allclose(r32["rmsd"][same_path], r64["rmsd"][same_path], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(r32["tm"][same_path], r64["tm"][same_path], rtol=1e-4, atol=1e-6)
+    assert same_path.all() and same == tot, (same / tot, same_path.mean())
+    np.testing.assert_allclose(r32["score"], r64["score"], rtol=1e-4)
+    np.testing.assert_allclose(r32["rmsd"], r64["rmsd"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(r32["tm"], r64["tm"], rtol=1e-4, atol=1e-6)
     # fp64 mode against the oracle (the restatement pinned on the reference) on 200 of the sampled pairs
     for q in rng.choice(len(samp), 200, replace=False):
         i, j = int(pi[samp[q]]), int(pj[samp[q]])
@@ -334,8 +330,5 @@ def test_c3_full_size_properties(eng):
     e200 = int(ch.offsets[200])
     eng.set_chains(ch.coords[:e200], ch.tensors[:e200], ch.offsets[:201].copy())
     sub32 = eng.pairwise_all(eng.params(precision=engine.FP32))
-    m = np.zeros((ch.n, ch.n), bool)
-    m[pi, pj] = within
-    m = (m | m.T)[:200, :200] | np.eye(200, dtype=bool)
-    np.testing.assert_allclose(sub32[m], S32[:200, :200][m], rtol=2e-5, atol=1e-30)
+    np.testing.assert_allclose(sub32, S32[:200, :200], rtol=2e-5, atol=1e-30)
     assert np.array_equal(eng.pairwise_all(eng.params(precision=engine.FP64)), S64[:200, :200])          # fp64: bit-identical

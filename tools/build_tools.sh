@@ -3,4 +3,4 @@
 cd "$(dirname "$0")"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 nvcc $ARCH -O3 -o microbench microbench.cu
-nvcc $ARCH -O3 -std=c++17 -lineinfo -I../caretta_b200/csrc -o fill_probe fill_probe.cu
+nvcc $ARCH -O3 -std=c++17 -lineinfo -DPROBE_V2 -I../caretta_b200/csrc -o fill_probe fill_probe.cu

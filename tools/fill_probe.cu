@@ -10,6 +10,7 @@
 #include "crt_fill_f32.cuh"
 #ifdef PROBE_V2
 #include "crt_fill1_v2.cuh"
+#include "crt_fill1_v4.cuh"
 #include "crt_fill2_v3.cuh"
 #endif
 
@@ -138,6 +139,14 @@ int main(int argc, char **argv)
         make_units(n, 10, 1);
         float ms = time_kernel([&] { k_fill1_v3<10, 10, false><<<n, 32>>>(d.units, n, a1, fo, d_offsets); });
         report("fill1_v3<10,10>", 10, 1, n, d, ms, L);
+    }
+    if (want("v4")) for (int k : per_sm) {
+        if (k > 16 || (only_k && k != only_k)) continue;
+        const int n = g_sms * k;
+        make_units(n, 10, 1);
+        const TieArgs tie{64.f * 1.1102230246251565e-16f, 1e-4f};
+        float ms = time_kernel([&] { k_fill1_v4<10, 10, false><<<n, 32>>>(d.units, n, a1, fo, d_offsets, tie); });
+        report("fill1_v4<10,10>", 10, 1, n, d, ms, L);
     }
 #endif
     if (want("c6")) for (int k : per_sm) {
