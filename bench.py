@@ -349,7 +349,7 @@ def main():
                 dev_ms += self.step()
             sync_all()
             wall = 1e3 * (time.perf_counter() - t)
-            return max_over_ranks(dev_ms) / steps, wall / steps
+            return max_over_ranks(dev_ms) / max(steps, 1), wall / max(steps, 1)
 
     # ------------------------------------------------------------------ headline: weak-scaled C3, resident inputs
     total_pairs = n * (n - 1) // 2

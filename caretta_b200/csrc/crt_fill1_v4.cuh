@@ -52,8 +52,11 @@ __device__ __forceinline__ unsigned umin3(unsigned a, unsigned b, unsigned c) { 
         a = v;                                                                                        \
     }
 
+#ifndef CRT_V4_MINB
+#define CRT_V4_MINB 1
+#endif
 template <int D, int C, bool MULTI>
-__global__ void __launch_bounds__(32, 1) k_fill1_v4(const Unit *__restrict__ units, int n_units, Fill1Args args, FillOut out,
+__global__ void __launch_bounds__(32, CRT_V4_MINB) k_fill1_v4(const Unit *__restrict__ units, int n_units, Fill1Args args, FillOut out,
                                                     const long long *__restrict__ offsets, TieArgs tie)
 {
     constexpr int CP = C / 2;

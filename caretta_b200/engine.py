@@ -622,6 +622,13 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ device-resident MSA
     def msa_begin(self, consensus_weight: float) -> int:
         """Starts a progressive alignment on the chains of this engine: they become sequences 0..N-1 of the device pool."""
+        # the nodes of the previous progressive alignment live in the pool this call replaces: whoever still holds a lazy view of
+        # them (MultipleAlignment.final_sequences / final_consensus_weights) gets them fetched first, like the reference's lists
+        prev = getattr(self, "_msa_outstanding", None)
+        prev = prev() if prev is not None else None
+        if prev is not None:
+            prev.fetch()
+        self._msa_outstanding = None
         n = C.c_int32()
         self._check(self.lib.crt_msa_begin(self.h, float(consensus_weight), C.byref(n)), "crt_msa_begin")
         self._msa_generation = getattr(self, "_msa_generation", 0) + 1
@@ -693,8 +700,14 @@ class Engine:
         self._check(self.lib.crt_msa_fetch(self.h, _p(ids), len(ids), _p(T), _p(X), _p(W)), "crt_msa_fetch")
         return [(T[off[q]:off[q + 1]], X[off[q]:off[q + 1]], W[off[q]:off[q + 1]].reshape(-1, 1)) for q in range(len(ids))]
 
+    def msa_track(self, nodes):
+        """Registers the lazy view of the pool's nodes (weakly): it is fetched before the pool is replaced or released."""
+        import weakref
+        self._msa_outstanding = weakref.ref(nodes)
+
     def msa_end(self):
         self._check(self.lib.crt_msa_end(self.h), "crt_msa_end")
+        self._msa_outstanding = None
 
     # ------------------------------------------------------------------------------------------------ alignment consumers
     def _aln(self, aln, need_chains=True):

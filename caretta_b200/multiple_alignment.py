@@ -232,19 +232,23 @@ class _NodeAlignments(collections.abc.Mapping):
 
 class _PoolNodes:
     """The intermediate nodes of a progressive alignment that ran on the device pool (crt_msa_*): fetched from the device in one
-    call the first time any of them is read.  The pool is replaced by the next progressive alignment on the same engine; reading
-    after that raises (CARETTA_B200_FETCH_NODES=1 fetches eagerly)."""
+    call the first time any of them is read -- or, when nobody has read them yet, right before the next progressive alignment on
+    the same engine replaces the pool (Engine.msa_begin fetches the outstanding view), so they stay readable for as long as the
+    MultipleAlignment lives, like the reference's lists (multiple_alignment.py:251-252).  The pool's device buffers are kept for
+    the next alignment (cudaMalloc / cudaFree of them cost more than an alignment); get_engine().msa_end() frees them."""
 
     def __init__(self, eng, ids, names):
         self.eng, self.ids, self.names = eng, list(ids), list(names)
         self.generation = eng._msa_generation
         self.data = None
+        track = getattr(eng, "msa_track", None)          # stand-in engines of the CPU tests have no pool to replace
+        if track is not None:
+            track(self)
 
     def fetch(self):
         if self.data is None:
             if self.eng._msa_generation != self.generation:
-                raise RuntimeError("the intermediate nodes of this alignment were not read before the next progressive alignment "
-                                   "replaced the device pool (set CARETTA_B200_FETCH_NODES=1 to fetch them eagerly)")
+                raise RuntimeError("the device pool of this alignment was replaced before its nodes were fetched")
             self.data = self.eng.msa_fetch(self.ids)
         return self.data
 
