@@ -1,0 +1,240 @@
+// tc_probe.cu -- PROTOTYPE (tools/, not product): can the 5th-generation tensor cores take the Gaussian exponent of the stage-1
+// fill off the FP32 pipe?  
+//
+// The fp32 fill computes, per residue pair (a, b), e = A_a + B_b + sum_k r_k(a) c_k(b) -- a rank-12 contraction E = R C^T -- with
+// 5 FFMA2 + 1/2 FADD2 per cell (11 of its ~24 issue cycles).  Here E comes from tcgen05.mma kind::tf32 with the hi/lo split
+//     E = Rhi Chi^T + Rhi Clo^T + Rlo Chi^T       (K = 3 x 16: 10 features, A, 1, 4 zeros; hi = tf32(x), lo = tf32(x - hi))
+// accumulated in TMEM in fp32, read back with tcgen05.ld (32 lanes x 16 columns per instruction), exponentiated with ex2.approx
+// and written to shared memory as the S tile the systolic DP warps would consume (lane l: row t - l, columns 10 l .. 10 l + 9).
+//
+// What it measures, per SM (one CTA: 4 "transposer" warps = TMEM lanes 0..127, 1 MMA warp):
+//   * max |E_tc - E_fp64| over a tile against the FFMA-chain fp32 value the production kernel computes (accuracy go/no-go);
+//   * produced cells per second (MMA + tcgen05.ld + ex2 + st.shared, operands staged with plain st.shared, no TMA): the
+//     production kernel k_fill1_v4 consumes 1.05e12 cells/s on the GPU, so the producer has to clear a multiple of that.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tc_probe tc_probe.cu && ./tc_probe
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <random>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int TM = 128;          // rows per tile = TMEM lanes
+constexpr int TN = 160;          // columns per MMA (N); a strip of 320 columns = two halves
+constexpr int NH = 2;            // halves
+constexpr int KF = 16;           // padded feature count
+constexpr int KT = 3 * KF;       // K of the split product
+constexpr int KCH = KT / 4;      // 16-byte chunks per operand row
+constexpr int SROW = NH * TN + 4;   // S tile row stride in floats (padding: the DP lanes read rows t - l at columns 10 l)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// canonical K-major, no-swizzle operand layout: core matrix = 8 rows x 16 bytes (contiguous 128 B); core matrices of one
+// 8-row group are KCH consecutive 128-byte blocks (LBO = 128 B), row groups follow at SBO = KCH * 128 B
+__host__ __device__ __forceinline__ int op_index(int r, int k) { return ((r >> 3) * KCH + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);                 // start address, 16-byte units
+    d |= (uint64_t)(128u >> 4) << 16;                         // leading byte offset: next K chunk
+    d |= (uint64_t)((KCH * 128u) >> 4) << 32;                 // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
+    return d;                                                 // layout type 0: no swizzle
+}
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// rhi / rlo / chi / clo: [rows or cols][KF] tf32-split features.  tiles: row tiles per CTA (each CTA walks the same `tiles`
+// tiles of rows starting at its own offset, modulo n_rows).  e_out: exponent of the CTA 0's first tile [TM][NH*TN] (check).
+__global__ void __launch_bounds__(160, 1) k_tc_probe(const float *__restrict__ rhi, const float *__restrict__ rlo, int n_rows,
+                                                     const float *__restrict__ chi, const float *__restrict__ clo, int tiles,
+                                                     float *__restrict__ e_out, float *__restrict__ sink)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float *opA = reinterpret_cast<float *>(smem_raw);                     // TM x KT
+    float *opB = opA + TM * KT;                                           // NH*TN x KT
+    float *S = opB + NH * TN * KT;                                        // TM x SROW
+    __shared__ __align__(8) unsigned long long bars[NH];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 4) {
+        if (lane == 0) { for (int h = 0; h < NH; ++h) mbar_init(smem_u32(&bars[h]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // the column operand of the unit: [Chi | Clo | Chi]
+    for (int q = tid; q < NH * TN * KF; q += blockDim.x) {
+        const int c = q / KF, k = q - c * KF;
+        const float h = chi[q], l = clo[q];
+        opB[op_index(c, k)] = h; opB[op_index(c, KF + k)] = l; opB[op_index(c, 2 * KF + k)] = h;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    float acc_sink = 0.f;
+
+    for (int t = 0; t < tiles; ++t) {
+        const int row0 = (int)(((long long)blockIdx.x * tiles + t) * TM % (n_rows - TM + 1));
+        // the row operand of this tile: [Rhi | Rhi | Rlo]
+        for (int q = tid; q < TM * KF; q += blockDim.x) {
+            const int r = q / KF, k = q - r * KF;
+            const float h = rhi[(long long)(row0 + r) * KF + k], l = rlo[(long long)(row0 + r) * KF + k];
+            opA[op_index(r, k)] = h; opA[op_index(r, KF + k)] = h; opA[op_index(r, 2 * KF + k)] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == 4) {
+            if (lane == 0) {
+                const uint32_t a0 = smem_u32(opA);
+                for (int h = 0; h < NH; ++h) {
+                    const uint32_t b0 = smem_u32(opB) + (uint32_t)h * (TN / 8) * KCH * 128u;
+#pragma unroll
+                    for (int ks = 0; ks < KT / 8; ++ks)
+                        mma_tf32(tmem + (uint32_t)h * TN, make_desc(a0 + ks * 256u), make_desc(b0 + ks * 256u), ks > 0 ? 1u : 0u);
+                    mma_commit(smem_u32(&bars[h]));
+                }
+            }
+            __syncwarp();
+        } else {
+            float *srow = S + (warp * 32 + lane) * SROW;
+            for (int h = 0; h < NH; ++h) {
+                mbar_wait(smem_u32(&bars[h]), (uint32_t)(t & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 2
+                for (int c = 0; c < TN; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h * TN + c), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (e_out && blockIdx.x == 0 && t == 0) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) e_out[(warp * 32 + lane) * (NH * TN) + h * TN + c + q] = __uint_as_float(v[q]);
+                    }
+                    float4 o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        o[q] = make_float4(ex2f(__uint_as_float(v[4 * q])), ex2f(__uint_as_float(v[4 * q + 1])), ex2f(__uint_as_float(v[4 * q + 2])),
+                                           ex2f(__uint_as_float(v[4 * q + 3])));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(srow + h * TN + c + 4 * q) = o[q];
+                    acc_sink += o[0].x;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();          // TMEM and opA are free for the next tile
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (acc_sink == 12345.678f) sink[0] = acc_sink + S[tid];
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+}
+
+static float tf32_round(float x)
+{
+    uint32_t u; memcpy(&u, &x, 4);
+    u += 0x00000FFFu + ((u >> 13) & 1u);        // round to nearest even at 13 dropped bits
+    u &= 0xFFFFE000u;
+    float y; memcpy(&y, &u, 4);
+    return y;
+}
+
+int main(int argc, char **argv)
+{
+    const int tiles = argc > 1 ? atoi(argv[1]) : 64;
+    cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
+    printf("device %s, %d SMs\n", pr.name, pr.multiProcessorCount);
+    const int n_rows = 1 << 16, n_cols = NH * TN;
+    // features like k_prep makes them: r = sqrt(2 g) (t - mean), t ~ N(0, 0.3), A = -g |t - mean|^2, g = 7 log2 e
+    std::mt19937 rng(7); std::normal_distribution<double> nd(0.0, 0.3);
+    const double g2 = 7.0 * 1.4426950408889634, sc = std::sqrt(2.0 * g2);
+    auto make = [&](int n, bool is_row, std::vector<float> &full, std::vector<float> &hi, std::vector<float> &lo) {
+        full.assign((size_t)n * KF, 0.f); hi.assign((size_t)n * KF, 0.f); lo.assign((size_t)n * KF, 0.f);
+        for (int r = 0; r < n; ++r) {
+            double nn = 0;
+            for (int k = 0; k < 10; ++k) { const double x = nd(rng); nn += x * x; full[(size_t)r * KF + k] = (float)(sc * x); }
+            full[(size_t)r * KF + (is_row ? 10 : 11)] = (float)(-g2 * nn);
+            full[(size_t)r * KF + (is_row ? 11 : 10)] = 1.f;
+            for (int k = 0; k < KF; ++k) {
+                const float x = full[(size_t)r * KF + k], h = tf32_round(x);
+                hi[(size_t)r * KF + k] = h; lo[(size_t)r * KF + k] = tf32_round(x - h);
+            }
+        }
+    };
+    std::vector<float> rf, rh, rl, cf, chh, cl;
+    make(n_rows, true, rf, rh, rl);
+    make(n_cols, false, cf, chh, cl);
+    float *d_rh, *d_rl, *d_ch, *d_cl, *d_e, *d_sink;
+    CK(cudaMalloc(&d_rh, rh.size() * 4)); CK(cudaMalloc(&d_rl, rl.size() * 4)); CK(cudaMalloc(&d_ch, chh.size() * 4)); CK(cudaMalloc(&d_cl, cl.size() * 4));
+    CK(cudaMalloc(&d_e, (size_t)TM * n_cols * 4)); CK(cudaMalloc(&d_sink, 1024));
+    CK(cudaMemcpy(d_rh, rh.data(), rh.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_rl, rl.data(), rl.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ch, chh.data(), chh.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_cl, cl.data(), cl.size() * 4, cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)(TM * KT + NH * TN * KT + TM * SROW) * 4 + 1024;
+    CK(cudaFuncSetAttribute(k_tc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    printf("dynamic smem %zu bytes, idesc 0x%08x\n", smem, IDESC);
+
+    // ---- accuracy: tile 0 of CTA 0 against fp64 and against the fp32 FFMA chain of the production kernel
+    k_tc_probe<<<1, 160, smem>>>(d_rh, d_rl, n_rows, d_ch, d_cl, 1, d_e, d_sink);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> e((size_t)TM * n_cols);
+    CK(cudaMemcpy(e.data(), d_e, e.size() * 4, cudaMemcpyDeviceToHost));
+    double max_tc = 0, max_f32 = 0, max_mag = 0; int bad = 0;
+    for (int r = 0; r < TM; ++r)
+        for (int c = 0; c < n_cols; ++c) {
+            double ref = 0; float f = cf[(size_t)c * KF + 11];              // B_c
+            for (int k = 0; k < 12; ++k) ref += (double)rf[(size_t)r * KF + k] * (double)cf[(size_t)c * KF + k];
+            for (int k = 0; k < 10; ++k) f = fmaf(rf[(size_t)r * KF + k], cf[(size_t)c * KF + k], f);
+            f = f + rf[(size_t)r * KF + 10];
+            const double d_tc = std::fabs((double)e[(size_t)r * n_cols + c] - ref), d_f = std::fabs((double)f - ref);
+            if (!(d_tc < 1e-2)) ++bad;
+            max_tc = std::max(max_tc, d_tc); max_f32 = std::max(max_f32, d_f); max_mag = std::max(max_mag, std::fabs(ref));
+        }
+    printf("exponent tile %d x %d: max |E_tc - E_fp64| = %.3e   (fp32 FFMA chain: %.3e; max |E| = %.1f; cells off by > 1e-2: %d)\n", TM, n_cols, max_tc, max_f32,
+           max_mag, bad);
+
+    // ---- throughput
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int k : {1, 2}) {
+        const int grid = pr.multiProcessorCount * k;
+        k_tc_probe<<<grid, 160, smem>>>(d_rh, d_rl, n_rows, d_ch, d_cl, tiles, nullptr, d_sink);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        k_tc_probe<<<grid, 160, smem>>>(d_rh, d_rl, n_rows, d_ch, d_cl, tiles, nullptr, d_sink);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double cells = (double)grid * tiles * TM * n_cols;
+        printf("grid %4d x %d tiles: %8.3f ms  %8.1f Gcell/s produced (S tile in shared memory; k_fill1_v4 consumes 1050 Gcell/s)\n", grid, tiles, ms,
+               cells / (ms * 1e-3) / 1e9);
+    }
+    return 0;
+}
