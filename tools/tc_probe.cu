@@ -29,7 +29,7 @@ constexpr int NH = 2;            // halves
 constexpr int KF = 16;           // padded feature count
 constexpr int KT = 3 * KF;       // K of the split product
 constexpr int KCH = KT / 4;      // 16-byte chunks per operand row
-constexpr int SROW = NH * TN + 4;   // S tile row stride in floats (padding: the DP lanes read rows t - l at columns 10 l)
+constexpr int SROW = TN + 4;     // S tile row stride in floats (one half at a time in the probe; padding against bank conflicts)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // canonical K-major, no-swizzle operand layout: core matrix = 8 rows x 16 bytes (contiguous 128 B); core matrices of one
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(160, 1) k_tc_probe(const float *__restrict__ r
                         o[q] = make_float4(ex2f(__uint_as_float(v[4 * q])), ex2f(__uint_as_float(v[4 * q + 1])), ex2f(__uint_as_float(v[4 * q + 2])),
                                            ex2f(__uint_as_float(v[4 * q + 3])));
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(srow + h * TN + c + 4 * q) = o[q];
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(srow + c + 4 * q) = o[q];
                     acc_sink += o[0].x;
                 }
             }
