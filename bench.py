@@ -412,6 +412,11 @@ def main():
             e = int(c4.offsets[1000])
             sub_record("c4_subset", synth.Chains(c4.coords[:e], c4.tensors[:e], c4.offsets[:1001].copy()), 3,
                        "first 1000 chains of BASELINE config 4 (lengths 50-1000 mixed; 499 500 pairs) on one GPU")
+            # experimental: stage 1 of the same C3 workload on the tensor-core kernel (k_fill1_tc, CARETTA_B200_TC=1)
+            os.environ["CARETTA_B200_TC"] = "1"
+            sub_record("c3_tensor_core_stage1", ch, 5, "the headline workload with stage 1 on tcgen05.mma (experimental, off by default: profiles/r02_tensor_core_stage1.md)")
+            configs["c3_tensor_core_stage1"]["tc_pairs"] = int(eng.last_tc_pairs())
+            os.environ["CARETTA_B200_TC"] = "0"
         else:
             sub_record("strong_c3", synth.config("C3"), 5, f"BASELINE config 3 strong-scaled: 1000 chains x 300 on {world} GPUs")
             if world >= 8:

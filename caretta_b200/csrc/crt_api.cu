@@ -5,6 +5,7 @@
 #include "crt_fill_f32.cuh"
 #include "crt_fill1_v2.cuh"
 #include "crt_fill1_v4.cuh"
+#include "crt_fill_tc.cuh"
 #include "crt_fill2_v3.cuh"
 #include "crt_dp_batch.cuh"
 #include "crt_nj.cuh"
@@ -101,7 +102,16 @@ struct HostUnit {
     double cost;    // G * m
 };
 
-struct Batch { size_t first, count; int C, multi; size_t tb_n, rows2_n, bnd_n, path_n; int n_dense; };
+struct Batch {
+    size_t first, count; int C, multi; size_t tb_n, rows2_n, bnd_n, path_n; int n_dense;
+    // tensor-core stage 1 (crt_fill_tc.cuh): the batch's pairs regrouped into rounds; what is left runs on k_fill1_v4 units
+    bool tc = false;
+    size_t tc_r0 = 0, tc_nr = 0;        // rounds [tc_r0, tc_r0 + tc_nr) of the run's round array
+    size_t tc_p0 = 0, tc_np = 0;        // partner records
+    size_t lf_u0 = 0, lf_nu = 0;        // left-over stage-1 units
+    int lf_dense = 0;                   // pairs of the left-over units
+    size_t tc_bnd_n = 0;                // floats of strip boundary values (rounds first, then the left-over units)
+};
 
 }  // namespace
 
@@ -144,6 +154,11 @@ struct crt_ctx {
     Workspace ws[MAX_WS];
     int n_streams = 3;
     DevBuf<Unit> d_units, d_units2;      // d_units2: the float64 re-run of the tie pairs
+    DevBuf<crt::TcRound> d_tc_rounds;    // tensor-core stage 1: rounds, partner records, left-over units of the run, round counters per batch
+    DevBuf<crt::TcPartner> d_tc_partners;
+    DevBuf<Unit> d_tc_left;
+    DevBuf<int> d_tc_counter;
+    long long tc_pairs = 0;              // pairs of the last run whose stage 1 ran on the tensor cores
     DevBuf<int> tie_list;                // [0] = count, [1..] = result slots marked ST_TIE
     long long rerun_pairs = 0;
     double rerun_ms = 0;
@@ -169,6 +184,9 @@ struct crt_ctx {
         size_t budget = 0;
         std::vector<Batch> batches;
         std::vector<Unit> hu;
+        std::vector<crt::TcRound> tc_rounds;
+        std::vector<crt::TcPartner> tc_partners;
+        std::vector<Unit> tc_left;
         long long n_pairs = 0;
         double cells = 0;
     } plan;
@@ -336,6 +354,8 @@ int pad_dim(int d)
 }
 
 bool env_pipe();
+bool env_tc();
+int env_tc_min_part();
 int env_batches();
 int env_streams();
 size_t env_budget();
@@ -532,6 +552,119 @@ bool env_tie_rerun()
     return e ? atoi(e) != 0 : true;
 }
 
+
+// ---------------------------------------------------------------------------------------------- tensor-core stage 1
+// CARETTA_B200_TC=1 moves stage 1 of the fp32 mode to the tensor-core kernel k_fill1_tc wherever a column chain has enough
+// partners for a round.  Off by default: the kernel is 1.45 x faster per cell than k_fill1_v4, but at 1000 chains a fifth of
+// the lanes of the rounds idle and the run gains 3 %; and its exponents (tf32 hi / lo split) carry about twice the error of the
+// fp32 FMA chain, which lets 1 pair of 499 500 (config C3) and 3 of 124 750 (C5) take an unmarked different path
+// (profiles/r02_tensor_core_stage1.md).
+bool env_tc()
+{
+    const char *e = getenv("CARETTA_B200_TC");
+    return e ? atoi(e) != 0 : false;
+}
+// a round with fewer partners than this costs more on the tensor-core kernel (a round takes the time of 128 lanes whatever it
+// holds) than on the systolic one (measured 1.45 x per cell): its pairs stay on k_fill1_v4
+int env_tc_min_part()
+{
+    const char *e = getenv("CARETTA_B200_TC_MIN");
+    const int n = e ? atoi(e) : 72;
+    return std::min(std::max(n, 1), TC_LANES);
+}
+
+// Regroups the pairs of one batch (units bu[0..count), slot order: column chain ascending) for k_fill1_tc: per column chain the
+// partner row chains are sorted by length (stable) and cut into rounds of 128; a tail shorter than env_tc_min_part() becomes
+// units of consecutive chains for k_fill1_v4.  Result slots are untouched.  Indices in the records are batch-local.
+void plan_tc_batch(const crt_ctx *c, const Unit *bu, size_t count, Batch &b, std::vector<TcRound> &rounds, std::vector<TcPartner> &parts,
+                   std::vector<Unit> &left)
+{
+    struct Cand { int i, n, slot; };
+    std::vector<Cand> cand, rest;
+    const int min_part = env_tc_min_part();
+    b.tc = true;
+    b.tc_r0 = rounds.size(); b.tc_p0 = parts.size(); b.lf_u0 = left.size();
+    size_t tb_n = 0, path_n = 0, bnd_n = 0;
+    int lf_dense = 0;
+    size_t k = 0;
+    while (k < count) {
+        const int j = bu[k].col_chain, m = bu[k].m;
+        cand.clear(); rest.clear();
+        size_t k2 = k;
+        for (; k2 < count && bu[k2].col_chain == j; ++k2)
+            for (int q = 0; q < bu[k2].n_pairs; ++q) {
+                const int i = bu[k2].row_chain0 + q;
+                cand.push_back(Cand{i, (int)(c->offsets[i + 1] - c->offsets[i]), bu[k2].pair_base + q});
+            }
+        std::stable_sort(cand.begin(), cand.end(), [](const Cand &x, const Cand &y) { return x.n > y.n; });
+        const int n_strips = (m + TC_SC - 1) / TC_SC;
+        const int strip_w = (((m + n_strips - 1) / n_strips + 15) / 16) * 16;
+        int tiles_row = 0;
+        for (int s = 0; s < n_strips; ++s) tiles_row += (std::min(strip_w, ((m - s * strip_w + 15) / 16) * 16) + TC_TILE - 1) / TC_TILE;
+        size_t pos = 0;
+        while (pos < cand.size()) {
+            const size_t cnt = std::min<size_t>(TC_LANES, cand.size() - pos);
+            if ((int)cnt < min_part) { rest.assign(cand.begin() + pos, cand.end()); break; }
+            TcRound R{};
+            R.col_base = bu[k].col_base; R.col_chain = j; R.m = m; R.n_strips = n_strips; R.strip_w = strip_w;
+            R.part_base = (int)(parts.size() - b.tc_p0); R.n_part = (int)cnt; R.max_rows = cand[pos].n;
+            R.bnd_base = (long long)bnd_n;
+            if (n_strips > 1) bnd_n += (size_t)R.max_rows * TC_LANES;
+            const int ridx = (int)(rounds.size() - b.tc_r0);
+            for (size_t q = pos; q < pos + cnt; ++q) {
+                TcPartner P{};
+                P.tb_base = (long long)tb_n; tb_n += (size_t)cand[q].n * tiles_row;
+                P.path_base = (long long)path_n; path_n += (size_t)cand[q].n + m;
+                P.row_base = (int)c->offsets[cand[q].i]; P.row_chain = cand[q].i; P.n = cand[q].n; P.slot = cand[q].slot; P.round = ridx;
+                parts.push_back(P);
+            }
+            rounds.push_back(R);
+            pos += cnt;
+        }
+        // what is left: runs of consecutive chains (consecutive slots) become systolic units, as build_all_units makes them
+        std::sort(rest.begin(), rest.end(), [](const Cand &x, const Cand &y) { return x.i < y.i; });
+        size_t q = 0;
+        while (q < rest.size()) {
+            HostUnit h{};
+            h.u.row_chain0 = rest[q].i; h.u.row_base = c->offsets[rest[q].i];
+            h.u.col_chain = j; h.u.col_base = bu[k].col_base; h.u.m = m; h.u.pair_base = rest[q].slot;
+            int cnt = 0, maxn = 0;
+            long long G = 0;
+            while (q < rest.size() && cnt < MAX_PAIRS_PER_UNIT && rest[q].i == h.u.row_chain0 + cnt && rest[q].slot == h.u.pair_base + cnt) {
+                if (cnt > 0 && G + rest[q].n > UNIT_ROWS_MAX) break;
+                G += rest[q].n; maxn = std::max(maxn, rest[q].n); ++cnt; ++q;
+            }
+            h.u.G = (int)G; h.u.n_pairs = cnt; h.u.path_stride = maxn + m;
+            finish_unit(c, h, CRT_FP32);
+            h.u.tb_base = (long long)tb_n; tb_n += (size_t)h.u.n_strips * h.u.tchunks * 32;
+            h.u.path_base = (long long)path_n; path_n += (size_t)cnt * h.u.path_stride;
+            h.u.bnd_base = (long long)bnd_n; if (h.multi) bnd_n += (size_t)h.u.tchunks * 4 + 8;
+            h.u.dense_base = lf_dense; lf_dense += cnt;
+            left.push_back(h.u);
+        }
+        k = k2;
+    }
+    b.tc_nr = rounds.size() - b.tc_r0; b.tc_np = parts.size() - b.tc_p0; b.lf_nu = left.size() - b.lf_u0; b.lf_dense = lf_dense;
+    b.tb_n = tb_n; b.path_n = path_n; b.tc_bnd_n = bnd_n;
+}
+
+template <int RS>
+int launch_fill1_tc(const TcFill1Args &a, int n_rounds, int sm_count, cudaStream_t st)
+{
+    constexpr int K = ((4 * RS + 7) / 8) * 8;
+    constexpr size_t smem = (size_t)(2 * TC_LANES + TC_SC) * K * 4;
+    static bool configured = false;
+    if (!configured) {
+        CU(cudaFuncSetAttribute(k_fill1_tc<RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_fill1_tc<RS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    const int grid = std::min(n_rounds, 2 * sm_count);
+    k_fill1_tc<RS><<<grid, TC_THREADS, smem, st>>>(a, n_rounds);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, long long n_pairs, PathSink *sink,
               bool use_cached_plan = false, bool store_plan = false)
 {
@@ -547,6 +680,8 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     const int NS = want_paths ? 1 : env_streams();
     const bool pipe = !want_paths && NS > 1 && env_pipe() && !flexible;
     const int NW = pipe ? 4 : NS;                 // workspace sets in flight
+    // stage 1 of the fp32 mode on the tensor cores (crt_fill_tc.cuh) wherever a column chain has enough partners for a round
+    const bool use_tc = f32 && !flexible && !c->stage1_only && env_tc() && (c->D == 10 || c->D == 16);
     int rc;
     if ((rc = c->score.ensure((size_t)n_pairs + 1))) return rc;
     if ((rc = c->score1.ensure((size_t)n_pairs + 1))) return rc;
@@ -613,28 +748,50 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     };
     std::vector<Batch> batches;
     std::vector<Unit> hu;
+    std::vector<TcRound> tcr;
+    std::vector<TcPartner> tcp;
+    std::vector<Unit> tcl;
     if (use_cached_plan) {
         batches = c->plan.batches;
         hu = c->plan.hu;
     } else {
     carve(units, prec, true, batches, hu);
-    if (store_plan) { c->plan.batches = batches; c->plan.hu = hu; }
+    if (use_tc)
+        for (auto &b : batches) plan_tc_batch(c, hu.data() + b.first, b.count, b, tcr, tcp, tcl);
+    if (store_plan) { c->plan.batches = batches; c->plan.hu = hu; c->plan.tc_rounds = tcr; c->plan.tc_partners = tcp; c->plan.tc_left = tcl; }
     }
+    const bool tc_on = !batches.empty() && batches[0].tc;
     // ---- size the workspaces once (no allocation inside the timed region after the first run of a shape)
     for (int w = 0; w < NW; ++w) {
         crt_ctx::Workspace &ws = c->ws[w];
-        size_t tb_n = 0, rows2_n = 0, bnd_n = 0, path_n = 0;
+        size_t tb_n = 0, rows2_n = 0, bnd_n = 0, path_n = 0, tc_bnd_n = 0;
         for (size_t k = w; k < batches.size(); k += NW) {
             tb_n = std::max(tb_n, batches[k].tb_n); rows2_n = std::max(rows2_n, batches[k].rows2_n);
             bnd_n = std::max(bnd_n, batches[k].bnd_n); path_n = std::max(path_n, batches[k].path_n);
+            tc_bnd_n = std::max(tc_bnd_n, batches[k].tc_bnd_n);
         }
         if ((rc = ws.tb.ensure(tb_n + 1))) return rc;
         if ((rc = ws.rows2.ensure((rows2_n + 2 * ROW_PAD) * row2sz))) return rc;
         if ((rc = ws.path.ensure(path_n + 1))) return rc;
-        if ((rc = ws.bnd.ensure(bnd_n * tsz + 16))) return rc;
+        if ((rc = ws.bnd.ensure(std::max(bnd_n * tsz, tc_bnd_n * 4) + 16))) return rc;
         if ((rc = ws.bnd2.ensure(bnd_n * tsz + 16))) return rc;
     }
     if ((rc = c->d_units.ensure(hu.size()))) return rc;
+    c->tc_pairs = 0;
+    if (tc_on) {
+        for (auto &b : batches) c->tc_pairs += (long long)b.tc_np;
+        if ((rc = c->d_tc_counter.ensure(batches.size()))) return rc;
+        CU(cudaMemsetAsync(c->d_tc_counter.p, 0, sizeof(int) * batches.size(), c->stream));
+        if (!use_cached_plan) {
+            if ((rc = c->d_tc_rounds.ensure(tcr.size() + 1))) return rc;
+            if ((rc = c->d_tc_partners.ensure(tcp.size() + 1))) return rc;
+            if ((rc = c->d_tc_left.ensure(tcl.size() + 1))) return rc;
+            CU(cudaMemcpyAsync(c->d_tc_rounds.p, tcr.data(), sizeof(TcRound) * tcr.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->d_tc_partners.p, tcp.data(), sizeof(TcPartner) * tcp.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->d_tc_left.p, tcl.data(), sizeof(Unit) * tcl.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));        // the host vectors go out of scope with this call
+        }
+    }
 
     c->tb_bytes = 0;
     for (auto &b : batches) c->tb_bytes += (double)b.tb_n * 16.0;
@@ -654,6 +811,24 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         FillOut fo{};
         fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
         fo.pair_score = flexible ? c->score.p : c->score1.p; fo.bnd = ws.bnd.p;
+        if (f32x && b.tc) {
+            // rounds on the tensor cores, what is left of the batch on the systolic kernel (same result slots)
+            if (b.tc_nr > 0) {
+                TcFill1Args ta{};
+                ta.rec = c->rec32.p + (size_t)ROW_PAD * rs32; ta.rounds = c->d_tc_rounds.p + b.tc_r0; ta.partners = c->d_tc_partners.p + b.tc_p0;
+                ta.tb = ws.tb.p; ta.bnd = reinterpret_cast<float *>(ws.bnd.p); ta.pair_istar = c->pair_istar.p; ta.pair_zflag = c->pair_zflag.p;
+                ta.pair_score = c->score1.p; ta.counter = c->d_tc_counter.p + (&b - batches.data()); ta.tie = tie;
+                int r1 = c->D == 10 ? launch_fill1_tc<12>(ta, (int)b.tc_nr, c->sm_count, st) : launch_fill1_tc<20>(ta, (int)b.tc_nr, c->sm_count, st);
+                if (r1) return r1;
+            }
+            if (b.lf_nu > 0) {
+                Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
+                const Unit *lu = c->d_tc_left.p + b.lf_u0;
+                if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, lu, (int)b.lf_nu, a, fo, c->d_offsets.p, tie, st);
+                return launch_fill1_f32<16>(b.C, b.multi, lu, (int)b.lf_nu, a, fo, c->d_offsets.p, tie, st);
+            }
+            return 0;
+        }
         if (f32x) {
             Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
             if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, tie, st);
@@ -685,6 +860,18 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         ta.rows2_f32 = r32 ? 1 : 0;
         ta.skip_byproducts = c->stage1_only ? 1 : 0;
         int r2;
+        if (do_trace && f32x && b.tc) {
+            if (b.tc_np > 0) {
+                ta.tc_rounds = c->d_tc_rounds.p + b.tc_r0; ta.tc_partners = c->d_tc_partners.p + b.tc_p0;
+                k_trace_tc<<<(unsigned)((b.tc_np + TRACE_THREADS - 1) / TRACE_THREADS), TRACE_THREADS, 0, st>>>(ta, (int)b.tc_np);
+                CU(cudaGetLastError());
+            }
+            if (b.lf_nu > 0) {
+                TraceArgs tl = ta;
+                tl.units = c->d_tc_left.p + b.lf_u0;
+                if ((r2 = launch_trace(b.C, tl, (int)b.lf_nu, b.lf_dense, st, true))) return r2;
+            }
+        } else
         if (do_trace && (r2 = launch_trace(b.C, ta, nu, b.n_dense, st, f32x))) return r2;
         if (mid) CU(cudaEventRecord(mid, st));
         if (c->stage1_only || !do_rows2) return 0;
@@ -713,20 +900,32 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         CU(cudaMemcpyAsync(hp.data(), ws.path.p, b.path_n * sizeof(short2), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(hl.data(), c->path_len.p, (size_t)n_pairs * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        auto put = [&](int pidx, const short2 *pp) {
+            const int len = hl[pidx];
+            auto &v1 = sink->a1[pidx];
+            auto &v2 = sink->a2[pidx];
+            v1.resize(len); v2.resize(len);
+            for (int k2 = 0; k2 < len; ++k2) { v1[k2] = pp[len - 1 - k2].x; v2[k2] = pp[len - 1 - k2].y; }
+        };
+        if (b.tc && &hunits == &hu) {
+            // tensor-core batch of the main run: the paths lie where the partner records / left-over units say
+            for (size_t k = b.tc_p0; k < b.tc_p0 + b.tc_np; ++k) put(tcp[k].slot, hp.data() + tcp[k].path_base);
+            for (size_t k = b.lf_u0; k < b.lf_u0 + b.lf_nu; ++k)
+                for (int q = 0; q < tcl[k].n_pairs; ++q) put(tcl[k].pair_base + q, hp.data() + tcl[k].path_base + (size_t)q * tcl[k].path_stride);
+            return 0;
+        }
         for (size_t k = b.first; k < b.first + b.count; ++k) {
             const Unit &u = hunits[k];
-            for (int q = 0; q < u.n_pairs; ++q) {
-                const int pidx = u.pair_base + q, len = hl[pidx];
-                const short2 *pp = hp.data() + u.path_base + (size_t)q * u.path_stride;
-                auto &v1 = sink->a1[pidx];
-                auto &v2 = sink->a2[pidx];
-                v1.resize(len); v2.resize(len);
-                for (int k2 = 0; k2 < len; ++k2) { v1[k2] = pp[len - 1 - k2].x; v2[k2] = pp[len - 1 - k2].y; }
-            }
+            for (int q = 0; q < u.n_pairs; ++q) put(u.pair_base + q, hp.data() + u.path_base + (size_t)q * u.path_stride);
         }
         return 0;
     };
     const Unit *DU = c->d_units.p;
+    auto batch_launches = [&](const Batch &b) -> long long {
+        if (flexible) return 1;
+        if (!b.tc) return 4;
+        return 2 + 2 * ((b.tc_nr > 0 ? 1 : 0) + (b.lf_nu > 0 ? 1 : 0));
+    };
 
     if (pipe) {
         // ---- stage pipeline: s_f1[] run the stage-1 fills (alternating, so consecutive launches overlap at their
@@ -771,7 +970,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             if ((rc = stage2(b, ws, sf2, DU, f32))) return rc;
             mark1(sf2);
             CU(cudaEventRecord(ws.e_f2, sf2));
-            c->launches += 4;
+            c->launches += batch_launches(b);
         }
         if (timeline) {
             CU(cudaDeviceSynchronize());
@@ -804,7 +1003,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         if ((rc = stage_trace(b, ws, st, timed ? ws.ev[2] : nullptr, DU, f32))) return rc;
         if ((rc = stage2(b, ws, st, DU, f32))) return rc;
         if (timed) CU(cudaEventRecord(ws.ev[3], st));
-        c->launches += flexible ? 1 : 4;
+        c->launches += batch_launches(b);
 
         if (timed) {
             // one stream: phase timing (and, for the tests, the paths) per batch
@@ -1157,7 +1356,7 @@ int crt_pairwise_shard(crt_ctx *c, const crt_params *prm, int32_t rank, int32_t 
     if (world < 1 || rank < 0 || rank >= world) return fail(CRT_E_ARG, "bad rank/world %d/%d", rank, world);
     CU(cudaSetDevice(c->device));
     if ((rc = ensure_prepared(c, prm))) return rc;
-    const int ns = env_streams() + 100 * (env_pipe() ? 1 : 0) + 1000 * env_batches() + 100000 * (env_unit_rows() / 64);
+    const int ns = env_streams() + 100 * (env_pipe() ? 1 : 0) + 1000 * env_batches() + 100000 * (env_unit_rows() / 64) + (env_tc() ? 50 + 10000000 * env_tc_min_part() : 0);
     const size_t budget = env_budget();
     crt_ctx::PlanCache &pc = c->plan;
     if (pc.valid && pc.offsets_hash == c->offsets_hash && pc.rank == rank && pc.world == world && pc.prec == prm->precision &&
@@ -1322,6 +1521,7 @@ int crt_last_rerun(crt_ctx *c, int64_t *pairs, double *ms)
     if (ms) *ms = c->rerun_ms;
     return 0;
 }
+int64_t crt_last_tc_pairs(crt_ctx *c) { return c ? c->tc_pairs : -1; }
 double crt_last_cell_updates(crt_ctx *c) { return c ? c->cell_updates : -1.0; }
 double crt_last_traceback_bytes(crt_ctx *c) { return c ? c->tb_bytes : -1.0; }
 

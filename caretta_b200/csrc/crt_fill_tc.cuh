@@ -17,10 +17,10 @@
 //   * columns are processed in strips of <= 160 (TMEM budget of a CTA: 96 columns of exponent tiles in a ring of three
 //     32-column tiles + 160 columns of state = 256, so two CTAs share an SM and hide each other's latencies); the value
 //     crossing a strip boundary goes through a [rows][128] float array in global memory (L2).
-//   * tf32 has 11 significant bits, so every operand is split  x = hi + lo  (both tf32) and E = hi.hi + hi.lo + lo.hi is the
-//     sum of three K-blocks in ONE accumulation (K = 3 x 12 -> 40); A_a and B_b enter as three-level splits against ones, so
-//     they are exact.  Measured: max |E - E_fp64| = 5e-6 for |E| <= 64 (tools/tc_fill_probe.cu), the fp32 FFMA chain of the
-//     systolic kernel: 7e-6.
+//   * tf32 has 11 significant bits, so every operand is split  x = hi + lo  (both tf32) and E = hi.hi + hi.lo + lo.hi + lo.lo
+//     is the sum of four K-blocks in ONE accumulation (K = 4 x 12 = 48: six K = 8 instructions per tile -- the tensor pipe is
+//     ~15 % busy); A_a and B_b enter as three-level splits against ones, so they are exact.  What is left is the fp32
+//     accumulation inside the tensor core.
 //
 // Traceback codes: 3 bits per cell as in k_fill1_v4 (S attains the maximum, left attains it, suspect), 96 bits per 32-column
 // tile, one 16-byte store per tile: [pair][strip][row][tile] uint4 (x, y, z = the 96 bits in push order, MSB first).
@@ -190,7 +190,7 @@ template <int RS>
 __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n_rounds)
 {
     constexpr int GCH = RS / 4;                          // 16-byte chunks per K-block (one record)
-    constexpr int K = ((3 * RS + 7) / 8) * 8;
+    constexpr int K = ((4 * RS + 7) / 8) * 8;
     constexpr int KCH = K / 4;
     constexpr int D = RS == 12 ? 10 : 16;                // index of A inside a record
     constexpr int A_FLOATS = TC_LANES * K, B_FLOATS = TC_SC * K;
@@ -250,22 +250,24 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n
 #pragma unroll
         for (int q = 0; q < GCH; ++q) xr[q] = __ldg(src + q);
     };
-    // stage it into A buffer `buf`:  [hi(r), A_hi, 1 | hi(r), A_mid, 1 | lo(r), A_lo, 1]
+    // stage it into A buffer `buf`:  [hi(r), A_hi, 1 | hi(r), A_mid, 1 | lo(r), A_lo, 1 | lo(r), 0, 0]
     auto stage_row = [&](uint32_t buf) {
-        float x[RS], hi[RS], lo[RS], mid[RS];
+        float x[RS], hi[RS], lo[RS], mid[RS], l2[RS];
 #pragma unroll
         for (int q = 0; q < GCH; ++q) { x[4 * q] = xr[q].x; x[4 * q + 1] = xr[q].y; x[4 * q + 2] = xr[q].z; x[4 * q + 3] = xr[q].w; }
 #pragma unroll
-        for (int k = 0; k < RS; ++k) { hi[k] = tcg::tf32_rn(x[k]); lo[k] = x[k] - hi[k]; mid[k] = hi[k]; }
+        for (int k = 0; k < RS; ++k) { hi[k] = tcg::tf32_rn(x[k]); lo[k] = x[k] - hi[k]; mid[k] = hi[k]; l2[k] = lo[k]; }
         mid[D] = tcg::tf32_rn(lo[D]);                    // A = hi + mid + lo, against the column's ones
         lo[D] = lo[D] - mid[D];
         lo[D + 1] = 1.f;                                 // the ones that carry the column's B_mid, B_lo
+        l2[D] = 0.f; l2[D + 1] = 0.f;                    // fourth block: lo(r) . lo(c) only
         float *dst = opA + buf * A_FLOATS + ((tid >> 3) * KCH) * 32 + (tid & 7) * 4;
 #pragma unroll
         for (int q = 0; q < GCH; ++q) {
             *reinterpret_cast<float4 *>(dst + q * 32) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
             *reinterpret_cast<float4 *>(dst + (GCH + q) * 32) = make_float4(mid[4 * q], mid[4 * q + 1], mid[4 * q + 2], mid[4 * q + 3]);
             *reinterpret_cast<float4 *>(dst + (2 * GCH + q) * 32) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            *reinterpret_cast<float4 *>(dst + (3 * GCH + q) * 32) = make_float4(l2[4 * q], l2[4 * q + 1], l2[4 * q + 2], l2[4 * q + 3]);
         }
         tcg::fence_async_smem();
         tcg::mbar_arrive(bar_a + 8 * buf);
@@ -278,16 +280,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n
         const bool half_last = (w_cols & 16) != 0;                            // plus one 16-column tile
         const int n_tiles = n_full + (half_last ? 1 : 0);
         const bool last_strip = strip == R.n_strips - 1;
-        // ---- column operand of the strip: [hi(c), 1, B_hi | lo(c), 1, B_mid | hi(c), 1, B_lo]; padded columns: B_hi = -1e30
+        // ---- column operand of the strip: [hi(c), 1, B_hi | lo(c), 1, B_mid | hi(c), 1, B_lo | lo(c), 0, 0]; padded columns: B_hi = -1e30
         if (strip > 0) __syncthreads();                                       // every MMA of the previous strip has been consumed
         for (int q = tid; q < n_tiles * TC_TILE * GCH; q += TC_THREADS) {
             const int c = q / GCH, part = q - c * GCH;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool real = c0 + c < R.m;
             if (real) v = __ldg(reinterpret_cast<const float4 *>(g.rec + ((long long)R.col_base + c0 + c) * RS) + part);
-            float x[4] = {v.x, v.y, v.z, v.w}, hi[4], lo[4], h2[4];
+            float x[4] = {v.x, v.y, v.z, v.w}, hi[4], lo[4], h2[4], l2[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { hi[k] = tcg::tf32_rn(x[k]); lo[k] = x[k] - hi[k]; h2[k] = hi[k]; }
+            for (int k = 0; k < 4; ++k) { hi[k] = tcg::tf32_rn(x[k]); lo[k] = x[k] - hi[k]; h2[k] = hi[k]; l2[k] = lo[k]; }
             if (part == D / 4) {                                              // the chunk that holds (A, 1): becomes (1, B)
                 constexpr int ka = D % 4;                                     // position of A inside the chunk (2 for D = 10, 0 for D = 16)
                 const float B = real ? x[ka] : -1e30f;
@@ -295,11 +297,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n
                 hi[ka] = 1.f; hi[ka + 1] = bh;
                 lo[ka] = 1.f; lo[ka + 1] = bm;
                 h2[ka] = 1.f; h2[ka + 1] = bl;
+                l2[ka] = 0.f; l2[ka + 1] = 0.f;
             }
             float *dst = opB + ((c >> 3) * KCH) * 32 + (c & 7) * 4;
             *reinterpret_cast<float4 *>(dst + part * 32) = make_float4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<float4 *>(dst + (GCH + part) * 32) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             *reinterpret_cast<float4 *>(dst + (2 * GCH + part) * 32) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+            *reinterpret_cast<float4 *>(dst + (3 * GCH + part) * 32) = make_float4(l2[0], l2[1], l2[2], l2[3]);
         }
         tcg::fence_async_smem();
         if (dp) {
@@ -384,6 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n
                 }
                 for (int q = 0; q < n_full; ++q) {
                     tcg::tmem_wait_ld();                                             // first half in registers
+                    tcg::tmem_wait_st();                                             // uB has left for tensor memory (previous tile)
                     tcg::tmem_ld16(st_addr + 16, uB);
                     tcg::tmem_ld16(lane_taddr + e_slot * TC_TILE + 16, eB);
                     tc_cells16<0>(eA, uA, a, th, neg_eps, word, w);
@@ -393,6 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n
                     if (lane == 0) tcg::mbar_arrive(bar_ee + 8 * e_slot);
                     if (++e_slot == TC_RING) { e_slot = 0; e_par ^= 1; }
                     if (q + 1 < n_tiles) {
+                        tcg::tmem_wait_st();                                         // uA has left for tensor memory
                         tcg::tmem_ld16(st_addr + 32, uA);
                         TC_T(t_b);
                         tcg::mbar_wait(bar_ef + 8 * e_slot, e_par);
@@ -444,6 +450,102 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n
     tcg::fence_before();
     __syncthreads();
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_trace_tc: k_trace (crt_kernels.cuh) on the code layout of k_fill1_tc.  One thread per pair (= per partner record of the
+// batch): start cell = first row-major maximum (dynamic_time_warping.py:241-247), walk with priority diag > left > up
+// (:255-277), then the shared tail (Kabsch, by-products).  Codes of pair p: [strip][row][tile] uint4, 3 bits per column in push
+// order (S attains the maximum, left attains it, suspect), MSB first.  A pair with a zero region (S[0][0] == 0: the reference's
+// walk can stop inside the matrix) is handed to the float64 re-run: the exponents of the tensor-core tile are not bit-identical
+// to a scalar re-evaluation, so the stop state is not emulated here.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace_tc(TraceArgs a, int n_part)
+{
+    const int gid = blockIdx.x * TRACE_THREADS + threadIdx.x;
+    if (gid >= n_part) return;
+    const TcPartner P = a.tc_partners[gid];
+    const TcRound R = a.tc_rounds[P.round];
+    const int pair = P.slot, n = P.n, m = R.m;
+    const double *A = a.coords + (long long)P.row_base * 3;
+    const double *B = a.coords + (long long)R.col_base * 3;
+    const double *ceni = a.centroid + (long long)P.row_chain * 3, *cenj = a.centroid + (long long)R.col_chain * 3;
+    short2 *path = a.path + P.path_base;
+    const int tiles_full = (R.strip_w + TC_TILE - 1) / TC_TILE;
+    const uint4 *tbp = a.tb + P.tb_base;
+
+    // position of the walk: strip, column inside the strip, 0-based row; nt = tiles per row of the current strip
+    int w_strip = 0, w_c = 0, w_row = 0, nt = tiles_full;
+    auto strip_tiles = [&](int strip) {
+        const int w_cols = min(R.strip_w, ((m - strip * R.strip_w + 15) / 16) * 16);
+        return (w_cols + TC_TILE - 1) / TC_TILE;
+    };
+    auto seek = [&](int i, int j) {
+        w_strip = (j - 1) / R.strip_w;
+        w_c = (j - 1) - w_strip * R.strip_w;
+        w_row = i - 1;
+        nt = strip_tiles(w_strip);
+    };
+    auto col_left = [&]() {
+        if (--w_c < 0) { --w_strip; w_c = R.strip_w - 1; nt = tiles_full; }
+    };
+    long long cidx = -1;
+    uint4 cw = make_uint4(0, 0, 0, 0);
+    unsigned tie = 0;
+    auto code = [&]() -> unsigned {                       // (H != diag + S) << 1 | (H != left) of the current cell
+        const long long idx = ((long long)w_strip * n * tiles_full) + (long long)w_row * nt + (w_c >> 5);
+        if (idx != cidx) {
+            cw = tbp[idx]; cidx = idx;
+            if (w_row >= 2) {                             // the walk moves up and to the left
+                prefetch_tb(tbp + idx - nt);
+                prefetch_tb(tbp + idx - 2 * nt);
+                if ((w_c & 31) < 2 && (w_c >> 5) > 0) prefetch_tb(tbp + idx - nt - 1);
+            }
+        }
+        const int p = 3 * (w_c & 31);
+        const unsigned hi = p < 32 ? cw.x : (p < 64 ? cw.y : cw.z), lo = p < 32 ? cw.y : (p < 64 ? cw.z : 0u);
+        const unsigned raw = __funnelshift_l(lo, hi, p & 31) >> 29;      // (S attains) << 2 | (left attains) << 1 | suspect
+        // suspect cell, or S and the left value attain the maximum together (an exact fp32 tie the reference may not share)
+        tie |= (raw & 1u) | (raw >= 6u ? 1u : 0u);
+        return ((raw ^ 6u) >> 1) & 3u;
+    };
+
+    const bool zreg = a.pair_zflag[pair] != 0;
+    int wi = 0, wj = 0;
+    auto is_zero_cell = [&](int i, int j) -> bool {
+        if (wi > 0 && wi <= i && wj <= j) return false;
+        for (int ii = 1; ii <= i; ++ii)
+            for (int jj = 1; jj <= j; ++jj)
+                if (!s1_is_zero(a, (long long)P.row_base + ii - 1, (long long)R.col_base + jj - 1)) { wi = ii; wj = jj; return false; }
+        return true;
+    };
+
+    int i = a.pair_istar[pair], j = m;
+    int st = 0, len = 0, c = 0;
+    if (i & ISTAR_TIE) { tie = 1; i &= ~ISTAR_TIE; }
+    if (zreg) tie = 1;
+    if (i <= 0) {
+        st |= 2;                      // CRT_ST_NO_POSITIVE
+    } else {
+        seek(i, j);
+        while (j > 1 && (code() & 1u) == 0u) { --j; col_left(); }      // first column of row i* that attains the maximum
+        while (i > 0 && j > 0) {
+            if (zreg && is_zero_cell(i, j)) break;
+            const unsigned cd = code();
+            if ((cd & 2u) == 0u) {
+                --i; --j; --w_row; col_left();
+                path[len++] = make_short2((short)i, (short)j);
+                ++c;
+            } else if ((cd & 1u) == 0u) {
+                --j; col_left();
+                path[len++] = make_short2((short)-1, (short)j);
+            } else {
+                --i; --w_row;
+                path[len++] = make_short2((short)i, (short)-1);
+            }
+        }
+    }
+    trace_tail(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);
 }
 
 }  // namespace crt

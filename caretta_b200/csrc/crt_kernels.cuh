@@ -358,8 +358,12 @@ __device__ inline void kabsch_rotation(const double Cm[9], double R[9])
 // priority diag > left > up (:255-277), common positions (helper.py:12-42), Kabsch (superposition_functions.py:6-60),
 // by-products RMSD / TM (score_functions.py:14-19, multiple_alignment.py:59-70), stage-2 row records.
 // ------------------------------------------------------------------------------------------------------------
+struct TcRound;
+struct TcPartner;
 struct TraceArgs {
     const Unit *units;
+    const TcRound *tc_rounds;     // k_trace_tc: the rounds / partners of the batch (crt_fill_tc.cuh)
+    const TcPartner *tc_partners;
     const uint4 *tb;
     const int *pair_istar;
     const int *pair_zflag;
@@ -397,11 +401,96 @@ __device__ inline bool s1_is_zero(const TraceArgs &a, long long ri, long long ci
     return exp(__dmul_rn(a.neg_gamma_t, acc)) == 0.0;
 }
 
+constexpr int XF = 16;                // doubles per pair in the transform array: R[9], m1[3], m2[3], superpose flag
+
+// Passes 2 and 3 of the traceback kernels: Kabsch on the matched residues of a walked path (superposition_functions.py:6-60),
+// transform record for k_rows2, by-products RMSD / TM (score_functions.py:14-19, multiple_alignment.py:59-70).
+// path: len entries as walked (descending), (-1, j) / (i, -1) = gaps; c = matched residues; st = status bits so far.
+__device__ __forceinline__ void trace_tail(const TraceArgs &a, int pair, const short2 *path, int len, int c, int st, unsigned tie, int n, int m,
+                                           const double *A, const double *B, const double *ceni, const double *cenj)
+{
+    const double ca0 = ceni[0], ca1 = ceni[1], ca2 = ceni[2], cb0 = cenj[0], cb1 = cenj[1], cb2 = cenj[2];
+    a.path_len[pair] = len;
+    a.ncommon[pair] = c;
+    if (tie) st |= ST_TIE;
+
+    // ---- pass 2: moments of the matched residues, relative to the chains' own centroids (translation does not change
+    // the covariance; it keeps the raw-moment form well conditioned).  Same summation order as the walk (descending).
+    double s1x = 0, s1y = 0, s1z = 0, s2x = 0, s2y = 0, s2z = 0;
+    double cxx = 0, cxy = 0, cxz = 0, cyx = 0, cyy = 0, cyz = 0, czx = 0, czy = 0, czz = 0;
+    const bool superpose = c > 3;
+    if (superpose) {
+#pragma unroll 4
+        for (int q = 0; q < len; ++q) {
+            const short2 e = path[q];
+            if (e.x < 0 || e.y < 0) continue;
+            const double x1 = A[e.x * 3] - ca0, y1 = A[e.x * 3 + 1] - ca1, z1 = A[e.x * 3 + 2] - ca2;
+            const double x2 = B[e.y * 3] - cb0, y2 = B[e.y * 3 + 1] - cb1, z2 = B[e.y * 3 + 2] - cb2;
+            s1x += x1; s1y += y1; s1z += z1; s2x += x2; s2y += y2; s2z += z2;
+            cxx += x2 * x1; cxy += x2 * y1; cxz += x2 * z1;
+            cyx += y2 * x1; cyy += y2 * y1; cyz += y2 * z1;
+            czx += z2 * x1; czy += z2 * y1; czz += z2 * z1;
+        }
+    }
+
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
+    if (!superpose) st |= 1;          // CRT_ST_FEW_COMMON: multiple_alignment.py:337-342
+    if (superpose) {
+        const double inv = 1.0 / (double)c;
+        const double p1[3] = {s1x * inv, s1y * inv, s1z * inv}, p2[3] = {s2x * inv, s2y * inv, s2z * inv};
+        double Cm[9];                 // sum (x2 - mean2)(x1 - mean1)^T = raw moments - c * mean2 mean1^T
+        Cm[0] = cxx - s2x * p1[0]; Cm[1] = cxy - s2x * p1[1]; Cm[2] = cxz - s2x * p1[2];
+        Cm[3] = cyx - s2y * p1[0]; Cm[4] = cyy - s2y * p1[1]; Cm[5] = cyz - s2y * p1[2];
+        Cm[6] = czx - s2z * p1[0]; Cm[7] = czy - s2z * p1[1]; Cm[8] = czz - s2z * p1[2];
+        kabsch_rotation(Cm, R);
+        m1[0] = p1[0] + ca0; m1[1] = p1[1] + ca1; m1[2] = p1[2] + ca2;
+        m2[0] = p2[0] + cb0; m2[1] = p2[1] + cb1; m2[2] = p2[2] + cb2;
+    }
+    // translation of apply_rotran: t = m1 - m2 R
+    double tr[3];
+    for (int b = 0; b < 3; ++b) tr[b] = m1[b] - (m2[0] * R[b] + m2[1] * R[3 + b] + m2[2] * R[6 + b]);
+    double *xf = a.xform + (long long)pair * XF;
+    for (int q = 0; q < 9; ++q) xf[q] = R[q];
+    for (int q = 0; q < 3; ++q) { xf[9 + q] = m1[q]; xf[12 + q] = m2[q]; }
+    xf[15] = superpose ? 1.0 : 0.0;
+    // ---- pass 3: by-products over the matched residues, ascending residue order like the reference's sums
+    double rmsd = 0.0, tm = 0.0;
+    if (c >= 1 && !a.skip_byproducts) {
+        const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
+        double ss = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll 2
+        for (int q = len - 1; q >= 0; --q) {
+            const short2 e = path[q];
+            if (e.x < 0 || e.y < 0) continue;
+            double sm = 0.0;
+            const double *y = B + e.y * 3;
+            const double y0 = y[0], y1 = y[1], y2 = y[2];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const double yr = superpose ? (y0 * R[b] + y1 * R[3 + b] + y2 * R[6 + b]) + tr[b] : (b == 0 ? y0 : (b == 1 ? y1 : y2));
+                const double df = A[e.x * 3 + b] - yr;
+                ss += df * df;
+                sm += df;
+            }
+            const double q1 = sm / d1, q2 = sm / d2;
+            t1 += 1 / (1 + q1 * q1);
+            t2 += 1 / (1 + q2 * q2);
+        }
+        rmsd = sqrt(ss / (double)c);
+        t1 = (1.0 / (double)n) * t1;
+        t2 = (1.0 / (double)m) * t2;
+        tm = t1 > t2 ? t1 : t2;
+    }
+    a.rmsd[pair] = rmsd;
+    a.tm[pair] = tm;
+    a.status[pair] = st;
+}
+
 #ifndef CRT_TRACE_MINB
 #define CRT_TRACE_MINB 6
 #endif
 constexpr int TRACE_THREADS = 128;    // threads (= pairs) per CTA of k_trace
-constexpr int XF = 16;                // doubles per pair in the transform array: R[9], m1[3], m2[3], superpose flag
 
 __device__ __forceinline__ void prefetch_tb(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -435,7 +524,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
     const double *A = a.coords + ro * 3;
     const double *B = a.coords + (long long)u.col_base * 3;
     const double *ceni = a.centroid + (long long)ci * 3, *cenj = a.centroid + (long long)u.col_chain * 3;
-    const double ca0 = ceni[0], ca1 = ceni[1], ca2 = ceni[2], cb0 = cenj[0], cb1 = cenj[1], cb2 = cenj[2];
     short2 *path = a.path + u.path_base + (long long)tid * u.path_stride;
     constexpr int SW = 32 * C;
 
@@ -518,81 +606,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
             }
         }
     }
-    a.path_len[pair] = len;
-    a.ncommon[pair] = c;
-    if (tie) st |= ST_TIE;
-
-    // ---- pass 2: moments of the matched residues, relative to the chains' own centroids (translation does not change
-    // the covariance; it keeps the raw-moment form well conditioned).  Same summation order as the walk (descending).
-    double s1x = 0, s1y = 0, s1z = 0, s2x = 0, s2y = 0, s2z = 0;
-    double cxx = 0, cxy = 0, cxz = 0, cyx = 0, cyy = 0, cyz = 0, czx = 0, czy = 0, czz = 0;
-    const bool superpose = c > 3;
-    if (superpose) {
-#pragma unroll 4
-        for (int q = 0; q < len; ++q) {
-            const short2 e = path[q];
-            if (e.x < 0 || e.y < 0) continue;
-            const double x1 = A[e.x * 3] - ca0, y1 = A[e.x * 3 + 1] - ca1, z1 = A[e.x * 3 + 2] - ca2;
-            const double x2 = B[e.y * 3] - cb0, y2 = B[e.y * 3 + 1] - cb1, z2 = B[e.y * 3 + 2] - cb2;
-            s1x += x1; s1y += y1; s1z += z1; s2x += x2; s2y += y2; s2z += z2;
-            cxx += x2 * x1; cxy += x2 * y1; cxz += x2 * z1;
-            cyx += y2 * x1; cyy += y2 * y1; cyz += y2 * z1;
-            czx += z2 * x1; czy += z2 * y1; czz += z2 * z1;
-        }
-    }
-
-    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
-    if (!superpose) st |= 1;          // CRT_ST_FEW_COMMON: multiple_alignment.py:337-342
-    if (superpose) {
-        const double inv = 1.0 / (double)c;
-        const double p1[3] = {s1x * inv, s1y * inv, s1z * inv}, p2[3] = {s2x * inv, s2y * inv, s2z * inv};
-        double Cm[9];                 // sum (x2 - mean2)(x1 - mean1)^T = raw moments - c * mean2 mean1^T
-        Cm[0] = cxx - s2x * p1[0]; Cm[1] = cxy - s2x * p1[1]; Cm[2] = cxz - s2x * p1[2];
-        Cm[3] = cyx - s2y * p1[0]; Cm[4] = cyy - s2y * p1[1]; Cm[5] = cyz - s2y * p1[2];
-        Cm[6] = czx - s2z * p1[0]; Cm[7] = czy - s2z * p1[1]; Cm[8] = czz - s2z * p1[2];
-        kabsch_rotation(Cm, R);
-        m1[0] = p1[0] + ca0; m1[1] = p1[1] + ca1; m1[2] = p1[2] + ca2;
-        m2[0] = p2[0] + cb0; m2[1] = p2[1] + cb1; m2[2] = p2[2] + cb2;
-    }
-    // translation of apply_rotran: t = m1 - m2 R
-    double tr[3];
-    for (int b = 0; b < 3; ++b) tr[b] = m1[b] - (m2[0] * R[b] + m2[1] * R[3 + b] + m2[2] * R[6 + b]);
-    double *xf = a.xform + (long long)pair * XF;
-    for (int q = 0; q < 9; ++q) xf[q] = R[q];
-    for (int q = 0; q < 3; ++q) { xf[9 + q] = m1[q]; xf[12 + q] = m2[q]; }
-    xf[15] = superpose ? 1.0 : 0.0;
-    // ---- pass 3: by-products over the matched residues, ascending residue order like the reference's sums
-    double rmsd = 0.0, tm = 0.0;
-    if (c >= 1 && !a.skip_byproducts) {
-        const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
-        double ss = 0.0, t1 = 0.0, t2 = 0.0;
-#pragma unroll 2
-        for (int q = len - 1; q >= 0; --q) {
-            const short2 e = path[q];
-            if (e.x < 0 || e.y < 0) continue;
-            double sm = 0.0;
-            const double *y = B + e.y * 3;
-            const double y0 = y[0], y1 = y[1], y2 = y[2];
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                const double yr = superpose ? (y0 * R[b] + y1 * R[3 + b] + y2 * R[6 + b]) + tr[b] : (b == 0 ? y0 : (b == 1 ? y1 : y2));
-                const double df = A[e.x * 3 + b] - yr;
-                ss += df * df;
-                sm += df;
-            }
-            const double q1 = sm / d1, q2 = sm / d2;
-            t1 += 1 / (1 + q1 * q1);
-            t2 += 1 / (1 + q2 * q2);
-        }
-        rmsd = sqrt(ss / (double)c);
-        t1 = (1.0 / (double)n) * t1;
-        t2 = (1.0 / (double)m) * t2;
-        tm = t1 > t2 ? t1 : t2;
-    }
-    a.rmsd[pair] = rmsd;
-    a.tm[pair] = tm;
-    a.status[pair] = st;
+    trace_tail(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);
 }
 
 // Stage-2 row records, one thread per row of the unit's stream: (x - m1) R^T + m2  == the reference's frame up

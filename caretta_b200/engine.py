@@ -22,7 +22,7 @@ GC_FLEXIBLE, GC_FLEXIBLE_SCORE = -1.0, -2.0
 EXPORTS = [
     "crt_last_error", "crt_version", "crt_create", "crt_destroy", "crt_device_info", "crt_set_chains", "crt_set_coords",
     "crt_pairwise_shard", "crt_shard_size", "crt_shard_pairs", "crt_plan_shard_size", "crt_plan_shard_pairs", "crt_fetch", "crt_fetch_device",
-    "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_rerun", "crt_last_cell_updates", "crt_last_traceback_bytes", "crt_pairwise_all", "crt_pairwise_list",
+    "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_rerun", "crt_last_tc_pairs", "crt_last_cell_updates", "crt_last_traceback_bytes", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node", "crt_progressive_level",
     "crt_score_matrix", "crt_mean_function", "crt_mean_weights",
     "crt_msa_begin", "crt_msa_level", "crt_msa_lengths", "crt_msa_fetch", "crt_msa_end",
@@ -77,6 +77,8 @@ def load_library():
     L.crt_last_launches.restype = i64
     L.crt_last_rerun.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.crt_last_rerun.restype = C.c_int
+    L.crt_last_tc_pairs.argtypes = [vp]
+    L.crt_last_tc_pairs.restype = C.c_int64
     L.crt_last_cell_updates.argtypes = [vp]
     L.crt_last_cell_updates.restype = dbl
     L.crt_last_traceback_bytes.argtypes = [vp]
@@ -413,6 +415,10 @@ class Engine:
         n, ms = C.c_int64(0), C.c_double(0.0)
         self._check(self.lib.crt_last_rerun(self.h, C.byref(n), C.byref(ms)), "crt_last_rerun")
         return int(n.value), float(ms.value)
+
+    def last_tc_pairs(self) -> int:
+        """Pairs of the last run whose stage-1 fill ran on the tensor-core kernel (CARETTA_B200_TC=1)."""
+        return int(self.lib.crt_last_tc_pairs(self.h))
 
     def last_cell_updates(self) -> float:
         return float(self.lib.crt_last_cell_updates(self.h))

@@ -117,6 +117,8 @@ int crt_last_phase_ms(crt_ctx *ctx, double *out4);
 int64_t crt_last_launches(crt_ctx *ctx);         /* kernels launched by the last run */
 /* CRT_FP32 runs: how many pairs the tie detection sent through the float64 kernels, and the device time that took */
 int crt_last_rerun(crt_ctx *ctx, int64_t *pairs, double *ms);
+/* pairs of the last run whose stage-1 fill ran on the tensor-core kernel (environment CARETTA_B200_TC=1, experimental; 0 otherwise) */
+int64_t crt_last_tc_pairs(crt_ctx *ctx);
 double crt_last_cell_updates(crt_ctx *ctx);      /* sum over pairs of 2 * L1 * L2 */
 /* bytes of traceback words the stage-1 fills of the last run wrote (from the allocation: strips x chunks x 32 lanes x 16 B per
  * unit) -- the HBM traffic of the dominant kernel */

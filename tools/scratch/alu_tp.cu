@@ -1,0 +1,54 @@
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+// throughput (warp-instr/clk/SMSP) and dependent latency of the ALU-pipe ops of the stage-1 cell
+template <int MODE> __global__ void k(unsigned *out, int iters, long long *cyc)
+{
+    unsigned x[8]; float f[8];
+    for (int q = 0; q < 8; ++q) { x[q] = threadIdx.x * 2654435761u + q * 40503u; f[q] = 1.0f + threadIdx.x * 1e-3f + q; }
+    unsigned w = threadIdx.x;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (MODE == 0) x[q] = __vimin3_u32(x[q], x[(q + 1) & 7] + 1u, w);
+                if (MODE == 1) f[q] = fmaxf(fmaxf(f[q], f[(q + 1) & 7]), 0.5f);
+                if (MODE == 2) f[q] = fminf(f[q], f[(q + 1) & 7]);
+                if (MODE == 3) x[q] = __funnelshift_l(x[(q + 1) & 7], x[q], 1);
+                if (MODE == 4) f[q] = __fadd_rd(f[q], f[(q + 1) & 7]);
+                if (MODE == 5) f[q] = __fadd_rn(f[q], f[(q + 1) & 7]);
+                if (MODE == 6) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[q])); }
+                if (MODE == 7) x[0] = __vimin3_u32(x[0], x[1], w) + 1;   // dependent chain (with an IADD)
+                if (MODE == 8) f[0] = fmaxf(fmaxf(f[0], f[1]), 0.5f) ;   // dependent chain FMNMX3
+                if (MODE == 9) f[0] = __fadd_rd(fmaxf(fmaxf(f[0], f[1]), f[2]), -f[1]);   // the cell's critical path: FMNMX3 -> FADD.RM
+            }
+    }
+    long long t1 = clock64();
+    unsigned s = w; for (int q = 0; q < 8; ++q) s ^= x[q] ^ __float_as_uint(f[q]);
+    if (s == 0x1234567u) out[0] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+int main()
+{
+    long long *d, h; cudaMalloc(&d, 8);
+    const char *names[] = {"VIMNMX3.U32 (+IADD)", "FMNMX3", "FMNMX", "SHF.L.W", "FADD.RM", "FADD", "MUFU.EX2", "dep VIMNMX3+IADD", "dep FMNMX3", "dep FMNMX3->FADD.RM"};
+    const int iters = 2048;
+    for (int mode = 0; mode < 10; ++mode) {
+        for (int warps : {1, 4}) {       // warps per SMSP
+            dim3 g(148), b(128 * warps);
+            switch (mode) {
+            case 0: k<0><<<g, b>>>(nullptr, iters, d); break; case 1: k<1><<<g, b>>>(nullptr, iters, d); break; case 2: k<2><<<g, b>>>(nullptr, iters, d); break;
+            case 3: k<3><<<g, b>>>(nullptr, iters, d); break; case 4: k<4><<<g, b>>>(nullptr, iters, d); break; case 5: k<5><<<g, b>>>(nullptr, iters, d); break;
+            case 6: k<6><<<g, b>>>(nullptr, iters, d); break; case 7: k<7><<<g, b>>>(nullptr, iters, d); break; case 8: k<8><<<g, b>>>(nullptr, iters, d); break;
+            case 9: k<9><<<g, b>>>(nullptr, iters, d); break;
+            }
+            cudaDeviceSynchronize(); cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+            const double n = (double)iters * 32;
+            printf("%-22s %d warps/SMSP: %6.2f cycles per op per warp, %5.2f cycles per op per SMSP\n", names[mode], warps, h / n, h / n / warps);
+        }
+    }
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}

@@ -72,7 +72,7 @@ int main(int argc, char **argv)
     a.rec = d_rec + 48 * RS; a.rounds = d_rounds; a.partners = d_parts; a.tb = d_tb; a.bnd = d_bnd; a.pair_istar = d_istar; a.pair_zflag = d_zflag;
     a.pair_score = d_score; a.counter = d_counter;
     long long *d_prof; CK(cudaMalloc(&d_prof, 64)); CK(cudaMemset(d_prof, 0, 64)); a.prof = d_prof; a.tie = TieArgs{(float)(8.0 * 1.1102230246251565e-16), 1e-4f};
-    const size_t smem = (size_t)(2 * TC_LANES + TC_SC) * 40 * 4;
+    const size_t smem = (size_t)(2 * TC_LANES + TC_SC) * 48 * 4;
     CK(cudaFuncSetAttribute(k_fill1_tc<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_fill1_tc<12>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fill1_tc<12>, TC_THREADS, smem));
