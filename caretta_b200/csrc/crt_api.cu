@@ -651,7 +651,11 @@ void plan_tc_batch(const crt_ctx *c, const Unit *bu, size_t count, Batch &b, std
 template <int RS>
 int launch_fill1_tc(const TcFill1Args &a, int n_rounds, int sm_count, cudaStream_t st)
 {
+#ifdef TC_SPLIT3
+    constexpr int K = ((6 * RS + 7) / 8) * 8;
+#else
     constexpr int K = ((4 * RS + 7) / 8) * 8;
+#endif
     constexpr size_t smem = (size_t)(2 * TC_LANES + TC_SC) * K * 4;
     static bool configured = false;
     if (!configured) {

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
             double sc[DPC];
 #pragma unroll
             for (int c = 0; c < DPC; ++c) sc[c] = slot[c][lane];
-            const double b1 = slot[DPC][0], b2 = slot[DPC + 1][0];
+            double b1 = 0.0, b2 = 0.0;        // boundary values: lane 0 fetched them, lane 0 alone reads them
+            if (lane == 0) { b1 = slot[DPC][0]; b2 = slot[DPC + 1][0]; }
             prefetch(t + DTW_PF);            // refills this slot; every lane has read its entries above
             double L1 = shfl_up_d(out1), L2 = shfl_up_d(out2);
             if (lane == 0) {

@@ -187,10 +187,18 @@ __device__ __forceinline__ void tc_cells16(const uint32_t *e, uint32_t *ub, floa
 // RS: floats per record (12 for d <= 10, 20 for d <= 16).  K = 3 RS rounded up to a multiple of 8.
 // Persistent CTAs: each takes rounds from g.counter until none is left (TMEM, barriers and their phases live across rounds).
 template <int RS>
+#ifdef TC_SPLIT3
+__global__ void __launch_bounds__(TC_THREADS, 1) k_fill1_tc(TcFill1Args g, int n_rounds)
+#else
 __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n_rounds)
+#endif
 {
     constexpr int GCH = RS / 4;                          // 16-byte chunks per K-block (one record)
+#ifdef TC_SPLIT3
+    constexpr int K = ((6 * RS + 7) / 8) * 8;           // experiment: three-level split of the features, six product blocks
+#else
     constexpr int K = ((4 * RS + 7) / 8) * 8;
+#endif
     constexpr int KCH = K / 4;
     constexpr int D = RS == 12 ? 10 : 16;                // index of A inside a record
     constexpr int A_FLOATS = TC_LANES * K, B_FLOATS = TC_SC * K;
@@ -269,6 +277,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n
             *reinterpret_cast<float4 *>(dst + (2 * GCH + q) * 32) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
             *reinterpret_cast<float4 *>(dst + (3 * GCH + q) * 32) = make_float4(l2[4 * q], l2[4 * q + 1], l2[4 * q + 2], l2[4 * q + 3]);
         }
+#ifdef TC_SPLIT3
+        {   // blocks: [h, A_h, 1 | h, A_m, 1 | m, A_l, 1 | m, 0, 0 | h, 0, 0 | l, 0, 0] with x = h + m + l exactly (tf32 each)
+            float m3[RS], l3[RS], h0[RS], b2[RS];
+#pragma unroll
+            for (int k = 0; k < RS; ++k) { const float r1 = x[k] - hi[k]; m3[k] = tcg::tf32_rn(r1); l3[k] = r1 - m3[k]; h0[k] = hi[k]; b2[k] = m3[k]; }
+            b2[D] = lo[D]; b2[D + 1] = 1.f;           // third block carries A_l and the one
+            m3[D] = 0.f; m3[D + 1] = 0.f; h0[D] = 0.f; h0[D + 1] = 0.f; l3[D] = 0.f; l3[D + 1] = 0.f;
+#pragma unroll
+            for (int q = 0; q < GCH; ++q) {
+                *reinterpret_cast<float4 *>(dst + (2 * GCH + q) * 32) = make_float4(b2[4 * q], b2[4 * q + 1], b2[4 * q + 2], b2[4 * q + 3]);
+                *reinterpret_cast<float4 *>(dst + (3 * GCH + q) * 32) = make_float4(m3[4 * q], m3[4 * q + 1], m3[4 * q + 2], m3[4 * q + 3]);
+                *reinterpret_cast<float4 *>(dst + (4 * GCH + q) * 32) = make_float4(h0[4 * q], h0[4 * q + 1], h0[4 * q + 2], h0[4 * q + 3]);
+                *reinterpret_cast<float4 *>(dst + (5 * GCH + q) * 32) = make_float4(l3[4 * q], l3[4 * q + 1], l3[4 * q + 2], l3[4 * q + 3]);
+            }
+        }
+#endif
         tcg::fence_async_smem();
         tcg::mbar_arrive(bar_a + 8 * buf);
     };
@@ -304,6 +328,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_fill1_tc(TcFill1Args g, int n
             *reinterpret_cast<float4 *>(dst + (GCH + part) * 32) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             *reinterpret_cast<float4 *>(dst + (2 * GCH + part) * 32) = make_float4(h2[0], h2[1], h2[2], h2[3]);
             *reinterpret_cast<float4 *>(dst + (3 * GCH + part) * 32) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+#ifdef TC_SPLIT3
+            {   // blocks: [h, 1, B_h | m, 1, B_m | h, 1, B_l | m, 0, 0 | l, 0, 0 | h, 0, 0]
+                float m3[4], l3[4], m1[4], h5[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float r1 = x[k] - tcg::tf32_rn(x[k]); m3[k] = tcg::tf32_rn(r1); l3[k] = r1 - m3[k]; m1[k] = m3[k]; h5[k] = tcg::tf32_rn(x[k]); }
+                if (part == D / 4) {
+                    constexpr int ka = D % 4;
+                    m1[ka] = lo[ka]; m1[ka + 1] = lo[ka + 1];      // (1, B_m) as computed above
+                    m3[ka] = 0.f; m3[ka + 1] = 0.f; l3[ka] = 0.f; l3[ka + 1] = 0.f; h5[ka] = 0.f; h5[ka + 1] = 0.f;
+                }
+                *reinterpret_cast<float4 *>(dst + (GCH + part) * 32) = make_float4(m1[0], m1[1], m1[2], m1[3]);
+                *reinterpret_cast<float4 *>(dst + (3 * GCH + part) * 32) = make_float4(m3[0], m3[1], m3[2], m3[3]);
+                *reinterpret_cast<float4 *>(dst + (4 * GCH + part) * 32) = make_float4(l3[0], l3[1], l3[2], l3[3]);
+                *reinterpret_cast<float4 *>(dst + (5 * GCH + part) * 32) = make_float4(h5[0], h5[1], h5[2], h5[3]);
+            }
+#endif
         }
         tcg::fence_async_smem();
         if (dp) {
