@@ -95,6 +95,13 @@ __global__ void k_mark_status(int *status, const int *list, int n, int bit)
     if (q < n) status[list[q]] |= bit;
 }
 
+// end of an overlapped re-run: the marked slots lose ST_TIE (it only kept the stage-2 fill of the main run off them) and get `bit`
+__global__ void k_finish_status(int *status, const int *list, int n, int bit)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) status[list[q]] = (status[list[q]] & ~ST_TIE) | bit;
+}
+
 struct HostUnit {
     Unit u;
     int C;          // columns per lane
@@ -152,6 +159,8 @@ struct crt_ctx {
                                                                                               // streams: the tail of one launch overlaps the head of the next
     static constexpr int MAX_WS = 4;
     Workspace ws[MAX_WS];
+    Workspace ws_rr;                     // the float64 re-run of the marked pairs: own buffers and stream, so that it overlaps the last batches
+    cudaEvent_t e_traces = nullptr, e_rr = nullptr;
     int n_streams = 3;
     DevBuf<Unit> d_units, d_units2;      // d_units2: the float64 re-run of the tie pairs
     DevBuf<crt::TcRound> d_tc_rounds;    // tensor-core stage 1: rounds, partner records, left-over units of the run, round counters per batch
@@ -809,6 +818,11 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     // ---- the three stages of one batch (dunits / f32x: the main run's units in the run's precision, or the float64 re-run
     //      of the pairs the fp32 traceback marked)
     const TieArgs tie = env_tie();
+    // the float64 re-run overlaps the last batches of the stage pipeline: the main run's stage 2 leaves marked pairs alone and the
+    // re-run's tracebacks keep ST_TIE up (CARETTA_B200_RERUN_OVERLAP=0: after the pipeline has drained, as in the first version)
+    const bool overlap_rr = pipe && f32 && !flexible && env_tie_rerun() && !(getenv("CARETTA_B200_RERUN_OVERLAP") && atoi(getenv("CARETTA_B200_RERUN_OVERLAP")) == 0);
+    int status_or_cur = 0;
+    bool skip_tie_cur = false;
     auto stage1 = [&](const Batch &b, crt_ctx::Workspace &ws, cudaStream_t st, const Unit *dunits, bool f32x) -> int {
         const Unit *du = dunits + b.first;
         const int nu = (int)b.count;
@@ -863,6 +877,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         ta.precision = f32x ? CRT_FP32 : CRT_FP64;
         ta.rows2_f32 = r32 ? 1 : 0;
         ta.skip_byproducts = c->stage1_only ? 1 : 0;
+        ta.status_or = status_or_cur;
         int r2;
         if (do_trace && f32x && b.tc) {
             if (b.tc_np > 0) {
@@ -889,6 +904,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         FillOut fo{};
         fo.tb = ws.tb.p; fo.pair_istar = c->pair_istar.p; fo.pair_zflag = c->pair_zflag.p;
         fo.pair_score = c->score.p; fo.bnd = pipe ? ws.bnd2.p : ws.bnd.p;
+        fo.skip_status = skip_tie_cur ? c->status.p : nullptr;
         if (c->stage1_only || flexible) return 0;
         if (f32x) {
             Fill2Args a{reinterpret_cast<const float4 *>(ws.rows2.p) + ROW_PAD, c->cols2.p};
@@ -931,6 +947,82 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         return 2 + 2 * ((b.tc_nr > 0 ? 1 : 0) + (b.lf_nu > 0 ? 1 : 0));
     };
 
+    // ---- fp32 production mode: the pairs whose traceback met a decision the reference's float64 DP may take differently
+    //      (ST_TIE, crt_fill1_v4.cuh) are computed again by the float64 parity kernels, one pair per unit, into the same slots
+    auto rerun = [&](cudaStream_t rs, crt_ctx::Workspace &ws, bool overlapped) -> int {
+        if ((rc = c->tie_list.ensure((size_t)n_pairs + 1))) return rc;
+        CU(cudaMemsetAsync(c->tie_list.p, 0, sizeof(int), rs));
+        k_collect_tie<<<(unsigned)((n_pairs + 255) / 256), 256, 0, rs>>>(c->status.p, n_pairs, c->tie_list.p + 1, c->tie_list.p);
+        CU(cudaGetLastError());
+        int n_tie = 0;
+        CU(cudaMemcpyAsync(&n_tie, c->tie_list.p, sizeof(int), cudaMemcpyDeviceToHost, rs));
+        CU(cudaStreamSynchronize(rs));
+        if (n_tie > 0) {
+            CU(cudaEventRecord(c->ev2, rs));
+            std::vector<int> slots((size_t)n_tie);
+            CU(cudaMemcpyAsync(slots.data(), c->tie_list.p + 1, sizeof(int) * (size_t)n_tie, cudaMemcpyDeviceToHost, rs));
+            CU(cudaStreamSynchronize(rs));
+            std::sort(slots.begin(), slots.end());
+            std::vector<std::pair<int, int>> by_base(hu.size());          // (pair_base, unit) -> the (i, j) of a result slot
+            for (size_t k = 0; k < hu.size(); ++k) by_base[k] = {hu[k].pair_base, (int)k};
+            std::sort(by_base.begin(), by_base.end());
+            std::vector<HostUnit> ru((size_t)n_tie);
+            for (int q = 0; q < n_tie; ++q) {
+                auto it = std::upper_bound(by_base.begin(), by_base.end(), std::make_pair(slots[q], 0x7fffffff));
+                const Unit &src = hu[(size_t)(it - 1)->second];
+                const int i = src.row_chain0 + (slots[q] - src.pair_base), j = src.col_chain;
+                HostUnit h{};
+                h.u.row_chain0 = i; h.u.row_base = c->offsets[i];
+                h.u.col_chain = j; h.u.col_base = (int)c->offsets[j]; h.u.m = (int)(c->offsets[j + 1] - c->offsets[j]);
+                h.u.G = (int)(c->offsets[i + 1] - c->offsets[i]); h.u.n_pairs = 1; h.u.pair_base = slots[q];
+                h.u.path_stride = h.u.G + h.u.m;
+                finish_unit(c, h, CRT_FP64);
+                ru[(size_t)q] = h;
+            }
+            // stage 1 + traceback in float64 (the reference's decisions), stage 2 by the fp32 kernel on the float64 alignment:
+            // two unit lists over the same pairs, each with the columns-per-lane / strips of its precision
+            std::vector<HostUnit> ru32 = ru;
+            for (auto &h : ru32) finish_unit(c, h, CRT_FP32);
+            std::vector<Batch> rb, rb32;
+            std::vector<Unit> rhu, rhu32;
+            carve(ru, CRT_FP64, false, rb, rhu);
+            carve(ru32, CRT_FP32, false, rb32, rhu32);
+            size_t tb_n = 0, rows2_n = 0, bnd_n = 0, bnd32_n = 0, path_n = 0;
+            for (auto &b : rb) { tb_n = std::max(tb_n, b.tb_n); bnd_n = std::max(bnd_n, b.bnd_n); path_n = std::max(path_n, b.path_n); }
+            for (auto &b : rb32) { rows2_n = std::max(rows2_n, b.rows2_n); bnd32_n = std::max(bnd32_n, b.bnd_n); }
+            if ((rc = ws.tb.ensure(tb_n + 1))) return rc;
+            if ((rc = ws.rows2.ensure((rows2_n + 2 * ROW_PAD) * 16))) return rc;
+            if ((rc = ws.path.ensure(path_n + 1))) return rc;
+            if ((rc = ws.bnd.ensure(std::max(bnd_n * 8, bnd32_n * 4) + 16))) return rc;
+            if ((rc = ws.bnd2.ensure(std::max(bnd_n * 8, bnd32_n * 4) + 16))) return rc;
+            if ((rc = c->d_units2.ensure(rhu.size() + rhu32.size()))) return rc;
+            CU(cudaMemcpyAsync(c->d_units2.p, rhu.data(), sizeof(Unit) * rhu.size(), cudaMemcpyHostToDevice, rs));
+            CU(cudaMemcpyAsync(c->d_units2.p + rhu.size(), rhu32.data(), sizeof(Unit) * rhu32.size(), cudaMemcpyHostToDevice, rs));
+            status_or_cur = overlapped ? ST_TIE : 0;
+            skip_tie_cur = false;
+            for (auto &b : rb) {
+                if ((rc = stage1(b, ws, rs, c->d_units2.p, false))) return rc;
+                if ((rc = stage_trace(b, ws, rs, nullptr, c->d_units2.p, false, true, false))) return rc;
+                c->launches += 2;
+                if (want_paths && (rc = fetch_paths(b, ws, rs, rhu))) return rc;
+            }
+            for (auto &b : rb32) {
+                if ((rc = stage_trace(b, ws, rs, nullptr, c->d_units2.p + rhu.size(), false, false, true, true))) return rc;
+                if ((rc = stage2(b, ws, rs, c->d_units2.p + rhu.size(), true))) return rc;
+                c->launches += 2;
+            }
+            if (!overlapped) {
+                k_mark_status<<<(unsigned)((n_tie + 255) / 256), 256, 0, rs>>>(c->status.p, c->tie_list.p + 1, n_tie, CRT_ST_FP64);
+                CU(cudaGetLastError());
+            }
+            c->launches += 2;
+            CU(cudaEventRecord(c->ev3, rs));
+            c->rerun_pairs = n_tie;
+        }
+        return 0;
+    };
+    c->rerun_pairs = 0; c->rerun_ms = 0;
+
     if (pipe) {
         // ---- stage pipeline: s_f1[] run the stage-1 fills (alternating, so consecutive launches overlap at their
         //      tails), s_tr (high priority) the tracebacks, s_f2[] the stage-2 fills.  Workspace set w = k % NW is reused by batch k + NW:
@@ -971,7 +1063,9 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             CU(cudaEventRecord(ws.e_t, c->s_tr));
             CU(cudaStreamWaitEvent(sf2, ws.e_t, 0));
             mark0("fill2", bi, sf2);
+            skip_tie_cur = overlap_rr;
             if ((rc = stage2(b, ws, sf2, DU, f32))) return rc;
+            skip_tie_cur = false;
             mark1(sf2);
             CU(cudaEventRecord(ws.e_f2, sf2));
             c->launches += batch_launches(b);
@@ -989,10 +1083,29 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
                 cudaEventDestroy(mk.e0); cudaEventDestroy(mk.e1);
             }
         }
+        if (overlap_rr) {
+            // every traceback of the run is on s_tr: once they are through, the marked slots are known and the float64 re-run starts
+            // on its own stream and buffers, beside the stage-2 fills of the last batches (which leave the marked slots alone)
+            CU(cudaEventRecord(c->e_traces, c->s_tr));
+            CU(cudaStreamWaitEvent(c->ws_rr.stream, c->e_traces, 0));
+            if ((rc = rerun(c->ws_rr.stream, c->ws_rr, true))) return rc;
+            status_or_cur = 0;
+            CU(cudaEventRecord(c->e_rr, c->ws_rr.stream));
+            CU(cudaStreamWaitEvent(c->stream, c->e_rr, 0));
+        }
         cudaStream_t all5[5] = {c->s_f1[0], c->s_f1[1], c->s_f2[0], c->s_f2[1], c->s_tr};
         for (int k = 0; k < 5; ++k) {
             CU(cudaEventRecord(c->ws[k % crt_ctx::MAX_WS].ev[k / crt_ctx::MAX_WS], all5[k]));
             CU(cudaStreamWaitEvent(c->stream, c->ws[k % crt_ctx::MAX_WS].ev[k / crt_ctx::MAX_WS], 0));
+        }
+        if (overlap_rr && c->rerun_pairs > 0) {
+            const int n_tie = (int)c->rerun_pairs;
+            k_finish_status<<<(unsigned)((n_tie + 255) / 256), 256, 0, c->stream>>>(c->status.p, c->tie_list.p + 1, n_tie, CRT_ST_FP64);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(c->stream));
+            float rms = 0;
+            CU(cudaEventElapsedTime(&rms, c->ev2, c->ev3));
+            c->rerun_ms = rms;
         }
     } else {
     for (int w = 0; w < NS; ++w) CU(cudaStreamWaitEvent(c->ws[w].stream, c->ev1, 0));
@@ -1025,79 +1138,13 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         CU(cudaStreamWaitEvent(c->stream, c->ws[w].done, 0));
     }
     }
-    // ---- fp32 production mode: the pairs whose traceback met a decision the reference's float64 DP may take differently
-    //      (ST_TIE, crt_fill1_v4.cuh) are computed again by the float64 parity kernels, one pair per unit, into the same slots
-    c->rerun_pairs = 0; c->rerun_ms = 0;
-    if (f32 && !flexible && env_tie_rerun()) {
-        if ((rc = c->tie_list.ensure((size_t)n_pairs + 1))) return rc;
-        CU(cudaMemsetAsync(c->tie_list.p, 0, sizeof(int), c->stream));
-        k_collect_tie<<<(unsigned)((n_pairs + 255) / 256), 256, 0, c->stream>>>(c->status.p, n_pairs, c->tie_list.p + 1, c->tie_list.p);
-        CU(cudaGetLastError());
-        int n_tie = 0;
-        CU(cudaMemcpyAsync(&n_tie, c->tie_list.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        if (n_tie > 0) {
-            CU(cudaEventRecord(c->ev2, c->stream));
-            std::vector<int> slots((size_t)n_tie);
-            CU(cudaMemcpyAsync(slots.data(), c->tie_list.p + 1, sizeof(int) * (size_t)n_tie, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            std::sort(slots.begin(), slots.end());
-            std::vector<std::pair<int, int>> by_base(hu.size());          // (pair_base, unit) -> the (i, j) of a result slot
-            for (size_t k = 0; k < hu.size(); ++k) by_base[k] = {hu[k].pair_base, (int)k};
-            std::sort(by_base.begin(), by_base.end());
-            std::vector<HostUnit> ru((size_t)n_tie);
-            for (int q = 0; q < n_tie; ++q) {
-                auto it = std::upper_bound(by_base.begin(), by_base.end(), std::make_pair(slots[q], 0x7fffffff));
-                const Unit &src = hu[(size_t)(it - 1)->second];
-                const int i = src.row_chain0 + (slots[q] - src.pair_base), j = src.col_chain;
-                HostUnit h{};
-                h.u.row_chain0 = i; h.u.row_base = c->offsets[i];
-                h.u.col_chain = j; h.u.col_base = (int)c->offsets[j]; h.u.m = (int)(c->offsets[j + 1] - c->offsets[j]);
-                h.u.G = (int)(c->offsets[i + 1] - c->offsets[i]); h.u.n_pairs = 1; h.u.pair_base = slots[q];
-                h.u.path_stride = h.u.G + h.u.m;
-                finish_unit(c, h, CRT_FP64);
-                ru[(size_t)q] = h;
-            }
-            // stage 1 + traceback in float64 (the reference's decisions), stage 2 by the fp32 kernel on the float64 alignment:
-            // two unit lists over the same pairs, each with the columns-per-lane / strips of its precision
-            std::vector<HostUnit> ru32 = ru;
-            for (auto &h : ru32) finish_unit(c, h, CRT_FP32);
-            std::vector<Batch> rb, rb32;
-            std::vector<Unit> rhu, rhu32;
-            carve(ru, CRT_FP64, false, rb, rhu);
-            carve(ru32, CRT_FP32, false, rb32, rhu32);
-            crt_ctx::Workspace &ws = c->ws[0];
-            size_t tb_n = 0, rows2_n = 0, bnd_n = 0, bnd32_n = 0, path_n = 0;
-            for (auto &b : rb) { tb_n = std::max(tb_n, b.tb_n); bnd_n = std::max(bnd_n, b.bnd_n); path_n = std::max(path_n, b.path_n); }
-            for (auto &b : rb32) { rows2_n = std::max(rows2_n, b.rows2_n); bnd32_n = std::max(bnd32_n, b.bnd_n); }
-            if ((rc = ws.tb.ensure(tb_n + 1))) return rc;
-            if ((rc = ws.rows2.ensure((rows2_n + 2 * ROW_PAD) * 16))) return rc;
-            if ((rc = ws.path.ensure(path_n + 1))) return rc;
-            if ((rc = ws.bnd.ensure(std::max(bnd_n * 8, bnd32_n * 4) + 16))) return rc;
-            if ((rc = ws.bnd2.ensure(std::max(bnd_n * 8, bnd32_n * 4) + 16))) return rc;
-            if ((rc = c->d_units2.ensure(rhu.size() + rhu32.size()))) return rc;
-            CU(cudaMemcpyAsync(c->d_units2.p, rhu.data(), sizeof(Unit) * rhu.size(), cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync(c->d_units2.p + rhu.size(), rhu32.data(), sizeof(Unit) * rhu32.size(), cudaMemcpyHostToDevice, c->stream));
-            for (auto &b : rb) {
-                if ((rc = stage1(b, ws, c->stream, c->d_units2.p, false))) return rc;
-                if ((rc = stage_trace(b, ws, c->stream, nullptr, c->d_units2.p, false, true, false))) return rc;
-                c->launches += 2;
-                if (want_paths && (rc = fetch_paths(b, ws, c->stream, rhu))) return rc;
-            }
-            for (auto &b : rb32) {
-                if ((rc = stage_trace(b, ws, c->stream, nullptr, c->d_units2.p + rhu.size(), false, false, true, true))) return rc;
-                if ((rc = stage2(b, ws, c->stream, c->d_units2.p + rhu.size(), true))) return rc;
-                c->launches += 2;
-            }
-            k_mark_status<<<(unsigned)((n_tie + 255) / 256), 256, 0, c->stream>>>(c->status.p, c->tie_list.p + 1, n_tie, CRT_ST_FP64);
-            CU(cudaGetLastError());
-            c->launches += 2;
-            CU(cudaEventRecord(c->ev3, c->stream));
+    if (f32 && !flexible && env_tie_rerun() && !overlap_rr) {
+        if ((rc = rerun(c->stream, c->ws[0], false))) return rc;
+        if (c->rerun_pairs > 0) {
             CU(cudaStreamSynchronize(c->stream));
             float rms = 0;
             CU(cudaEventElapsedTime(&rms, c->ev2, c->ev3));
             c->rerun_ms = rms;
-            c->rerun_pairs = n_tie;
         }
     }
     CU(cudaEventRecord(c->ev1, c->stream));
@@ -1168,6 +1215,9 @@ int crt_create(int device, crt_ctx **out)
         CU(cudaStreamCreateWithPriority(&c->s_f2[k], cudaStreamNonBlocking, prio_lo));
     }
     CU(cudaStreamCreateWithPriority(&c->s_tr, cudaStreamNonBlocking, prio_hi));     // short latency-bound kernels go first
+    CU(cudaStreamCreateWithPriority(&c->ws_rr.stream, cudaStreamNonBlocking, prio_hi));
+    CU(cudaEventCreateWithFlags(&c->e_traces, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->e_rr, cudaEventDisableTiming));
     *out = c;
     return 0;
 }
@@ -1204,6 +1254,11 @@ int crt_destroy(crt_ctx *c)
         if (c->s_f2[k]) cudaStreamDestroy(c->s_f2[k]);
     }
     if (c->s_tr) cudaStreamDestroy(c->s_tr);
+    if (c->ws_rr.stream) cudaStreamDestroy(c->ws_rr.stream);
+    c->ws_rr.tb.release(); c->ws_rr.rows2.release(); c->ws_rr.bnd.release(); c->ws_rr.bnd2.release(); c->ws_rr.path.release();
+    if (c->e_traces) cudaEventDestroy(c->e_traces);
+    if (c->e_rr) cudaEventDestroy(c->e_rr);
+    c->d_tc_rounds.release(); c->d_tc_partners.release(); c->d_tc_left.release(); c->d_tc_counter.release();
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;

@@ -114,8 +114,10 @@ __global__ void __launch_bounds__(32, MULTI ? 1 : CRT_FILL2_MINB) k_fill2_v3(con
                     float left = __shfl_up_sync(FULL, carry, 1);
                     if (lane == 0) left = (MULTI && strip > 0) ? (q == 0 ? bq.x : q == 1 ? bq.y : q == 2 ? bq.z : bq.w) : 0.f;
                     if (((meta_prev & 2) | (meta_cur & 1)) != 0) {
-                        if ((meta_prev & 2) && emitter && (unsigned)(g - 1) < (unsigned)G)
-                            out.pair_score[u.pair_base + (meta_prev >> 2) - u.row_chain0] = (double)carry;
+                        if ((meta_prev & 2) && emitter && (unsigned)(g - 1) < (unsigned)G) {
+                            const int pidx = u.pair_base + (meta_prev >> 2) - u.row_chain0;
+                            if (!out.skip_status || !(out.skip_status[pidx] & ST_TIE)) out.pair_score[pidx] = (double)carry;
+                        }
                         if (meta_cur & 1) {
 #pragma unroll
                             for (int c = 0; c < C; ++c) prev[c] = 0.f;
@@ -170,8 +172,10 @@ __global__ void __launch_bounds__(32, MULTI ? 1 : CRT_FILL2_MINB) k_fill2_v3(con
                 meta_nxt = __float_as_int(gb[3].w);
             }
         }
-        if ((meta_prev & 2) && emitter && (unsigned)(steps4 - 1 - lane) < (unsigned)G)
-            out.pair_score[u.pair_base + (meta_prev >> 2) - u.row_chain0] = (double)carry;
+        if ((meta_prev & 2) && emitter && (unsigned)(steps4 - 1 - lane) < (unsigned)G) {
+            const int pidx = u.pair_base + (meta_prev >> 2) - u.row_chain0;
+            if (!out.skip_status || !(out.skip_status[pidx] & ST_TIE)) out.pair_score[pidx] = (double)carry;
+        }
         if (MULTI) __syncwarp();
     }
 }

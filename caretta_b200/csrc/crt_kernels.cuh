@@ -151,6 +151,8 @@ struct FillOut {
     int *pair_zflag;     // 1 if S[0][0] == 0 (a zero region exists, k_trace handles the stop state)
     double *pair_score;  // stage 1: H[n][m] of the tensor SW; stage 2: the pair score
     void *bnd;           // strip boundary values
+    const int *skip_status;   // stage 2 of the fp32 mode: pairs whose status carries ST_TIE are not written (the float64 re-run owns their
+                              // slots and may already be running); nullptr = write every pair
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -384,6 +386,7 @@ struct TraceArgs {
     int precision;                // 0 fp64, 1 fp32: the stage-1 fill that ran (records of the exact zero test)
     int rows2_f32;                // format of the stage-2 row records: 1 = float4 (fp32 stage 2), 0 = double[4]
     int skip_byproducts;          // 1: no RMSD / TM pass over the path (node contexts only use the transform)
+    int status_or;                // bits OR-ed into every status written (the overlapped float64 re-run keeps ST_TIE up until the run ends)
 };
 
 __device__ inline bool s1_is_zero(const TraceArgs &a, long long ri, long long ci)
@@ -484,7 +487,7 @@ __device__ __forceinline__ void trace_tail(const TraceArgs &a, int pair, const s
     }
     a.rmsd[pair] = rmsd;
     a.tm[pair] = tm;
-    a.status[pair] = st;
+    a.status[pair] = st | a.status_or;
 }
 
 #ifndef CRT_TRACE_MINB
