@@ -732,7 +732,9 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         size_t budget = env_budget();
         budget = std::min(budget, std::max<size_t>(c->mem_total / 20, (size_t)64 << 20));
         if (main_run) {
-            if (pipe) budget = std::min(budget, std::max<size_t>(total_bytes / env_batches() + 1, (size_t)64 << 20));
+            // 2 % of slack: the units do not cut the total into exactly equal parts, and a ninth batch of a few units would only
+            // lengthen the tail of the pipeline
+            if (pipe) budget = std::min(budget, std::max<size_t>(total_bytes / env_batches() + total_bytes / (50 * (size_t)env_batches()) + 1, (size_t)64 << 20));
             else if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
         }
         hout.resize(uv.size());
@@ -1130,6 +1132,12 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             CU(cudaEventElapsedTime(&m12, ws.ev[1], ws.ev[2]));
             CU(cudaEventElapsedTime(&m23, ws.ev[2], ws.ev[3]));
             c->phase_ms[0] += m01; c->phase_ms[1] += m12; c->phase_ms[3] += m23;
+            if (getenv("CARETTA_B200_TIMELINE") && atoi(getenv("CARETTA_B200_TIMELINE")) != 0) {      // serial schedule: per-variant rates
+                double cells = 0;
+                for (size_t k = b.first; k < b.first + b.count; ++k) cells += (double)hu[k].G * hu[k].m;
+                fprintf(stderr, "[serial] batch %3zu C=%2d multi=%d units=%6zu Mcells=%9.1f  fill1 %8.3f ms (%7.1f Gcell/s)  trace %7.3f ms  rows2 + fill2 %8.3f ms (%7.1f Gcell/s)\n",
+                        bi, b.C, b.multi, b.count, cells * 1e-6, m01, cells / (m01 * 1e-3) / 1e9, m12, m23, cells / (m23 * 1e-3) / 1e9);
+            }
         }
         if (want_paths && (rc = fetch_paths(b, ws, st, hu))) return rc;
     }
