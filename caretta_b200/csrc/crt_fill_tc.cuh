@@ -572,17 +572,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace_tc(Trac
         while (i > 0 && j > 0) {
             if (zreg && is_zero_cell(i, j)) break;
             const unsigned cd = code();
-            if ((cd & 2u) == 0u) {
-                --i; --j; --w_row; col_left();
-                path[len++] = make_short2((short)i, (short)j);
-                ++c;
-            } else if ((cd & 1u) == 0u) {
-                --j; col_left();
-                path[len++] = make_short2((short)-1, (short)j);
-            } else {
-                --i; --w_row;
-                path[len++] = make_short2((short)i, (short)-1);
-            }
+            const bool diag = (cd & 2u) == 0u, left = !diag && (cd & 1u) == 0u;
+            const bool di = diag || !left, dj = diag || left;
+            i -= di ? 1 : 0; j -= dj ? 1 : 0; w_row -= di ? 1 : 0;
+            if (dj) col_left();
+            path[len++] = make_short2(di ? (short)i : (short)-1, dj ? (short)j : (short)-1);
+            c += diag ? 1 : 0;
         }
     }
     trace_tail(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);

@@ -552,9 +552,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
         const int idx = (w_strip * u.tchunks + (t >> 2)) * 32 + w_l;
         if (idx != cidx) {
             cw = tbu[idx]; cidx = idx;
-            if ((t >> 2) >= 2) {                          // the walk moves up and to the left
+#ifndef CRT_TRACE_PF
+#define CRT_TRACE_PF 3
+#endif
+            if (CRT_TRACE_PF > 0 && (t >> 2) >= 2) {      // the walk moves up and to the left
                 prefetch_tb(tbu + idx - 64);
-                if (w_l > 0) { prefetch_tb(tbu + idx - 33); prefetch_tb(tbu + idx - 65); }
+                if (CRT_TRACE_PF > 1 && w_l > 0) { prefetch_tb(tbu + idx - 33); if (CRT_TRACE_PF > 2) prefetch_tb(tbu + idx - 65); }
             }
         }
         const int q = t & 3;
@@ -595,18 +598,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
         while (j > 1 && (code() & 1u) == 0u) { --j; col_left(); }      // first column of row i* that attains the maximum
         while (i > 0 && j > 0) {
             if (zreg && is_zero_cell(i, j)) break;
+            // one instruction stream for the three moves (the threads of a warp walk different pairs): diag = H == diag + S,
+            // left = H == left (and not diag), up otherwise; priority diag > left > up (dynamic_time_warping.py:260-277)
             const unsigned cd = code();
-            if ((cd & 2u) == 0u) {
-                --i; --j; --w_trow; col_left();
-                path[len++] = make_short2((short)i, (short)j);
-                ++c;
-            } else if ((cd & 1u) == 0u) {
-                --j; col_left();
-                path[len++] = make_short2((short)-1, (short)j);
-            } else {
-                --i; --w_trow;
-                path[len++] = make_short2((short)i, (short)-1);
-            }
+            const bool diag = (cd & 2u) == 0u, left = !diag && (cd & 1u) == 0u;
+            const bool di = diag || !left, dj = diag || left;
+            i -= di ? 1 : 0; j -= dj ? 1 : 0; w_trow -= di ? 1 : 0;
+            if (dj) col_left();
+            path[len++] = make_short2(di ? (short)i : (short)-1, dj ? (short)j : (short)-1);
+            c += diag ? 1 : 0;
         }
     }
     trace_tail(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);
