@@ -6,6 +6,7 @@
 #include "crt_fill1_v2.cuh"
 #include "crt_fill1_v4.cuh"
 #include "crt_fill_tc.cuh"
+#include "crt_node_fill.cuh"
 #include "crt_fill2_v3.cuh"
 #include "crt_dp_batch.cuh"
 #include "crt_nj.cuh"
@@ -118,6 +119,10 @@ struct Batch {
     size_t lf_u0 = 0, lf_nu = 0;        // left-over stage-1 units
     int lf_dense = 0;                   // pairs of the left-over units
     size_t tc_bnd_n = 0;                // floats of strip boundary values (rounds first, then the left-over units)
+    // node contexts: stage 1 from precomputed scores (crt_node_fill.cuh)
+    size_t s_n = 0;                     // doubles of score matrices
+    long long max_tiles = 0;            // most 16 x 64 score tiles of a unit
+    bool single = true;                 // every unit holds one pair
 };
 
 }  // namespace
@@ -151,6 +156,7 @@ struct crt_ctx {
         DevBuf<uint4> tb;
         DevBuf<unsigned char> rows2, bnd, bnd2;      // bnd: stage-1 strip boundaries, bnd2: stage-2 (the two fills of
         DevBuf<short2> path;                         // different batches run concurrently in pipeline mode)
+        DevBuf<double> svals;                        // node contexts: precomputed stage-1 scores of the batch
         cudaEvent_t e_f1 = nullptr, e_t = nullptr, e_f2 = nullptr;   // pipeline mode: stage completion of the last batch here
     };
     // pipeline mode: one stream per stage, so that stage 1 of batch k+1, the traceback of batch k and stage 2 of
@@ -752,6 +758,9 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
                 h.u.tb_base = (long long)b.tb_n; h.u.rows2_base = (long long)b.rows2_n;
                 h.u.path_base = (long long)b.path_n; h.u.bnd_base = (long long)b.bnd_n;
                 h.u.dense_base = b.n_dense; b.n_dense += h.u.n_pairs;
+                h.u.s_base = (long long)b.s_n; b.s_n += (size_t)h.u.G * (size_t)h.u.m;
+                b.max_tiles = std::max(b.max_tiles, (long long)((h.u.G + 15) / 16) * ((h.u.m + 63) / 64));
+                if (h.u.n_pairs != 1) b.single = false;
                 b.tb_n += tb_u; b.rows2_n += rows_u; b.path_n += path_u; b.bnd_n += bnd_u;
                 hout[end] = h.u;
                 ++end;
@@ -820,6 +829,10 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     // ---- the three stages of one batch (dunits / f32x: the main run's units in the run's precision, or the float64 re-run
     //      of the pairs the fp32 traceback marked)
     const TieArgs tie = env_tie();
+    // node contexts (stage 1 only, float64): the fill reads precomputed scores (CARETTA_B200_NODE_RING=0: the generic parity kernel)
+    // (worth it where the level waits for single warps: up to CARETTA_B200_NODE_RING_MAX units per batch, default 128)
+    const int node_ring_max = getenv("CARETTA_B200_NODE_RING_MAX") ? atoi(getenv("CARETTA_B200_NODE_RING_MAX")) : 128;
+    const bool node_ring = !f32 && c->stage1_only && !want_paths && !(getenv("CARETTA_B200_NODE_RING") && atoi(getenv("CARETTA_B200_NODE_RING")) == 0);
     // the float64 re-run overlaps the last batches of the stage pipeline: the main run's stage 2 leaves marked pairs alone and the
     // re-run's tracebacks keep ST_TIE up (CARETTA_B200_RERUN_OVERLAP=0: after the pipeline has drained, as in the first version)
     const bool overlap_rr = pipe && f32 && !flexible && env_tie_rerun() && !(getenv("CARETTA_B200_RERUN_OVERLAP") && atoi(getenv("CARETTA_B200_RERUN_OVERLAP")) == 0);
@@ -853,6 +866,24 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             Fill1Args a{c->rec32.p + (size_t)ROW_PAD * rs32, c->meta.p + ROW_PAD};
             if (c->D == 10) return launch_fill1_f32<10>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, tie, st);
             return launch_fill1_f32<16>(b.C, b.multi, du, nu, a, fo, c->d_offsets.p, tie, st);
+        }
+        if (node_ring && b.single && b.C >= 2 && b.C <= 4 && nu <= node_ring_max) {
+            // progressive-alignment nodes: scores of every unit by a cell-parallel kernel, then the recurrence alone (crt_node_fill.cuh)
+            int r1;
+            if ((r1 = ws.svals.ensure(b.s_n + 1))) return r1;
+            NodeScoreArgs sa{du, c->rec64.p, -prm->gamma_tensor, ws.svals.p, c->D};
+            const unsigned gx = (unsigned)b.max_tiles;
+            k_pair_scores64<<<dim3(gx, (unsigned)nu), 256, 0, st>>>(sa);
+            CU(cudaGetLastError());
+#define CRT_NODE_CASE(CC)                                                                        \
+            case CC:                                                                             \
+                if (b.multi) k_fill_s64<CC, true><<<nu, 32, 0, st>>>(du, nu, ws.svals.p, fo);    \
+                else k_fill_s64<CC, false><<<nu, 32, 0, st>>>(du, nu, ws.svals.p, fo);           \
+                break;
+            switch (b.C) { CRT_NODE_CASE(2) CRT_NODE_CASE(3) CRT_NODE_CASE(4) }
+#undef CRT_NODE_CASE
+            CU(cudaGetLastError());
+            return 0;
         }
         if (c->D == 10) { P1F64<10>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor}; return launch_fill_c<P1F64<10>, false, true, 4>(b.C, b.multi, du, nu, a, fo, st); }
         P1F64<16>::Args a{c->rec64.p, c->meta.p + ROW_PAD, -prm->gamma_tensor};

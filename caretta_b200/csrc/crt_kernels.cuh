@@ -43,6 +43,7 @@ struct Unit {
     int path_stride;       // path entries reserved per pair
     int tchunks;           // 128-bit traceback chunks per lane per strip = ceil((G + 31) / 4)
     int dense_base;        // pairs of the batch's earlier units (k_trace maps threads densely onto pairs)
+    long long s_base;      // node contexts: first element of the unit's precomputed score matrix [G][m] (crt_node_fill.cuh)
 };
 
 // per-residue row meta: bit0 = first residue of its chain, bit1 = last, bits 2.. = chain index
