@@ -2190,7 +2190,19 @@ int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, u
         CU(cudaEventRecord(c->ev0, st));
         k_nj_rowsums<<<(unsigned)(((size_t)N * 32 + 255) / 256), 256, 0, st>>>(A, N, S0);
         int n = N;
+        // the small end of the run in one cooperative launch (CARETTA_B200_NJ_PERSIST=0: two launches per iteration throughout)
+        const int persist_max = getenv("CARETTA_B200_NJ_PERSIST") ? atoi(getenv("CARETTA_B200_NJ_PERSIST")) : 2048;
         while (n > 3 && e == cudaSuccess) {
+            if (n <= persist_max) {
+                ok(cudaFuncSetAttribute(k_nj_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NJ_REBUILD_SMEM));
+                int nb = std::min(c->sm_count, max_part);
+                int nn = n, NN_ = N;
+                void *args[] = {&A, &B, &S0, &S1, &t0, &t1, &nn, &NN_, &pq, &plin, &sel, &d_tree, &d_bl};
+                ok(cudaLaunchCooperativeKernel((const void *)k_nj_persistent, dim3((unsigned)nb), dim3(NJ_REBUILD_THREADS), args, NJ_REBUILD_SMEM, st));
+                if ((n - 3) & 1) { std::swap(A, B); std::swap(S0, S1); std::swap(t0, t1); }       // n - 3 iterations ran on the device
+                n = 3;
+                break;
+            }
             const int n_part = std::min(max_part, n);                    // one block per row, rows beyond max_part wrap around
             k_nj_argmin<<<n_part, NJ_ARGMIN_THREADS, 0, st>>>(A, S0, n, pq, plin, N, t0, sel, d_tree, d_bl, ticket);
             k_nj_rebuild<<<(unsigned)((n - 1 + NJ_ROWS - 1) / NJ_ROWS), NJ_REBUILD_THREADS, NJ_REBUILD_SMEM, st>>>(A, n, sel, N, t0, t1, B, S1);

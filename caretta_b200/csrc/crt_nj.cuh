@@ -12,6 +12,7 @@
 // adds them in index order through shuffles, so the result is bit-identical to the sequential loop.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 namespace crt {
@@ -72,14 +73,13 @@ __device__ void nj_select_block(const double *A, const double *S, int n, int N, 
                                 const long long *true_idx, NjSel *sel, unsigned long long *tree, double *bl, double *sq, long long *sl);
 
 // The last block to finish (ticket counter) also runs the selection, so that one iteration is two launches, not three.
-__global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A, const double *S, int n, double *pq, long long *plin,
-                                                                 int N, const long long *true_idx, NjSel *sel, unsigned long long *tree,
-                                                                 double *bl, unsigned *ticket)
+// rows bid, bid + nb, ... of the scan, then the block reduction: the block's best (q, linear index) ends in sq[0] / sl[0]
+__device__ __forceinline__ void nj_argmin_block(const double *A, const double *S, int n, int bid, int nb, double *sq, long long *sl)
 {
     const double nm2 = (double)(n - 2);
     double bq = INFINITY;
     long long blin = 0;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    for (int i = bid; i < n; i += nb) {
         const double *row = A + (size_t)i * n;
         const double si = S[i];
         const long long base = (long long)i * n;
@@ -101,8 +101,6 @@ __global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A
             if (nj_better(q, base + j, bq, blin)) { bq = q; blin = base + j; }
         }
     }
-    __shared__ double sq[NJ_ARGMIN_THREADS];
-    __shared__ long long sl[NJ_ARGMIN_THREADS];
     sq[threadIdx.x] = bq; sl[threadIdx.x] = blin;
     __syncthreads();
     for (int w = NJ_ARGMIN_THREADS / 2; w > 0; w >>= 1) {
@@ -111,6 +109,16 @@ __global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A
         }
         __syncthreads();
     }
+}
+
+// The last block to finish (ticket counter) also runs the selection, so that one iteration is two launches, not three.
+__global__ void __launch_bounds__(NJ_ARGMIN_THREADS) k_nj_argmin(const double *A, const double *S, int n, double *pq, long long *plin,
+                                                                 int N, const long long *true_idx, NjSel *sel, unsigned long long *tree,
+                                                                 double *bl, unsigned *ticket)
+{
+    __shared__ double sq[NJ_ARGMIN_THREADS];
+    __shared__ long long sl[NJ_ARGMIN_THREADS];
+    nj_argmin_block(A, S, n, blockIdx.x, gridDim.x, sq, sl);
     __shared__ unsigned last;
     if (threadIdx.x == 0) {
         pq[blockIdx.x] = sq[0]; plin[blockIdx.x] = sl[0];
@@ -170,14 +178,12 @@ __device__ void nj_select_block(const double *A, const double *S, int n, int N, 
 constexpr int NJ_ROWS = 16, NJ_TCOLS = 256, NJ_TSTRIDE = NJ_TCOLS + 1, NJ_REBUILD_THREADS = 256;
 constexpr size_t NJ_REBUILD_SMEM = sizeof(double) * 2 * NJ_ROWS * NJ_TSTRIDE;
 
-__global__ void __launch_bounds__(NJ_REBUILD_THREADS) k_nj_rebuild(const double *A, int n, const NjSel *sel, int N, const long long *ti_old,
-                                                                   long long *ti_new, double *B, double *S_new)
+__device__ __forceinline__ void nj_rebuild_block(const double *A, int n, int mi, int mj, long long new_node, const long long *ti_old,
+                                                 long long *ti_new, double *B, double *S_new, int row_block, double *nj_tile)
 {
-    extern __shared__ double nj_tile[];                 // [2][NJ_ROWS][NJ_TSTRIDE]
     const int nn = n - 1;
-    const int r0 = blockIdx.x * NJ_ROWS;
+    const int r0 = row_block * NJ_ROWS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mi = sel->mi, mj = sel->mj;
     const int lo = min(mi, mj), hi = max(mi, mj);
     auto old_of = [&](int a) { int o = a; if (o >= lo) ++o; if (o >= hi) ++o; return o; };      // a-th remaining node -> old index
     const double dij = A[(size_t)mi * n + mj];
@@ -236,8 +242,74 @@ __global__ void __launch_bounds__(NJ_REBUILD_THREADS) k_nj_rebuild(const double 
     if (warp == 0 && lane < rows) {
         const int r = r0 + lane;
         S_new[r] = acc;
-        ti_new[r] = r == 0 ? (sel->n_inter - 1 + N) : ti_old[old_of(r - 1)];
+        ti_new[r] = r == 0 ? new_node : ti_old[old_of(r - 1)];
     }
+}
+
+__global__ void __launch_bounds__(NJ_REBUILD_THREADS) k_nj_rebuild(const double *A, int n, const NjSel *sel, int N, const long long *ti_old,
+                                                                   long long *ti_new, double *B, double *S_new)
+{
+    extern __shared__ double nj_tile[];                 // [2][NJ_ROWS][NJ_TSTRIDE]
+    nj_rebuild_block(A, n, sel->mi, sel->mj, sel->n_inter - 1 + N, ti_old, ti_new, B, S_new, blockIdx.x, nj_tile);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// All iterations from n down to 4 in ONE cooperative launch (one CTA per SM, two grid-wide barriers per iteration instead of two
+// dependent launches): below a few thousand nodes an iteration moves a few megabytes that sit in L2, and the ~14 us of launch
+// turn-around were most of its 22 us.  Same device functions as the two-launch path, so the same bits: every CTA reduces the
+// block partials itself (first row-major minimum), CTA 0 writes the two tree rows; the joined pair and the counters live in
+// registers.  The host knows which buffer holds the final matrix from the number of iterations.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NJ_REBUILD_THREADS) k_nj_persistent(double *A, double *B, double *S0, double *S1, long long *t0, long long *t1,
+                                                                      int n, int N, double *pq, long long *plin, NjSel *sel,
+                                                                      unsigned long long *tree, double *bl)
+{
+    extern __shared__ double nj_tile[];                 // [2][NJ_ROWS][NJ_TSTRIDE]
+    __shared__ double sq[NJ_ARGMIN_THREADS];
+    __shared__ long long sl[NJ_ARGMIN_THREADS];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int bid = blockIdx.x, nb = gridDim.x;
+    long long rows = sel->rows, n_inter = sel->n_inter;
+    while (n > 3) {
+        nj_argmin_block(A, S0, n, bid, nb, sq, sl);
+        if (threadIdx.x == 0) { pq[bid] = sq[0]; plin[bid] = sl[0]; }
+        grid.sync();
+        // every CTA: the first row-major minimum over the block partials
+        double bq = INFINITY;
+        long long blin = 0;
+        for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+            const double q = __ldcg(pq + k);
+            const long long l = __ldcg(plin + k);
+            if (nj_better(q, l, bq, blin)) { bq = q; blin = l; }
+        }
+        __syncthreads();
+        sq[threadIdx.x] = bq; sl[threadIdx.x] = blin;
+        __syncthreads();
+        for (int w = NJ_ARGMIN_THREADS / 2; w > 0; w >>= 1) {
+            if ((int)threadIdx.x < w && nj_better(sq[threadIdx.x + w], sl[threadIdx.x + w], sq[threadIdx.x], sl[threadIdx.x])) {
+                sq[threadIdx.x] = sq[threadIdx.x + w]; sl[threadIdx.x] = sl[threadIdx.x + w];
+            }
+            __syncthreads();
+        }
+        const long long lin = sl[0];
+        const int mi = (int)(lin / n), mj = (int)(lin - (long long)mi * n);
+        const long long node = n_inter + N;
+        if (bid == 0 && threadIdx.x == 0) {
+            const double dij = A[(size_t)mi * n + mj];
+            // _find_branch_length, neighbor_joining.py:137-157
+            const double di = __dadd_rn(__dmul_rn(0.5, dij), __dmul_rn(0.5 / (double)(n - 2), __dsub_rn(S0[mi], S0[mj])));
+            const double dj = __dsub_rn(dij, di);
+            tree[2 * rows] = (unsigned long long)t0[mi]; tree[2 * rows + 1] = (unsigned long long)node; bl[rows] = di;
+            tree[2 * rows + 2] = (unsigned long long)t0[mj]; tree[2 * rows + 3] = (unsigned long long)node; bl[rows + 1] = dj;
+        }
+        __syncthreads();                                // sq / sl are reused by the next scan
+        for (int rb = bid; rb * NJ_ROWS < n - 1; rb += nb) nj_rebuild_block(A, n, mi, mj, node, t0, t1, B, S1, rb, nj_tile);
+        rows += 2; n_inter += 1;
+        grid.sync();
+        { double *x = A; A = B; B = x; x = S0; S0 = S1; S1 = x; long long *y = t0; t0 = t1; t1 = y; }
+        --n;
+    }
+    if (bid == 0 && threadIdx.x == 0) { sel->rows = rows; sel->n_inter = n_inter; }
 }
 
 // the last three nodes, neighbor_joining.py:80-98 (n == 3)

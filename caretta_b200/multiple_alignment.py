@@ -782,9 +782,17 @@ def superpose(alignment, proteins, gap=-1):
     """multiple_alignment.py:854-867: core superposition when at least half of the columns are gap-free, else onto the
     reference structure (the protein with the most aligned residues)."""
     _check_gap(gap)
-    proteins, res = _superpose_on_device(alignment, proteins, _engine.SUP_AUTO)
-    print("Core indices", res["n_core"])                                   # the reference prints this, :863
-    return proteins
+    # the reference's own rule, on the host (ADVICE round 1): the reference structure is the FIRST key of `alignment` (its order is
+    # the guide-tree traversal order, not the order of `proteins`) among those with the most aligned residues -- sorted() is
+    # stable, also with reverse=True --, and the core columns are gap-free over EVERY entry of the alignment
+    keys = list(alignment.keys())
+    rows = np.stack([np.asarray(alignment[k]) for k in keys])
+    reference_name = sorted(keys, key=lambda k: int(np.count_nonzero(np.asarray(alignment[k]) != -1)), reverse=True)[0]
+    core_indices = np.nonzero(np.all(rows != -1, axis=0))[0]
+    print("Core indices", len(core_indices))                               # the reference prints this, :906
+    if len(core_indices) < rows.shape[1] // 2:
+        return superpose_reference(alignment, proteins, reference_name)
+    return superpose_core(alignment, proteins, reference_name, core_indices)
 
 
 def superpose_core(alignment, proteins, reference_name, core_indices: np.ndarray = None, gap=-1):

@@ -285,3 +285,31 @@ def test_coordinates_only_chain_set(cons, eng):
         eng.pairwise_all(eng.params())
     eng.set_chains(ch.coords, ch.tensors, ch.offsets)
     assert eng.pairwise_all(eng.params()).shape == (ch.n, ch.n)
+
+
+def test_superpose_takes_the_first_alignment_key_among_ties(capsys):
+    """superpose() (multiple_alignment.py:896-910): the reference structure is the first key of `alignment` -- guide-tree order,
+    not the order of `proteins` -- among those with the most aligned residues (sorted() is stable), and the core columns are
+    gap-free over every entry of the alignment, also over entries whose protein is not in `proteins`."""
+    rng = np.random.default_rng(9)
+    n = 40
+    base = np.cumsum(rng.normal(size=(n, 3)), axis=0) * 3.8
+    def prot(name, noise):
+        return MA.Protein(name, rng.normal(size=(n, 10)), base @ _rot(rng) + rng.normal(size=3) * 10 + rng.normal(size=(n, 3)) * noise, "A" * n)
+    def _rot(r):
+        q, _ = np.linalg.qr(r.normal(size=(3, 3)))
+        return q * np.sign(np.linalg.det(q))
+    full = np.arange(n, dtype=np.int64)
+    proteins = [prot("a", 0.3), prot("b", 0.3), prot("c", 0.3)]
+    alignment = {"c": full.copy(), "a": full.copy(), "b": full.copy()}             # all tie on length: the reference is "c"
+    want = MA.superpose_core(alignment, [MA.Protein(p.name, p.tensors, p.coordinates.copy(), p.sequence) for p in proteins], "c")
+    got = MA.superpose(alignment, [MA.Protein(p.name, p.tensors, p.coordinates.copy(), p.sequence) for p in proteins])
+    assert "Core indices 40" in capsys.readouterr().out
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g.coordinates, w.coordinates)
+    other = MA.superpose_core(alignment, [MA.Protein(p.name, p.tensors, p.coordinates.copy(), p.sequence) for p in proteins], "a")
+    assert not np.allclose(other[1].coordinates, want[1].coordinates)
+    # an alignment entry without a protein still counts for the core columns: its gaps shrink the core to 30 columns
+    alignment["ghost"] = np.concatenate([full[:30], -np.ones(10, np.int64)])
+    MA.superpose(alignment, [MA.Protein(p.name, p.tensors, p.coordinates.copy(), p.sequence) for p in proteins])
+    assert "Core indices 30" in capsys.readouterr().out
