@@ -23,10 +23,18 @@ __device__ __forceinline__ void stage_block2(float4 *srow2, const float4 *rows_u
     cp_async_commit();
 }
 
+// Scores of one row against the lane's C columns: 2^(-|r - c|^2) on the scaled coordinates (score_functions.py:6-11 with
+// gamma folded into the scale).  CRT_FILL2_DIRECT: the differences squared (6 packed instructions per two cells); default: the
+// expanded form  -|r|^2 - |c|^2 + r . (2c)  with the column constant as the addend of the first FMA (4 packed instructions per
+// two cells: the stage-2 fill is issue-bound, 9.6 -> 7.6 issue cycles per cell against 7.8 of MUFU.EX2).  The expanded form
+// rounds at the magnitude of |c|^2 (scaled units: (0.208 A^-1 x)^2, ~20 for a 300-residue chain) instead of |r - c|^2: the
+// exponent of a matched cell carries ~2e-6 of absolute error, random per cell, the pair score ~1e-6 relative (tolerance 1e-4).
 template <int CP>
-__device__ __forceinline__ void rbf_row2(const float4 rv, const float2 (&nx)[CP], const float2 (&ny)[CP], const float2 (&nz)[CP], float (&s)[2 * CP])
+__device__ __forceinline__ void rbf_row2(const float4 rv, const float2 (&nx)[CP], const float2 (&ny)[CP], const float2 (&nz)[CP], const float2 (&bc)[CP],
+                                         float (&s)[2 * CP])
 {
     const float2 rx = make_float2(rv.x, rv.x), ry = make_float2(rv.y, rv.y), rz = make_float2(rv.z, rv.z);
+#ifdef CRT_FILL2_DIRECT
 #pragma unroll
     for (int cp = 0; cp < CP; ++cp) {
         const float2 dx = __fadd2_rn(rx, nx[cp]), dy = __fadd2_rn(ry, ny[cp]), dz = __fadd2_rn(rz, nz[cp]);
@@ -36,6 +44,19 @@ __device__ __forceinline__ void rbf_row2(const float4 rv, const float2 (&nx)[CP]
         s[2 * cp] = ex2_approx(-e2.x);
         s[2 * cp + 1] = ex2_approx(-e2.y);
     }
+#else
+    const float ar = -__fmaf_rn(rv.z, rv.z, __fmaf_rn(rv.y, rv.y, rv.x * rv.x));
+    const float2 ar2 = make_float2(ar, ar);
+#pragma unroll
+    for (int cp = 0; cp < CP; ++cp) {
+        float2 e2 = __ffma2_rn(rx, nx[cp], bc[cp]);
+        e2 = __ffma2_rn(ry, ny[cp], e2);
+        e2 = __ffma2_rn(rz, nz[cp], e2);
+        e2 = __fadd2_rn(e2, ar2);
+        s[2 * cp] = ex2_approx(e2.x);
+        s[2 * cp + 1] = ex2_approx(e2.y);
+    }
+#endif
 }
 
 template <int C, bool MULTI>
@@ -53,14 +74,26 @@ __global__ void __launch_bounds__(32, MULTI ? 1 : CRT_FILL2_MINB) k_fill2_v3(con
     __shared__ float4 srow2[RING + 3];
 
     for (int strip = 0; strip < (MULTI ? u.n_strips : 1); ++strip) {
-        float2 nx[CP], ny[CP], nz[CP];       // NEGATED column coordinates, two columns per register pair
+        // two columns per register pair.  CRT_FILL2_DIRECT: the NEGATED coordinates; default: TWICE the coordinates and -|c|^2
+        float2 nx[CP], ny[CP], nz[CP], bc[CP];
         const int c0 = (strip * 32 + lane) * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
+#ifdef CRT_FILL2_DIRECT
             float4 v = make_float4(-1e18f, -1e18f, -1e18f, 0.f);      // padded column: distance^2 ~ 3e36 -> S = 0
             if (c0 + c < u.m) { v = args.cols[(long long)u.col_base + c0 + c]; v.x = -v.x; v.y = -v.y; v.z = -v.z; }
-            if (c & 1) { nx[c / 2].y = v.x; ny[c / 2].y = v.y; nz[c / 2].y = v.z; }
-            else { nx[c / 2].x = v.x; ny[c / 2].x = v.y; nz[c / 2].x = v.z; }
+            const float b = 0.f;
+#else
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            float b = -INFINITY;                                      // padded column: 2^-inf = 0
+            if (c0 + c < u.m) {
+                v = args.cols[(long long)u.col_base + c0 + c];
+                b = -__fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, v.x * v.x));
+                v.x = 2.f * v.x; v.y = 2.f * v.y; v.z = 2.f * v.z;
+            }
+#endif
+            if (c & 1) { nx[c / 2].y = v.x; ny[c / 2].y = v.y; nz[c / 2].y = v.z; bc[c / 2].y = b; }
+            else { nx[c / 2].x = v.x; ny[c / 2].x = v.y; nz[c / 2].x = v.z; bc[c / 2].x = b; }
         }
         const bool last_strip = !MULTI || strip == u.n_strips - 1;
         const bool emitter = last_strip && lane == 31;
@@ -84,7 +117,7 @@ __global__ void __launch_bounds__(32, MULTI ? 1 : CRT_FILL2_MINB) k_fill2_v3(con
         {
             const float4 rv0 = srow2[max(slot - 2, 0)];          // row -lane (lane 31: clamped, any record will do)
             meta_cur = __float_as_int(rv0.w);
-            rbf_row2<CP>(rv0, nx, ny, nz, s_cur);
+            rbf_row2<CP>(rv0, nx, ny, nz, bc, s_cur);
             rv_nxt = srow2[slot - 1];                            // row 1 - lane
             meta_nxt = __float_as_int(rv_nxt.w);
         }
@@ -133,7 +166,7 @@ __global__ void __launch_bounds__(32, MULTI ? 1 : CRT_FILL2_MINB) k_fill2_v3(con
                         prev[c] = h;
                         diag = up; left = h;
                     }
-                    rbf_row2<CP>(rv_nxt, nx, ny, nz, s_cur);
+                    rbf_row2<CP>(rv_nxt, nx, ny, nz, bc, s_cur);
                     carry = left;
                     dsave = in;
                     if (MULTI && !last_strip && lane == 31 && (unsigned)g < (unsigned)G) bnd[g] = carry;
@@ -160,7 +193,7 @@ __global__ void __launch_bounds__(32, MULTI ? 1 : CRT_FILL2_MINB) k_fill2_v3(con
                         prev[c] = h;
                         diag = up; left = h;
                     }
-                    rbf_row2<CP>(rv_nxt, nx, ny, nz, s_cur);
+                    rbf_row2<CP>(rv_nxt, nx, ny, nz, bc, s_cur);
                     carry = left;
                     dsave = in;
                     if (MULTI && !last_strip && lane == 31 && (unsigned)(t - 31) < (unsigned)G) bnd[t - 31] = carry;

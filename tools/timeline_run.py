@@ -21,3 +21,4 @@ for _ in range(3):
 print(f"{name}: {eng.last_elapsed_ms():.3f} ms per step, phases {eng.last_phase_ms()}", file=sys.stderr)
 os.environ["CARETTA_B200_TIMELINE"] = "1"
 eng.pairwise_shard(prm, 0, 1)
+print(f"{name}: timeline run itself {eng.last_elapsed_ms():.3f} ms", file=sys.stderr)
