@@ -2175,6 +2175,63 @@ int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, u
     auto cleanup = [&]() {};
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return e == cudaSuccess; };
+    // ---- in-place path (crt_nj.cuh, second half): reversed storage, joins append, the host compacts every n / 8 joins
+    //      from CARETTA_B200_NJ_INPLACE_MIN nodes on (default 512: below that the segments' extra launches cost more than the
+    //      moved matrix; 4 = always, 0 = never)
+    const int inplace_min = getenv("CARETTA_B200_NJ_INPLACE_MIN") ? atoi(getenv("CARETTA_B200_NJ_INPLACE_MIN")) : 512;
+    if (N > 3 && inplace_min > 0 && N >= inplace_min) {
+        const int seg_min = 64;                          // joins per segment: n / 8, at least this many
+        const int ld = ((N + std::max(N / 8, seg_min) + 2 + 15) / 16) * 16;
+        double *in = nullptr, *D0 = nullptr, *D1 = nullptr, *Sa = nullptr, *Sb = nullptr;
+        long long *ta = nullptr, *tb = nullptr, *pkey = nullptr;
+        int *al_a = nullptr, *al_b = nullptr, *map = nullptr, *cnt = nullptr;
+        cudaStream_t st = c->stream;
+        const size_t LL = (size_t)ld * ld;
+        if (ok(sc.alloc(&D0, LL)) && ok(sc.alloc(&D1, LL)) && ok(sc.alloc(&Sa, (size_t)ld)) && ok(sc.alloc(&Sb, (size_t)ld)) &&
+            ok(sc.alloc(&ta, (size_t)ld)) && ok(sc.alloc(&tb, (size_t)ld)) && ok(sc.alloc(&al_a, (size_t)ld)) && ok(sc.alloc(&al_b, (size_t)ld)) &&
+            ok(sc.alloc(&map, (size_t)ld)) && ok(sc.alloc(&cnt, 1)) && ok(sc.alloc(&pq, (size_t)max_part)) && ok(sc.alloc(&pkey, (size_t)max_part)) &&
+            ok(sc.alloc(&d_tree, rows_max * 2)) && ok(sc.alloc(&d_bl, rows_max)) && ok(sc.alloc(&sel, 1))) {
+            in = D1;                                     // the upload lands in the second buffer (N * N <= ld * ld)
+            ok(cudaMemcpyAsync(in, distance_matrix, NN * 8, cudaMemcpyHostToDevice, st));
+            ok(cudaMemsetAsync(sel, 0, sizeof(NjSel), st));
+            ok(cudaFuncSetAttribute(k_nj2_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NJ2_SMEM));
+            int per_sm = 0;
+            ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nj2_persistent, NJ_REBUILD_THREADS, NJ2_SMEM));
+            const int nb_max = std::min(max_part, std::max(1, per_sm) * c->sm_count);
+            CU(cudaEventRecord(c->ev0, st));
+            k_nj2_load<<<dim3((unsigned)((N + 255) / 256), (unsigned)N), 256, 0, st>>>(in, N, D0, ld, ta, al_a, nullptr);
+            k_nj2_rowsums<<<(unsigned)(((size_t)N * 32 + 255) / 256), 256, 0, st>>>(D0, N, ld, Sa);
+            int n = N;
+            while (n > 3 && e == cudaSuccess) {
+                // one segment: `iters` joins on a compact matrix of n nodes (the extent grows to n + iters <= ld), then compaction
+                const int iters = std::min(n - 3, std::max(seg_min, n / 8));
+                Nj2Args a{D0, ld, Sa, ta, al_a, n, n, iters, N, pq, pkey, sel, d_tree, d_bl};
+                // enough CTAs for every row group of the join to run at once (the add chain of a row is n dependent adds), no more
+                const int groups = (n + iters + NJ_ROWS) / NJ_ROWS;
+                int nb = nb_max;                         // (the scan wants every CTA the device holds: loads in flight)
+                (void)groups;
+                void *args[] = {&a};
+                ok(cudaLaunchCooperativeKernel((const void *)k_nj2_persistent, dim3((unsigned)nb), dim3(NJ_REBUILD_THREADS), args, NJ2_SMEM, st));
+                const int W = n + iters;
+                n -= iters;
+                k_nj2_map<<<1, 1024, 0, st>>>(al_a, W, map, cnt);
+                k_nj2_compact<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, st>>>(D0, ld, map, n, D1, ld, Sa, Sb, ta, tb, al_b);
+                std::swap(D0, D1); std::swap(Sa, Sb); std::swap(ta, tb); std::swap(al_a, al_b);
+                ok(cudaGetLastError());
+            }
+            k_nj2_last3<<<1, 32, 0, st>>>(D0, ld, Sa, N, ta, sel, d_tree, d_bl);
+            ok(cudaGetLastError());
+            CU(cudaEventRecord(c->ev1, st));
+            ok(cudaMemcpyAsync(tree, d_tree, rows_max * 16, cudaMemcpyDeviceToHost, st));
+            ok(cudaMemcpyAsync(branch_lengths, d_bl, rows_max * 8, cudaMemcpyDeviceToHost, st));
+            ok(cudaStreamSynchronize(st));
+            float ms = 0;
+            if (e == cudaSuccess && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->elapsed_ms = ms;
+        }
+        if (e != cudaSuccess) return fail(CRT_E_CUDA, "crt_neighbor_joining: %s", cudaGetErrorString(e));
+        if (n_rows) *n_rows = (int64_t)rows_max;
+        return 0;
+    }
     std::vector<long long> ident((size_t)N);
     for (int q = 0; q < N; ++q) ident[(size_t)q] = q;
     cudaStream_t st = c->stream;

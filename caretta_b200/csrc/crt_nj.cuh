@@ -329,4 +329,312 @@ __global__ void k_nj_last3(const double *A, const double *S, int N, const long l
     sel->rows = r; sel->n_inter += 1;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// IN-PLACE neighbor joining (round 2).  The two-buffer path above reads the matrix twice and WRITES it once per iteration
+// (k_nj_rebuild moves every remaining row to put the new node at index 0).  Here nothing moves: the matrix is stored in
+// REVERSED order (physical index p = logical index from the back), so "new node at logical index 0, the rest in their previous
+// order" (neighbor_joining.py:59-77) is "append at the physical end"; the two joined nodes stay where they are as dead rows (never
+// read again) and ZEROED columns (adding +0.0 leaves a left-to-right float64 sum bit for bit unchanged, so the row sums of numba's
+// np.sum order come out of a plain descending sweep).  An iteration is
+//   scan   Q over the alive rows, first row-major minimum of the LOGICAL order = largest (p, q) among equal values
+//   join   every CTA: rows of the extent W + 1 in groups of NJ_ROWS, tiles of NJ_TCOLS columns from the back; the gather writes
+//          the new column / row and the zeros of the two dead columns as it passes them, warp 0 runs the add chains
+// = 2 n^2 reads and O(n) writes instead of 2 n^2 reads + n^2 writes, and the working set is ONE matrix (L2 holds it below ~3900
+// nodes instead of ~2700).  The extent grows by one per join; the host compacts into the second buffer (same order) every n / 8
+// joins.  Same arithmetic per element and per sum as the path above: bit-identical trees (tests/test_gpu_nj.py).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool nj2_better(double q, long long key, double bq, long long bkey)
+{
+    return q < bq || (q == bq && key > bkey);
+}
+
+// D[p][q] = in[N-1-p][N-1-q]
+__global__ void __launch_bounds__(256) k_nj2_load(const double *in, int N, double *D, int ld, long long *tidx, int *alive, double *S_unused)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (q >= N) return;
+    D[(size_t)p * ld + q] = in[(size_t)(N - 1 - p) * N + (N - 1 - q)];
+    if (p == 0) { tidx[q] = N - 1 - q; alive[q] = 1; }
+}
+
+// row sums in logical order (descending physical column) of a compact matrix: one warp per row, shuffle chain
+__global__ void __launch_bounds__(256) k_nj2_rowsums(const double *D, int W, int ld, double *S)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= W) return;
+    const double *row = D + (size_t)warp * ld;
+    double acc = 0.0;
+    for (int c0 = 0; c0 < W; c0 += 32) {
+        const int k = c0 + lane;                           // position in the logical order
+        const double v = k < W ? row[W - 1 - k] : 0.0;
+        acc = nj_chain32(acc, v, min(32, W - c0));
+    }
+    if (lane == 0) S[warp] = acc;
+}
+
+constexpr int NJ2_RU = 4;                 // rows of the scan a thread keeps in flight
+constexpr int NJ2_TC = 128, NJ2_TS = NJ2_TC + 2, NJ2_NBUF = 4;      // row stride even: 16-byte cp.async destinations
+constexpr size_t NJ2_SMEM = sizeof(double) * NJ2_NBUF * NJ_ROWS * NJ2_TS;
+__device__ __forceinline__ void cp_async16_nj(void *smem_dst, const void *gsrc)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_nj() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_nj() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct Nj2Args {
+    double *D; int ld;
+    double *S; long long *tidx; int *alive;
+    int n, W, iters, N;
+    double *pq; long long *pkey;
+    NjSel *sel; unsigned long long *tree; double *bl;
+};
+
+__global__ void __launch_bounds__(NJ_REBUILD_THREADS, 3) k_nj2_persistent(Nj2Args a)
+{
+    extern __shared__ double nj_tile[];                 // [NJ2_NBUF][NJ_ROWS][NJ2_TS]
+    __shared__ double sq[NJ_ARGMIN_THREADS];
+    __shared__ long long sl[NJ_ARGMIN_THREADS];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int bid = blockIdx.x, nb = gridDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *D = a.D;
+    const int ld = a.ld;
+    int n = a.n, W = a.W;
+    long long rows = a.sel->rows, n_inter = a.sel->n_inter;
+    for (int it = 0; it < a.iters; ++it) {
+        // ---- scan
+        {
+            const double nm2 = (double)(n - 2);
+            double bq = INFINITY;
+            long long bkey = -1;
+            // The CTA's rows bid, bid + nb, ... are taken NJ2_RU at a time: a thread holds one pair of adjacent columns (16-byte
+            // loads: ld and the column pairs are even) of NJ2_RU rows in flight and reads the column sums once for all of them --
+            // rows one after the other would leave one load per thread in flight and pay a memory round trip per row.
+            const double2 *S2 = reinterpret_cast<const double2 *>(a.S);
+            const int W2 = W >> 1;
+            for (int p0 = bid; p0 < W; p0 += NJ2_RU * nb) {
+                const double2 *row2[NJ2_RU];
+                double sp[NJ2_RU];
+                int pr[NJ2_RU];
+#pragma unroll
+                for (int u = 0; u < NJ2_RU; ++u) {
+                    const int p = p0 + u * nb;
+                    const bool on = p < W && a.alive[p];
+                    pr[u] = on ? p : -1;
+                    row2[u] = reinterpret_cast<const double2 *>(D + (size_t)(on ? p : 0) * ld);
+                    sp[u] = on ? a.S[p] : -INFINITY;          // a row that is not there: q = +inf everywhere
+                }
+                for (int c2 = threadIdx.x; c2 < W2; c2 += NJ_ARGMIN_THREADS) {
+                    double2 v[NJ2_RU];
+#pragma unroll
+                    for (int u = 0; u < NJ2_RU; ++u) v[u] = row2[u][c2];
+                    const double2 sc = S2[c2];
+                    const int cc = 2 * c2;
+#pragma unroll
+                    for (int u = 0; u < NJ2_RU; ++u) {
+                        const double q0 = __dsub_rn(__dsub_rn(__dmul_rn(nm2, v[u].x), sp[u]), sc.x);      // dead column: S = -inf, q = +inf
+                        const double q1 = __dsub_rn(__dsub_rn(__dmul_rn(nm2, v[u].y), sp[u]), sc.y);
+                        const long long base = (long long)pr[u] * ld;
+                        if (cc != pr[u] && nj2_better(q0, base + cc, bq, bkey)) { bq = q0; bkey = base + cc; }
+                        if (cc + 1 != pr[u] && nj2_better(q1, base + cc + 1, bq, bkey)) { bq = q1; bkey = base + cc + 1; }
+                    }
+                }
+                if ((W & 1) && threadIdx.x == 0) {          // the odd last column
+                    const int cc = W - 1;
+#pragma unroll
+                    for (int u = 0; u < NJ2_RU; ++u) {
+                        if (pr[u] < 0 || pr[u] == cc) continue;
+                        const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, D[(size_t)pr[u] * ld + cc]), sp[u]), a.S[cc]);
+                        if (nj2_better(q, (long long)pr[u] * ld + cc, bq, bkey)) { bq = q; bkey = (long long)pr[u] * ld + cc; }
+                    }
+                }
+            }
+            sq[threadIdx.x] = bq; sl[threadIdx.x] = bkey;
+            __syncthreads();
+            for (int w = NJ_ARGMIN_THREADS / 2; w > 0; w >>= 1) {
+                if ((int)threadIdx.x < w && nj2_better(sq[threadIdx.x + w], sl[threadIdx.x + w], sq[threadIdx.x], sl[threadIdx.x])) {
+                    sq[threadIdx.x] = sq[threadIdx.x + w]; sl[threadIdx.x] = sl[threadIdx.x + w];
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) { a.pq[bid] = sq[0]; a.pkey[bid] = sl[0]; }
+        }
+        grid.sync();
+        // ---- every CTA: the winner over the block partials
+        {
+            double bq = INFINITY;
+            long long bkey = -1;
+            for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+                const double q = __ldcg(a.pq + k);
+                const long long l = __ldcg(a.pkey + k);
+                if (nj2_better(q, l, bq, bkey)) { bq = q; bkey = l; }
+            }
+            __syncthreads();
+            sq[threadIdx.x] = bq; sl[threadIdx.x] = bkey;
+            __syncthreads();
+            for (int w = NJ_ARGMIN_THREADS / 2; w > 0; w >>= 1) {
+                if ((int)threadIdx.x < w && nj2_better(sq[threadIdx.x + w], sl[threadIdx.x + w], sq[threadIdx.x], sl[threadIdx.x])) {
+                    sq[threadIdx.x] = sq[threadIdx.x + w]; sl[threadIdx.x] = sl[threadIdx.x + w];
+                }
+                __syncthreads();
+            }
+        }
+        const long long key = sl[0];
+        const int pi = (int)(key / ld), pj = (int)(key - (long long)pi * ld);       // row = the reference's min_i, column = min_j
+        const long long node = n_inter + a.N;
+        const double dij = D[(size_t)pi * ld + pj];
+        __syncthreads();                                // sq / sl are reused by the next scan
+        if (bid == 0 && threadIdx.x == 0) {
+            // _find_branch_length, neighbor_joining.py:137-157
+            const double di = __dadd_rn(__dmul_rn(0.5, dij), __dmul_rn(0.5 / (double)(n - 2), __dsub_rn(a.S[pi], a.S[pj])));
+            const double dj = __dsub_rn(dij, di);
+            a.tree[2 * rows] = (unsigned long long)a.tidx[pi]; a.tree[2 * rows + 1] = (unsigned long long)node; a.bl[rows] = di;
+            a.tree[2 * rows + 2] = (unsigned long long)a.tidx[pj]; a.tree[2 * rows + 3] = (unsigned long long)node; a.bl[rows + 1] = dj;
+            // the two joined nodes die, the new one takes the end of the extent (nobody reads these entries before the next barrier:
+            // the join below names pi, pj and W explicitly)
+            a.S[pi] = -INFINITY; a.S[pj] = -INFINITY;
+            a.alive[pi] = 0; a.alive[pj] = 0; a.alive[W] = 1;
+            a.tidx[W] = node;
+        }
+        // ---- join + row sums of the new matrix.  Per CTA and group of NJ_ROWS rows: warps 1..4 stream the row segments into a
+        //      ring of NJ2_NBUF tiles with cp.async (no register staging: NJ2_NBUF - 1 tiles stay in flight), warp 0 patches the
+        //      three special columns of a tile (new column, the two joined ones) and runs the add chains -- the chain of n
+        //      dependent float64 adds per row is what an iteration of this pass costs, the loads hide under it
+        {
+            const double *Dpi = D + (size_t)pi * ld, *Dpj = D + (size_t)pj * ld;
+            const int We = W + 1;                           // extent with the new node at physical index W
+            const int n_tiles = (We + NJ2_TC - 1) / NJ2_TC; // tile tau = columns [128 tau, 128 tau + 128), walked from the last to the first
+            for (int rb = bid; rb * NJ_ROWS < We; rb += nb) {
+                const int r0 = rb * NJ_ROWS;
+                const int prow = r0 + lane;                 // warp 0: the row whose add chain this lane runs
+                double jpa = 0.0, jpb = 0.0;                // (loaded before the flags below are waited for: one round trip, not two)
+                if (warp == 0 && lane < NJ_ROWS) { jpa = Dpi[prow]; jpb = Dpj[prow]; }
+                unsigned act = 0;                           // rows of the group that belong to the new matrix
+#pragma unroll
+                for (int rr = 0; rr < NJ_ROWS; ++rr) {
+                    const int p = r0 + rr;
+                    if (p == W || (p < W && p != pi && p != pj && a.alive[p])) act |= 1u << rr;
+                }
+                if (act == 0) continue;
+                const int rr_new = W - r0;                  // the new node's row, if 0 <= rr_new < NJ_ROWS
+                // gather thread g = 0..127 (warps 1..4): columns 2 (g & 63), +1 of the tile, rows 8 (g >> 6) .. + 7 of the group
+                const int g = (int)threadIdx.x - 32;
+                auto issue = [&](int t) {                   // t-th tile of the walk = tile tau = n_tiles - 1 - t
+                    if (g < 0 || g >= 128 || t >= n_tiles) return;
+                    double *buf = nj_tile + (size_t)(t % NJ2_NBUF) * NJ_ROWS * NJ2_TS;
+                    const int k = 2 * (g & 63), c = (n_tiles - 1 - t) * NJ2_TC + k;
+                    if (c >= We) return;                    // (c + 1 == We is read and not used: the row has ld >= We + 1 elements)
+#pragma unroll
+                    for (int q = 0; q < NJ_ROWS / 2; ++q) {
+                        const int rr = (g >> 6) * (NJ_ROWS / 2) + q;
+                        if (!((act >> rr) & 1u)) continue;
+                        double *dst = buf + rr * NJ2_TS + k;
+                        if (rr == rr_new) {
+                            // the new node's row: 0 at itself and at dead columns (neighbor_joining.py:59-77)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int cc = c + h;
+                                double jc = 0.0;
+                                if (cc < W && cc != pi && cc != pj && a.alive[cc]) jc = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Dpi[cc], Dpj[cc]), dij));
+                                dst[h] = jc;
+                                if (cc < We) D[(size_t)W * ld + cc] = jc;
+                            }
+                        } else {
+                            cp_async16_nj(dst, D + (size_t)(r0 + rr) * ld + c);
+                        }
+                    }
+                };
+                double acc = 0.0, jp = 0.0;                 // jp: the new node's distance to this lane's row
+                const bool chain = warp == 0 && lane < NJ_ROWS && ((act >> lane) & 1u);
+                if (chain && lane != rr_new) jp = __dmul_rn(0.5, __dsub_rn(__dadd_rn(jpa, jpb), dij));
+                __syncthreads();                            // the ring is free (previous group)
+                for (int t = 0; t < NJ2_NBUF - 1; ++t) { issue(t); cp_async_commit_nj(); }
+                for (int t = 0; t < n_tiles; ++t) {
+                    cp_async_wait_nj<NJ2_NBUF - 2>();        // this thread's copies of tile t have landed
+                    __syncthreads();                        // everybody's have, and warp 0 is through with tile t - 1
+                    issue(t + NJ2_NBUF - 1);                // into the buffer of tile t - 1
+                    cp_async_commit_nj();
+                    if (chain) {
+                        double *rowv = nj_tile + (size_t)(t % NJ2_NBUF) * NJ_ROWS * NJ2_TS + lane * NJ2_TS;
+                        const int c0 = (n_tiles - 1 - t) * NJ2_TC;      // column of position 0
+                        if (lane != rr_new) {
+                            // special columns of an ordinary row: the new column (the join value), the joined nodes' columns (zero)
+                            const int kw = W - c0, ki = pi - c0, kj = pj - c0;
+                            if (kw >= 0 && kw < NJ2_TC) { rowv[kw] = jp; D[(size_t)prow * ld + W] = jp; }
+                            if (ki >= 0 && ki < NJ2_TC) { rowv[ki] = 0.0; D[(size_t)prow * ld + pi] = 0.0; }
+                            if (kj >= 0 && kj < NJ2_TC) { rowv[kj] = 0.0; D[(size_t)prow * ld + pj] = 0.0; }
+                        }
+                        // logical order = descending physical column
+                        const int hi = min(NJ2_TC, We - c0) - 1;
+                        if (hi == NJ2_TC - 1) {
+#pragma unroll 16
+                            for (int k = NJ2_TC - 1; k >= 0; --k) acc = __dadd_rn(acc, rowv[k]);
+                        } else {
+                            for (int k = hi; k >= 0; --k) acc = __dadd_rn(acc, rowv[k]);
+                        }
+                    }
+                }
+                cp_async_wait_nj<0>();
+                if (chain) a.S[prow] = acc;
+            }
+        }
+        grid.sync();
+        rows += 2; n_inter += 1; --n; ++W;
+    }
+    if (bid == 0 && threadIdx.x == 0) { a.sel->rows = rows; a.sel->n_inter = n_inter; }
+}
+
+// compaction: map[p'] = p-th alive physical index (one block), then a gather of rows and columns in the same order
+__global__ void __launch_bounds__(1024) k_nj2_map(const int *alive, int W, int *map, int *count)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < W; c0 += 1024) {
+        const int p = c0 + threadIdx.x;
+        const int f = p < W && alive[p] ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) wsum[w] = __popc(bal);
+        __syncthreads();
+        int before = carry;
+        for (int k = 0; k < w; ++k) before += wsum[k];
+        if (f) map[before + __popc(bal & ((1u << lane) - 1u))] = p;
+        __syncthreads();
+        if (threadIdx.x == 0) { int s = 0; for (int k = 0; k < 32; ++k) s += wsum[k]; carry += s; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry;
+}
+__global__ void __launch_bounds__(256) k_nj2_compact(const double *Ds, int lds, const int *map, int n, double *Dd, int ldd, const double *Ss,
+                                                     double *Sd, const long long *ts, long long *td, int *alive_d)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (q >= n) return;
+    Dd[(size_t)p * ldd + q] = Ds[(size_t)map[p] * lds + map[q]];
+    if (p == 0) { Sd[q] = Ss[map[q]]; td[q] = ts[map[q]]; alive_d[q] = 1; }
+}
+
+// the last three nodes (neighbor_joining.py:80-98) on a compact reversed matrix: logical index a = physical 2 - a
+__global__ void k_nj2_last3(const double *D, int ld, const double *S, int N, const long long *tidx, NjSel *sel, unsigned long long *tree, double *bl)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = 3;
+    auto A = [&](int i, int j) { return D[(size_t)(2 - i) * ld + (2 - j)]; };
+    const double d12 = A(1, 2);
+    const double di = __dadd_rn(__dmul_rn(0.5, d12), __dmul_rn(0.5 / (double)(n - 2), __dsub_rn(S[2 - 1], S[2 - 2])));
+    const double dj = __dsub_rn(d12, di);
+    const long long node = sel->n_inter + N;
+    long long r = sel->rows;
+    tree[2 * r] = (unsigned long long)tidx[2 - 1]; tree[2 * r + 1] = (unsigned long long)node; bl[r] = di; ++r;
+    tree[2 * r] = (unsigned long long)tidx[2 - 2]; tree[2 * r + 1] = (unsigned long long)node; bl[r] = dj; ++r;
+    tree[2 * r] = (unsigned long long)tidx[2 - 0]; tree[2 * r + 1] = (unsigned long long)node;
+    bl[r] = __dmul_rn(0.5, __dsub_rn(__dadd_rn(A(1, 0), A(2, 0)), A(1, 2))); ++r;
+    sel->rows = r; sel->n_inter += 1;
+}
+
 }  // namespace crt

@@ -12,11 +12,19 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["default", "inplace", "two_buffer"])
+def eng(request):
+    """default: the in-place kernels from 512 nodes on; inplace / two_buffer: one path for every size (the golden cases are small)."""
+    old = os.environ.get("CARETTA_B200_NJ_INPLACE_MIN")
+    if request.param != "default":
+        os.environ["CARETTA_B200_NJ_INPLACE_MIN"] = "4" if request.param == "inplace" else "0"
     e = engine.Engine()
     yield e
     e.close()
+    if old is None:
+        os.environ.pop("CARETTA_B200_NJ_INPLACE_MIN", None)
+    else:
+        os.environ["CARETTA_B200_NJ_INPLACE_MIN"] = old
 
 
 def test_nj_golden_bit_exact(eng):
@@ -30,7 +38,7 @@ def test_nj_golden_bit_exact(eng):
 
 def test_nj_larger_vs_oracle(eng):
     rng = np.random.default_rng(11)
-    for n in (257, 600):
+    for n in (257, 600, 1100):
         A = rng.random((n, n)) * 3
         A = (A + A.T) / 2
         np.fill_diagonal(A, 0)
