@@ -535,12 +535,20 @@ int env_batches()
 }
 
 // tie3: the codes come from k_fill1_v4 (3 bits per cell); otherwise from the float64 k_fill (2 bits per cell)
-int launch_trace(int C, const TraceArgs &ta, int nu, int n_dense, cudaStream_t st, bool tie3)
+int launch_trace(int C, const TraceArgs &ta, int nu, int n_dense, cudaStream_t st, bool tie3, bool warp = false)
 {
-    const int grid = (n_dense + TRACE_THREADS - 1) / TRACE_THREADS;
+    // warp: a warp per pair, the passes over the path by the warp (k_trace_w).  Chosen by CONTEXT, never by the size of the batch
+    // -- tree levels and the float64 re-run of the fp32 mode, whose batches are small and latency-bound --, so that a pair's bits do
+    // not depend on how a run is cut into batches or shards (CARETTA_B200_TRACE_WARP=0: a thread per pair everywhere)
+    static const bool warp_on = !(getenv("CARETTA_B200_TRACE_WARP") && atoi(getenv("CARETTA_B200_TRACE_WARP")) == 0);
+    const bool wp = warp && warp_on;
+    const int grid = wp ? (n_dense * 32 + TRACE_THREADS - 1) / TRACE_THREADS : (n_dense + TRACE_THREADS - 1) / TRACE_THREADS;
 #define CRT_CASE(CC)                                                                          \
     case CC:                                                                                  \
-        if (tie3) k_trace<CC, true><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense);          \
+        if (wp) {                                                                             \
+            if (tie3) k_trace_w<CC, true><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense);    \
+            else k_trace_w<CC, false><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense);       \
+        } else if (tie3) k_trace<CC, true><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense);   \
         else k_trace<CC, false><<<grid, TRACE_THREADS, 0, st>>>(ta, nu, n_dense);             \
         break;
     switch (C) {
@@ -924,7 +932,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
                 if ((r2 = launch_trace(b.C, tl, (int)b.lf_nu, b.lf_dense, st, true))) return r2;
             }
         } else
-        if (do_trace && (r2 = launch_trace(b.C, ta, nu, b.n_dense, st, f32x))) return r2;
+        if (do_trace && (r2 = launch_trace(b.C, ta, nu, b.n_dense, st, f32x, c->stage1_only || dunits == c->d_units2.p))) return r2;
         if (mid) CU(cudaEventRecord(mid, st));
         if (c->stage1_only || !do_rows2) return 0;
         k_rows2<<<nu, 256, 0, st>>>(ta, nu);

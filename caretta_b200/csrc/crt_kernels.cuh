@@ -491,6 +491,131 @@ __device__ __forceinline__ void trace_tail(const TraceArgs &a, int pair, const s
     a.status[pair] = st | a.status_or;
 }
 
+// Passes 2 and 3 of ONE pair by its warp (k_trace_w: small batches -- tree levels, the float64 re-run, small inputs --, where a
+// thread per pair leaves the device empty and each pass is ~n + m dependent round trips of one thread).  Lane l takes the steps
+// l, l + 32, ... of the path, two (pass 3: four) at a time and branch-free, so the loads of a warp fall into a few sectors and
+// several are in flight; 15 + 3 shuffle-tree sums; lane 0 keeps the 3 x 3 SVD and writes the results.  The sums run in another
+// order than trace_tail's (differences of a few ulp in the rotation: the goldens hold to 1e-9 / 1e-8, the alignments are unchanged).
+__device__ __forceinline__ double warp_sum_t(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void trace_tail_warp(const TraceArgs &a, int pair, const short2 *path, int len, int c, int st, unsigned tie, int n, int m,
+                                                const double *A, const double *B, const double *ceni, const double *cenj)
+{
+    const int lane = threadIdx.x & 31;
+    const double ca0 = ceni[0], ca1 = ceni[1], ca2 = ceni[2], cb0 = cenj[0], cb1 = cenj[1], cb2 = cenj[2];
+    if (tie) st |= ST_TIE;
+    const bool superpose = c > 3;
+    double mom[15];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) mom[k] = 0.0;
+    if (superpose) {
+        for (int q0 = lane; q0 < len; q0 += 64) {
+            double v[2][6], w[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = q0 + 32 * h;
+                const short2 e = q < len ? path[q] : make_short2(-1, -1);
+                const bool ok = e.x >= 0 && e.y >= 0;
+                const int ia = ok ? e.x * 3 : 0, ib = ok ? e.y * 3 : 0;
+                w[h] = ok ? 1.0 : 0.0;
+                v[h][0] = A[ia]; v[h][1] = A[ia + 1]; v[h][2] = A[ia + 2];
+                v[h][3] = B[ib]; v[h][4] = B[ib + 1]; v[h][5] = B[ib + 2];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double x1 = (v[h][0] - ca0) * w[h], y1 = (v[h][1] - ca1) * w[h], z1 = (v[h][2] - ca2) * w[h];
+                const double x2 = (v[h][3] - cb0) * w[h], y2 = (v[h][4] - cb1) * w[h], z2 = (v[h][5] - cb2) * w[h];
+                mom[0] += x1; mom[1] += y1; mom[2] += z1; mom[3] += x2; mom[4] += y2; mom[5] += z2;
+                mom[6] += x2 * x1; mom[7] += x2 * y1; mom[8] += x2 * z1;
+                mom[9] += y2 * x1; mom[10] += y2 * y1; mom[11] += y2 * z1;
+                mom[12] += z2 * x1; mom[13] += z2 * y1; mom[14] += z2 * z1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 15; ++k) mom[k] = warp_sum_t(mom[k]);
+    }
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
+    if (!superpose) st |= 1;          // CRT_ST_FEW_COMMON: multiple_alignment.py:337-342
+    if (superpose && lane == 0) {
+        const double inv = 1.0 / (double)c;
+        const double p1[3] = {mom[0] * inv, mom[1] * inv, mom[2] * inv}, p2[3] = {mom[3] * inv, mom[4] * inv, mom[5] * inv};
+        double Cm[9];
+        Cm[0] = mom[6] - mom[3] * p1[0]; Cm[1] = mom[7] - mom[3] * p1[1]; Cm[2] = mom[8] - mom[3] * p1[2];
+        Cm[3] = mom[9] - mom[4] * p1[0]; Cm[4] = mom[10] - mom[4] * p1[1]; Cm[5] = mom[11] - mom[4] * p1[2];
+        Cm[6] = mom[12] - mom[5] * p1[0]; Cm[7] = mom[13] - mom[5] * p1[1]; Cm[8] = mom[14] - mom[5] * p1[2];
+        kabsch_rotation(Cm, R);
+        m1[0] = p1[0] + ca0; m1[1] = p1[1] + ca1; m1[2] = p1[2] + ca2;
+        m2[0] = p2[0] + cb0; m2[1] = p2[1] + cb1; m2[2] = p2[2] + cb2;
+    }
+    double tr[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) tr[b] = m1[b] - (m2[0] * R[b] + m2[1] * R[3 + b] + m2[2] * R[6 + b]);
+    if (lane == 0) {
+        a.path_len[pair] = len;
+        a.ncommon[pair] = c;
+        double *xf = a.xform + (long long)pair * XF;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) xf[q] = R[q];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { xf[9 + q] = m1[q]; xf[12 + q] = m2[q]; }
+        xf[15] = superpose ? 1.0 : 0.0;
+    }
+    double rmsd = 0.0, tm = 0.0;
+    if (c >= 1 && !a.skip_byproducts) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = __shfl_sync(FULL, R[k], 0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tr[k] = __shfl_sync(FULL, tr[k], 0);
+        const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
+        double ss = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int q0 = lane; q0 < len; q0 += 128) {
+            double v[4][6], w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int q = q0 + 32 * h;
+                const short2 e = q < len ? path[q] : make_short2(-1, -1);
+                const bool ok = e.x >= 0 && e.y >= 0;
+                const int ia = ok ? e.x * 3 : 0, ib = ok ? e.y * 3 : 0;
+                w[h] = ok ? 1.0 : 0.0;
+                v[h][0] = A[ia]; v[h][1] = A[ia + 1]; v[h][2] = A[ia + 2];
+                v[h][3] = B[ib]; v[h][4] = B[ib + 1]; v[h][5] = B[ib + 2];
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                double sm = 0.0, sq = 0.0;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    // (R = identity, t = 0 without a superposition: the products and sums are then exact)
+                    const double yr = (v[h][3] * R[b] + v[h][4] * R[3 + b] + v[h][5] * R[6 + b]) + tr[b];
+                    const double df = v[h][b] - yr;
+                    sq += df * df;
+                    sm += df;
+                }
+                const double q1 = sm / d1, q2 = sm / d2;
+                ss += w[h] * sq;
+                t1 += w[h] / (1 + q1 * q1);
+                t2 += w[h] / (1 + q2 * q2);
+            }
+        }
+        ss = warp_sum_t(ss); t1 = warp_sum_t(t1); t2 = warp_sum_t(t2);
+        rmsd = sqrt(ss / (double)c);
+        t1 = (1.0 / (double)n) * t1;
+        t2 = (1.0 / (double)m) * t2;
+        tm = t1 > t2 ? t1 : t2;
+    }
+    if (lane == 0) {
+        a.rmsd[pair] = rmsd;
+        a.tm[pair] = tm;
+        a.status[pair] = st | a.status_or;
+    }
+}
+
 #ifndef CRT_TRACE_MINB
 #define CRT_TRACE_MINB 6
 #endif
@@ -508,10 +633,11 @@ __device__ __forceinline__ void prefetch_tb(const void *p) { asm volatile("prefe
 // TIE3 = false: 2 bits per cell, (H != diag + S) << 1 | (H != left), written by the float64 k_fill.
 // TIE3 = true : 3 bits per cell, (S attains the maximum) << 2 | (left attains it) << 1 | suspect, written by k_fill1_v4; a walk
 //               that meets a suspect cell sets ST_TIE in the pair's status (the host re-runs those pairs in float64).
-template <int C, bool TIE3>
-__global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceArgs a, int n_units, int n_dense)
+// WARP = true (k_trace_w below): a warp per pair; lane 0 walks, the warp does the passes over the path (trace_tail_warp).
+template <int C, bool TIE3, bool WARP>
+__device__ __forceinline__ void trace_pair(const TraceArgs &a, int n_units, int n_dense)
 {
-    const int gid = blockIdx.x * TRACE_THREADS + threadIdx.x;
+    const int gid = WARP ? (int)((blockIdx.x * TRACE_THREADS + threadIdx.x) >> 5) : (int)(blockIdx.x * TRACE_THREADS + threadIdx.x);
     if (gid >= n_dense) return;
     int lo = 0, hi = n_units - 1;             // last unit with dense_base <= gid
     while (lo < hi) {
@@ -587,7 +713,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
     int i = a.pair_istar[pair], j = m;
     int st = 0, len = 0, c = 0;
     if (i & ISTAR_TIE) { tie = 1; i &= ~ISTAR_TIE; }
-    if (i <= 0) {
+    if (WARP && (threadIdx.x & 31) != 0) {
+        // the other lanes of the pair's warp wait for lane 0's walk (the shuffles below)
+    } else if (i <= 0) {
         st |= 2;                      // CRT_ST_NO_POSITIVE
     } else {
         seek(i, j);
@@ -610,7 +738,24 @@ __global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceAr
             c += diag ? 1 : 0;
         }
     }
-    trace_tail(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);
+    if (WARP) {
+        __syncwarp();                 // lane 0's path stores are visible to the warp
+        len = __shfl_sync(FULL, len, 0); c = __shfl_sync(FULL, c, 0); st = __shfl_sync(FULL, st, 0); tie = __shfl_sync(FULL, tie, 0);
+        trace_tail_warp(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);
+    } else {
+        trace_tail(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);
+    }
+}
+
+template <int C, bool TIE3>
+__global__ void __launch_bounds__(TRACE_THREADS, CRT_TRACE_MINB) k_trace(TraceArgs a, int n_units, int n_dense)
+{
+    trace_pair<C, TIE3, false>(a, n_units, n_dense);
+}
+template <int C, bool TIE3>
+__global__ void __launch_bounds__(TRACE_THREADS, 4) k_trace_w(TraceArgs a, int n_units, int n_dense)
+{
+    trace_pair<C, TIE3, true>(a, n_units, n_dense);
 }
 
 // Stage-2 row records, one thread per row of the unit's stream: (x - m1) R^T + m2  == the reference's frame up
