@@ -118,7 +118,7 @@ int level_core(crt_ctx *c, crt_ctx *nc, int32_t n_nodes, int32_t d, const int64_
         if (lp.flexible_mean())   // mean_function(flexible=True) makes no coordinates (:359-360): flag 0 = no superposition, raw means (unused)
             CU(cudaMemsetAsync(c->lv_xf2.p + (size_t)k0 * XF, 0, sizeof(double) * (size_t)nk * XF, st));
         else
-            k_level_kabsch<<<(nk + 31) / 32, 32, 0, st>>>(dp, nk, nc->coords.p, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0, c->lv_xf2.p + (size_t)k0 * XF);
+            k_level_kabsch<<<nk, 32, 0, st>>>(dp, nk, nc->coords.p, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0, c->lv_xf2.p + (size_t)k0 * XF);
         k_level_mean<<<dim3((unsigned)((ml + 127) / 128), (unsigned)nk), 128, 0, st>>>(dp, nc->tensors.p, nc->coords.p, c->nd_w.p, d, c->nd_a1.p,
                                                                                       c->nd_a2.p, c->nd_len.p + k0, c->lv_xf2.p + (size_t)k0 * XF,
                                                                                       d_out_off ? d_out_off + k0 : nullptr, t_out, c_out, w_out);

@@ -93,76 +93,88 @@ __global__ void __launch_bounds__(256) k_level_score_flex(const DpProblem *probs
 }
 
 // Superposition of mean_function (multiple_alignment.py:362-372) over the common positions of the DTW alignment.
-// One thread: the sums run in alignment order like helper.nb_mean_axis_0 (helper.py:45-53).  xf2: same record layout as xf.
-__device__ inline void node_kabsch_one(const double *c1, const double *c2, const int *aln1, const int *aln2, int len, double *xf2)
+// One WARP per node (round 2): lane l takes the alignment columns l, l + 32, ... (two at a time, branch-free: the loads of both
+// are in flight together), shuffle-tree sums, lane 0 keeps the 3 x 3 SVD.  One thread summing in alignment order like
+// helper.nb_mean_axis_0 (helper.py:45-53) was ~600 dependent round trips twice over (180 us of every tree level); the order of
+// the sums moves the rotation by a few ulp, far inside the 1e-9 the goldens hold (the reference's own SVD is LAPACK's).  The
+// single-node kernel and the level kernel call the same function, so node-by-node, level and pool paths stay bit-identical.
+// xf2: same record layout as xf.  Every lane of the warp must call this.
+__device__ inline void node_kabsch_warp(const double *c1, const double *c2, const int *aln1, const int *aln2, int len, double *xf2)
 {
-    // The sums run in alignment order (one thread); the loads of four columns are issued together before their adds, so that
-    // the walk is not one memory round trip per column.
-    int c = 0;
-    double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
-    for (int q0 = 0; q0 < len; q0 += 4) {
-        int xs[4], ys[4];
-        double v1[4][3], v2[4][3];
+    const int lane = threadIdx.x & 31;
+    double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0}, cnt = 0.0;
+    for (int q0 = lane; q0 < len; q0 += 64) {
+        double v1[2][3], v2[2][3], w[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { xs[u] = q0 + u < len ? aln1[q0 + u] : -1; ys[u] = q0 + u < len ? aln2[q0 + u] : -1; }
+        for (int u = 0; u < 2; ++u) {
+            const int q = q0 + 32 * u;
+            const int x = q < len ? aln1[q] : -1, y = q < len ? aln2[q] : -1;
+            const bool ok = x >= 0 && y >= 0;
+            w[u] = ok ? 1.0 : 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const bool ok = xs[u] >= 0 && ys[u] >= 0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { v1[u][k] = ok ? c1[xs[u] * 3 + k] : 0.0; v2[u][k] = ok ? c2[ys[u] * 3 + k] : 0.0; }
+            for (int k = 0; k < 3; ++k) { v1[u][k] = c1[(ok ? x : 0) * 3 + k]; v2[u][k] = c2[(ok ? y : 0) * 3 + k]; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (xs[u] < 0 || ys[u] < 0) continue;
-            ++c;
-            for (int k = 0; k < 3; ++k) { s1[k] += v1[u][k]; s2[k] += v2[u][k]; }
+        for (int u = 0; u < 2; ++u) {
+            cnt += w[u];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { s1[k] += w[u] * v1[u][k]; s2[k] += w[u] * v2[u][k]; }
         }
     }
+    cnt = warp_sum_t(cnt);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { s1[k] = warp_sum_t(s1[k]); s2[k] = warp_sum_t(s2[k]); }
+    const int c = (int)cnt;
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
     const bool superpose = c > 3;
     if (superpose) {
+#pragma unroll
         for (int k = 0; k < 3; ++k) { m1[k] = s1[k] / (double)c; m2[k] = s2[k] / (double)c; }
         double Cm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int q0 = 0; q0 < len; q0 += 4) {
-            int xs[4], ys[4];
-            double v1[4][3], v2[4][3];
+        for (int q0 = lane; q0 < len; q0 += 64) {
+            double v1[2][3], v2[2][3], w[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { xs[u] = q0 + u < len ? aln1[q0 + u] : -1; ys[u] = q0 + u < len ? aln2[q0 + u] : -1; }
+            for (int u = 0; u < 2; ++u) {
+                const int q = q0 + 32 * u;
+                const int x = q < len ? aln1[q] : -1, y = q < len ? aln2[q] : -1;
+                const bool ok = x >= 0 && y >= 0;
+                w[u] = ok ? 1.0 : 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool ok = xs[u] >= 0 && ys[u] >= 0;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { v1[u][k] = ok ? c1[xs[u] * 3 + k] : 0.0; v2[u][k] = ok ? c2[ys[u] * 3 + k] : 0.0; }
+                for (int k = 0; k < 3; ++k) { v1[u][k] = c1[(ok ? x : 0) * 3 + k]; v2[u][k] = c2[(ok ? y : 0) * 3 + k]; }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (xs[u] < 0 || ys[u] < 0) continue;
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
                 for (int a = 0; a < 3; ++a)
+#pragma unroll
                     for (int b = 0; b < 3; ++b)
-                        Cm[a * 3 + b] = __dadd_rn(Cm[a * 3 + b], __dmul_rn(__dsub_rn(v2[u][a], m2[a]), __dsub_rn(v1[u][b], m1[b])));
-            }
+                        Cm[a * 3 + b] += w[u] * ((v2[u][a] - m2[a]) * (v1[u][b] - m1[b]));
         }
-        kabsch_rotation(Cm, R);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Cm[k] = warp_sum_t(Cm[k]);
+        if (lane == 0) kabsch_rotation(Cm, R);
     }
-    for (int q = 0; q < 9; ++q) xf2[q] = R[q];
-    for (int q = 0; q < 3; ++q) { xf2[9 + q] = m1[q]; xf2[12 + q] = m2[q]; }
-    xf2[15] = superpose ? 1.0 : 0.0;
+    if (lane == 0) {
+        for (int q = 0; q < 9; ++q) xf2[q] = R[q];
+        for (int q = 0; q < 3; ++q) { xf2[9 + q] = m1[q]; xf2[12 + q] = m2[q]; }
+        xf2[15] = superpose ? 1.0 : 0.0;
+    }
 }
 
-__global__ void k_node_kabsch(const double *c1, const double *c2, const int *aln1, const int *aln2, const int *len_p, double *xf2)
+__global__ void __launch_bounds__(32) k_node_kabsch(const double *c1, const double *c2, const int *aln1, const int *aln2, const int *len_p, double *xf2)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    node_kabsch_one(c1, c2, aln1, aln2, *len_p, xf2);
+    if (blockIdx.x != 0) return;
+    node_kabsch_warp(c1, c2, aln1, aln2, *len_p, xf2);
 }
 
 __global__ void __launch_bounds__(32) k_level_kabsch(const DpProblem *probs, int n_nodes, const double *coords, const int *aln1,
                                                      const int *aln2, const int *aln_len, double *xf2)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.x;                 // one warp per node
     if (p >= n_nodes) return;
     const DpProblem pr = probs[p];
-    node_kabsch_one(coords + pr.aln_off * 3, coords + (pr.aln_off + pr.n) * 3, aln1 + pr.aln_off, aln2 + pr.aln_off, aln_len[p],
-                    xf2 + (long long)p * XF);
+    node_kabsch_warp(coords + pr.aln_off * 3, coords + (pr.aln_off + pr.n) * 3, aln1 + pr.aln_off, aln2 + pr.aln_off, aln_len[p],
+                     xf2 + (long long)p * XF);
 }
 
 // Intermediate node: tensors_mean [len, d], coordinates_mean [len, 3], mean weights [len]; one thread per alignment column.

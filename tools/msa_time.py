@@ -36,9 +36,15 @@ def main():
     depth = max(lv.values())
     if os.environ.get("MSA_TIME_COLD", "0") == "0":
         MA.StructureMultiple.from_chains(ch).progressive_align(tree, 1.0, 0.01, 1.0, 0.03, prm, dict(flexible=False))
-    t5 = time.perf_counter()
-    aln = msa.progressive_align(tree, 1.0, 0.01, 1.0, 0.03, prm, dict(flexible=False))
-    t6 = time.perf_counter()
+    reps = int(os.environ.get("MSA_REPS", "1"))          # > 1: the fastest of several runs
+    best = None
+    for _ in range(reps):
+        t5 = time.perf_counter()
+        aln = msa.progressive_align(tree, 1.0, 0.01, 1.0, 0.03, prm, dict(flexible=False))
+        t6 = time.perf_counter()
+        if best is None or t6 - t5 < best:
+            best = t6 - t5
+    t5, t6 = 0.0, best
     A = len(next(iter(aln.values())))
     print(json.dumps({"N": n, "L": L, "pair_matrix_ms": (t2 - t1) * 1e3, "pair_matrix_first_ms": (t1 - t0) * 1e3, "nj_ms": (t4 - t3) * 1e3,
                       "progressive_ms": (t6 - t5) * 1e3, "nodes": n - 1, "ms_per_node": (t6 - t5) * 1e3 / (n - 1), "tree_depth": depth,
