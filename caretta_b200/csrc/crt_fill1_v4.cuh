@@ -33,6 +33,18 @@ struct TieArgs {
 
 __device__ __forceinline__ unsigned umin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u32(a, b, c); }
 
+// The suspect bit: sign of z - (eps d + min(theta, y)).  Default (round 2, last session): the threshold by one FFMA and the
+// comparison as an INTEGER subtraction of the bit patterns (both are non-negative floats, or z = 0x80000000 when all three
+// candidates attain the maximum: then the difference is positive) -- one instruction moves from the FMA pipe, which bounds this
+// kernel (16.2 of its cycles per cell against 13 on the ALU pipe), to the ALU pipe.  CRT_V4_FSUB: the float form of the first
+// version, z - min(theta, y) - eps d by FADD + FFMA.
+#ifdef CRT_V4_FSUB
+#define CRT_V4_SUSPECT()                                                                              \
+        const unsigned rbits = __float_as_uint(__fmaf_rn(d, neg_eps, __uint_as_float(z) - fminf(th, y)));
+#else
+#define CRT_V4_SUSPECT()                                                                              \
+        const unsigned rbits = z - __float_as_uint(__fmaf_rn(d, -neg_eps, fminf(th, y)));
+#endif
 // one row of the lane's C cells; a: value entering from the left (vertical difference of the left neighbour)
 #define CRT_V4_ROW()                                                                                  \
     _Pragma("unroll")                                                                                 \
@@ -44,10 +56,10 @@ __device__ __forceinline__ unsigned umin3(unsigned a, unsigned b, unsigned c) { 
         const float u = __fadd_rd(d, -a);                                                             \
         const float v = __fadd_rd(d, -b);                                                             \
         const unsigned z = umin3(__float_as_uint(y), __float_as_uint(u), __float_as_uint(v));         \
-        const float r = __fmaf_rn(d, neg_eps, __uint_as_float(z) - fminf(th, y));                     \
+        CRT_V4_SUSPECT()                                                                              \
         word = __funnelshift_l(__float_as_uint(y), word, 1);                                          \
         word = __funnelshift_l(__float_as_uint(u), word, 1);                                          \
-        word = __funnelshift_l(__float_as_uint(r), word, 1);                                          \
+        word = __funnelshift_l(rbits, word, 1);                                                       \
         uprev[c] = u;                                                                                 \
         a = v;                                                                                        \
     }

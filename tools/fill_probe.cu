@@ -117,7 +117,7 @@ int main(int argc, char **argv)
     Fill1Args a1{d.rec + (size_t)ROW_PAD * RS, d.meta + ROW_PAD};
     Fill2Args a2{d.rows2 + ROW_PAD, d.cols2 + ROW_PAD};
 
-    const int per_sm[] = {1, 2, 4, 6, 8, 12, 16, 24, 32};
+    const int per_sm[] = {1, 2, 4, 6, 8, 9, 10, 11, 12, 16, 24, 32};
     if (want("v1")) for (int k : per_sm) {
         if (k > 16 || (only_k && k != only_k)) continue;
         const int n = g_sms * k;
