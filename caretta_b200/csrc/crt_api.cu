@@ -2216,8 +2216,10 @@ int crt_neighbor_joining(crt_ctx *c, const double *distance_matrix, int32_t N, u
                 Nj2Args a{D0, ld, Sa, ta, al_a, n, n, iters, N, pq, pkey, sel, d_tree, d_bl};
                 // enough CTAs for every row group of the join to run at once (the add chain of a row is n dependent adds), no more
                 const int groups = (n + iters + NJ_ROWS) / NJ_ROWS;
-                int nb = nb_max;                         // (the scan wants every CTA the device holds: loads in flight)
-                (void)groups;
+                // every row group of the join at once; beyond that the scan wants loads in flight (large n) and the two grid
+                // barriers of a join want few CTAs (small n): CARETTA_B200_NJ_NB overrides (experiments)
+                int nb = std::min(nb_max, std::max(groups, n >= 2048 ? nb_max : (n >= 1024 ? 2 * c->sm_count : c->sm_count)));
+                if (getenv("CARETTA_B200_NJ_NB")) nb = std::max(1, std::min(nb_max, atoi(getenv("CARETTA_B200_NJ_NB"))));
                 void *args[] = {&a};
                 ok(cudaLaunchCooperativeKernel((const void *)k_nj2_persistent, dim3((unsigned)nb), dim3(NJ_REBUILD_THREADS), args, NJ2_SMEM, st));
                 const int W = n + iters;

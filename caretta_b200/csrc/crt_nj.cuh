@@ -348,6 +348,31 @@ __device__ __forceinline__ bool nj2_better(double q, long long key, double bq, l
     return q < bq || (q == bq && key > bkey);
 }
 
+// block-wide winner (value, key): shuffles inside the warps, then one warp over the 8 warp winners; the result in every thread
+__device__ __forceinline__ void nj2_block_best(double &bq, long long &bkey, double *sq, long long *sl)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double q = __shfl_xor_sync(0xffffffffu, bq, o);
+        const long long k = __shfl_xor_sync(0xffffffffu, bkey, o);
+        if (nj2_better(q, k, bq, bkey)) { bq = q; bkey = k; }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();                                    // sq / sl of an earlier use are no longer read
+    if (lane == 0) { sq[warp] = bq; sl[warp] = bkey; }
+    __syncthreads();
+    constexpr int NW = NJ_ARGMIN_THREADS / 32;
+    bq = lane < NW ? sq[lane] : INFINITY;
+    bkey = lane < NW ? sl[lane] : -1;
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        const double q = __shfl_xor_sync(0xffffffffu, bq, o);
+        const long long k = __shfl_xor_sync(0xffffffffu, bkey, o);
+        if (nj2_better(q, k, bq, bkey)) { bq = q; bkey = k; }
+    }
+    bq = __shfl_sync(0xffffffffu, bq, 0); bkey = __shfl_sync(0xffffffffu, bkey, 0);
+}
+
 // D[p][q] = in[N-1-p][N-1-q]
 __global__ void __launch_bounds__(256) k_nj2_load(const double *in, int N, double *D, int ld, long long *tidx, int *alive, double *S_unused)
 {
@@ -452,18 +477,12 @@ __global__ void __launch_bounds__(NJ_REBUILD_THREADS, 3) k_nj2_persistent(Nj2Arg
                     }
                 }
             }
-            sq[threadIdx.x] = bq; sl[threadIdx.x] = bkey;
-            __syncthreads();
-            for (int w = NJ_ARGMIN_THREADS / 2; w > 0; w >>= 1) {
-                if ((int)threadIdx.x < w && nj2_better(sq[threadIdx.x + w], sl[threadIdx.x + w], sq[threadIdx.x], sl[threadIdx.x])) {
-                    sq[threadIdx.x] = sq[threadIdx.x + w]; sl[threadIdx.x] = sl[threadIdx.x + w];
-                }
-                __syncthreads();
-            }
-            if (threadIdx.x == 0) { a.pq[bid] = sq[0]; a.pkey[bid] = sl[0]; }
+            nj2_block_best(bq, bkey, sq, sl);
+            if (threadIdx.x == 0) { a.pq[bid] = bq; a.pkey[bid] = bkey; }
         }
         grid.sync();
         // ---- every CTA: the winner over the block partials
+        long long key;
         {
             double bq = INFINITY;
             long long bkey = -1;
@@ -472,21 +491,12 @@ __global__ void __launch_bounds__(NJ_REBUILD_THREADS, 3) k_nj2_persistent(Nj2Arg
                 const long long l = __ldcg(a.pkey + k);
                 if (nj2_better(q, l, bq, bkey)) { bq = q; bkey = l; }
             }
-            __syncthreads();
-            sq[threadIdx.x] = bq; sl[threadIdx.x] = bkey;
-            __syncthreads();
-            for (int w = NJ_ARGMIN_THREADS / 2; w > 0; w >>= 1) {
-                if ((int)threadIdx.x < w && nj2_better(sq[threadIdx.x + w], sl[threadIdx.x + w], sq[threadIdx.x], sl[threadIdx.x])) {
-                    sq[threadIdx.x] = sq[threadIdx.x + w]; sl[threadIdx.x] = sl[threadIdx.x + w];
-                }
-                __syncthreads();
-            }
+            nj2_block_best(bq, bkey, sq, sl);
+            key = bkey;
         }
-        const long long key = sl[0];
         const int pi = (int)(key / ld), pj = (int)(key - (long long)pi * ld);       // row = the reference's min_i, column = min_j
         const long long node = n_inter + a.N;
         const double dij = D[(size_t)pi * ld + pj];
-        __syncthreads();                                // sq / sl are reused by the next scan
         if (bid == 0 && threadIdx.x == 0) {
             // _find_branch_length, neighbor_joining.py:137-157
             const double di = __dadd_rn(__dmul_rn(0.5, dij), __dmul_rn(0.5 / (double)(n - 2), __dsub_rn(a.S[pi], a.S[pj])));
