@@ -20,7 +20,8 @@
 // A lower-priority candidate within theta of a non-diagonal winner is flagged too (harmless: rare).
 //
 // Cost per cell against k_fill1_v3: y replaces the integer difference, u the negated difference, v is the value handed to
-// the right as before; new are the 3-input unsigned minimum, one FMNMX, one FADD, one FFMA and one funnel shift.
+// the right as before; new are the 3-input unsigned minimum, one FMNMX, one FFMA (the threshold eps d + min(theta, y)), one integer
+// subtraction (z - threshold on the bit patterns: its sign is the suspect bit, see CRT_V4_SUSPECT) and one funnel shift.
 #pragma once
 #include "crt_fill1_v2.cuh"
 
