@@ -534,6 +534,20 @@ int env_batches()
     return std::min(std::max(n, 1), 256);
 }
 
+// Batches of the stage pipeline for a run of `cells` residue pairs between chains of mean length `mean_len`.  The tracebacks of the
+// batches run one after the other on their stream and a traceback launch has a latency floor (one thread walks a pair: ~0.5 ms +
+// 1.7 us per path step, whatever the number of pairs), so a SMALL run -- a shard of a strong-scaled job -- cut into 8 batches waits
+// for 8 floors: measured on rank 0's shard of C3 over 8 ranks, 8 batches 11.8 ms, 3 batches 8.4 ms (4 ranks: 16.1 -> 15.3 ms; the
+// whole of C3 on one GPU: 8 batches 59.4 ms, 6 batches 59.9 ms).  Rule: the floors may take 40 % of the fills' time; 2 <= batches <= 8.
+// CARETTA_B200_BATCHES overrides.
+int auto_batches(double cells, double mean_len)
+{
+    if (getenv("CARETTA_B200_BATCHES")) return env_batches();
+    const double fill_ms = cells * 1.3e-9, floor_ms = 0.5 + 0.0017 * 2.0 * mean_len;
+    const int b = (int)(0.4 * fill_ms / floor_ms);
+    return std::min(std::max(b, 2), 8);
+}
+
 // tie3: the codes come from k_fill1_v4 (3 bits per cell); otherwise from the float64 k_fill (2 bits per cell)
 int launch_trace(int C, const TraceArgs &ta, int nu, int n_dense, cudaStream_t st, bool tie3, bool warp = false)
 {
@@ -748,7 +762,12 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         if (main_run) {
             // 2 % of slack: the units do not cut the total into exactly equal parts, and a ninth batch of a few units would only
             // lengthen the tail of the pipeline
-            if (pipe) budget = std::min(budget, std::max<size_t>(total_bytes / env_batches() + total_bytes / (50 * (size_t)env_batches()) + 1, (size_t)64 << 20));
+            if (pipe) {
+                double cells_all = 0;
+                for (auto &h : uv) cells_all += h.cost;
+                const size_t nbat = (size_t)auto_batches(cells_all, c->N > 0 ? (double)c->total / c->N : 300.0);
+                budget = std::min(budget, std::max<size_t>(total_bytes / nbat + total_bytes / (50 * nbat) + 1, (size_t)64 << 20));
+            }
             else if (NS > 1) budget = std::min(budget, std::max<size_t>(total_bytes / (2 * NS) + 1, (size_t)64 << 20));
         }
         hout.resize(uv.size());

@@ -7,6 +7,7 @@ import numpy as np
 from caretta_b200 import engine, synth
 
 name = sys.argv[1]
+world = int(os.environ.get("SWEEP_WORLD", "1"))          # > 1: rank 0's shard of a world of that size (strong scaling on one GPU)
 knobs = [(a.split("=")[0], a.split("=")[1].split(",")) for a in sys.argv[2:]]
 if name == "C4sub":
     c4 = synth.config("C4"); e = int(c4.offsets[1000])
@@ -21,7 +22,7 @@ for combo in itertools.product(*[v for _, v in knobs]):
         os.environ[k] = v
     ts = []
     for it in range(7):
-        eng.pairwise_shard(prm, 0, 1)
+        eng.pairwise_shard(prm, 0, world)
         if it >= 2:
             ts.append(eng.last_elapsed_ms())
     print(name, " ".join(f"{k.replace('CARETTA_B200_', '')}={v}" for (k, _), v in zip(knobs, combo)),
