@@ -411,12 +411,19 @@ int unit_rows_cap(double target_rowsteps, int m)
     return (int)std::min<double>(std::max<double>(r, UNIT_ROWS_MIN), UNIT_ROWS_MAX);
 }
 
-void finish_unit(const crt_ctx *c, HostUnit &h, int precision)
+// one_variant (the float64 re-run of the fp32 mode): every unit on the widest multi-strip kernel of the precision, whatever its
+// length, so that the re-run is ONE batch per stage: its batches run one after the other and each waits for its longest
+// single-warp pair (on the first 1000 chains of C4, lengths 50 - 1000, the re-run fell into ~10 batches: 27 ms for 4 353 pairs)
+void finish_unit(const crt_ctx *c, HostUnit &h, int precision, bool one_variant = false)
 {
     Choice ch = choose_cols(h.u.m, precision, c->D);
+    if (one_variant) {
+        ch.C = cmax_for(precision, c->D);
+        ch.n_strips = std::max(1, (h.u.m + 32 * ch.C - 1) / (32 * ch.C));
+    }
     h.C = ch.C;
     h.u.n_strips = ch.n_strips;
-    h.multi = ch.n_strips > 1;
+    h.multi = one_variant || ch.n_strips > 1;
     h.u.tchunks = (h.u.G + 31 + 3) / 4;
     h.cost = (double)h.u.G * (double)h.u.m;
     (void)c;
@@ -1036,13 +1043,16 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
                 h.u.col_chain = j; h.u.col_base = (int)c->offsets[j]; h.u.m = (int)(c->offsets[j + 1] - c->offsets[j]);
                 h.u.G = (int)(c->offsets[i + 1] - c->offsets[i]); h.u.n_pairs = 1; h.u.pair_base = slots[q];
                 h.u.path_stride = h.u.G + h.u.m;
-                finish_unit(c, h, CRT_FP64);
+                finish_unit(c, h, CRT_FP64, true);
                 ru[(size_t)q] = h;
             }
             // stage 1 + traceback in float64 (the reference's decisions), stage 2 by the fp32 kernel on the float64 alignment:
             // two unit lists over the same pairs, each with the columns-per-lane / strips of its precision
+            // longest pairs first: a pair is one warp's work from start to end (a 1000 x 1000 pair ~5 ms in float64), so the order of
+            // the blocks decides how long the last one runs alone
+            std::stable_sort(ru.begin(), ru.end(), [](const HostUnit &x, const HostUnit &y) { return x.cost > y.cost; });
             std::vector<HostUnit> ru32 = ru;
-            for (auto &h : ru32) finish_unit(c, h, CRT_FP32);
+            for (auto &h : ru32) finish_unit(c, h, CRT_FP32, true);
             std::vector<Batch> rb, rb32;
             std::vector<Unit> rhu, rhu32;
             carve(ru, CRT_FP64, false, rb, rhu);
