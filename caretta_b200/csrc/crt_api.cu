@@ -90,6 +90,11 @@ __global__ void k_collect_tie(const int *status, long long n, int *list, int *co
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q < n && (status[q] & ST_TIE)) list[atomicAdd(count, 1)] = (int)q;
 }
+__global__ void k_gather_tie(const crt::TieInfo *info, const int *list, int n, crt::TieInfo *out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) out[q] = info[list[q]];
+}
 __global__ void k_mark_status(int *status, const int *list, int n, int bit)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,6 +180,9 @@ struct crt_ctx {
     DevBuf<int> d_tc_counter;
     long long tc_pairs = 0;              // pairs of the last run whose stage 1 ran on the tensor cores
     DevBuf<int> tie_list;                // [0] = count, [1..] = result slots marked ST_TIE
+    DevBuf<crt::TieInfo> tie_info, tie_info_list;     // windowed re-run: per result slot / gathered for the marked slots
+    DevBuf<short2> tie_pool;             // saved path prefixes of the marked pairs
+    DevBuf<unsigned long long> tie_pool_used;
     long long rerun_pairs = 0;
     double rerun_ms = 0;
     double tb_bytes = 0;                 // traceback words the stage-1 fills of the last run wrote (all batches)
@@ -863,6 +871,20 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
     // ---- the three stages of one batch (dunits / f32x: the main run's units in the run's precision, or the float64 re-run
     //      of the pairs the fp32 traceback marked)
     const TieArgs tie = env_tie();
+    // windowed re-run (crt_kernels.cuh: TieInfo): the float64 re-run of a marked pair fills only the rows and columns up to the cell
+    // where the fp32 walk first met a marked decision and resumes the walk there (CARETTA_B200_RERUN_WINDOW=0: the whole pair)
+    const bool window_rr = f32 && !flexible && env_tie_rerun() && !c->stage1_only &&
+                           !(getenv("CARETTA_B200_RERUN_WINDOW") && atoi(getenv("CARETTA_B200_RERUN_WINDOW")) == 0);
+    const Unit *DU_main = c->d_units.p;
+    if (window_rr) {
+        // pool: the prefixes of up to ~5 % of the pairs at the longest path (what does not fit is re-run whole)
+        const size_t want = std::max<size_t>((size_t)1 << 22, (size_t)((double)n_pairs * 0.05 * 2.0 * (double)c->max_len));
+        if ((rc = c->tie_info.ensure((size_t)n_pairs + 1))) return rc;
+        if ((rc = c->tie_pool.ensure(want))) return rc;
+        if ((rc = c->tie_pool_used.ensure(1))) return rc;
+        CU(cudaMemsetAsync(c->tie_pool_used.p, 0, sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(c->tie_info.p, 0, sizeof(TieInfo) * (size_t)n_pairs, c->stream));      // (pairs traced by k_trace_tc: no window)
+    }
     // node contexts (stage 1 only, float64): the fill reads precomputed scores (CARETTA_B200_NODE_RING=0: the generic parity kernel)
     // (worth it where the level waits for single warps: up to CARETTA_B200_NODE_RING_MAX units per batch, default 128)
     const int node_ring_max = getenv("CARETTA_B200_NODE_RING_MAX") ? atoi(getenv("CARETTA_B200_NODE_RING_MAX")) : 128;
@@ -945,6 +967,11 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         ta.rows2_f32 = r32 ? 1 : 0;
         ta.skip_byproducts = c->stage1_only ? 1 : 0;
         ta.status_or = status_or_cur;
+        if (window_rr) {
+            ta.tie_pool = c->tie_pool.p; ta.tie_pool_used = c->tie_pool_used.p; ta.tie_pool_cap = (unsigned long long)c->tie_pool.cap;
+            if (f32x && dunits == DU_main) ta.tie_out = c->tie_info.p;                      // the main run's fp32 traceback
+            if (!f32x && dunits == c->d_units2.p && do_trace) ta.tie_in = c->tie_info.p;      // the re-run's float64 traceback
+        }
         int r2;
         if (do_trace && f32x && b.tc) {
             if (b.tc_np > 0) {
@@ -1027,9 +1054,25 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         if (n_tie > 0) {
             CU(cudaEventRecord(c->ev2, rs));
             std::vector<int> slots((size_t)n_tie);
+            std::vector<TieInfo> winfo;
             CU(cudaMemcpyAsync(slots.data(), c->tie_list.p + 1, sizeof(int) * (size_t)n_tie, cudaMemcpyDeviceToHost, rs));
+            if (window_rr) {
+                if ((rc = c->tie_info_list.ensure((size_t)n_tie))) return rc;
+                k_gather_tie<<<(unsigned)((n_tie + 255) / 256), 256, 0, rs>>>(c->tie_info.p, c->tie_list.p + 1, n_tie, c->tie_info_list.p);
+                CU(cudaGetLastError());
+                winfo.resize((size_t)n_tie);
+                CU(cudaMemcpyAsync(winfo.data(), c->tie_info_list.p, sizeof(TieInfo) * (size_t)n_tie, cudaMemcpyDeviceToHost, rs));
+            }
             CU(cudaStreamSynchronize(rs));
-            std::sort(slots.begin(), slots.end());
+            {   // ascending slots (and their windows with them)
+                std::vector<int> ord((size_t)n_tie);
+                for (int q = 0; q < n_tie; ++q) ord[(size_t)q] = q;
+                std::sort(ord.begin(), ord.end(), [&](int x, int y) { return slots[(size_t)x] < slots[(size_t)y]; });
+                std::vector<int> s2((size_t)n_tie);
+                std::vector<TieInfo> w2(winfo.size());
+                for (int q = 0; q < n_tie; ++q) { s2[(size_t)q] = slots[(size_t)ord[(size_t)q]]; if (!winfo.empty()) w2[(size_t)q] = winfo[(size_t)ord[(size_t)q]]; }
+                slots.swap(s2); winfo.swap(w2);
+            }
             std::vector<std::pair<int, int>> by_base(hu.size());          // (pair_base, unit) -> the (i, j) of a result slot
             for (size_t k = 0; k < hu.size(); ++k) by_base[k] = {hu[k].pair_base, (int)k};
             std::sort(by_base.begin(), by_base.end());
@@ -1047,11 +1090,24 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
                 ru[(size_t)q] = h;
             }
             // stage 1 + traceback in float64 (the reference's decisions), stage 2 by the fp32 kernel on the float64 alignment:
+            // two unit lists over the same pairs; the float64 one may be a WINDOW of the pair (rows and columns up to the marked cell)
+            std::vector<HostUnit> ru_full = ru;
+            if (window_rr)
+                for (int q = 0; q < n_tie; ++q) {
+                    const TieInfo &w = winfo[(size_t)q];
+                    HostUnit &h = ru[(size_t)q];
+                    if (w.i > 0 && w.i <= h.u.G && w.j > 0 && w.j <= h.u.m) {
+                        h.u.G = w.i; h.u.m = w.j;            // path_stride stays the whole pair's: prefix + the resumed walk
+                        finish_unit(c, h, CRT_FP64, true);
+                    }
+                }
+            // stage 1 + traceback in float64 (the reference's decisions), stage 2 by the fp32 kernel on the float64 alignment:
             // two unit lists over the same pairs, each with the columns-per-lane / strips of its precision
             // longest pairs first: a pair is one warp's work from start to end (a 1000 x 1000 pair ~5 ms in float64), so the order of
             // the blocks decides how long the last one runs alone
             std::stable_sort(ru.begin(), ru.end(), [](const HostUnit &x, const HostUnit &y) { return x.cost > y.cost; });
-            std::vector<HostUnit> ru32 = ru;
+            std::stable_sort(ru_full.begin(), ru_full.end(), [](const HostUnit &x, const HostUnit &y) { return x.cost > y.cost; });
+            std::vector<HostUnit> ru32 = ru_full;
             for (auto &h : ru32) finish_unit(c, h, CRT_FP32, true);
             std::vector<Batch> rb, rb32;
             std::vector<Unit> rhu, rhu32;

@@ -363,6 +363,11 @@ __device__ inline void kabsch_rotation(const double Cm[9], double R[9])
 // ------------------------------------------------------------------------------------------------------------
 struct TcRound;
 struct TcPartner;
+// fp32 production mode, where the walk of a pair FIRST met a decision the reference may take differently (windowed re-run):
+// everything the walk did before that cell is the reference's, so the float64 re-run only fills rows 1..i x columns 1..j (H there
+// does not depend on the rest), resumes the walk AT cell (i, j) and keeps the first `len` path entries (saved at `off` of the pool).
+// i = 0: no window (the start row itself was in doubt, a zero-region pair, or the pool was full): the whole pair is re-run.
+struct TieInfo { int i, j, len, c; long long off; };
 struct TraceArgs {
     const Unit *units;
     const TcRound *tc_rounds;     // k_trace_tc: the rounds / partners of the batch (crt_fill_tc.cuh)
@@ -388,6 +393,9 @@ struct TraceArgs {
     int rows2_f32;                // format of the stage-2 row records: 1 = float4 (fp32 stage 2), 0 = double[4]
     int skip_byproducts;          // 1: no RMSD / TM pass over the path (node contexts only use the transform)
     int status_or;                // bits OR-ed into every status written (the overlapped float64 re-run keeps ST_TIE up until the run ends)
+    // windowed re-run: the main fp32 traceback writes tie_out / the pool, the float64 traceback of the re-run reads tie_in
+    TieInfo *tie_out; const TieInfo *tie_in;
+    short2 *tie_pool; unsigned long long *tie_pool_used; unsigned long long tie_pool_cap;
 };
 
 __device__ inline bool s1_is_zero(const TraceArgs &a, long long ri, long long ci)
@@ -649,7 +657,8 @@ __device__ __forceinline__ void trace_pair(const TraceArgs &a, int n_units, int 
     const int ci = u.row_chain0 + tid;
     const int pair = u.pair_base + tid;
     const long long ro = a.offsets[ci];
-    const int n = (int)(a.offsets[ci + 1] - ro), m = u.m;
+    const int n = (int)(a.offsets[ci + 1] - ro), m = u.m;      // m: the unit's columns (a window of the re-run: fewer than the chain's)
+    const int m_full = (int)(a.offsets[u.col_chain + 1] - a.offsets[u.col_chain]);
     const int g0 = (int)(ro - u.row_base);
     const double *A = a.coords + ro * 3;
     const double *B = a.coords + (long long)u.col_base * 3;
@@ -712,6 +721,18 @@ __device__ __forceinline__ void trace_pair(const TraceArgs &a, int n_units, int 
     // ---- pass 1: the walk
     int i = a.pair_istar[pair], j = m;
     int st = 0, len = 0, c = 0;
+    // windowed re-run (float64 traceback of a pair the fp32 walk marked): resume at the marked cell behind the saved prefix
+    TieInfo ti{0, 0, 0, 0, 0};
+    if (!TIE3 && a.tie_in) ti = a.tie_in[pair];
+    const bool resume = ti.i > 0;
+    if (resume) {
+        const short2 *src = a.tie_pool + ti.off;
+        for (int q = WARP ? (int)(threadIdx.x & 31) : 0; q < ti.len; q += WARP ? 32 : 1) path[q] = src[q];
+        if (WARP) __syncwarp();
+        i = ti.i; j = ti.j; len = ti.len; c = ti.c;      // (j == m: the window's last column)
+    }
+    int ts_i = 0, ts_j = 0, ts_len = 0, ts_c = 0;        // TIE3: where the walk first met a marked cell
+    bool ts_seen = false;
     if (i & ISTAR_TIE) { tie = 1; i &= ~ISTAR_TIE; }
     if (WARP && (threadIdx.x & 31) != 0) {
         // the other lanes of the pair's warp wait for lane 0's walk (the shuffles below)
@@ -724,12 +745,15 @@ __device__ __forceinline__ void trace_pair(const TraceArgs &a, int n_units, int 
             const int idx = (w_strip * u.tchunks + (t >> 2)) * 32 + w_l;
             if ((t >> 2) >= 1) { prefetch_tb(tbu + idx - 32); if (w_l > 0) prefetch_tb(tbu + idx - 33); }
         }
-        while (j > 1 && (code() & 1u) == 0u) { --j; col_left(); }      // first column of row i* that attains the maximum
+        if (!resume)
+            while (j > 1 && (code() & 1u) == 0u) { --j; col_left(); }      // first column of row i* that attains the maximum
+        if (tie) ts_seen = true;      // in doubt before the first move: no window
         while (i > 0 && j > 0) {
             if (zreg && is_zero_cell(i, j)) break;
             // one instruction stream for the three moves (the threads of a warp walk different pairs): diag = H == diag + S,
             // left = H == left (and not diag), up otherwise; priority diag > left > up (dynamic_time_warping.py:260-277)
             const unsigned cd = code();
+            if (TIE3 && tie && !ts_seen) { ts_seen = true; ts_i = i; ts_j = j; ts_len = len; ts_c = c; }
             const bool diag = (cd & 2u) == 0u, left = !diag && (cd & 1u) == 0u;
             const bool di = diag || !left, dj = diag || left;
             i -= di ? 1 : 0; j -= dj ? 1 : 0; w_trow -= di ? 1 : 0;
@@ -738,12 +762,24 @@ __device__ __forceinline__ void trace_pair(const TraceArgs &a, int n_units, int 
             c += diag ? 1 : 0;
         }
     }
+    if (TIE3 && tie && a.tie_out && (!WARP || (threadIdx.x & 31) == 0)) {
+        // save the prefix of a marked pair for the windowed re-run (0.5 % of the pairs of C3)
+        TieInfo t{0, 0, 0, 0, 0};
+        if (ts_i > 0 && !zreg) {
+            const unsigned long long off = atomicAdd(a.tie_pool_used, (unsigned long long)ts_len);
+            if (off + (unsigned long long)ts_len <= a.tie_pool_cap) {
+                for (int q = 0; q < ts_len; ++q) a.tie_pool[off + q] = path[q];
+                t = TieInfo{ts_i, ts_j, ts_len, ts_c, (long long)off};
+            }
+        }
+        a.tie_out[pair] = t;
+    }
     if (WARP) {
         __syncwarp();                 // lane 0's path stores are visible to the warp
         len = __shfl_sync(FULL, len, 0); c = __shfl_sync(FULL, c, 0); st = __shfl_sync(FULL, st, 0); tie = __shfl_sync(FULL, tie, 0);
-        trace_tail_warp(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);
+        trace_tail_warp(a, pair, path, len, c, st, tie, n, m_full, A, B, ceni, cenj);
     } else {
-        trace_tail(a, pair, path, len, c, st, tie, n, m, A, B, ceni, cenj);
+        trace_tail(a, pair, path, len, c, st, tie, n, m_full, A, B, ceni, cenj);
     }
 }
 
