@@ -236,6 +236,7 @@ struct crt_ctx {
     DevBuf<char> arena;                   // scratch of the consumer / neighbor-joining calls (crt_consumers_api.inl: Scratch)
     bool coords_only = false;             // chain set made by crt_set_coords: consumers only, no pair runs
     bool stage1_only = false;             // node contexts: the run stops after the traceback / Kabsch (no stage-2 fill)
+    bool no_byproducts = false;           // crt_pairwise_all without RMSD / TM matrices: the tracebacks skip the by-product pass
     DevBuf<DpProblem> lv_probs;           // crt_progressive_level: per-node problem records and packed level buffers
     DevBuf<double> lv_mult, lv_xf2;
     DevBuf<long long> lv_off;
@@ -965,7 +966,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         ta.scale2 = (float)std::sqrt(prm->gamma_coords * 1.4426950408889634);
         ta.precision = f32x ? CRT_FP32 : CRT_FP64;
         ta.rows2_f32 = r32 ? 1 : 0;
-        ta.skip_byproducts = c->stage1_only ? 1 : 0;
+        ta.skip_byproducts = (c->stage1_only || c->no_byproducts) ? 1 : 0;
         ta.status_or = status_or_cur;
         if (window_rr) {
             ta.tie_pool = c->tie_pool.p; ta.tie_pool_used = c->tie_pool_used.p; ta.tie_pool_cap = (unsigned long long)c->tie_pool.cap;
@@ -1719,7 +1720,12 @@ double crt_last_traceback_bytes(crt_ctx *c) { return c ? c->tb_bytes : -1.0; }
 int crt_pairwise_all(crt_ctx *c, const crt_params *prm, double *out_score, double *out_rmsd, double *out_tm)
 {
     if (!out_score) return fail(CRT_E_ARG, "null out_score");
+    if (!c) return fail(CRT_E_ARG, "null context");
+    // the reference's make_pairwise_matrix returns the scores alone (multiple_alignment.py:158-170): without RMSD / TM matrices to
+    // fill, the tracebacks leave out the by-product pass over the paths (crt_fetch then reports 0 for both)
+    c->no_byproducts = !out_rmsd && !out_tm;
     int rc = crt_pairwise_shard(c, prm, 0, 1);
+    c->no_byproducts = false;
     if (rc) return rc;
     // symmetric fill on the device (multiple_alignment.py:164), then one copy per requested matrix
     const size_t N = (size_t)c->N, np = (size_t)c->run_pairs;

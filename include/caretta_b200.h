@@ -150,7 +150,8 @@ int crt_multi_pairwise_all(crt_multi *m, const crt_params *prm, double *out_scor
 int crt_multi_last_timing(crt_multi *m, double *out3, int64_t *rerun_pairs);
 
 /* make_pairwise_matrix: dense symmetric float64 [N,N], diagonal 0 (rmsd/tm by-products: diagonal 0 / 1).
- * Convenience wrapper = crt_pairwise_shard(world=1) + crt_fetch + scatter. out_rmsd/out_tm may be NULL. */
+ * Convenience wrapper = crt_pairwise_shard(world=1) + crt_fetch + scatter. out_rmsd/out_tm may be NULL; when BOTH are NULL (what the
+ * reference's method returns: the scores alone) the per-pair RMSD / TM by-products are not computed at all (crt_fetch reports 0). */
 int crt_pairwise_all(crt_ctx *ctx, const crt_params *prm, double *out_score, double *out_rmsd, double *out_tm);
 /* Page-locked host buffers for inputs/outputs of the calls above (optional; pageable memory works, slower). */
 int crt_host_alloc(size_t bytes, void **out);
