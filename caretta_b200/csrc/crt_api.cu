@@ -127,6 +127,7 @@ struct Batch {
     // node contexts: stage 1 from precomputed scores (crt_node_fill.cuh)
     size_t s_n = 0;                     // doubles of score matrices
     long long max_tiles = 0;            // most 16 x 64 score tiles of a unit
+    int max_strips = 1;                 // most strips of a unit
     bool single = true;                 // every unit holds one pair
 };
 
@@ -803,6 +804,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
                 h.u.dense_base = b.n_dense; b.n_dense += h.u.n_pairs;
                 h.u.s_base = (long long)b.s_n; b.s_n += (size_t)h.u.G * (size_t)h.u.m;
                 b.max_tiles = std::max(b.max_tiles, (long long)((h.u.G + 15) / 16) * ((h.u.m + 63) / 64));
+                b.max_strips = std::max(b.max_strips, h.u.n_strips);
                 if (h.u.n_pairs != 1) b.single = false;
                 b.tb_n += tb_u; b.rows2_n += rows_u; b.path_n += path_u; b.bnd_n += bnd_u;
                 hout[end] = h.u;
@@ -932,9 +934,17 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             const unsigned gx = (unsigned)b.max_tiles;
             k_pair_scores64<<<dim3(gx, (unsigned)nu), 256, 0, st>>>(sa);
             CU(cudaGetLastError());
+            // multi-strip nodes: a warp per strip, in lockstep (k_fill_s64_mw; CARETTA_B200_NODE_MW=0: the strips one after the other)
+            static const bool node_mw = !(getenv("CARETTA_B200_NODE_MW") && atoi(getenv("CARETTA_B200_NODE_MW")) == 0);
+            const int mw_nw = std::min(b.max_strips, NODE_MW_MAX);
 #define CRT_NODE_CASE(CC)                                                                        \
             case CC:                                                                             \
-                if (b.multi) k_fill_s64<CC, true><<<nu, 32, 0, st>>>(du, nu, ws.svals.p, fo);    \
+                if (b.multi && node_mw && mw_nw > 1) {                                           \
+                    const size_t sm = (size_t)mw_nw * (NODE_PF * CC * 32 + 64) * sizeof(double); \
+                    if (sm > 48 * 1024)                                                          \
+                        CU(cudaFuncSetAttribute(k_fill_s64_mw<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+                    k_fill_s64_mw<CC><<<nu, 32 * mw_nw, sm, st>>>(du, nu, ws.svals.p, fo, mw_nw); \
+                } else if (b.multi) k_fill_s64<CC, true><<<nu, 32, 0, st>>>(du, nu, ws.svals.p, fo); \
                 else k_fill_s64<CC, false><<<nu, 32, 0, st>>>(du, nu, ws.svals.p, fo);           \
                 break;
             switch (b.C) { CRT_NODE_CASE(2) CRT_NODE_CASE(3) CRT_NODE_CASE(4) }
