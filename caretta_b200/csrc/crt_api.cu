@@ -1900,7 +1900,9 @@ int dp_batch(crt_ctx *c, bool affine, const double *S, const int64_t *shape_off,
     CUT(cudaMemcpyAsync(dP.p, probs.data(), sizeof(DpProblem) * (size_t)n_problems, cudaMemcpyHostToDevice, st));
     const int tb = 64, tg = (n_problems + tb - 1) / tb;
     if (affine) {
-        k_dtw_fill<<<n_problems, 32, 0, st>>>(dP.p, n_problems, dS.p, dB.p, dBnd.p, dF.p, p0, p1);
+        int max_m = 0;
+        for (const DpProblem &q : probs) max_m = std::max(max_m, q.m);
+        CUT(launch_dtw_fill(dP.p, n_problems, max_m, dS.p, dB.p, dBnd.p, dF.p, p0, p1, st));
         k_dtw_trace_w<<<n_problems, 32, 0, st>>>(dP.p, n_problems, dB.p, dF.p, dA1.p, dA2.p, dLen.p, dScore.p);
     } else {
         k_sw_fill<<<n_problems, 32, 0, st>>>(dP.p, n_problems, dS.p, dW.p, dBnd.p, dF.p, dIdx.p, p0);
@@ -2098,7 +2100,7 @@ int crt_progressive_node(crt_ctx *c, const double *tensors1, const double *coord
     const double *dt1 = nc->tensors.p, *dt2 = nc->tensors.p + (size_t)n * d;
     k_node_score<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(dc1, n, dc2, m, nc->xform.p, c->nd_w.p, c->nd_w.p + n, mult1, mult2,
                                                                  -gamma_coords, -gamma_weight, c->nd_S.p);
-    k_dtw_fill<<<1, 32, 0, st>>>(d_pr, 1, c->nd_S.p, c->nd_B.p, c->nd_bnd.p, c->nd_f.p, gap_open, gap_extend);
+    CU(launch_dtw_fill(d_pr, 1, m, c->nd_S.p, c->nd_B.p, c->nd_bnd.p, c->nd_f.p, gap_open, gap_extend, st));
     k_dtw_trace_w<<<1, 32, 0, st>>>(d_pr, 1, c->nd_B.p, c->nd_f.p, c->nd_a1.p, c->nd_a2.p, c->nd_len.p, c->nd_score.p);
     k_node_kabsch<<<1, 32, 0, st>>>(dc1, dc2, c->nd_a1.p, c->nd_a2.p, c->nd_len.p, c->nd_xf2.p);
     k_node_mean<<<(unsigned)((alen + 127) / 128), 128, 0, st>>>(dt1, dc1, c->nd_w.p, dt2, dc2, c->nd_w.p + n, d, c->nd_a1.p, c->nd_a2.p,

@@ -9,6 +9,7 @@
 #pragma once
 #include "crt_kernels.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace crt {
 
@@ -133,6 +134,148 @@ __global__ void __launch_bounds__(32) k_dtw_fill(const DpProblem *probs, int n_p
         dtw_cp_wait<0>();
         __syncwarp();
     }
+}
+
+// The strips of a problem on concurrent warps (the scheme of k_fill_s64_mw, crt_node_fill.cuh): warp w runs strip s0 + w,
+// DTW_SKEW steps behind warp w - 1, all warps in lockstep with one __syncthreads per four steps; lane 31 of a warp hands
+// M[i][cend][1], [2] to lane 0 of the next through a 64-row ring in shared memory (written at global step i + 30 + DTW_SKEW w, read
+// at i - 1 + DTW_SKEW (w + 1): five steps later, behind a barrier).  n + 31 + 36 (strips - 1) steps instead of (n + 31) strips; same
+// operands in the same order per cell, so the same codes and final values.  Used for tree levels of a few nodes, where the
+// level waits for single warps; rounds of NW strips when a problem has more strips than the CTA has warps.
+constexpr int DTW_SKEW = 36;
+constexpr int DTW_MW_MAX = 12;
+__global__ void __launch_bounds__(32 * DTW_MW_MAX) k_dtw_fill_mw(const DpProblem *probs, int n_probs, const double *S_all, unsigned char *B_all,
+                                                                 double *bnd_all, double *final3, double open, double ext, int NW)
+{
+    extern __shared__ double dtw_dyn[];
+    if ((int)blockIdx.x >= n_probs) return;
+    const DpProblem pr = probs[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = pr.n, m = pr.m;
+    double (*ring)[DPC + 2][32] = reinterpret_cast<double (*)[DPC + 2][32]>(dtw_dyn + (size_t)warp * DTW_PF * (DPC + 2) * 32);
+    double *xch = dtw_dyn + (size_t)NW * DTW_PF * (DPC + 2) * 32;     // [NW][64][2]
+    const double *S = S_all + pr.s_off;
+    unsigned char *B = B_all + pr.b_off;                              // [n][dtw_pitch(m)]
+    const int mp = dtw_pitch(m);
+    double *bnd1 = bnd_all + pr.bnd_off * 2, *bnd2 = bnd1 + n;
+    const double MINF = -DBL_MAX;
+    const int n_strips = (m + DPSTRIP - 1) / DPSTRIP;
+    for (int q = 0; q < DTW_PF * (DPC + 2); ++q) (&ring[0][0][0])[q * 32 + lane] = 0.0;     // columns past m are never fetched
+    for (int q = threadIdx.x; q < NW * 128; q += blockDim.x) xch[q] = 0.0;
+    __syncthreads();
+    for (int s0 = 0; s0 < n_strips; s0 += NW) {
+        const int strip = s0 + warp;
+        const int nwr = min(NW, n_strips - s0);
+        const bool active = warp < nwr;
+        const bool to_ring = warp + 1 < nwr;
+        const int c0 = strip * DPSTRIP + lane * DPC;                 // 0-based first owned column
+        double P0[DPC], P1[DPC];
+#pragma unroll
+        for (int c = 0; c < DPC; ++c) { P0[c] = MINF - open; P1[c] = 0.0; }      // row 0: (MIN - open, 0, 0)
+        double out1 = 0.0, out2 = 0.0;
+        double dsave = 0.0;
+        const bool last_strip = strip == n_strips - 1;
+        const double *xin = xch + (size_t)(warp > 0 ? warp - 1 : 0) * 128;
+        double *xout = xch + (size_t)warp * 128;
+        auto prefetch = [&](int t) {         // one (possibly empty) cp.async group per wavefront step
+            const int i = t - lane + 1;
+            if (i >= 1 && i <= n) {
+                double (*slot)[32] = ring[t & (DTW_PF - 1)];
+                const double *src = S + (long long)(i - 1) * m + c0;
+#pragma unroll
+                for (int c = 0; c < DPC; ++c)
+                    if (c0 + c < m) dtw_cp_async8(&slot[c][lane], src + c);
+                if (lane == 0 && warp == 0 && strip > 0) { dtw_cp_async8(&slot[DPC][0], bnd1 + i - 1); dtw_cp_async8(&slot[DPC + 1][0], bnd2 + i - 1); }
+            }
+            dtw_cp_commit();
+        };
+        if (active)
+            for (int u = 0; u < DTW_PF; ++u) prefetch(u);
+        const int T = n + 31;
+        const int T4 = (T + 3) & ~3;
+        const int total = T4 + DTW_SKEW * (nwr - 1);
+        for (int G0 = 0; G0 < total; G0 += 4) {
+            const int t0 = G0 - DTW_SKEW * warp;
+            if (active && t0 >= 0 && t0 < T) {
+#pragma unroll 1
+                for (int t = t0; t < min(t0 + 4, T); ++t) {
+                    const int i = t - lane + 1;      // 1-based row
+                    const bool valid = i >= 1 && i <= n;
+                    dtw_cp_wait<DTW_PF - 1>();
+                    double (*slot)[32] = ring[t & (DTW_PF - 1)];
+                    double sc[DPC];
+#pragma unroll
+                    for (int c = 0; c < DPC; ++c) sc[c] = slot[c][lane];
+                    double b1 = 0.0, b2 = 0.0;
+                    if (lane == 0) {
+                        if (warp > 0) { const int e = (max(i, 1) - 1) & 63; b1 = xin[2 * e]; b2 = xin[2 * e + 1]; }
+                        else { b1 = slot[DPC][0]; b2 = slot[DPC + 1][0]; }
+                    }
+                    prefetch(t + DTW_PF);
+                    double L1 = shfl_up_d(out1), L2 = shfl_up_d(out2);
+                    if (lane == 0) {
+                        if (strip == 0) { L1 = 0.0; L2 = MINF - open; }       // column 0: (0, 0, MIN - open)
+                        else if (valid) { L1 = b1; L2 = b2; }
+                    }
+                    if (i == 1) dsave = 0.0;          // M[0][j][1] = 0
+                    const double in1 = L1;
+                    double D1 = dsave;
+                    if (valid) {
+                        unsigned codes = 0;
+#pragma unroll
+                        for (int c = 0; c < DPC; ++c) {
+                            const int j = c0 + c;     // 0-based column
+                            const double s = sc[c];
+                            const double l0 = P0[c] - ext, l1 = P1[c] - open;
+                            const int ql = l1 > l0 ? 1 : 0;
+                            const double lower = ql ? l1 : l0;
+                            const double u0 = L1 - open, u1 = L2 - ext;
+                            const int qu = u1 > u0 ? 1 : 0;
+                            const double upper = qu ? u1 : u0;
+                            const double dg = D1 + s;
+                            double v = lower; int q = 0;
+                            if (dg > v) { v = dg; q = 1; }
+                            if (upper > v) { v = upper; q = 2; }
+                            codes |= (unsigned)(ql | (q << 1) | (qu << 3)) << (8 * c);
+                            if (i == n && j == m - 1) { final3[blockIdx.x * 3] = lower; final3[blockIdx.x * 3 + 1] = v; final3[blockIdx.x * 3 + 2] = upper; }
+                            D1 = P1[c];
+                            P0[c] = lower; P1[c] = v;
+                            L1 = v; L2 = upper;
+                        }
+                        if (c0 < m) *reinterpret_cast<unsigned *>(B + (long long)(i - 1) * mp + c0) = codes;
+                        out1 = L1; out2 = L2;
+                        dsave = in1;
+                        if (!last_strip && lane == 31) {
+                            if (to_ring) { const int e = (i - 1) & 63; xout[2 * e] = out1; xout[2 * e + 1] = out2; }
+                            else { bnd1[i - 1] = out1; bnd2[i - 1] = out2; }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        dtw_cp_wait<0>();
+        __syncthreads();
+    }
+}
+
+// k_dtw_fill for a batch: strips on concurrent warps where the batch is small enough to be latency-bound (at most mw_max problems)
+// and has multi-strip problems; CARETTA_B200_DTW_MW=0: always the one-warp kernel.
+inline cudaError_t launch_dtw_fill(const DpProblem *probs, int n_probs, int max_m, const double *S_all, unsigned char *B_all, double *bnd_all,
+                                   double *final3, double open, double ext, cudaStream_t st, int mw_max = 128)
+{
+    static const bool mw_on = !(getenv("CARETTA_B200_DTW_MW") && atoi(getenv("CARETTA_B200_DTW_MW")) == 0);
+    const int strips = (max_m + DPSTRIP - 1) / DPSTRIP;
+    const int nw = strips < DTW_MW_MAX ? strips : DTW_MW_MAX;
+    if (mw_on && nw > 1 && n_probs <= mw_max) {
+        const size_t sm = (size_t)nw * (DTW_PF * (DPC + 2) * 32 + 128) * sizeof(double);
+        if (sm > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_dtw_fill_mw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (e != cudaSuccess) return e;
+        }
+        k_dtw_fill_mw<<<n_probs, 32 * nw, sm, st>>>(probs, n_probs, S_all, B_all, bnd_all, final3, open, ext, nw);
+    } else
+        k_dtw_fill<<<n_probs, 32, 0, st>>>(probs, n_probs, S_all, B_all, bnd_all, final3, open, ext);
+    return cudaGetLastError();
 }
 
 __global__ void k_dtw_trace(const DpProblem *probs, int n_probs, const unsigned char *B_all, const double *final3,

@@ -99,10 +99,11 @@ int level_core(crt_ctx *c, crt_ctx *nc, int32_t n_nodes, int32_t d, const int64_
         DpProblem *dp = c->lv_probs.p + k0;
         CU(cudaMemcpyAsync(dp, probs.data() + k0, sizeof(DpProblem) * (size_t)nk, cudaMemcpyHostToDevice, st));
         long long mc = 0;
-        int ml = 0;
+        int ml = 0, mm = 0;
         for (int k = k0; k < k1; ++k) {
             mc = std::max(mc, (long long)probs[(size_t)k].n * probs[(size_t)k].m);
             ml = std::max(ml, probs[(size_t)k].n + probs[(size_t)k].m);
+            mm = std::max(mm, probs[(size_t)k].m);
         }
         if (flexible)
             k_level_score_flex<<<dim3((unsigned)((mc + 255) / 256), (unsigned)nk), 256, 0, st>>>(dp, nc->tensors.p, d, c->nd_w.p,
@@ -112,7 +113,7 @@ int level_core(crt_ctx *c, crt_ctx *nc, int32_t n_nodes, int32_t d, const int64_
             k_level_score<<<dim3((unsigned)((mc + 255) / 256), (unsigned)nk), 256, 0, st>>>(dp, nc->coords.p, c->nd_w.p, nc->xform.p + (size_t)k0 * XF,
                                                                                            c->lv_mult.p + (size_t)k0 * 2, -lp.gamma_coords,
                                                                                            -lp.gamma_weight, c->nd_S.p);
-        k_dtw_fill<<<nk, 32, 0, st>>>(dp, nk, c->nd_S.p, c->nd_B.p, c->nd_bnd.p, c->nd_f.p + (size_t)k0 * 3, lp.gap_open, lp.gap_extend);
+        CU(launch_dtw_fill(dp, nk, mm, c->nd_S.p, c->nd_B.p, c->nd_bnd.p, c->nd_f.p + (size_t)k0 * 3, lp.gap_open, lp.gap_extend, st));
         k_dtw_trace_w<<<nk, 32, 0, st>>>(dp, nk, c->nd_B.p, c->nd_f.p + (size_t)k0 * 3, c->nd_a1.p, c->nd_a2.p, c->nd_len.p + k0,
                                                    c->nd_score.p + k0);
         if (lp.flexible_mean())   // mean_function(flexible=True) makes no coordinates (:359-360): flag 0 = no superposition, raw means (unused)
