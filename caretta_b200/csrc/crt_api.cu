@@ -231,6 +231,10 @@ struct crt_ctx {
         DevBuf<double> t, c, w;               // tensors [rows, d], coordinates [rows, 3], consensus weights [rows]
         std::vector<long long> off;           // first row of every sequence
         std::vector<int> len;                 // its length
+        // bookkeeping of crt_msa_compose: the children and the two alignments of every node made since crt_msa_begin
+        int n_leaves = 0;
+        std::vector<int> ch1, ch2;
+        std::vector<std::vector<int32_t>> al1, al2;
     } pool;
     DevBuf<long long> lv_tab, lv_out_off;
 
@@ -1374,7 +1378,7 @@ int crt_destroy(crt_ctx *c)
     c->chain_of.release(); c->stats.release(); c->flag.release(); c->meta.release(); c->rec32.release(); c->cols2.release(); c->d_units.release();
     for (int w = 0; w < crt_ctx::MAX_WS; ++w) {
         crt_ctx::Workspace &ws = c->ws[w];
-        ws.tb.release(); ws.rows2.release(); ws.bnd.release(); ws.bnd2.release(); ws.path.release();
+        ws.tb.release(); ws.rows2.release(); ws.bnd.release(); ws.bnd2.release(); ws.path.release(); ws.svals.release();
         if (ws.done) cudaEventDestroy(ws.done);
         if (ws.e_f1) cudaEventDestroy(ws.e_f1);
         if (ws.e_t) cudaEventDestroy(ws.e_t);
@@ -1398,7 +1402,7 @@ int crt_destroy(crt_ctx *c)
     }
     if (c->s_tr) cudaStreamDestroy(c->s_tr);
     if (c->ws_rr.stream) cudaStreamDestroy(c->ws_rr.stream);
-    c->ws_rr.tb.release(); c->ws_rr.rows2.release(); c->ws_rr.bnd.release(); c->ws_rr.bnd2.release(); c->ws_rr.path.release();
+    c->ws_rr.tb.release(); c->ws_rr.rows2.release(); c->ws_rr.bnd.release(); c->ws_rr.bnd2.release(); c->ws_rr.path.release(); c->ws_rr.svals.release();
     if (c->e_traces) cudaEventDestroy(c->e_traces);
     if (c->e_rr) cudaEventDestroy(c->e_rr);
     c->d_tc_rounds.release(); c->d_tc_partners.release(); c->d_tc_left.release(); c->d_tc_counter.release();

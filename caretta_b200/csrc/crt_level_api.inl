@@ -215,6 +215,8 @@ int crt_msa_begin(crt_ctx *c, double consensus_weight, int32_t *n_sequences)
     for (int p = 0; p < c->N; ++p) P.len[(size_t)p] = (int)(c->offsets[(size_t)p + 1] - c->offsets[(size_t)p]);
     P.used = total;
     P.active = true;
+    P.n_leaves = c->N;
+    P.ch1.clear(); P.ch2.clear(); P.al1.clear(); P.al2.clear();
     if (n_sequences) *n_sequences = c->N;
     return 0;
 }
@@ -282,6 +284,9 @@ int crt_msa_level(crt_ctx *c, int32_t n_nodes, const int32_t *child1, const int3
         P.off.push_back(out_off[(size_t)k]);
         P.len.push_back(aln_len[k]);
         aln_off[k] = offsets[(size_t)2 * k];
+        P.ch1.push_back(child1[k]); P.ch2.push_back(child2[k]);
+        P.al1.emplace_back(aln1 + aln_off[k], aln1 + aln_off[k] + aln_len[k]);
+        P.al2.emplace_back(aln2 + aln_off[k], aln2 + aln_off[k] + aln_len[k]);
     }
     aln_off[n_nodes] = total;
     P.used = need;
@@ -342,10 +347,59 @@ int crt_msa_fetch(crt_ctx *c, const int32_t *ids, int32_t count, double *tensors
     return 0;
 }
 
+/* Index arrays of the sequences under node `root` in the frame of that node (the bookkeeping of multiple_alignment.py:219-232,
+ * composed top-down: the map columns of the frame -> columns of a child is one gather through the node's alignment per edge, and at
+ * a leaf the map is the index array).  Host-side integer bookkeeping on the alignments crt_msa_level returned; no device work.
+ * Rows of `out` [n_under][A] (A = length of `root`) in the reference's dictionary order (first child's sequences first). */
+int crt_msa_compose(crt_ctx *c, int32_t root, int32_t *leaf_ids, int32_t leaf_cap, int32_t *n_under, int64_t *out, int64_t out_cap)
+{
+    if (!c || !leaf_ids || !n_under || !out) return fail(CRT_E_ARG, "null argument");
+    crt_ctx::MsaPool &P = c->pool;
+    if (!P.active) return fail(CRT_E_STATE, "crt_msa_begin has not been called");
+    const int n_seq = (int)P.len.size(), nl = P.n_leaves;
+    if (root < 0 || root >= n_seq) return fail(CRT_E_ARG, "sequence %d is not in the pool", root);
+    const long long A = P.len[(size_t)root];
+    struct Item { int node; std::vector<int32_t> map; };
+    std::vector<Item> stack;
+    {
+        Item it{root, std::vector<int32_t>((size_t)A)};
+        for (long long x = 0; x < A; ++x) it.map[(size_t)x] = (int32_t)x;
+        stack.push_back(std::move(it));
+    }
+    int count = 0;
+    while (!stack.empty()) {
+        Item it = std::move(stack.back());
+        stack.pop_back();
+        if (it.node < nl) {
+            if (count >= leaf_cap || (long long)(count + 1) * A > out_cap) return fail(CRT_E_ARG, "output holds %d rows, more needed", count);
+            leaf_ids[count] = it.node;
+            int64_t *o = out + (long long)count * A;
+            for (long long x = 0; x < A; ++x) o[x] = it.map[(size_t)x];
+            ++count;
+            continue;
+        }
+        const size_t q = (size_t)(it.node - nl);
+        const std::vector<int32_t> *al[2] = {&P.al1[q], &P.al2[q]};
+        const int ch[2] = {P.ch1[q], P.ch2[q]};
+        for (int s = 1; s >= 0; --s) {                     // second child first onto the stack: the first child's subtree comes out first
+            Item nx{ch[s], std::vector<int32_t>((size_t)A)};
+            const int32_t *a = al[s]->data();
+            for (long long x = 0; x < A; ++x) {
+                const int32_t v = it.map[(size_t)x];
+                nx.map[(size_t)x] = v < 0 ? -1 : a[v];
+            }
+            stack.push_back(std::move(nx));
+        }
+    }
+    *n_under = count;
+    return 0;
+}
+
 int crt_msa_end(crt_ctx *c)
 {
     if (!c) return fail(CRT_E_ARG, "null context");
     c->pool.active = false;
+    c->pool.ch1.clear(); c->pool.ch2.clear(); c->pool.al1.clear(); c->pool.al2.clear();
     c->pool.t.release(); c->pool.c.release(); c->pool.w.release();
     c->pool.off.clear(); c->pool.len.clear(); c->pool.used = 0;
     return 0;

@@ -25,7 +25,7 @@ EXPORTS = [
     "crt_last_elapsed_ms", "crt_last_phase_ms", "crt_last_launches", "crt_last_rerun", "crt_last_tc_pairs", "crt_last_cell_updates", "crt_last_traceback_bytes", "crt_pairwise_all", "crt_pairwise_list",
     "crt_sw_align_batch", "crt_dtw_align_batch", "crt_rmsd_cov_tm", "crt_rmsd_cov_tm_superposed", "crt_fp32_peak", "crt_host_alloc", "crt_host_free", "crt_neighbor_joining", "crt_progressive_node", "crt_progressive_level",
     "crt_score_matrix", "crt_mean_function", "crt_mean_weights",
-    "crt_msa_begin", "crt_msa_level", "crt_msa_lengths", "crt_msa_fetch", "crt_msa_end",
+    "crt_msa_begin", "crt_msa_level", "crt_msa_lengths", "crt_msa_fetch", "crt_msa_compose", "crt_msa_end",
     "crt_pack_results", "crt_scatter_gathered", "crt_multi_create", "crt_multi_destroy", "crt_multi_devices", "crt_multi_ctx",
     "crt_multi_set_chains", "crt_multi_pairwise_all", "crt_multi_last_timing",
     "crt_coverage_gap_matrix", "crt_superpose", "crt_superpose_pairs", "crt_format_matrix", "crt_format_fasta", "crt_text_fetch", "crt_count_matrix", "crt_braycurtis",
@@ -101,6 +101,7 @@ def load_library():
     L.crt_msa_level.argtypes = [vp, i32, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, vp, vp, i64, vp, vp, vp, vp, C.POINTER(i32)]
     L.crt_msa_lengths.argtypes = [vp, C.POINTER(i32), vp, i32]
     L.crt_msa_fetch.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.crt_msa_compose.argtypes = [vp, i32, vp, i32, C.POINTER(i32), vp, i64]
     L.crt_msa_end.argtypes = [vp]
     L.crt_coverage_gap_matrix.argtypes = [vp, vp, i32, i64, vp, vp]
     L.crt_superpose.argtypes = [vp, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
@@ -705,6 +706,16 @@ class Engine:
         T, X, W = np.empty((rows, dd)), np.empty((rows, 3)), np.empty(rows)
         self._check(self.lib.crt_msa_fetch(self.h, _p(ids), len(ids), _p(T), _p(X), _p(W)), "crt_msa_fetch")
         return [(T[off[q]:off[q + 1]], X[off[q]:off[q + 1]], W[off[q]:off[q + 1]].reshape(-1, 1)) for q in range(len(ids))]
+
+    def msa_compose(self, root: int):
+        """(pool ids of the sequences under `root` in dictionary order, int64 [n_under, A] index arrays in root's frame): crt_msa_compose."""
+        A = int(self._msa_lengths[root])
+        cap = len(self._offsets) - 1
+        ids = np.empty(cap, np.int32)
+        out = np.empty((cap, A), np.int64)
+        n = C.c_int32()
+        self._check(self.lib.crt_msa_compose(self.h, int(root), _p(ids), cap, C.byref(n), _p(out), out.size), "crt_msa_compose")
+        return ids[:n.value], out[:n.value]
 
     def msa_track(self, nodes):
         """Registers the lazy view of the pool's nodes (weakly): it is fetched before the pool is replaced or released."""

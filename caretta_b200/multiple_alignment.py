@@ -560,7 +560,12 @@ class MultipleAlignment:
 
         final_alignments = _NodeAlignments(node_names, node_alignments)
         last = n_total - 1
-        alignment = {node_names[leaf]: arr for leaf, arr in leaf_maps(last, np.arange(node_len[last], dtype=np.int32))}
+        if use_pool and steps and hasattr(eng, "msa_compose") and os.environ.get("CARETTA_B200_MSA_COMPOSE", "1") != "0":
+            # the same top-down composition inside the library (crt_msa_compose): rows of one [N, A] int64 array, dictionary order
+            ids, rows = eng.msa_compose(pool_id[last])
+            alignment = {node_names[leaf]: rows[r] for r, leaf in enumerate(ids.tolist())}
+        else:
+            alignment = {node_names[leaf]: arr for leaf, arr in leaf_maps(last, np.arange(node_len[last], dtype=np.int32))}
         self.final_consensus_weights = final_consensus_weights
         self.final_alignments = final_alignments
         self.final_sequences = final_sequences

@@ -245,6 +245,10 @@ int crt_msa_level(crt_ctx *ctx, int32_t n_nodes, const int32_t *child1, const in
                   int64_t aln_cap, int64_t *aln_off, int32_t *aln_len, double *score, int32_t *status, int32_t *first_new_id);
 int crt_msa_lengths(crt_ctx *ctx, int32_t *n_sequences, int32_t *lengths, int32_t cap);
 int crt_msa_fetch(crt_ctx *ctx, const int32_t *ids, int32_t count, double *tensors, double *coords, double *weights);
+/* crt_msa_compose: the index arrays (int64, -1 = gap) of the n_under sequences under pool sequence `root`, in the frame of `root`
+ * (length A = its length): rows of out [n_under][A] in the reference's dictionary order (multiple_alignment.py:219-232: the first
+ * child's sequences first), their pool ids in leaf_ids.  root = the last node gives progressive_align's return value (:253). */
+int crt_msa_compose(crt_ctx *ctx, int32_t root, int32_t *leaf_ids, int32_t leaf_cap, int32_t *n_under, int64_t *out, int64_t out_cap);
 int crt_msa_end(crt_ctx *ctx);
 
 /* Neighbor joining on the device: replaces caretta/neighbor_joining.py:17-99 (`neighbor_joining(distance_matrix)`, called
