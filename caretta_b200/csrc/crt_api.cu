@@ -1543,7 +1543,7 @@ int ensure_prepared(crt_ctx *c, const crt_params *prm)
     a.rs32 = ((c->D + 2 + 3) / 4) * 4; a.d32 = c->D; a.rec32 = c->rec32.p + (size_t)ROW_PAD * a.rs32;
     a.rec64 = c->rec64.p; a.d64 = c->D;
     a.meta = c->meta.p + ROW_PAD; a.cols2 = c->cols2.p; a.centroid = c->centroid.p;
-    k_centroid<<<(c->N + 127) / 128, 128, 0, c->stream>>>(a);
+    k_centroid<<<(c->N + 3) / 4, 128, 0, c->stream>>>(a);
     CU(cudaGetLastError());
     k_prep<<<(unsigned)((c->total + 127) / 128), 128, 0, c->stream>>>(a);
     CU(cudaGetLastError());
