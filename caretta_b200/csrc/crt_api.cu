@@ -939,7 +939,7 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
             k_pair_scores64<<<dim3(gx, (unsigned)nu), 256, 0, st>>>(sa);
             CU(cudaGetLastError());
             // multi-strip nodes: a warp per strip, in lockstep (k_fill_s64_mw; CARETTA_B200_NODE_MW=0: the strips one after the other)
-            static const bool node_mw = !(getenv("CARETTA_B200_NODE_MW") && atoi(getenv("CARETTA_B200_NODE_MW")) == 0);
+            const bool node_mw = !(getenv("CARETTA_B200_NODE_MW") && atoi(getenv("CARETTA_B200_NODE_MW")) == 0);
             const int mw_nw = std::min(b.max_strips, NODE_MW_MAX);
 #define CRT_NODE_CASE(CC)                                                                        \
             case CC:                                                                             \

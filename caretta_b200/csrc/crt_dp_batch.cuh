@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(32 * DTW_MW_MAX) k_dtw_fill_mw(const DpProblem
 inline cudaError_t launch_dtw_fill(const DpProblem *probs, int n_probs, int max_m, const double *S_all, unsigned char *B_all, double *bnd_all,
                                    double *final3, double open, double ext, cudaStream_t st, int mw_max = 128)
 {
-    static const bool mw_on = !(getenv("CARETTA_B200_DTW_MW") && atoi(getenv("CARETTA_B200_DTW_MW")) == 0);
+    const bool mw_on = !(getenv("CARETTA_B200_DTW_MW") && atoi(getenv("CARETTA_B200_DTW_MW")) == 0);
     const int strips = (max_m + DPSTRIP - 1) / DPSTRIP;
     const int nw = strips < DTW_MW_MAX ? strips : DTW_MW_MAX;
     if (mw_on && nw > 1 && n_probs <= mw_max) {
