@@ -117,7 +117,7 @@ def _on_fused_path(sequences) -> bool:
     return all(getattr(s, "tensors", None) is not None for s in sequences)
 
 
-def pack_sequences(sequences, need_coordinates: bool = True) -> typing.Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def pack_sequences(sequences, need_coordinates: bool = True, staging=None) -> typing.Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """List of Protein-like objects (anything with .tensors [L,d] and .coordinates [L,3]) -> packed chain set.
     need_coordinates=False (flexible=True runs, where the reference never reads them, multiple_alignment.py:323-326): a sequence
     whose coordinates are None gets zeros."""
@@ -140,9 +140,47 @@ def pack_sequences(sequences, need_coordinates: bool = True) -> typing.Tuple[np.
         cs.append(c)
     offsets = np.zeros(len(sequences) + 1, np.int64)
     np.cumsum([t.shape[0] for t in ts], out=offsets[1:])
+    if staging is not None:
+        coords, tensors = staging.views(int(offsets[-1]), d)
+        np.concatenate(cs, out=coords)
+        np.concatenate(ts, out=tensors)
+        return coords, tensors, offsets
     coords = np.concatenate(cs, dtype=np.float64)
     tensors = np.concatenate(ts, dtype=np.float64)
     return coords, tensors, offsets
+
+
+class _PinnedStaging:
+    """Page-locked staging buffers for the packed chain set of the mirror's own engine calls: set_chains copies from them at the
+    full PCIe rate instead of through the driver's bounce buffers (a third of progressive_align's host time at N = 1000), and
+    returns only when the copy is done, so the next call may overwrite them.  They grow and are never handed to the caller."""
+
+    def __init__(self):
+        self.coords = self.tensors = None
+
+    def views(self, rows: int, d: int):
+        if self.coords is None or self.coords.size < rows * 3:
+            self.coords = _engine.pinned_empty(max(rows * 3 + rows * 3 // 4, 1))
+        if self.tensors is None or self.tensors.size < rows * d:
+            self.tensors = _engine.pinned_empty(max(rows * d + rows * d // 4, 1))
+        return self.coords[:rows * 3].reshape(rows, 3), self.tensors[:rows * d].reshape(rows, d)
+
+
+_staging: typing.Optional[_PinnedStaging] = None
+
+
+def _pack_staged(sequences, need_coordinates: bool = True):
+    """pack_sequences into the process's pinned staging buffers (for an immediate set_chains); plain arrays if pinning fails or
+    CARETTA_B200_PINNED_STAGING=0."""
+    global _staging
+    if os.environ.get("CARETTA_B200_PINNED_STAGING", "1") == "0":
+        return pack_sequences(sequences, need_coordinates)
+    if _staging is None:
+        _staging = _PinnedStaging()
+    try:
+        return pack_sequences(sequences, need_coordinates, staging=_staging)
+    except _engine.CrtError:
+        return pack_sequences(sequences, need_coordinates)
 
 
 def pack_coordinates(sequences) -> typing.Tuple[np.ndarray, np.ndarray]:
@@ -333,7 +371,7 @@ class MultipleAlignment:
         if not _on_fused_path(self.sequences):
             return self._pairwise_matrix_generic(score_function_params or {})
         prm = self._params(score_function_params)
-        packed = pack_sequences(self.sequences, need_coordinates=not prm.flags & _engine.FLAG_FLEXIBLE)
+        packed = _pack_staged(self.sequences, need_coordinates=not prm.flags & _engine.FLAG_FLEXIBLE)
         n = len(self.sequences)
         lens = np.diff(packed[2]).astype(np.float64)
         cells = 0.5 * (lens.sum() ** 2 - (lens ** 2).sum())
@@ -507,7 +545,7 @@ class MultipleAlignment:
             levels[level[n_leaves + q] - 1].append(q)
         if use_pool:
             # the sequences stay on the device: leaves = pool ids 0..N-1, every level appends its nodes; only alignments come back
-            eng.set_chains(*pack_sequences(self.sequences, need_coordinates=need_xyz))
+            eng.set_chains(*_pack_staged(self.sequences, need_coordinates=need_xyz))
             eng.msa_begin(consensus_weight)
             pool_id = list(range(n_leaves)) + [None] * len(steps)
             level_call = getattr(eng, "msa_level_ext", None)          # alignments come back with the sentinel in place: no copies
@@ -632,7 +670,7 @@ class MultipleAlignment:
     def make_pairwise_matrices(self, score_function_params=None):
         """Engine by-product: (score, rmsd, tm) over the stage-1 matched residues, each float64 [N,N]."""
         eng = get_engine()
-        eng.set_chains(*pack_sequences(self.sequences))
+        eng.set_chains(*_pack_staged(self.sequences))
         return eng.pairwise_all(self._params(score_function_params), want_rmsd_tm=True)
 
 
