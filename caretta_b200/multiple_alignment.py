@@ -215,25 +215,32 @@ _shared_multi: typing.Optional[_engine.MultiEngine] = None
 MULTI_GPU_MIN_CELLS = 2.0e9
 
 
+_multi_probe: typing.Optional[str] = None
+
+
 def get_multi_engine() -> typing.Optional[_engine.MultiEngine]:
     """Every visible GPU behind the one call the reference makes (multiple_alignment.py:498-500): crt_multi_* (one context per
     device, NCCL all-gather inside the library).  CARETTA_B200_DEVICES = "all" (default), "1" / "0,2,3" (a list of device ids);
     a single id, a torchrun launch (LOCAL_RANK set: one process per GPU, caretta_b200.distributed) or a one-GPU box -> None."""
-    global _shared_multi
+    global _shared_multi, _multi_probe
     if _shared_multi is not None:
         return _shared_multi
     spec = os.environ.get("CARETTA_B200_DEVICES", "all").strip().lower()
     if "LOCAL_RANK" in os.environ or "CARETTA_B200_DEVICE" in os.environ:
         return None
+    if _multi_probe == spec:                   # this device list was tried before and gave fewer than two devices:
+        return None                            # creating and destroying a context set costs 10 ms and more per call
     devices = None if spec in ("all", "") else [int(x) for x in spec.split(",") if x.strip() != ""]
     if devices is not None and len(devices) < 2:
         return None
     try:
         m = _engine.MultiEngine(devices)
     except _engine.CrtError:
+        _multi_probe = spec
         return None
     if m.n_devices < 2:
         m.close()
+        _multi_probe = spec
         return None
     _shared_multi = m
     return m
