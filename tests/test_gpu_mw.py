@@ -77,3 +77,20 @@ def test_progressive_alignment_same_bits_with_and_without():
             assert np.array_equal(got[0][k], ref[0][k]), (env, k)
         for x, y in zip(got[1:], ref[1:]):
             assert np.array_equal(x, y), env
+
+
+def test_long_nodes_rounds_of_strips():
+    """Three chains of ~1600 residues: the nodes have 13 - 15 strips of 128 columns, i.e. two rounds of the 12-warp kernels, with the
+    boundary column of a round going through global memory."""
+    ch = synth.make_chains(3, [1600, 1580, 1650], 10, seed=77, family_size=3)
+    prm = dict(MA.DEFAULT_SCORE_PARAMS)
+    tree = np.array([[0, 3], [1, 3], [3, 2]], dtype=np.int64)     # (0, 1) -> node 3, then (3, 2) -> int-final
+    with _Env(CARETTA_B200_NODE_MW=1, CARETTA_B200_DTW_MW=1):
+        ref = _align(ch, tree, prm)
+    assert len(next(iter(ref[0].values()))) >= 1650
+    with _Env(CARETTA_B200_NODE_MW=0, CARETTA_B200_DTW_MW=0):
+        got = _align(ch, tree, prm)
+    for k in ref[0]:
+        assert np.array_equal(got[0][k], ref[0][k]), k
+    for x, y in zip(got[1:], ref[1:]):
+        assert np.array_equal(x, y)
