@@ -313,10 +313,10 @@ __global__ void k_dtw_trace(const DpProblem *probs, int n_probs, const unsigned 
 }
 
 // The same traceback with one warp per problem: the backtrack bytes the walk can reach next -- a tile of DTT_ROWS rows x DTT_COLS
-// columns ending at the current cell -- are fetched by the whole warp (one row per lane, aligned 32-bit loads) into shared
+// columns ending at the current cell -- are fetched by the whole warp (rows dealt to the lanes, aligned 32-bit loads) into shared
 // memory, lane 0 walks inside the tile, and the warp reloads when the walk leaves it.  One memory round trip per tile instead
 // of one per step; identical output.
-constexpr int DTT_ROWS = 32, DTT_COLS = 64, DTT_WORDS = DTT_COLS / 4 + 1;
+constexpr int DTT_ROWS = 64, DTT_COLS = 128, DTT_WORDS = DTT_COLS / 4 + 1;      // (32 x 64 until the end of round 2: four times the reloads)
 
 __global__ void __launch_bounds__(32) k_dtw_trace_w(const DpProblem *probs, int n_probs, const unsigned char *B_all, const double *final3,
                                                     int *aln1, int *aln2, int *aln_len, double *score)
@@ -340,14 +340,18 @@ __global__ void __launch_bounds__(32) k_dtw_trace_w(const DpProblem *probs, int 
         const int r_hi = n - 1, c_hi = m - 1;
         const int r_lo = max(0, r_hi - DTT_ROWS + 1), c_lo = max(0, c_hi - DTT_COLS + 1);
         if (n > 0 && m > 0) {
-            const int r = r_lo + lane;
-            if (r <= r_hi) {
-                const unsigned long long addr = (unsigned long long)(B + (long long)r * mm + c_lo);
-                const unsigned *src = reinterpret_cast<const unsigned *>(addr & ~3ull);
-                const int sh = (int)(addr & 3ull);
-                const int words = (sh + (c_hi - c_lo + 1) + 3) >> 2;
-                for (int w = 0; w < words; ++w) tile[lane][w] = src[w];
-                tshift[lane] = sh;
+#pragma unroll
+            for (int rr = lane; rr < DTT_ROWS; rr += 32) {
+                const int r = r_lo + rr;
+                if (r <= r_hi) {
+                    const unsigned long long addr = (unsigned long long)(B + (long long)r * mm + c_lo);
+                    const unsigned *src = reinterpret_cast<const unsigned *>(addr & ~3ull);
+                    const int sh = (int)(addr & 3ull);
+                    const int words = (sh + (c_hi - c_lo + 1) + 3) >> 2;
+#pragma unroll 4
+                    for (int w = 0; w < words; ++w) tile[rr][w] = src[w];
+                    tshift[rr] = sh;
+                }
             }
         }
         __syncwarp();
