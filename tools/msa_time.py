@@ -39,6 +39,11 @@ def main():
     reps = int(os.environ.get("MSA_REPS", "1"))          # > 1: the fastest of several runs
     best = None
     for _ in range(reps):
+        # a run starts like the first one of a process: nobody holds the previous run's lazy nodes (final_sequences /
+        # final_consensus_weights), which the engine would otherwise fetch from the pool before replacing it (40 ms at N = 5000);
+        # MSA_TIME_KEEP=1 keeps them (the numbers of round 2 before its last session were measured that way)
+        if os.environ.get("MSA_TIME_KEEP", "0") == "0":
+            msa.final_sequences = msa.final_consensus_weights = None
         t5 = time.perf_counter()
         aln = msa.progressive_align(tree, 1.0, 0.01, 1.0, 0.03, prm, dict(flexible=False))
         t6 = time.perf_counter()
