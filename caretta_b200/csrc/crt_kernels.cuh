@@ -470,6 +470,7 @@ __device__ __forceinline__ void trace_tail(const TraceArgs &a, int pair, const s
     double rmsd = 0.0, tm = 0.0;
     if (c >= 1 && !a.skip_byproducts) {
         const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
+        const double id1 = 1.0 / d1, id2 = 1.0 / d2;
         double ss = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll 2
         for (int q = len - 1; q >= 0; --q) {
@@ -485,9 +486,14 @@ __device__ __forceinline__ void trace_tail(const TraceArgs &a, int pair, const s
                 ss += df * df;
                 sm += df;
             }
-            const double q1 = sm / d1, q2 = sm / d2;
-            t1 += 1 / (1 + q1 * q1);
-            t2 += 1 / (1 + q2 * q2);
+            // 1 / (1 + (sm / d)^2) for both normalisations by ONE division (a float64 division is ~30 instructions, and this
+            // pass ran four per matched residue): x_k = 1 + (sm / d_k)^2, r = 1 / (x_1 x_2), 1 / x_1 = r x_2.  A few ulp
+            // from tm_score's own operation order (multiple_alignment.py:60-70); the by-products are tested to 1e-8.
+            const double q1 = sm * id1, q2 = sm * id2;
+            const double x1 = 1 + q1 * q1, x2 = 1 + q2 * q2;
+            const double r = 1 / (x1 * x2);
+            t1 += r * x2;
+            t2 += r * x1;
         }
         rmsd = sqrt(ss / (double)c);
         t1 = (1.0 / (double)n) * t1;
@@ -581,6 +587,7 @@ __device__ __forceinline__ void trace_tail_warp(const TraceArgs &a, int pair, co
 #pragma unroll
         for (int k = 0; k < 3; ++k) tr[k] = __shfl_sync(FULL, tr[k], 0);
         const double d1 = 1.24 * (double)(n - 15) / 3 - 1.8, d2 = 1.24 * (double)(m - 15) / 3 - 1.8;
+        const double id1 = 1.0 / d1, id2 = 1.0 / d2;
         double ss = 0.0, t1 = 0.0, t2 = 0.0;
         for (int q0 = lane; q0 < len; q0 += 128) {
             double v[4][6], w[4];
@@ -605,10 +612,12 @@ __device__ __forceinline__ void trace_tail_warp(const TraceArgs &a, int pair, co
                     sq += df * df;
                     sm += df;
                 }
-                const double q1 = sm / d1, q2 = sm / d2;
+                const double q1 = sm * id1, q2 = sm * id2;            // one division for both terms, as in trace_tail
+                const double x1 = 1 + q1 * q1, x2 = 1 + q2 * q2;
+                const double r = w[h] / (x1 * x2);
                 ss += w[h] * sq;
-                t1 += w[h] / (1 + q1 * q1);
-                t2 += w[h] / (1 + q2 * q2);
+                t1 += r * x2;
+                t2 += r * x1;
             }
         }
         ss = warp_sum_t(ss); t1 = warp_sum_t(t1); t2 = warp_sum_t(t2);
