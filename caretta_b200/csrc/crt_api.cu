@@ -1065,6 +1065,11 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
         CU(cudaGetLastError());
         int n_tie = 0;
         CU(cudaMemcpyAsync(&n_tie, c->tie_list.p, sizeof(int), cudaMemcpyDeviceToHost, rs));
+        // (pair_base, unit) -> the (i, j) of a result slot: sorted while the device still works on the batches -- the
+        // synchronisation below returns when the last traceback is through, and from there on every host millisecond is tail
+        std::vector<std::pair<int, int>> by_base(hu.size());
+        for (size_t k = 0; k < hu.size(); ++k) by_base[k] = {hu[k].pair_base, (int)k};
+        std::sort(by_base.begin(), by_base.end());
         CU(cudaStreamSynchronize(rs));
         if (n_tie > 0) {
             CU(cudaEventRecord(c->ev2, rs));
@@ -1088,9 +1093,6 @@ int run_units(crt_ctx *c, const crt_params *prm, std::vector<HostUnit> &units, l
                 for (int q = 0; q < n_tie; ++q) { s2[(size_t)q] = slots[(size_t)ord[(size_t)q]]; if (!winfo.empty()) w2[(size_t)q] = winfo[(size_t)ord[(size_t)q]]; }
                 slots.swap(s2); winfo.swap(w2);
             }
-            std::vector<std::pair<int, int>> by_base(hu.size());          // (pair_base, unit) -> the (i, j) of a result slot
-            for (size_t k = 0; k < hu.size(); ++k) by_base[k] = {hu[k].pair_base, (int)k};
-            std::sort(by_base.begin(), by_base.end());
             std::vector<HostUnit> ru((size_t)n_tie);
             for (int q = 0; q < n_tie; ++q) {
                 auto it = std::upper_bound(by_base.begin(), by_base.end(), std::make_pair(slots[q], 0x7fffffff));
